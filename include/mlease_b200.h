@@ -1,0 +1,173 @@
+/*
+ * mlease_b200.h -- C ABI of the B200-native ADMM logistic-regression hot path.
+ *
+ * Drop-in boundary for ONE path of linkedin/ml-ease: the body of
+ * RegressionAdmmTrain.run() (jobs/RegressionAdmmTrain.java:278-501), the reducer it drives
+ * (AdmmReducer.reduce, :642-718 -> LibLinear.train, llf/LibLinear.java:200-208), the scoring
+ * of RegressionTest/RegressionTestLoglik and the per-key fits of RegressionNaiveTrain.
+ * The reference has no FFI seam (it is 100% Java); these are the entry points a JNI shim
+ *  binds.  Paths cited below are relative to
+ * /root/reference/src/main/java/com/linkedin/mlease/ unless they start with bw/ (= de/bwaldvogel/liblinear/).
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (message via
+ * mlease_last_error(), thread-local).  Plain pointers and sizes only.  "host-or-device"
+ * pointers may be either (UVA); everything else says which.  Feature ids are the GLOBAL
+ * dictionary 0..num_features-1; the intercept "(INTERCEPT)" is index num_features (last), the
+ * bias column the reference appends to every row (regression/liblinearfunc/LibLinearDataset.java:592-614).
+ * One host thread drives a session (the reference's driver and reducers are single threaded).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef MLEASE_B200_H
+#define MLEASE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mlease_session mlease_session;
+
+#define MLEASE_OK 0
+#define MLEASE_ERR_INVALID 1   /* bad argument / config (reference: IOException in the job) */
+#define MLEASE_ERR_CUDA 2      /* CUDA failure (reference: IOException("Model fitting error!"), jobs/RegressionAdmmTrain.java:713-716) */
+#define MLEASE_ERR_NUMERIC 3   /* a fit did not converge / Hessian not SPD (same mapping) */
+#define MLEASE_ERR_STATE 4     /* call order (e.g. partitions missing: RuntimeException("Some models failed!"), utils/LinearModelUtils.java:80-83) */
+
+const char* mlease_last_error(void);
+int mlease_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Session = one RegressionAdmmTrain job on one GPU (one process per GPU; partitions are
+ * sharded over processes, the caller owns the inter-process all-reduce).
+ * Config keys mirrored (jobs/RegressionAdmmTrain.java:78-122,138-185):
+ *   num.blocks, lambda (list, Float.parseFloat), rho (list or NULL -> 1 if lambda<=100 else 10),
+ *   regularizer (must be 2 here; 1 = L1 is out of scope, anything else -> "Only L1 and L2
+ *   regularization supported!"), penalize.intercept, epsilon, rho.adapt.coefficient,
+ *   aggressive.liblinear.epsilon.decay (pure control: only moves the stop rule :493-496).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t device;              /* CUDA ordinal */
+  int32_t num_blocks;          /* P, partitions over ALL processes */
+  int32_t num_features;        /* global dictionary size, intercept excluded */
+  int32_t num_lambdas;         /* L */
+  const float* lambdas;        /* [L] host */
+  const float* rhos;           /* [L] host or NULL */
+  const float* lambda_map;     /* [num_features] host or NULL; >0 entries override lambda per feature (:382-386) */
+  int32_t regularizer;         /* 2 */
+  int32_t penalize_intercept;  /* default 0 */
+  int32_t aggressive_decay;    /* default 0 */
+  int32_t binary_feature;      /* binary.feature: ignore values, use 1 (regression/liblinearfunc/LibLinearBinaryDataset.java) */
+  double epsilon;              /* outer stop, default 1e-4 (:473) */
+  float rho_adapt_coefficient; /* default 0 (:323-327) */
+  /* solver knobs (no reference equivalent: the inner solve is exact Newton, not TRON) */
+  double newton_xtol;          /* stop when |dir|_inf <= xtol*max(|beta|_inf,1e-2); 0 -> 1e-8 */
+  int32_t max_newton;          /* max accepted Newton steps per x-update; 0 -> 50 */
+  int32_t hessian_policy;      /* 0 adaptive chord (refresh when contraction is poor), 1 every step */
+  void* stream;                /* cudaStream_t to run on (NULL = legacy default stream) */
+} mlease_admm_config;
+
+int mlease_session_create(const mlease_admm_config* cfg, mlease_session** out);
+int mlease_session_destroy(mlease_session* s);
+
+/* Replaces the per-iteration re-ingest LibLinearDataset.addInstanceAvro/finish
+ * (regression/liblinearfunc/LibLinearDataset.java:413-484,586-658; jobs/RegressionAdmmTrain.java:677-690):
+ * records are uploaded ONCE and stay resident in HBM.  Rows are RegressionPrepareOutput records
+ * (src/main/avro/RegressionPrepareOutput.avsc): response in {1,0,-1} (0 -> -1), weight >= 0, float32
+ * values.  Pointers are host-or-device; the library copies.
+ * dense: X row-major [nrows x num_features], leading dimension ldx (floats).
+ * csr:   rowptr [nrows+1] (int64), colidx (global ids, any order, duplicates add), vals. */
+int mlease_add_partition_dense(mlease_session* s, int32_t partition_id, int64_t nrows, const float* X, int64_t ldx,
+                               const int32_t* response, const float* weight, const float* offset);
+int mlease_add_partition_csr(mlease_session* s, int32_t partition_id, int64_t nrows, const int64_t* rowptr,
+                             const int32_t* colidx, const float* vals, const int32_t* response, const float* weight,
+                             const float* offset);
+
+/* ADMM loop, one iteration = jobs/RegressionAdmmTrain.java:281-497 :
+ *   begin      : z = {}, u = {}  (:155-185, :312), schedule reset (:278-279)
+ *   local_step : x-update of every local (partition, lambda) (AdmmReducer.reduce :642-718) and
+ *                exchange[l][k] = sum over LOCAL partitions of float(x_p)[k] + u_p[k]   (device, double,
+ *                [L][num_features+1]) -- the only data that crosses GPUs
+ *   consensus  : given the exchange buffer summed over ALL processes (one all-reduce), the z-update
+ *                (:362-404), convergence (:456-472), schedule + stop rule (:338-346,:493-496) and next u
+ *                (computeU :736-765).  *stop is 1 when the reference would break.
+ * mlease_admm_run drives these for a single-process job (allreduce == NULL) or with a caller-supplied
+ * all-reduce (sum, double, in place on `buf` which is DEVICE memory, ordered on `stream`). */
+typedef int (*mlease_allreduce_fn)(void* ctx, double* buf, size_t count, void* stream);
+int mlease_admm_begin(mlease_session* s);
+int mlease_admm_local_step(mlease_session* s, double* exchange_dev);
+int mlease_admm_consensus(mlease_session* s, const double* exchange_sum_dev, double* maxdiff, int32_t* stop);
+int mlease_admm_run(mlease_session* s, int32_t num_iters, mlease_allreduce_fn allreduce, void* ctx, int32_t* iters_done);
+
+/* State readback (host buffers).  z: driver-side double z (:365-404); final model = float(z)
+ * (models/LinearModel.java:697-720 toAvro).  x / u / uplusx: the reducer outputs of the last iteration
+ * (:706-711) for iter-<i>/{model,u} files.  Length num_features+1, intercept last. */
+int mlease_get_z(mlease_session* s, int32_t lambda_idx, double* out);
+int mlease_get_final_model(mlease_session* s, int32_t lambda_idx, float* out);
+int mlease_get_x(mlease_session* s, int32_t partition_id, int32_t lambda_idx, double* out);
+int mlease_get_u(mlease_session* s, int32_t partition_id, int32_t lambda_idx, float* out);
+int mlease_get_uplusx(mlease_session* s, int32_t partition_id, int32_t lambda_idx, float* out);
+
+typedef struct {
+  int64_t k1_passes;        /* fused score/reweight/gradient passes over X (all problems) */
+  int64_t gram_builds;      /* Gram + Cholesky refreshes */
+  int64_t newton_steps;     /* accepted Newton steps */
+  int64_t rejected_steps;   /* line-search rejections */
+  int64_t kernel_launches;  /* kernels launched by this session */
+  int32_t not_converged;    /* x-updates that hit max_newton */
+  int32_t last_iter_slots;  /* evaluation slots used by the last local_step */
+  double last_maxdiff;
+  float liblinear_epsilon;  /* schedule variable (:279,338-346), control only */
+} mlease_stats;
+int mlease_get_stats(mlease_session* s, mlease_stats* out);
+
+/* ---------------------------------------------------------------------------------------
+ * Function-level entry points (parity tests against the oracle's fun/grad/hessian):
+ * LogisticRegressionL2.fun/grad/hessian (regression/liblinearfunc/LogisticRegressionL2.java:156-297)
+ * evaluated on a resident partition at host vector w, prior mean m, prior precision q (=1/priorVar),
+ * all of length num_features+1.  Any output may be NULL.  H is [Dt x Dt] row-major (full, symmetric).
+ * tensor != 0 builds H with the tcgen05 Gram kernel (bf16 operands), 0 with the fp32 SIMT debug kernel.
+ * ------------------------------------------------------------------------------------- */
+int mlease_objective(mlease_session* s, int32_t partition_id, const double* w, const double* m, const double* q,
+                     double* f, double* g, double* H, int32_t tensor);
+/* LibLinear.train(dataset, init, priorMean, priorVar...) (regression/liblinearfunc/LibLinear.java:200-208) for one
+ * resident partition: exact Newton solve of the same objective.  x: in = init, out = minimiser. */
+int mlease_fit_partition(mlease_session* s, int32_t partition_id, double* x, const double* m, const double* q,
+                         int32_t* newton_steps);
+
+/* ---------------------------------------------------------------------------------------
+ * RegressionNaiveTrain (jobs/RegressionNaiveTrain.java:302-415): K independent fits, key k owns rows
+ * [key_rowstart[k], key_rowstart[k+1]) of a dense row-major matrix (host-or-device).  priorVar = 1/lambda,
+ * intercept variance 100000 unless penalize_intercept (:333-343), per-feature lambda_map, prior.mean,
+ * has.intercept, data.size.threshold (skipped keys -> skipped[k]=1, model 0).  out_model [K][D+1] double.
+ * ------------------------------------------------------------------------------------- */
+int mlease_naive_train_dense(int32_t device, void* stream, int32_t num_keys, int32_t num_features,
+                             const int64_t* key_rowstart, const float* X, int64_t ldx, const int32_t* response,
+                             const float* weight, const float* offset, float lambda, const float* lambda_map,
+                             float prior_mean, int32_t penalize_intercept, int32_t has_intercept,
+                             int32_t data_size_threshold, double* out_model, int32_t* skipped);
+
+/* ---------------------------------------------------------------------------------------
+ * RegressionTest / RegressionTestLoglik.
+ * score: pred = float(offset + interceptTerm + sum beta_k x_k), interceptTerm = -log(n-1+n*exp(-b)),
+ *        n = num.click.replicates (models/LinearModel.java:241-257,491-554; jobs/RegressionTest.java:163).
+ *        dense (colidx==NULL: X = vals, ld = ldx) or CSR.  All data pointers host-or-device; pred host-or-device.
+ * test_loglik: mapper float cast, combiner partial sums cast to float per `combiner_block` records
+ *        (<=0: no combiner), reducer float(sum/count) (jobs/RegressionTestLoglik.java:124-200).
+ * ------------------------------------------------------------------------------------- */
+int mlease_score(int32_t device, void* stream, int32_t num_features, int64_t nrows, const int64_t* rowptr,
+                 const int32_t* colidx, const float* vals, int64_t ldx, const float* offset, const double* model,
+                 int32_t num_click_replicates, int32_t binary_feature, float* pred);
+int mlease_test_loglik(int32_t device, void* stream, int64_t nrows, const int32_t* response, const float* pred,
+                       const float* weight, int64_t combiner_block, float* out_loglik, double* out_count);
+
+/* Bench / profiling hooks (not part of the reference surface): time one fused K1 pass or one Gram build
+ * on a resident partition with CUDA events on the session stream, `reps` launches, returns avg ms. */
+int mlease_time_kernel(mlease_session* s, int32_t partition_id, int32_t which /*1=K1,2=Gram tcgen05,3=cholesky*/,
+                       int32_t reps, int32_t emit_scaled, float* avg_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLEASE_B200_H */

@@ -1,0 +1,199 @@
+// common.cuh -- shared device structures and sm_100a PTX wrappers (mbarrier, bulk-copy TMA,
+// tensor-map TMA, tcgen05/TMEM).  B200 only: compile with -gencode arch=compute_100a,code=sm_100a.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mlease {
+
+// ------------------------------------------------------------------------------------------
+// Per-problem control block, device resident.  A "problem" is one (local partition, lambda)
+// x-update = one AdmmReducer.reduce call (jobs/RegressionAdmmTrain.java:642-718).
+// Every kernel of the Newton slot reads these flags and exits early when it has nothing to
+// do, so the host launches a fixed kernel sequence per slot and never branches on device data.
+// ------------------------------------------------------------------------------------------
+struct Ctrl {
+  int done;          // x-update finished (converged or gave up)
+  int have_dir;      // a Newton direction exists for the accepted point
+  int need_solve;    // accepted a point this slot -> compute a new direction
+  int need_hess;     // ... and rebuild Gram + Cholesky first
+  int emit;          // K1 must write the sqrt(d)-scaled bf16 copy (a Hessian rebuild may follow)
+  int hess_valid;    // a Cholesky factor exists (possibly stale -> chord Newton)
+  int fail;          // 1 = not SPD, 2 = line search gave up, 3 = max_newton hit
+  int newton_steps;  // accepted steps in this x-update
+  int evals;         // K1 passes in this x-update
+  int rejects;       // rejected trial points in this x-update
+  int hess_builds;   // Gram+Cholesky rebuilds in this x-update
+  int stall;         // consecutive poor contractions
+  double alpha;      // current step length along dir
+  double phi0;       // g_acc . dir  (< 0)
+  double f_acc, f_t; // objective at accepted / trial point
+  double gnorm;      // |g_acc|_inf
+  double gnorm_prev;
+  double dirnorm;    // |dir|_inf
+  double xtol;
+  int max_newton;
+  int hess_policy;   // 0 adaptive chord, 1 every step
+  // cumulative counters (never reset by begin-of-iteration)
+  long long tot_evals, tot_newton, tot_rejects, tot_hess;
+};
+
+// One problem's device pointers.  Vectors have length ldv (= ldx, multiple of 4, >= Dt) and are
+// zero in [Dt, ldv).  The bias column is PHYSICAL: column Dt-1 of X is 1.0f for every row when the
+// problem has an intercept (llf/LibLinearDataset.java:592-614), so no kernel special-cases it.
+struct Problem {
+  // data (shared by the L problems of one partition)
+  const float* X;          // dense [n][ldx] fp32, or nullptr for CSR
+  long long n;             // rows
+  int ldx;                 // leading dim in floats (multiple of 4)
+  int Dt;                  // columns incl. bias
+  const signed char* y;    // +1 / -1
+  const float* w;          // weight
+  const float* o;          // offset
+  const long long* rowptr; // CSR (bias NOT stored; handled by the kernels)
+  const int* colidx;
+  const float* vals;
+  __nv_bfloat16* Xt;       // [n][Dp] bf16 = sqrt(d_i) * x_ij  (Gram operand), zero in [ldx, Dp)
+  int Dp;                  // multiple of 128
+  // solver state
+  double* beta;            // accepted iterate
+  double* beta_t;          // trial iterate
+  float* beta_tf;          // float copy of the trial iterate (what K1 reads)
+  double* m;               // prior mean  (z - u)
+  double* q;               // prior precision 1/priorVar (rho for ADMM)
+  double* g_t;             // gradient at trial
+  double* g_acc;           // gradient at accepted
+  double* dir;             // Newton direction
+  double* gpart;           // [k1_ctas][ldx] per-CTA partial X^T r
+  double* fpart;           // [k1_ctas] per-CTA partial loss
+  int k1_ctas;
+  float* Hpart;            // [gram_slices][Dp][Dp] split-K partial Gram (lower tiles)
+  int gram_slices;
+  double* Lc;              // [ldh][ldh] Cholesky factor (lower), ldh multiple of 32
+  double* Ldiag;           // [ldh][32] factorised diagonal blocks (side buffer, see k3_cholesky.cu)
+  int ldh;
+  Ctrl* ctrl;
+  // ADMM per-problem vectors (float, as the reference's avro files hold them)
+  float* u_f;              // u used by this iteration
+  float* uplusx_f;         // float(u + x)
+  float* x_f;              // float(x)
+  int lambda_idx;
+  int part_local;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// 1-D bulk copy global -> shared (TMA engine, no tensor map): SASS UBLKCP.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// 2-D tensor-map TMA load: SASS UTMALDG.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// tcgen05 / TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16/fp16 inputs, fp32 accumulate): SASS UTCHMMA.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive when all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (SASS LDTM).
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// warp / block reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace mlease

@@ -1,0 +1,100 @@
+// k4_consensus.cu -- K4: the consensus step of one ADMM iteration, fused around the single all-reduce.
+//
+//   admm_pack      (before the all-reduce)  per local problem: x_f = float(x), uplusx_f = float(u + x)
+//                  (jobs/RegressionAdmmTrain.java:706-711, models/LinearModel.java:703,716) and the local
+//                  exchange vector  S_local[l][k] = sum_p float(x_p)[k] + u_p[k]  in double.
+//   admm_consensus (after the all-reduce)   z = wz * S / P   (:362-404; wz = P rho/(lambda+P rho) computed on
+//                  the host in the reference's float arithmetic :381, 1 for the unpenalised intercept :392-403,
+//                  per-feature lambda.map weights :382-386), |z - z_prev|_inf (:456-472), and the NEXT
+//                  iteration's reducer inputs: u = float(uplusx - z) (computeU :736-765), z as float (:330-331),
+//                  prior mean m = z_f - u (:695-698), init = z_f (:692-693), prior precision rho_eff (:652-658,705).
+//
+// Latency-bound, O(P_local * L * D') work: one CTA per lambda.
+#include "kernels.cuh"
+
+namespace mlease {
+
+__global__ void admm_reset_kernel(const Problem* __restrict__ probs, int L, double* __restrict__ z, int ldv,
+                                  const double* __restrict__ rho_eff) {
+  const Problem& pb = probs[blockIdx.x];
+  const int l = pb.lambda_idx;
+  for (int k = threadIdx.x; k < ldv; k += blockDim.x) {
+    pb.u_f[k] = 0.f; pb.uplusx_f[k] = 0.f; pb.x_f[k] = 0.f;
+    pb.m[k] = 0.0;                       // z - u with both maps empty (:155-185, :312)
+    pb.beta[k] = 0.0;                    // init = z = {}
+    pb.q[k] = k < pb.Dt ? rho_eff[l] : 1.0;
+    if (pb.part_local == 0) z[(size_t)l * ldv + k] = 0.0;
+  }
+  if (threadIdx.x == 0) pb.ctrl->hess_valid = 0;
+}
+
+__global__ void admm_pack_kernel(const Problem* __restrict__ probs, int nparts, int L, int Dt, double* __restrict__ exch) {
+  const int l = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Dt) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; p++) {
+    const Problem& pb = probs[p * L + l];
+    const double x = pb.beta[k];
+    const float xf = (float)x;
+    const float uf = pb.u_f[k];
+    pb.x_f[k] = xf;
+    pb.uplusx_f[k] = (float)(1.0 * (double)uf + 1.0 * x);
+    s += (double)xf + (double)uf;
+  }
+  exch[(size_t)l * Dt + k] = s;
+}
+
+__global__ void __launch_bounds__(256) admm_consensus_kernel(const Problem* __restrict__ probs, int nparts, int L, int Dt, int ldv,
+                                                             int P, const double* __restrict__ exch, double* __restrict__ z,
+                                                             const double* __restrict__ wz, const double* __restrict__ rho_next,
+                                                             double* __restrict__ diff) {
+  const int l = blockIdx.x;
+  __shared__ double sc[8];
+  double dmax = 0.0;
+  const double invP = 1.0 / (double)P;
+  for (int k = threadIdx.x; k < Dt; k += 256) {
+    const double zn = wz[(size_t)l * ldv + k] * (exch[(size_t)l * Dt + k] * invP);
+    const double zo = z[(size_t)l * ldv + k];
+    dmax = fmax(dmax, fabs(zo - zn));
+    z[(size_t)l * ldv + k] = zn;
+    const float zf = (float)zn;
+    for (int p = 0; p < nparts; p++) {
+      const Problem& pb = probs[p * L + l];
+      const float un = (float)((double)pb.uplusx_f[k] - zn);
+      pb.u_f[k] = un;
+      pb.m[k] = -1.0 * (double)un + 1.0 * (double)zf;
+      pb.beta[k] = (double)zf;
+      pb.q[k] = rho_next[l];
+    }
+  }
+  dmax = warp_max(dmax);
+  if ((threadIdx.x & 31) == 0) sc[threadIdx.x >> 5] = dmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double d = 0.0;
+    for (int w = 0; w < 8; w++) d = fmax(d, sc[w]);
+    diff[l] = d;
+  }
+}
+
+cudaError_t admm_reset(const Problem* d_probs, int nprob, int L, double* d_z, int ldv, const double* d_rho_eff, cudaStream_t st,
+                       int* launches) {
+  admm_reset_kernel<<<nprob, 256, 0, st>>>(d_probs, L, d_z, ldv, d_rho_eff);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+cudaError_t admm_pack(const Problem* d_probs, int nlocal_parts, int L, int Dt, double* d_exchange, cudaStream_t st, int* launches) {
+  admm_pack_kernel<<<dim3((Dt + 255) / 256, L), 256, 0, st>>>(d_probs, nlocal_parts, L, Dt, d_exchange);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+cudaError_t admm_consensus(const Problem* d_probs, int nlocal_parts, int L, int Dt, int ldv, int P, const double* d_exchange_sum,
+                           double* d_z, const double* d_wz, const double* d_rho_eff_next, double* d_diff, cudaStream_t st,
+                           int* launches) {
+  admm_consensus_kernel<<<L, 256, 0, st>>>(d_probs, nlocal_parts, L, Dt, ldv, P, d_exchange_sum, d_z, d_wz, d_rho_eff_next, d_diff);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace mlease

@@ -1,0 +1,46 @@
+// kernels.cuh -- launcher declarations shared by the translation units of libmlease_b200.so
+#pragma once
+#include "common.cuh"
+
+namespace mlease {
+
+// K1 (k1_score_grad.cu)
+bool k1_dense_plan(int ldx, int* R_out, int* S_out, int* G_out, size_t* smem_out);
+cudaError_t k1_launch(const Problem* d_probs, int nprob, bool csr, int ldx, int has_bias, int ctas_per_problem,
+                      int force_emit, cudaStream_t stream, int* launches);
+
+// Newton state machine (newton.cu)
+cudaError_t newton_begin(const Problem* d_probs, int nprob, double xtol, int max_newton, int hess_policy,
+                         int invalidate_hess, cudaStream_t st, int* launches);
+cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, cudaStream_t st, int* launches);
+cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches);
+cudaError_t newton_poll(const Problem* d_probs, int nprob, int* d_flag, cudaStream_t st, int* launches);
+
+// K2 (k2_gram.cu)
+int gram_make_tensor_map(void* out_map_host, const void* xt, long long n, int Dp);
+int gram_tile_list(int Dp, short* bi_bj_pairs, int max_tiles);
+cudaError_t gram_launch_tcgen05(const Problem* d_probs, int nprob, const void* d_tmaps, const void* d_tiles, int ntiles,
+                                int nslices, int force, cudaStream_t st, int* launches);
+cudaError_t gram_launch_simt(const Problem* d_probs, int nprob, int Dp, int force, cudaStream_t st, int* launches);
+
+// K3 (k3_cholesky.cu)
+cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches);
+
+// K4 (k4_consensus.cu)
+cudaError_t admm_reset(const Problem* d_probs, int nprob, int L, double* d_z, int ldv, const double* d_rho_eff,
+                       cudaStream_t st, int* launches);
+cudaError_t admm_pack(const Problem* d_probs, int nlocal_parts, int L, int Dt, double* d_exchange, cudaStream_t st,
+                      int* launches);
+cudaError_t admm_consensus(const Problem* d_probs, int nlocal_parts, int L, int Dt, int ldv, int P, const double* d_exchange_sum,
+                           double* d_z, const double* d_wz, const double* d_rho_eff_next, double* d_diff, cudaStream_t st,
+                           int* launches);
+
+// K5 (k5_score.cu)
+cudaError_t score_launch(int Dg, long long nrows, const long long* rowptr, const int* colidx, const float* vals, long long ldx,
+                         const float* offset, const double* d_model, double intercept_term, int binary_feature, float* pred,
+                         cudaStream_t st);
+cudaError_t loglik_launch(long long nrows, const int* response, const float* pred, const float* weight, long long combiner_block,
+                          float* d_ll, double* d_block_sum, double* d_block_cnt, int* d_bad, cudaStream_t st);
+
+// upload helpers (session.cu)
+}  // namespace mlease

@@ -1,0 +1,291 @@
+// newton.cu -- the device-side Newton / line-search state machine around K1-K3.
+//
+// One "slot" = K1 (evaluate f,g at the trial point) -> k1_reduce_decide (accept / shrink) ->
+// [Gram K2 -> chol_prep -> Cholesky K3] (only when ctrl.need_hess) -> newton_solve (two
+// triangular solves, next trial point, termination test).  All decisions are taken on the
+// device from Ctrl flags; the host launches the same kernel sequence every slot.
+//
+// Replaces bw/Tron.java:30-124 (TRON outer loop) + :126-179 (CG) for the x-update
+// argmin_b  sum_i w_i log(1+exp(-y_i(x_i.b+o_i))) + 1/2 sum_k q_k (b_k-m_k)^2
+// (llf/LogisticRegressionL2.java:30-47).  Same unique minimiser; the reference stops TRON at a
+// loose tolerance, this path solves to |dir|_inf <= xtol*max(|b|_inf,1e-2) (parity protocol).
+#include "kernels.cuh"
+
+namespace mlease {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ double block_sum(double v, double* sc) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sc[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += sc[w];
+  return s;
+}
+__device__ __forceinline__ double block_max(double v, double* sc) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sc[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) s = fmax(s, sc[w]);
+  return s;
+}
+
+// Start of an x-update: beta = beta_t = init, flags reset.  init/m/q were written by the caller
+// (ADMM consensus kernel or mlease_fit_partition).
+__global__ void newton_begin_kernel(const Problem* __restrict__ probs, double xtol, int max_newton, int hess_policy,
+                                    int invalidate_hess) {
+  const Problem& pb = probs[blockIdx.x];
+  Ctrl* c = pb.ctrl;
+  for (int k = threadIdx.x; k < pb.ldx; k += blockDim.x) {
+    const double b = k < pb.Dt ? pb.beta[k] : 0.0;
+    pb.beta[k] = b;
+    pb.beta_t[k] = b;
+    pb.beta_tf[k] = (float)b;
+    pb.dir[k] = 0.0;
+  }
+  if (threadIdx.x == 0) {
+    if (invalidate_hess) c->hess_valid = 0;
+    c->done = 0; c->have_dir = 0; c->need_solve = 0; c->need_hess = 0; c->fail = 0;
+    c->newton_steps = 0; c->evals = 0; c->rejects = 0; c->hess_builds = 0; c->stall = 0;
+    c->alpha = 1.0; c->phi0 = 0.0; c->f_acc = 0.0; c->f_t = 0.0; c->gnorm = 0.0; c->gnorm_prev = 0.0; c->dirnorm = 0.0;
+    c->xtol = xtol; c->max_newton = max_newton; c->hess_policy = hess_policy;
+    c->emit = (hess_policy == 1 || !c->hess_valid) ? 1 : 0;
+  }
+}
+
+// Fixed-order reduction of the K1 partials + prior term, then the accept/shrink decision.
+//   g_t = sum_cta gpart + q*(beta_t - m)           (llf/LogisticRegressionL2.java:223-224)
+//   f_t = sum_cta fpart + 1/2 sum q (beta_t-m)^2   (:181-190)
+__global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __restrict__ probs) {
+  const Problem& pb = probs[blockIdx.x];
+  Ctrl* c = pb.ctrl;
+  if (c->done) return;
+  __shared__ double sc[NT / 32];
+  __shared__ int s_action;  // 1 accept, 0 retry
+  __shared__ double s_alpha;
+  const int Dt = pb.Dt, ldx = pb.ldx, nct = pb.k1_ctas;
+  const bool have_dir = c->have_dir != 0;
+  double prior2 = 0.0, ginf = 0.0, phi = 0.0;
+  for (int k = threadIdx.x; k < Dt; k += NT) {
+    double s = 0.0;
+    for (int t = 0; t < nct; t++) s += pb.gpart[(size_t)t * ldx + k];
+    const double dlt = pb.beta_t[k] - pb.m[k];
+    const double g = s + pb.q[k] * dlt;
+    pb.g_t[k] = g;
+    prior2 += pb.q[k] * dlt * dlt;
+    ginf = fmax(ginf, fabs(g));
+    if (have_dir) phi += g * pb.dir[k];
+  }
+  double lossp = 0.0;
+  for (int t = threadIdx.x; t < nct; t += NT) lossp += pb.fpart[t];
+  prior2 = block_sum(prior2, sc);
+  phi = block_sum(phi, sc);
+  lossp = block_sum(lossp, sc);
+  ginf = block_max(ginf, sc);
+  if (threadIdx.x == 0) {
+    const double f_t = lossp + 0.5 * prior2;
+    c->f_t = f_t;
+    c->evals++; c->tot_evals++;
+    int action = 1;
+    double alpha = c->alpha;
+    if (have_dir) {
+      // phi'(alpha) = g(beta + alpha dir).dir ; phi'(0) = phi0 < 0.  Accept while the directional
+      // derivative has not overshot by more than half of |phi'(0)| (a relaxed curvature condition on
+      // a convex 1-D function); otherwise shrink alpha towards the secant root of phi'.
+      const double a0 = fabs(c->phi0);
+      if (!(phi <= 0.5 * a0)) {
+        action = 0;
+        double an = alpha * a0 / (phi + a0);  // secant between (0,-a0) and (alpha,phi)
+        an = fmin(fmax(an, 0.1 * alpha), 0.6 * alpha);
+        alpha = an;
+        c->rejects++; c->tot_rejects++;
+        if (c->rejects > 40 || !(phi == phi)) { c->fail = 2; c->done = 1; }
+      }
+    }
+    if (action == 1) {
+      c->gnorm_prev = c->gnorm;
+      c->gnorm = ginf;
+      c->f_acc = f_t;
+      if (have_dir) { c->newton_steps++; c->tot_newton++; }
+      if (ginf == 0.0) {
+        c->done = 1; c->need_solve = 0; c->need_hess = 0;
+      } else if (c->newton_steps >= c->max_newton) {
+        c->done = 1; c->fail = 3; c->need_solve = 0; c->need_hess = 0;
+      } else {
+        c->need_solve = 1;
+        // a rebuild happens only if K1 wrote the scaled copy at THIS point (emit was set before the pass)
+        c->need_hess = c->emit ? 1 : 0;
+        // policy for the NEXT accepted point: refresh when the chord step contracted poorly
+        if (c->hess_policy == 1) {
+          c->emit = 1;
+        } else {
+          const bool poor = have_dir && c->gnorm_prev > 0.0 && ginf > 0.25 * c->gnorm_prev;
+          c->emit = (poor && !c->need_hess) ? 1 : 0;
+          if (!c->need_hess && !c->hess_valid) { c->emit = 1; }
+        }
+      }
+    } else {
+      c->need_solve = 0; c->need_hess = 0;
+    }
+    c->alpha = alpha;
+    s_action = action;
+    s_alpha = alpha;
+  }
+  __syncthreads();
+  if (s_action == 1) {
+    for (int k = threadIdx.x; k < ldx; k += NT) {
+      pb.beta[k] = pb.beta_t[k];
+      pb.g_acc[k] = k < Dt ? pb.g_t[k] : 0.0;
+    }
+  } else {
+    const double a = s_alpha;
+    for (int k = threadIdx.x; k < ldx; k += NT) {
+      const double bt = k < Dt ? pb.beta[k] + a * pb.dir[k] : 0.0;
+      pb.beta_t[k] = bt;
+      pb.beta_tf[k] = (float)bt;
+    }
+  }
+}
+
+// dir = -(L L^T)^-1 g_acc with the (possibly stale) Cholesky factor; then either terminate
+// (|dir| tiny: take the step, done) or set the next trial point beta + dir.
+// Blocked forward/backward substitution, one CTA per problem, NB = 32.
+__global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restrict__ probs) {
+  const Problem& pb = probs[blockIdx.x];
+  Ctrl* c = pb.ctrl;
+  if (c->done || !c->need_solve) return;
+  extern __shared__ double sm[];
+  const int ldh = pb.ldh, Dt = pb.Dt, nb = ldh / 32;
+  double* rhs = sm;                  // [ldh]
+  double* blk = rhs + ldh;           // [32][33] diagonal block
+  double* part = blk + 32 * 33;      // [8][32] cross-warp partials
+  __shared__ double sc[NT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* L = pb.Lc;
+  for (int k = tid; k < ldh; k += NT) rhs[k] = k < Dt ? -pb.g_acc[k] : 0.0;
+  __syncthreads();
+  // forward: L y = rhs
+  for (int kb = 0; kb < nb; kb++) {
+    const int r0 = kb * 32;
+    // rhs[r0..r0+31] -= L[r0+r][0..r0) . y[0..r0)   (warp w owns rows 4w..4w+3, lanes stride columns)
+    for (int rr = 0; rr < 4; rr++) {
+      const int r = warp * 4 + rr;
+      const double* Lr = L + (size_t)(r0 + r) * ldh;
+      double a = 0.0;
+      for (int j = lane; j < r0; j += 32) a += Lr[j] * rhs[j];
+      a = warp_sum(a);
+      if (lane == 0) part[r] = a;
+    }
+    for (int e = tid; e < 32 * 32; e += NT) blk[(e >> 5) * 33 + (e & 31)] = L[(size_t)(r0 + (e >> 5)) * ldh + r0 + (e & 31)];
+    __syncthreads();
+    if (warp == 0) {
+      double v = rhs[r0 + lane] - part[lane];
+      for (int j = 0; j < 32; j++) {
+        const double yj = __shfl_sync(0xffffffffu, v, j) / blk[j * 33 + j];
+        if (lane == j) v = yj;
+        else if (lane > j) v -= blk[lane * 33 + j] * yj;
+      }
+      rhs[r0 + lane] = v;
+    }
+    __syncthreads();
+  }
+  // backward: L^T x = y
+  for (int kb = nb - 1; kb >= 0; kb--) {
+    const int r0 = kb * 32;
+    // acc[c] = sum_{r >= r0+32} L[r][r0+c] * x[r]    (lanes = 32 consecutive columns, warps stride rows)
+    double a = 0.0;
+    for (int r = r0 + 32 + warp; r < ldh; r += NT / 32) a += L[(size_t)r * ldh + r0 + lane] * rhs[r];
+    part[warp * 32 + lane] = a;
+    for (int e = tid; e < 32 * 32; e += NT) blk[(e >> 5) * 33 + (e & 31)] = L[(size_t)(r0 + (e >> 5)) * ldh + r0 + (e & 31)];
+    __syncthreads();
+    if (warp == 0) {
+      double s = 0.0;
+      for (int w = 0; w < NT / 32; w++) s += part[w * 32 + lane];
+      double v = rhs[r0 + lane] - s;
+      for (int j = 31; j >= 0; j--) {
+        const double xj = __shfl_sync(0xffffffffu, v, j) / blk[j * 33 + j];
+        if (lane == j) v = xj;
+        else if (lane < j) v -= blk[j * 33 + lane] * xj;
+      }
+      rhs[r0 + lane] = v;
+    }
+    __syncthreads();
+  }
+  // rhs now holds dir
+  double dinf = 0.0, binf = 0.0, phi0 = 0.0;
+  for (int k = tid; k < Dt; k += NT) {
+    const double d = rhs[k];
+    pb.dir[k] = d;
+    dinf = fmax(dinf, fabs(d));
+    binf = fmax(binf, fabs(pb.beta[k]));
+    phi0 += d * pb.g_acc[k];
+  }
+  dinf = block_max(dinf, sc);
+  binf = block_max(binf, sc);
+  phi0 = block_sum(phi0, sc);
+  __shared__ int s_final;
+  if (tid == 0) {
+    c->dirnorm = dinf;
+    c->phi0 = phi0;
+    c->alpha = 1.0;
+    c->have_dir = 1;
+    c->need_solve = 0;
+    c->rejects = 0;
+    int fin = 0;
+    if (!(phi0 < 0.0) || !(dinf == dinf)) { c->fail = 1; c->done = 1; fin = 2; }  // factor unusable
+    else if (dinf <= c->xtol * fmax(binf, 1e-2)) { c->done = 1; fin = 1; }
+    s_final = fin;
+  }
+  __syncthreads();
+  if (s_final == 2) return;
+  const bool fin = s_final == 1;
+  for (int k = tid; k < pb.ldx; k += NT) {
+    const double bt = k < Dt ? pb.beta[k] + rhs[k] : 0.0;
+    pb.beta_t[k] = bt;
+    pb.beta_tf[k] = (float)bt;
+    if (fin) pb.beta[k] = bt;  // final tiny step taken without another pass
+  }
+}
+
+// any problem still running? (host polls a pinned flag between slots)
+__global__ void newton_poll_kernel(const Problem* __restrict__ probs, int nprob, int* flag_out) {
+  int running = 0;
+  for (int b = threadIdx.x; b < nprob; b += blockDim.x) running |= (probs[b].ctrl->done == 0);
+  running = __syncthreads_or(running);
+  if (threadIdx.x == 0) *flag_out = running;
+}
+
+cudaError_t newton_begin(const Problem* d_probs, int nprob, double xtol, int max_newton, int hess_policy,
+                         int invalidate_hess, cudaStream_t st, int* launches) {
+  newton_begin_kernel<<<nprob, 256, 0, st>>>(d_probs, xtol, max_newton, hess_policy, invalidate_hess);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, cudaStream_t st, int* launches) {
+  k1_reduce_decide_kernel<<<nprob, NT, 0, st>>>(d_probs);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches) {
+  const size_t smem = ((size_t)ldh + 32 * 33 + 8 * 32) * sizeof(double);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(newton_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  newton_solve_kernel<<<nprob, NT, smem, st>>>(d_probs);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+cudaError_t newton_poll(const Problem* d_probs, int nprob, int* d_flag, cudaStream_t st, int* launches) {
+  newton_poll_kernel<<<1, 256, 0, st>>>(d_probs, nprob, d_flag);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace mlease

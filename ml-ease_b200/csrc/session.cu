@@ -1,0 +1,971 @@
+// session.cu -- host side of libmlease_b200.so: the C ABI of include/mlease_b200.h, device memory
+// management, partition upload, the Newton slot loop and the ADMM iteration driver.
+// No CPU fallback anywhere: every compute entry point needs a CUDA device and fails loudly without one.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mlease_b200.h"
+#include "kernels.cuh"
+
+using namespace mlease;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                                  \
+  do {                                                                                                            \
+    cudaError_t e__ = (call);                                                                                     \
+    if (e__ != cudaSuccess)                                                                                       \
+      return fail(MLEASE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                                       std::to_string(__LINE__) + ")");                                           \
+  } while (0)
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------
+// upload helpers
+// ------------------------------------------------------------------------------------------
+__global__ void fill_bias_pad_kernel(float* X, long long n, int ldx, int Dg, int has_bias) {
+  const int npad = ldx - Dg;
+  const long long total = n * npad;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / npad;
+    const int c = Dg + (int)(e % npad);
+    X[i * ldx + c] = (c == Dg && has_bias) ? 1.0f : 0.0f;
+  }
+}
+// response {1,0,-1} -> int8 {+1,-1,-1} (llf/LibLinearDataset.java:419-422); weight >= 0 (:428-429)
+__global__ void convert_labels_kernel(long long n, const int* resp, const float* w_in, const float* o_in, signed char* y, float* w,
+                                      float* o, int* bad) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = resp[i];
+    if (r != 1 && r != 0 && r != -1) atomicOr(bad, 1);
+    y[i] = (r == 1) ? 1 : -1;
+    const float ww = w_in ? w_in[i] : 1.0f;
+    if (!(ww >= 0.f)) atomicOr(bad, 2);
+    w[i] = ww;
+    o[i] = o_in ? o_in[i] : 0.0f;
+  }
+}
+__global__ void check_csr_kernel(long long nnz, const int* colidx, float* vals, int Dg, int binary, int* bad) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (long long)gridDim.x * blockDim.x) {
+    const int c = colidx[j];
+    if (c < 0 || c >= Dg) atomicOr(bad, 4);
+    if (binary) vals[j] = 1.0f;
+  }
+}
+__global__ void poll2_kernel(const Problem* probs, int nprob, int* flag_out) {
+  int running = 0, emit = 0;
+  for (int b = threadIdx.x; b < nprob; b += blockDim.x) {
+    const Ctrl* c = probs[b].ctrl;
+    if (!c->done) { running = 1; if (c->emit) emit = 1; }
+  }
+  running = __syncthreads_or(running);
+  emit = __syncthreads_or(emit);
+  if (threadIdx.x == 0) *flag_out = running | (emit << 1);
+}
+
+struct PartData {
+  int pid = -1;
+  long long n = 0;
+  bool csr = false;
+  float* X = nullptr;
+  signed char* y = nullptr;
+  float* w = nullptr;
+  float* o = nullptr;
+  long long* rowptr = nullptr;
+  int* colidx = nullptr;
+  float* vals = nullptr;
+  long long nnz = 0;
+};
+
+// A batch of problems with identical shape that advance in lockstep through the Newton slots.
+struct Batch {
+  int nprob = 0, Dt = 0, ldx = 0, Dp = 0, ldh = 0;
+  bool csr = false;
+  int has_bias = 1;
+  int k1_grid = 1, gram_slices = 1, ntiles = 0;
+  std::vector<Problem> h;
+  Problem* d = nullptr;
+  Ctrl* d_ctrl = nullptr;
+  void* d_tmaps = nullptr;
+  void* d_tiles = nullptr;
+  std::vector<void*> owned;
+  ~Batch() {
+    for (void* p : owned) cudaFree(p);
+  }
+};
+
+struct Counters {
+  long long k1_passes = 0, gram_builds = 0, newton_steps = 0, rejected = 0, launches = 0;
+  int not_converged = 0, last_slots = 0;
+};
+
+int dev_alloc(Batch& B, void** p, size_t bytes, bool zero = true) {
+  CK(cudaMalloc(p, bytes ? bytes : 16));
+  B.owned.push_back(*p);
+  if (zero) CK(cudaMemset(*p, 0, bytes ? bytes : 16));
+  return 0;
+}
+
+// Allocate the per-problem solver state.  Data pointers (X, y, ...) and n must be filled in h[] first.
+int batch_alloc(Batch& B, int num_sms) {
+  const int nprob = B.nprob, ldx = B.ldx;
+  B.Dp = round_up(B.ldx, 128);
+  B.ldh = round_up(B.Dt, 32);
+  long long maxn = 1;
+  for (auto& p : B.h) maxn = std::max(maxn, p.n);
+  if (B.csr) {
+    B.k1_grid = std::max(1, std::min((int)((maxn + 7) / 8), (num_sms * 8) / std::max(1, nprob)));
+  } else {
+    int R, S, G;
+    size_t smem;
+    if (!k1_dense_plan(ldx, &R, &S, &G, &smem))
+      return fail(MLEASE_ERR_INVALID, "dense partitions support at most 4095 features (+intercept); use CSR input beyond that");
+    const long long row_tiles = (maxn + R - 1) / R;
+    B.k1_grid = (int)std::max(1LL, std::min(row_tiles, (long long)std::max(1, num_sms / std::max(1, nprob))));
+  }
+  // Gram decomposition
+  std::vector<short> tiles(2 * 8192);
+  B.ntiles = gram_tile_list(B.Dp, tiles.data(), 8192);
+  if (B.ntiles <= 0) return fail(MLEASE_ERR_INVALID, "Gram tile list overflow");
+  {
+    const long long ksteps = (maxn + 63) / 64;
+    const long long base = (long long)B.ntiles * nprob;
+    int best = 1;
+    double best_eff = 0;
+    for (int s = 1; s <= 16; s++) {
+      if (s > ksteps) break;
+      const long long ctas = base * s;
+      const double eff = (double)ctas / (double)(((ctas + num_sms - 1) / num_sms) * num_sms);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+      if (eff >= 0.93 && ctas >= 2LL * num_sms) { best = s; break; }
+    }
+    // bound the split-K scratch to 1 GiB per batch
+    while (best > 1 && (double)best * B.Dp * B.Dp * 4.0 * nprob > 1024.0 * 1024 * 1024) best--;
+    B.gram_slices = best;
+  }
+  const size_t nd = (size_t)nprob * (7 * (size_t)ldx + (size_t)(B.csr ? 1 : B.k1_grid) * ldx + (size_t)B.k1_grid + 8);
+  const size_t nf = (size_t)nprob * 4 * ldx;
+  double* dd; float* ff; float* hp; double* lc; double* ld;
+  if (int rc = dev_alloc(B, (void**)&dd, nd * sizeof(double))) return rc;
+  if (int rc = dev_alloc(B, (void**)&ff, nf * sizeof(float))) return rc;
+  if (int rc = dev_alloc(B, (void**)&hp, (size_t)nprob * B.gram_slices * B.Dp * B.Dp * sizeof(float))) return rc;
+  if (int rc = dev_alloc(B, (void**)&lc, (size_t)nprob * B.ldh * B.ldh * sizeof(double))) return rc;
+  if (int rc = dev_alloc(B, (void**)&ld, (size_t)nprob * B.ldh * 32 * sizeof(double))) return rc;
+  if (int rc = dev_alloc(B, (void**)&B.d_ctrl, (size_t)nprob * sizeof(Ctrl))) return rc;
+  if (int rc = dev_alloc(B, (void**)&B.d, (size_t)nprob * sizeof(Problem))) return rc;
+  if (int rc = dev_alloc(B, &B.d_tmaps, (size_t)nprob * sizeof(CUtensorMap))) return rc;
+  if (int rc = dev_alloc(B, &B.d_tiles, (size_t)B.ntiles * 2 * sizeof(short))) return rc;
+  CK(cudaMemcpy(B.d_tiles, tiles.data(), (size_t)B.ntiles * 2 * sizeof(short), cudaMemcpyHostToDevice));
+  std::vector<CUtensorMap> maps(nprob);
+  for (int b = 0; b < nprob; b++) {
+    Problem& p = B.h[b];
+    p.ldx = ldx; p.Dt = B.Dt; p.Dp = B.Dp; p.ldh = B.ldh;
+    p.k1_ctas = B.csr ? 1 : B.k1_grid;
+    p.gram_slices = B.gram_slices;
+    double* q = dd;
+    p.beta = q; q += ldx; p.beta_t = q; q += ldx; p.m = q; q += ldx; p.q = q; q += ldx;
+    p.g_t = q; q += ldx; p.g_acc = q; q += ldx; p.dir = q; q += ldx;
+    p.gpart = q; q += (size_t)p.k1_ctas * ldx;
+    p.fpart = q; q += B.k1_grid + 8;
+    dd = q;
+    float* f = ff;
+    p.beta_tf = f; f += ldx; p.u_f = f; f += ldx; p.uplusx_f = f; f += ldx; p.x_f = f; f += ldx;
+    ff = f;
+    p.Hpart = hp + (size_t)b * B.gram_slices * B.Dp * B.Dp;
+    p.Lc = lc + (size_t)b * B.ldh * B.ldh;
+    p.Ldiag = ld + (size_t)b * B.ldh * 32;
+    p.ctrl = B.d_ctrl + b;
+    if (!p.Xt) {
+      void* xt;
+      if (int rc = dev_alloc(B, &xt, (size_t)p.n * B.Dp * sizeof(__nv_bfloat16))) return rc;
+      p.Xt = reinterpret_cast<__nv_bfloat16*>(xt);
+    }
+    if (gram_make_tensor_map(&maps[b], p.Xt, p.n, B.Dp) != 0) return fail(MLEASE_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  }
+  CK(cudaMemcpy(B.d_tmaps, maps.data(), (size_t)nprob * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(B.d, B.h.data(), (size_t)nprob * sizeof(Problem), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// One x-update for every problem of the batch: beta (init), m, q must already be on the device.
+int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int policy, int invalidate, int* h_flag, int* d_flag,
+                  Counters& cnt) {
+  int launches = 0;
+  CK(newton_begin(B.d, B.nprob, xtol, max_newton, policy, invalidate, st, &launches));
+  poll2_kernel<<<1, 256, 0, st>>>(B.d, B.nprob, d_flag);
+  launches++;
+  CK(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  int flag = *h_flag;
+  int slots = 0;
+  while ((flag & 1) && slots < 400) {
+    CK(k1_launch(B.d, B.nprob, B.csr, B.ldx, B.has_bias, B.k1_grid, -1, st, &launches));
+    CK(k1_reduce_decide(B.d, B.nprob, st, &launches));
+    if (flag & 2) {
+      CK(gram_launch_tcgen05(B.d, B.nprob, B.d_tmaps, B.d_tiles, B.ntiles, B.gram_slices, 0, st, &launches));
+      CK(cholesky_launch(B.d, B.nprob, B.ldh, st, &launches));
+    }
+    CK(newton_solve(B.d, B.nprob, B.ldh, st, &launches));
+    poll2_kernel<<<1, 256, 0, st>>>(B.d, B.nprob, d_flag);
+    launches++;
+    CK(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    flag = *h_flag;
+    slots++;
+  }
+  std::vector<Ctrl> hc(B.nprob);
+  CK(cudaMemcpyAsync(hc.data(), B.d_ctrl, (size_t)B.nprob * sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cnt.launches += launches;
+  cnt.last_slots = slots;
+  int bad_spd = 0, bad_ls = 0;
+  for (auto& c : hc) {
+    cnt.k1_passes += c.evals; cnt.newton_steps += c.newton_steps; cnt.rejected += c.rejects; cnt.gram_builds += c.hess_builds;
+    if (c.fail == 3 || !c.done) cnt.not_converged++;
+    if (c.fail == 1) bad_spd++;
+    if (c.fail == 2) bad_ls++;
+  }
+  if (bad_spd) return fail(MLEASE_ERR_NUMERIC, "Model fitting error! (Hessian not positive definite in " + std::to_string(bad_spd) + " problem(s))");
+  if (bad_ls) return fail(MLEASE_ERR_NUMERIC, "Model fitting error! (line search failed in " + std::to_string(bad_ls) + " problem(s))");
+  return 0;
+}
+
+}  // namespace
+
+// ============================================================================================
+struct mlease_session {
+  mlease_admm_config cfg;
+  std::vector<float> lambdas, rhos, lambda_map;
+  int Dg = 0, Dt = 0, ldx = 0, L = 0, P = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  std::vector<PartData> parts;
+  std::vector<void*> owned;
+  bool any_csr = false, any_dense = false;
+  Batch* batch = nullptr;    // ADMM problems, b = local_part * L + l
+  Batch* scratch = nullptr;  // 1 problem for mlease_objective / mlease_fit_partition / timing
+  int scratch_part = -1;
+  double* d_z = nullptr;
+  double* d_wz = nullptr;
+  double* d_rho = nullptr;   // [L] rho_eff of the coming iteration
+  double* d_diff = nullptr;
+  double* d_exch = nullptr;  // [L][Dt] for mlease_admm_run
+  int* d_flag = nullptr;
+  int* h_flag = nullptr;     // pinned
+  double* h_small = nullptr; // pinned, >= 4*L doubles
+  std::vector<double> rho_fact;  // rho_eff the current Cholesky factors were built with
+  int iter = 0;
+  float liblinear_eps = 0.01f;
+  double mindiff = 99999999;
+  double last_maxdiff = 0;
+  bool begun = false;
+  Counters cnt;
+  double xtol = 1e-8;
+  int max_newton = 50;
+  ~mlease_session() {
+    delete batch;
+    delete scratch;
+    for (void* p : owned) cudaFree(p);
+    if (h_flag) cudaFreeHost(h_flag);
+    if (h_small) cudaFreeHost(h_small);
+  }
+};
+
+namespace {
+
+int sess_alloc(mlease_session* s, void** p, size_t bytes) {
+  CK(cudaMalloc(p, bytes ? bytes : 16));
+  s->owned.push_back(*p);
+  CK(cudaMemset(*p, 0, bytes ? bytes : 16));
+  return 0;
+}
+
+int find_part(mlease_session* s, int pid) {
+  for (size_t i = 0; i < s->parts.size(); i++)
+    if (s->parts[i].pid == pid) return (int)i;
+  return -1;
+}
+
+void fill_problem_data(Problem& p, const PartData& pd) {
+  std::memset(&p, 0, sizeof(Problem));
+  p.X = pd.X; p.n = pd.n; p.y = pd.y; p.w = pd.w; p.o = pd.o;
+  p.rowptr = pd.rowptr; p.colidx = pd.colidx; p.vals = pd.vals;
+}
+
+int finalize(mlease_session* s) {
+  if (s->batch) return 0;
+  if (s->parts.empty()) return fail(MLEASE_ERR_STATE, "no partitions were added to this session");
+  if (s->any_csr && s->any_dense) return fail(MLEASE_ERR_INVALID, "a session must hold either dense or CSR partitions, not both");
+  std::sort(s->parts.begin(), s->parts.end(), [](const PartData& a, const PartData& b) { return a.pid < b.pid; });
+  Batch* B = new Batch();
+  s->batch = B;
+  B->nprob = (int)s->parts.size() * s->L;
+  B->Dt = s->Dt; B->ldx = s->ldx; B->csr = s->any_csr; B->has_bias = 1;
+  B->h.resize(B->nprob);
+  for (size_t pi = 0; pi < s->parts.size(); pi++)
+    for (int l = 0; l < s->L; l++) {
+      Problem& p = B->h[pi * s->L + l];
+      fill_problem_data(p, s->parts[pi]);
+      p.lambda_idx = l; p.part_local = (int)pi;
+    }
+  if (int rc = batch_alloc(*B, s->num_sms)) return rc;
+  const size_t ldv = s->ldx;
+  if (int rc = sess_alloc(s, (void**)&s->d_z, s->L * ldv * sizeof(double))) return rc;
+  if (int rc = sess_alloc(s, (void**)&s->d_wz, s->L * ldv * sizeof(double))) return rc;
+  if (int rc = sess_alloc(s, (void**)&s->d_rho, s->L * sizeof(double))) return rc;
+  if (int rc = sess_alloc(s, (void**)&s->d_diff, s->L * sizeof(double))) return rc;
+  if (int rc = sess_alloc(s, (void**)&s->d_exch, (size_t)s->L * s->Dt * sizeof(double))) return rc;
+  // z-update weights (jobs/RegressionAdmmTrain.java:381-386,392-403), in the reference's mixed float/double arithmetic
+  std::vector<double> wz(s->L * ldv, 0.0);
+  for (int l = 0; l < s->L; l++) {
+    const float lf = s->lambdas[l], rf = s->rhos[l];
+    const float pr = (float)s->P * rf;
+    const double weight = (double)(pr / (lf + pr));
+    for (int k = 0; k < s->Dg; k++) {
+      double w = weight;
+      if (!s->lambda_map.empty() && s->lambda_map[k] > 0.f) w = (double)pr / ((double)(s->lambda_map[k] + pr) + 0.0);
+      wz[l * ldv + k] = w;
+    }
+    wz[l * ldv + s->Dg] = s->cfg.penalize_intercept ? weight : 1.0;
+  }
+  CK(cudaMemcpy(s->d_wz, wz.data(), wz.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int ensure_scratch(mlease_session* s, int part_idx) {
+  if (s->scratch && s->scratch_part == part_idx) return 0;
+  delete s->scratch;
+  s->scratch = new Batch();
+  Batch* B = s->scratch;
+  B->nprob = 1; B->Dt = s->Dt; B->ldx = s->ldx; B->csr = s->parts[part_idx].csr; B->has_bias = 1;
+  B->h.resize(1);
+  fill_problem_data(B->h[0], s->parts[part_idx]);
+  s->scratch_part = part_idx;
+  return batch_alloc(*B, s->num_sms);
+}
+
+double rho_eff_for_iter(mlease_session* s, int l, int iter) {
+  // reducer: rho = lambdaRho[lambda] (float -> double), times rho.adapt.rate if != 1 (jobs/RegressionAdmmTrain.java:652-658);
+  // rate = (float) exp(-(i-1)*coef) for i > 1 (:323-327)
+  double r = (double)s->rhos[l];
+  if (iter > 1 && s->cfg.rho_adapt_coefficient > 0) {
+    const float rate = (float)std::exp(-(iter - 1) * s->cfg.rho_adapt_coefficient);
+    if (rate != 1.0f) r = r * (double)rate;
+  }
+  return r;
+}
+
+}  // namespace
+
+namespace {
+struct TmpDev {
+  std::vector<void*> ptrs;
+  ~TmpDev() { for (void* p : ptrs) cudaFree(p); }
+  template <class T> int get(T** p, size_t count) {
+    CK(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+    ptrs.push_back(*p);
+    return 0;
+  }
+};
+// returns a device pointer for host-or-device input (copies when the pointer is not device memory)
+template <class T> int to_device(TmpDev& t, const T* in, size_t count, const T** out, cudaStream_t st) {
+  if (!in) { *out = nullptr; return 0; }
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, in);
+  if (e == cudaSuccess && (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged)) { *out = in; return 0; }
+  cudaGetLastError();
+  T* d;
+  if (int rc = t.get(&d, count)) return rc;
+  CK(cudaMemcpyAsync(d, in, count * sizeof(T), cudaMemcpyDefault, st));
+  *out = d;
+  return 0;
+}
+
+__global__ void naive_init_kernel(const Problem* probs, const double* m, const double* q) {
+  const Problem& pb = probs[blockIdx.x];
+  for (int k = threadIdx.x; k < pb.ldx; k += blockDim.x) { pb.beta[k] = 0.0; pb.m[k] = m[k]; pb.q[k] = q[k]; }
+}
+__global__ void gather_beta_kernel(const Problem* probs, int Dt, double* out) {
+  const Problem& pb = probs[blockIdx.x];
+  for (int k = threadIdx.x; k < Dt; k += blockDim.x) out[(size_t)blockIdx.x * Dt + k] = pb.beta[k];
+}
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+const char* mlease_last_error(void) { return g_err.c_str(); }
+int mlease_abi_version(void) { return 1; }
+
+int mlease_session_create(const mlease_admm_config* cfg, mlease_session** out) {
+  if (!cfg || !out) return fail(MLEASE_ERR_INVALID, "null argument");
+  if (cfg->regularizer == 1) return fail(MLEASE_ERR_INVALID, "regularizer=1 (L1) is outside the accelerated path (SURVEY 8f-4)");
+  if (cfg->regularizer != 2) return fail(MLEASE_ERR_INVALID, "Only L1 and L2 regularization supported!");
+  if (cfg->num_blocks <= 0 || cfg->num_features <= 0 || cfg->num_lambdas <= 0 || !cfg->lambdas)
+    return fail(MLEASE_ERR_INVALID, "num.blocks, num_features and lambda must be set");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(MLEASE_ERR_CUDA, std::string("no CUDA device: this library has no CPU fallback (") + cudaGetErrorString(e) + ")");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(MLEASE_ERR_INVALID, "bad device ordinal");
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(MLEASE_ERR_CUDA, "this build targets sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+  mlease_session* s = new mlease_session();
+  s->cfg = *cfg;
+  s->L = cfg->num_lambdas; s->P = cfg->num_blocks; s->Dg = cfg->num_features; s->Dt = s->Dg + 1;
+  s->ldx = round_up(s->Dt, 4);
+  s->lambdas.assign(cfg->lambdas, cfg->lambdas + s->L);
+  for (int a = 0; a < s->L; a++)
+    for (int b = a + 1; b < s->L; b++)
+      if (s->lambdas[a] == s->lambdas[b]) { delete s; return fail(MLEASE_ERR_INVALID, "duplicate lambda"); }
+  s->rhos.resize(s->L);
+  for (int l = 0; l < s->L; l++) s->rhos[l] = cfg->rhos ? cfg->rhos[l] : (s->lambdas[l] <= 100 ? 1.0f : 10.0f);
+  if (cfg->lambda_map) s->lambda_map.assign(cfg->lambda_map, cfg->lambda_map + s->Dg);
+  s->cfg.lambdas = nullptr; s->cfg.rhos = nullptr; s->cfg.lambda_map = nullptr;
+  s->stream = reinterpret_cast<cudaStream_t>(cfg->stream);
+  s->num_sms = prop.multiProcessorCount;
+  s->xtol = cfg->newton_xtol > 0 ? cfg->newton_xtol : 1e-8;
+  s->max_newton = cfg->max_newton > 0 ? cfg->max_newton : 50;
+  if (cudaMallocHost((void**)&s->h_flag, 64) != cudaSuccess || cudaMallocHost((void**)&s->h_small, (size_t)(8 * s->L + 8) * sizeof(double)) != cudaSuccess) {
+    delete s;
+    return fail(MLEASE_ERR_CUDA, "cudaMallocHost failed");
+  }
+  void* f;
+  if (cudaMalloc(&f, 64) != cudaSuccess) { delete s; return fail(MLEASE_ERR_CUDA, "cudaMalloc failed"); }
+  s->owned.push_back(f);
+  s->d_flag = (int*)f;
+  *out = s;
+  return 0;
+}
+
+int mlease_session_destroy(mlease_session* s) {
+  if (!s) return 0;
+  cudaSetDevice(s->cfg.device);
+  cudaDeviceSynchronize();
+  delete s;
+  return 0;
+}
+
+static int add_common(mlease_session* s, PartData& pd, const int32_t* response, const float* weight, const float* offset) {
+  const long long n = pd.n;
+  void *y, *w, *o, *tmp_r, *tmp_w = nullptr, *tmp_o = nullptr;
+  if (int rc = sess_alloc(s, &y, n)) return rc;
+  if (int rc = sess_alloc(s, &w, n * 4)) return rc;
+  if (int rc = sess_alloc(s, &o, n * 4)) return rc;
+  CK(cudaMalloc(&tmp_r, std::max<long long>(n, 1) * 4));
+  CK(cudaMemcpyAsync(tmp_r, response, n * 4, cudaMemcpyDefault, s->stream));
+  if (weight) { CK(cudaMalloc(&tmp_w, std::max<long long>(n, 1) * 4)); CK(cudaMemcpyAsync(tmp_w, weight, n * 4, cudaMemcpyDefault, s->stream)); }
+  if (offset) { CK(cudaMalloc(&tmp_o, std::max<long long>(n, 1) * 4)); CK(cudaMemcpyAsync(tmp_o, offset, n * 4, cudaMemcpyDefault, s->stream)); }
+  CK(cudaMemsetAsync(s->d_flag, 0, 4, s->stream));
+  if (n > 0)
+    convert_labels_kernel<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, s->stream>>>(n, (const int*)tmp_r, (const float*)tmp_w, (const float*)tmp_o,
+                                                                                         (signed char*)y, (float*)w, (float*)o, s->d_flag);
+  CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  cudaFree(tmp_r); cudaFree(tmp_w); cudaFree(tmp_o);
+  if (*s->h_flag & 1) return fail(MLEASE_ERR_INVALID, "response (only 1, 0, -1 are allowed)");
+  if (*s->h_flag & 2) return fail(MLEASE_ERR_INVALID, "weight cannot < 0");
+  pd.y = (signed char*)y; pd.w = (float*)w; pd.o = (float*)o;
+  return 0;
+}
+
+int mlease_add_partition_dense(mlease_session* s, int32_t pid, int64_t nrows, const float* X, int64_t ldx_in, const int32_t* response,
+                               const float* weight, const float* offset) {
+  if (!s || !X || !response || nrows <= 0) return fail(MLEASE_ERR_INVALID, "bad argument (null pointer or empty partition)");
+  if (s->batch) return fail(MLEASE_ERR_STATE, "partitions must be added before the first ADMM call");
+  if (pid < 0 || pid >= s->P) return fail(MLEASE_ERR_INVALID, "Map key is wrong! key has to be in the range of [0,numPartitions-1].");
+  if (find_part(s, pid) >= 0) return fail(MLEASE_ERR_INVALID, "partition added twice");
+  if (s->cfg.binary_feature) return fail(MLEASE_ERR_INVALID, "binary.feature needs CSR input (every listed feature counts as 1)");
+  if (ldx_in < s->Dg) return fail(MLEASE_ERR_INVALID, "ldx < num_features");
+  CK(cudaSetDevice(s->cfg.device));
+  PartData pd;
+  pd.pid = pid; pd.n = nrows; pd.csr = false;
+  void* x;
+  CK(cudaMalloc(&x, (size_t)nrows * s->ldx * sizeof(float)));
+  s->owned.push_back(x);
+  pd.X = (float*)x;
+  CK(cudaMemcpy2DAsync(pd.X, (size_t)s->ldx * 4, X, (size_t)ldx_in * 4, (size_t)s->Dg * 4, (size_t)nrows, cudaMemcpyDefault, s->stream));
+  fill_bias_pad_kernel<<<1024, 256, 0, s->stream>>>(pd.X, nrows, s->ldx, s->Dg, 1);
+  if (int rc = add_common(s, pd, response, weight, offset)) return rc;
+  s->parts.push_back(pd);
+  s->any_dense = true;
+  return 0;
+}
+
+int mlease_add_partition_csr(mlease_session* s, int32_t pid, int64_t nrows, const int64_t* rowptr, const int32_t* colidx, const float* vals,
+                             const int32_t* response, const float* weight, const float* offset) {
+  if (!s || !rowptr || !response || nrows <= 0) return fail(MLEASE_ERR_INVALID, "bad argument (null pointer or empty partition)");
+  if (s->batch) return fail(MLEASE_ERR_STATE, "partitions must be added before the first ADMM call");
+  if (pid < 0 || pid >= s->P) return fail(MLEASE_ERR_INVALID, "Map key is wrong! key has to be in the range of [0,numPartitions-1].");
+  if (find_part(s, pid) >= 0) return fail(MLEASE_ERR_INVALID, "partition added twice");
+  CK(cudaSetDevice(s->cfg.device));
+  PartData pd;
+  pd.pid = pid; pd.n = nrows; pd.csr = true;
+  void *rp, *ci, *vv;
+  if (int rc = sess_alloc(s, &rp, (nrows + 1) * 8)) return rc;
+  CK(cudaMemcpyAsync(rp, rowptr, (nrows + 1) * 8, cudaMemcpyDefault, s->stream));
+  long long ends[2];
+  CK(cudaMemcpyAsync(&ends[0], rowptr, 8, cudaMemcpyDefault, s->stream));
+  CK(cudaMemcpyAsync(&ends[1], rowptr + nrows, 8, cudaMemcpyDefault, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  if (ends[0] != 0) return fail(MLEASE_ERR_INVALID, "rowptr[0] must be 0");
+  pd.nnz = ends[1];
+  if (pd.nnz > 0 && (!colidx || !vals)) return fail(MLEASE_ERR_INVALID, "null colidx/vals");
+  if (int rc = sess_alloc(s, &ci, pd.nnz * 4)) return rc;
+  if (int rc = sess_alloc(s, &vv, pd.nnz * 4)) return rc;
+  if (pd.nnz > 0) {
+    CK(cudaMemcpyAsync(ci, colidx, pd.nnz * 4, cudaMemcpyDefault, s->stream));
+    CK(cudaMemcpyAsync(vv, vals, pd.nnz * 4, cudaMemcpyDefault, s->stream));
+    CK(cudaMemsetAsync(s->d_flag, 0, 4, s->stream));
+    check_csr_kernel<<<(int)std::min<long long>((pd.nnz + 255) / 256, 4096), 256, 0, s->stream>>>(pd.nnz, (const int*)ci, (float*)vv, s->Dg, s->cfg.binary_feature, s->d_flag);
+    CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    if (*s->h_flag) return fail(MLEASE_ERR_INVALID, "feature index out of range");
+  }
+  pd.rowptr = (long long*)rp; pd.colidx = (int*)ci; pd.vals = (float*)vv;
+  if (int rc = add_common(s, pd, response, weight, offset)) return rc;
+  s->parts.push_back(pd);
+  s->any_csr = true;
+  return 0;
+}
+
+int mlease_admm_begin(mlease_session* s) {
+  if (!s) return fail(MLEASE_ERR_INVALID, "null session");
+  CK(cudaSetDevice(s->cfg.device));
+  if (int rc = finalize(s)) return rc;
+  s->iter = 0; s->liblinear_eps = 0.01f; s->mindiff = 99999999; s->last_maxdiff = 0;
+  for (int l = 0; l < s->L; l++) s->h_small[l] = rho_eff_for_iter(s, l, 1);
+  CK(cudaMemcpyAsync(s->d_rho, s->h_small, s->L * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  int launches = 0;
+  CK(admm_reset(s->batch->d, s->batch->nprob, s->L, s->d_z, s->ldx, s->d_rho, s->stream, &launches));
+  CK(cudaStreamSynchronize(s->stream));
+  s->cnt.launches += launches;
+  s->rho_fact.assign(s->L, -1.0);
+  s->begun = true;
+  return 0;
+}
+
+int mlease_admm_local_step(mlease_session* s, double* exchange_dev) {
+  if (!s || !exchange_dev) return fail(MLEASE_ERR_INVALID, "null argument");
+  if (!s->begun) return fail(MLEASE_ERR_STATE, "mlease_admm_begin was not called");
+  CK(cudaSetDevice(s->cfg.device));
+  s->iter++;
+  const int i = s->iter;
+  // tolerance schedule: control only (jobs/RegressionAdmmTrain.java:338-346)
+  if (i > 1 && s->mindiff < 0.001 && !s->cfg.aggressive_decay) s->liblinear_eps = s->liblinear_eps / 10;
+  else if (s->cfg.aggressive_decay && i > 5) s->liblinear_eps = s->liblinear_eps / 10;
+  int invalidate = 0;
+  for (int l = 0; l < s->L; l++) {
+    const double r = rho_eff_for_iter(s, l, i);
+    if (r != s->rho_fact[l]) invalidate = 1;   // prior precision changed -> stale factors are for another H
+    s->rho_fact[l] = r;
+  }
+  if (int rc = batch_xupdate(*s->batch, s->stream, s->xtol, s->max_newton, s->cfg.hessian_policy, invalidate, s->h_flag, s->d_flag, s->cnt)) return rc;
+  int launches = 0;
+  CK(admm_pack(s->batch->d, (int)s->parts.size(), s->L, s->Dt, exchange_dev, s->stream, &launches));
+  s->cnt.launches += launches;
+  return 0;
+}
+
+int mlease_admm_consensus(mlease_session* s, const double* exchange_sum_dev, double* maxdiff, int32_t* stop) {
+  if (!s || !exchange_sum_dev) return fail(MLEASE_ERR_INVALID, "null argument");
+  if (!s->begun || s->iter < 1) return fail(MLEASE_ERR_STATE, "consensus before local_step");
+  CK(cudaSetDevice(s->cfg.device));
+  for (int l = 0; l < s->L; l++) s->h_small[l] = rho_eff_for_iter(s, l, s->iter + 1);
+  CK(cudaMemcpyAsync(s->d_rho, s->h_small, s->L * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  int launches = 0;
+  CK(admm_consensus(s->batch->d, (int)s->parts.size(), s->L, s->Dt, s->ldx, s->P, exchange_sum_dev, s->d_z, s->d_wz, s->d_rho, s->d_diff, s->stream, &launches));
+  s->cnt.launches += launches;
+  double* hd = s->h_small + s->L;
+  CK(cudaMemcpyAsync(hd, s->d_diff, s->L * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  double mx = 0, mn = 99999999;
+  for (int l = 0; l < s->L; l++) { mx = std::max(mx, hd[l]); mn = std::min(mn, hd[l]); }
+  s->mindiff = mn; s->last_maxdiff = mx;
+  if (maxdiff) *maxdiff = mx;
+  const double eps = s->cfg.epsilon > 0 ? s->cfg.epsilon : 0.0001;
+  if (stop) *stop = (mx < eps && s->liblinear_eps <= 0.00001) ? 1 : 0;   // :493-496
+  return 0;
+}
+
+int mlease_admm_run(mlease_session* s, int32_t num_iters, mlease_allreduce_fn allreduce, void* ctx, int32_t* iters_done) {
+  if (!s) return fail(MLEASE_ERR_INVALID, "null session");
+  if (!allreduce && (int)s->parts.size() != s->P && s->batch == nullptr)
+    ;  // checked below once finalized
+  if (int rc = mlease_admm_begin(s)) return rc;
+  if (!allreduce && (int)s->parts.size() != s->P)
+    return fail(MLEASE_ERR_STATE, "Some models failed! (" + std::to_string(s->parts.size()) + " of " + std::to_string(s->P) + " partitions present and no all-reduce given)");
+  int done = 0;
+  for (int i = 1; i <= num_iters; i++) {
+    if (int rc = mlease_admm_local_step(s, s->d_exch)) return rc;
+    if (allreduce) {
+      if (allreduce(ctx, s->d_exch, (size_t)s->L * s->Dt, (void*)s->stream) != 0) return fail(MLEASE_ERR_CUDA, "all-reduce callback failed");
+    }
+    double md; int32_t stop;
+    if (int rc = mlease_admm_consensus(s, s->d_exch, &md, &stop)) return rc;
+    done = i;
+    if (stop) break;
+  }
+  if (iters_done) *iters_done = done;
+  return 0;
+}
+
+int mlease_get_z(mlease_session* s, int32_t l, double* out) {
+  if (!s || !out || l < 0 || l >= s->L || !s->batch) return fail(MLEASE_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(s->cfg.device));
+  CK(cudaMemcpyAsync(out, s->d_z + (size_t)l * s->ldx, s->Dt * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+int mlease_get_final_model(mlease_session* s, int32_t l, float* out) {
+  std::vector<double> z(s ? s->Dt : 0);
+  if (int rc = mlease_get_z(s, l, z.data())) return rc;
+  for (int k = 0; k < s->Dt; k++) out[k] = (float)z[k];   // models/LinearModel.java:703,716
+  return 0;
+}
+static int get_vec(mlease_session* s, int pid, int l, int which, void* out) {
+  if (!s || !out || l < 0 || l >= s->L || !s->batch) return fail(MLEASE_ERR_INVALID, "bad argument");
+  const int pi = find_part(s, pid);
+  if (pi < 0) return fail(MLEASE_ERR_INVALID, "partition not resident in this session");
+  CK(cudaSetDevice(s->cfg.device));
+  const Problem& p = s->batch->h[pi * s->L + l];
+  const void* src = which == 0 ? (const void*)p.beta : which == 1 ? (const void*)p.u_f : (const void*)p.uplusx_f;
+  CK(cudaMemcpyAsync(out, src, s->Dt * (which == 0 ? 8 : 4), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+int mlease_get_x(mlease_session* s, int32_t pid, int32_t l, double* out) { return get_vec(s, pid, l, 0, out); }
+int mlease_get_u(mlease_session* s, int32_t pid, int32_t l, float* out) { return get_vec(s, pid, l, 1, out); }
+int mlease_get_uplusx(mlease_session* s, int32_t pid, int32_t l, float* out) { return get_vec(s, pid, l, 2, out); }
+
+int mlease_get_stats(mlease_session* s, mlease_stats* out) {
+  if (!s || !out) return fail(MLEASE_ERR_INVALID, "null argument");
+  out->k1_passes = s->cnt.k1_passes; out->gram_builds = s->cnt.gram_builds; out->newton_steps = s->cnt.newton_steps;
+  out->rejected_steps = s->cnt.rejected; out->kernel_launches = s->cnt.launches; out->not_converged = s->cnt.not_converged;
+  out->last_iter_slots = s->cnt.last_slots; out->last_maxdiff = s->last_maxdiff; out->liblinear_epsilon = s->liblinear_eps;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// function-level entry points on the scratch problem
+// ------------------------------------------------------------------------------------------
+static int scratch_set(mlease_session* s, const double* w, const double* m, const double* q) {
+  Batch* B = s->scratch;
+  const Problem& p = B->h[0];
+  std::vector<double> buf(3 * (size_t)s->ldx, 0.0);
+  for (int k = 0; k < s->Dt; k++) { buf[k] = w[k]; buf[s->ldx + k] = m[k]; buf[2 * s->ldx + k] = q[k]; }
+  for (int k = s->Dt; k < s->ldx; k++) buf[2 * s->ldx + k] = 1.0;
+  CK(cudaMemcpyAsync(p.beta, buf.data(), s->ldx * 8, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(p.m, buf.data() + s->ldx, s->ldx * 8, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(p.q, buf.data() + 2 * s->ldx, s->ldx * 8, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int mlease_objective(mlease_session* s, int32_t pid, const double* w, const double* m, const double* q, double* f, double* g, double* H,
+                     int32_t tensor) {
+  if (!s || !w || !m || !q) return fail(MLEASE_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(s->cfg.device));
+  const int pi = find_part(s, pid);
+  if (pi < 0) return fail(MLEASE_ERR_INVALID, "partition not resident in this session");
+  if (int rc = ensure_scratch(s, pi)) return rc;
+  Batch* B = s->scratch;
+  if (int rc = scratch_set(s, w, m, q)) return rc;
+  int launches = 0;
+  CK(newton_begin(B->d, 1, 1e-8, 1, 1, 1, s->stream, &launches));
+  CK(k1_launch(B->d, 1, B->csr, B->ldx, 1, B->k1_grid, H ? 1 : 0, s->stream, &launches));
+  CK(k1_reduce_decide(B->d, 1, s->stream, &launches));
+  const Problem& p = B->h[0];
+  Ctrl c;
+  CK(cudaMemcpyAsync(&c, B->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
+  if (g) CK(cudaMemcpyAsync(g, p.g_t, s->Dt * 8, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  if (f) *f = c.f_t;
+  if (H) {
+    if (tensor) CK(gram_launch_tcgen05(B->d, 1, B->d_tmaps, B->d_tiles, B->ntiles, B->gram_slices, 1, s->stream, &launches));
+    else CK(gram_launch_simt(B->d, 1, B->Dp, 1, s->stream, &launches));
+    const size_t per = (size_t)B->Dp * B->Dp;
+    std::vector<float> hp(per * B->gram_slices);
+    CK(cudaMemcpyAsync(hp.data(), p.Hpart, hp.size() * 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    const int Dt = s->Dt;
+    for (int i = 0; i < Dt; i++)
+      for (int j = 0; j <= i; j++) {
+        double a = 0;
+        for (int t = 0; t < B->gram_slices; t++) a += (double)hp[t * per + (size_t)i * B->Dp + j];
+        if (i == j) a += q[i];
+        H[(size_t)i * Dt + j] = a;
+        H[(size_t)j * Dt + i] = a;
+      }
+  }
+  s->cnt.launches += launches;
+  return 0;
+}
+
+int mlease_fit_partition(mlease_session* s, int32_t pid, double* x, const double* m, const double* q, int32_t* newton_steps) {
+  if (!s || !x || !m || !q) return fail(MLEASE_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(s->cfg.device));
+  const int pi = find_part(s, pid);
+  if (pi < 0) return fail(MLEASE_ERR_INVALID, "partition not resident in this session");
+  if (int rc = ensure_scratch(s, pi)) return rc;
+  if (int rc = scratch_set(s, x, m, q)) return rc;
+  Counters c;
+  if (int rc = batch_xupdate(*s->scratch, s->stream, s->xtol, s->max_newton, s->cfg.hessian_policy, 1, s->h_flag, s->d_flag, c)) return rc;
+  s->cnt.launches += c.launches; s->cnt.k1_passes += c.k1_passes; s->cnt.gram_builds += c.gram_builds;
+  s->cnt.newton_steps += c.newton_steps; s->cnt.rejected += c.rejected; s->cnt.not_converged += c.not_converged;
+  CK(cudaMemcpyAsync(x, s->scratch->h[0].beta, s->Dt * 8, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  if (newton_steps) *newton_steps = (int)c.newton_steps;
+  if (c.not_converged) return fail(MLEASE_ERR_NUMERIC, "Model fitting error! (Newton did not converge within max_newton steps)");
+  return 0;
+}
+
+int mlease_time_kernel(mlease_session* s, int32_t pid, int32_t which, int32_t reps, int32_t emit_scaled, float* avg_ms) {
+  if (!s || !avg_ms || reps <= 0) return fail(MLEASE_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(s->cfg.device));
+  const int pi = find_part(s, pid);
+  if (pi < 0) return fail(MLEASE_ERR_INVALID, "partition not resident in this session");
+  if (int rc = ensure_scratch(s, pi)) return rc;
+  Batch* B = s->scratch;
+  std::vector<double> zero(s->Dt, 0.0), one(s->Dt, 1.0);
+  if (int rc = scratch_set(s, zero.data(), zero.data(), one.data())) return rc;
+  int launches = 0;
+  CK(newton_begin(B->d, 1, 1e-8, 1, 1, 1, s->stream, &launches));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  // warm-up launch (also produces the scaled copy the Gram needs)
+  CK(k1_launch(B->d, 1, B->csr, B->ldx, 1, B->k1_grid, 1, s->stream, &launches));
+  if (which == 3) {
+    CK(gram_launch_tcgen05(B->d, 1, B->d_tmaps, B->d_tiles, B->ntiles, B->gram_slices, 1, s->stream, &launches));
+    Ctrl c; std::memset(&c, 0, sizeof(c)); c.need_hess = 1;
+    CK(cudaMemcpyAsync(B->d_ctrl, &c, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
+  }
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaEventRecord(e0, s->stream));
+  for (int r = 0; r < reps; r++) {
+    if (which == 1) CK(k1_launch(B->d, 1, B->csr, B->ldx, 1, B->k1_grid, emit_scaled ? 1 : 0, s->stream, &launches));
+    else if (which == 2) CK(gram_launch_tcgen05(B->d, 1, B->d_tmaps, B->d_tiles, B->ntiles, B->gram_slices, 1, s->stream, &launches));
+    else if (which == 3) CK(cholesky_launch(B->d, 1, B->ldh, s->stream, &launches));
+    else return fail(MLEASE_ERR_INVALID, "which must be 1, 2 or 3");
+  }
+  CK(cudaEventRecord(e1, s->stream));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *avg_ms = ms / reps;
+  s->cnt.launches += launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// scoring / log-likelihood
+// ------------------------------------------------------------------------------------------
+static int need_device(int device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(MLEASE_ERR_CUDA, std::string("no CUDA device: this library has no CPU fallback (") + cudaGetErrorString(e) + ")");
+  if (device < 0 || device >= ndev) return fail(MLEASE_ERR_INVALID, "bad device ordinal");
+  CK(cudaSetDevice(device));
+  return 0;
+}
+
+int mlease_score(int32_t device, void* stream, int32_t Dg, int64_t nrows, const int64_t* rowptr, const int32_t* colidx, const float* vals,
+                 int64_t ldx, const float* offset, const double* model, int32_t num_click_replicates, int32_t binary_feature, float* pred) {
+  if (!vals || !model || !pred || nrows < 0) return fail(MLEASE_ERR_INVALID, "bad argument");
+  if (int rc = need_device(device)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  TmpDev t;
+  const long long* d_rp = nullptr; const int* d_ci = nullptr; const float* d_v = nullptr; const float* d_o = nullptr; const double* d_m = nullptr;
+  long long nnz = nrows * ldx;
+  if (colidx) {
+    if (!rowptr) return fail(MLEASE_ERR_INVALID, "null rowptr");
+    long long last;
+    CK(cudaMemcpy(&last, rowptr + nrows, 8, cudaMemcpyDefault));
+    nnz = last;
+    if (int rc = to_device(t, (const long long*)rowptr, (size_t)nrows + 1, &d_rp, st)) return rc;
+    if (int rc = to_device(t, colidx, (size_t)nnz, &d_ci, st)) return rc;
+  }
+  if (int rc = to_device(t, vals, (size_t)nnz, &d_v, st)) return rc;
+  if (int rc = to_device(t, offset, (size_t)nrows, &d_o, st)) return rc;
+  if (int rc = to_device(t, model, (size_t)Dg + 1, &d_m, st)) return rc;
+  double b;
+  CK(cudaMemcpy(&b, model + Dg, 8, cudaMemcpyDefault));
+  // intercept term  -log(n - 1 + n exp(-b))  (models/LinearModel.java:243-244)
+  const double ic = -std::log((double)num_click_replicates - 1 + (double)num_click_replicates * std::exp(-b));
+  cudaPointerAttributes a;
+  bool pred_dev = cudaPointerGetAttributes(&a, pred) == cudaSuccess && (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged);
+  cudaGetLastError();
+  float* d_pred = pred;
+  if (!pred_dev) { if (int rc = t.get(&d_pred, (size_t)nrows)) return rc; }
+  CK(score_launch(Dg, nrows, d_rp, d_ci, d_v, ldx, d_o, d_m, ic, binary_feature, d_pred, st));
+  if (!pred_dev) CK(cudaMemcpyAsync(pred, d_pred, (size_t)nrows * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int mlease_test_loglik(int32_t device, void* stream, int64_t nrows, const int32_t* response, const float* pred, const float* weight,
+                       int64_t combiner_block, float* out_loglik, double* out_count) {
+  if (!response || !pred || !out_loglik || !out_count || nrows <= 0) return fail(MLEASE_ERR_INVALID, "bad argument");
+  if (int rc = need_device(device)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  TmpDev t;
+  const int* d_r; const float* d_p; const float* d_w;
+  if (int rc = to_device(t, (const int*)response, (size_t)nrows, &d_r, st)) return rc;
+  if (int rc = to_device(t, pred, (size_t)nrows, &d_p, st)) return rc;
+  if (int rc = to_device(t, weight, (size_t)nrows, &d_w, st)) return rc;
+  const bool combine = combiner_block > 0;
+  const long long blk = combine ? combiner_block : 4096;
+  const long long nb = (nrows + blk - 1) / blk;
+  float* d_ll; double *d_bs, *d_bc; int* d_bad;
+  if (int rc = t.get(&d_ll, (size_t)nrows)) return rc;
+  if (int rc = t.get(&d_bs, (size_t)nb)) return rc;
+  if (int rc = t.get(&d_bc, (size_t)nb)) return rc;
+  if (int rc = t.get(&d_bad, 1)) return rc;
+  CK(cudaMemsetAsync(d_bad, 0, 4, st));
+  CK(loglik_launch(nrows, d_r, d_p, d_w, blk, d_ll, d_bs, d_bc, d_bad, st));
+  std::vector<double> bs(nb), bc(nb);
+  int bad = 0;
+  CK(cudaMemcpyAsync(bs.data(), d_bs, nb * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(bc.data(), d_bc, nb * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (bad) return fail(MLEASE_ERR_INVALID, "response should be 1,0 or -1!");
+  double sum = 0, n = 0;
+  for (long long b = 0; b < nb; b++) {
+    sum += combine ? (double)(float)bs[b] : bs[b];   // combiner casts its partial sum to float (jobs/RegressionTestLoglik.java:197)
+    n += bc[b];
+  }
+  *out_loglik = (float)(sum / n);                    // reducer (:173)
+  *out_count = n;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// RegressionNaiveTrain: K independent fits, processed in lockstep chunks.
+// ------------------------------------------------------------------------------------------
+int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg, const int64_t* key_rowstart, const float* X, int64_t ldx_in,
+                             const int32_t* response, const float* weight, const float* offset, float lambda, const float* lambda_map,
+                             float prior_mean, int32_t penalize_intercept, int32_t has_intercept, int32_t data_size_threshold,
+                             double* out_model, int32_t* skipped) {
+  if (K <= 0 || Dg <= 0 || !key_rowstart || !X || !response || !out_model) return fail(MLEASE_ERR_INVALID, "bad argument");
+  if (int rc = need_device(device)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(MLEASE_ERR_CUDA, "this build targets sm_100a (B200) only");
+  const int Dt = Dg + 1, ldx = round_up(Dt, 4);
+  std::vector<long long> krs(K + 1);
+  CK(cudaMemcpy(krs.data(), key_rowstart, (size_t)(K + 1) * 8, cudaMemcpyDefault));
+  const long long ntot = krs[K];
+  TmpDev t;
+  float* dX; signed char* dy; float *dw, *dofs; int* dflag; int* hflag;
+  if (int rc = t.get(&dX, (size_t)ntot * ldx)) return rc;
+  if (int rc = t.get(&dy, (size_t)ntot)) return rc;
+  if (int rc = t.get(&dw, (size_t)ntot)) return rc;
+  if (int rc = t.get(&dofs, (size_t)ntot)) return rc;
+  if (int rc = t.get(&dflag, 16)) return rc;
+  CK(cudaMallocHost((void**)&hflag, 64));
+  struct HF { int* p; ~HF() { cudaFreeHost(p); } } hf{hflag};
+  CK(cudaMemcpy2DAsync(dX, (size_t)ldx * 4, X, (size_t)ldx_in * 4, (size_t)Dg * 4, (size_t)ntot, cudaMemcpyDefault, st));
+  fill_bias_pad_kernel<<<1024, 256, 0, st>>>(dX, ntot, ldx, Dg, has_intercept ? 1 : 0);
+  {
+    const int* d_r; const float *d_wi, *d_oi;
+    if (int rc = to_device(t, (const int*)response, (size_t)ntot, &d_r, st)) return rc;
+    if (int rc = to_device(t, weight, (size_t)ntot, &d_wi, st)) return rc;
+    if (int rc = to_device(t, offset, (size_t)ntot, &d_oi, st)) return rc;
+    CK(cudaMemsetAsync(dflag, 0, 4, st));
+    convert_labels_kernel<<<(int)std::min<long long>((ntot + 255) / 256, 4096), 256, 0, st>>>(ntot, d_r, d_wi, d_oi, dy, dw, dofs, dflag);
+    CK(cudaMemcpyAsync(hflag, dflag, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (*hflag & 1) return fail(MLEASE_ERR_INVALID, "response (only 1, 0, -1 are allowed)");
+    if (*hflag & 2) return fail(MLEASE_ERR_INVALID, "weight cannot < 0");
+  }
+  // prior (jobs/RegressionNaiveTrain.java:333-343,395)
+  std::vector<double> q(ldx, 1.0), m(ldx, 0.0), zero(ldx, 0.0);
+  std::vector<float> lm;
+  if (lambda_map) { lm.resize(Dg); CK(cudaMemcpy(lm.data(), lambda_map, (size_t)Dg * 4, cudaMemcpyDefault)); }
+  for (int k = 0; k < Dg; k++) {
+    q[k] = (!lm.empty() && lm[k] > 0.f) ? 1.0 / (1.0 / (double)lm[k]) : 1.0 / (1.0 / (double)lambda);
+    m[k] = (double)prior_mean;
+  }
+  // intercept: variance 100000 unless penalised (then the default 1/lambda); without intercept the bias column is 0
+  q[Dg] = has_intercept ? (penalize_intercept ? 1.0 / (1.0 / (double)lambda) : 1.0 / 100000.0) : 1.0;
+  m[Dg] = has_intercept ? (double)prior_mean : 0.0;
+  for (int k = 0; k < K; k++) {
+    for (int j = 0; j < Dt; j++) out_model[(size_t)k * Dt + j] = 0.0;
+    if (skipped) skipped[k] = 0;
+  }
+  std::vector<int> todo;
+  for (int k = 0; k < K; k++) {
+    const long long nk = krs[k + 1] - krs[k];
+    if (nk < data_size_threshold || nk <= 0) { if (skipped) skipped[k] = 1; }
+    else todo.push_back(k);
+  }
+  // chunk size bounded by memory: Xt (n*Dp*2) + Hpart + Lc per problem
+  const int Dp = round_up(ldx, 128), ldh = round_up(Dt, 32);
+  size_t free_b, total_b;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  Counters cnt;
+  size_t pos = 0;
+  while (pos < todo.size()) {
+    size_t bytes = 0;
+    size_t end = pos;
+    while (end < todo.size() && end - pos < 16384) {
+      const long long nk = krs[todo[end] + 1] - krs[todo[end]];
+      const size_t need = (size_t)nk * Dp * 2 + (size_t)Dp * Dp * 4 + (size_t)ldh * ldh * 8 + (size_t)ldh * 32 * 8 + 64 * (size_t)ldx;
+      if (end > pos && bytes + need > free_b / 2) break;
+      bytes += need;
+      end++;
+    }
+    Batch B;
+    B.nprob = (int)(end - pos); B.Dt = Dt; B.ldx = ldx; B.csr = false; B.has_bias = has_intercept ? 1 : 0;
+    B.h.resize(B.nprob);
+    for (int b = 0; b < B.nprob; b++) {
+      const int k = todo[pos + b];
+      Problem& p = B.h[b];
+      std::memset(&p, 0, sizeof(Problem));
+      p.X = dX + (size_t)krs[k] * ldx; p.n = krs[k + 1] - krs[k];
+      p.y = dy + krs[k]; p.w = dw + krs[k]; p.o = dofs + krs[k];
+    }
+    if (int rc = batch_alloc(B, prop.multiProcessorCount)) return rc;
+    {
+      double *dm, *dq, *dout;
+      if (int rc = t.get(&dm, (size_t)ldx)) return rc;
+      if (int rc = t.get(&dq, (size_t)ldx)) return rc;
+      if (int rc = t.get(&dout, (size_t)B.nprob * Dt)) return rc;
+      CK(cudaMemcpyAsync(dm, m.data(), ldx * 8, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(dq, q.data(), ldx * 8, cudaMemcpyHostToDevice, st));
+      naive_init_kernel<<<B.nprob, 128, 0, st>>>(B.d, dm, dq);   // init = 0 (null initParam), prior mean / precision
+      if (int rc = batch_xupdate(B, st, 1e-8, 100, 0, 1, hflag, dflag, cnt)) return rc;
+      gather_beta_kernel<<<B.nprob, 128, 0, st>>>(B.d, Dt, dout);
+      std::vector<double> xs((size_t)B.nprob * Dt);
+      CK(cudaMemcpyAsync(xs.data(), dout, xs.size() * 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      for (int b = 0; b < B.nprob; b++) {
+        std::memcpy(out_model + (size_t)todo[pos + b] * Dt, xs.data() + (size_t)b * Dt, Dt * 8);
+        if (!has_intercept) out_model[(size_t)todo[pos + b] * Dt + Dg] = 0.0;
+      }
+    }
+    pos = end;
+  }
+  if (cnt.not_converged) return fail(MLEASE_ERR_NUMERIC, "Model fitting error! (" + std::to_string(cnt.not_converged) + " fits did not converge)");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,219 @@
+"""Host-side mirror of the reference's ADMM train job for the accelerated path.
+
+`AdmmSession` wraps the C ABI session = the body of RegressionAdmmTrain.run()
+(jobs/RegressionAdmmTrain.java:278-501): partitions are uploaded once
+(replacing AdmmReducer's per-iteration dataset rebuild, :677-690), `local_step` is the
+reducer phase (:642-718) for all resident (partition, lambda) pairs, `consensus` is the
+driver's z/u update (:362-404, :736-765).  Config keys keep the reference's names
+(with '.' -> '_').
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._native import ALLREDUCE_FN, AdmmConfigC, MleaseError, StatsC, check, lib, ptr
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _keep(a, dtype):
+    """numpy/torch passthrough with dtype/contiguity enforcement; returns (object_to_keep_alive)."""
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):  # torch tensor
+        import torch
+        td = {np.float32: torch.float32, np.int32: torch.int32, np.int64: torch.int64, np.float64: torch.float64}[dtype]
+        if a.dtype != td or not a.is_contiguous():
+            a = a.to(td).contiguous()
+        return a
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class AdmmSession:
+    def __init__(self, num_blocks, num_features, lambdas, rhos=None, *, device=0, stream=None, regularizer=2,
+                 penalize_intercept=False, epsilon=1e-4, rho_adapt_coefficient=0.0, aggressive_liblinear_epsilon_decay=False,
+                 binary_feature=False, lambda_map=None, newton_xtol=0.0, max_newton=0, hessian_policy=0):
+        self._h = None
+        self.num_blocks, self.num_features = int(num_blocks), int(num_features)
+        self.lambdas = _f32(np.atleast_1d(lambdas))
+        self.L = len(self.lambdas)
+        self.Dt = self.num_features + 1
+        self.device = int(device)
+        self._rhos = _f32(rhos)
+        self._lmap = _f32(lambda_map)
+        cfg = AdmmConfigC()
+        cfg.device, cfg.num_blocks, cfg.num_features, cfg.num_lambdas = self.device, self.num_blocks, self.num_features, self.L
+        cfg.lambdas = self.lambdas.ctypes.data_as(C.POINTER(C.c_float))
+        cfg.rhos = None if self._rhos is None else self._rhos.ctypes.data_as(C.POINTER(C.c_float))
+        cfg.lambda_map = None if self._lmap is None else self._lmap.ctypes.data_as(C.POINTER(C.c_float))
+        cfg.regularizer, cfg.penalize_intercept = int(regularizer), int(bool(penalize_intercept))
+        cfg.aggressive_decay, cfg.binary_feature = int(bool(aggressive_liblinear_epsilon_decay)), int(bool(binary_feature))
+        cfg.epsilon, cfg.rho_adapt_coefficient = float(epsilon), float(rho_adapt_coefficient)
+        cfg.newton_xtol, cfg.max_newton, cfg.hessian_policy = float(newton_xtol), int(max_newton), int(hessian_policy)
+        cfg.stream = stream
+        h = C.c_void_p()
+        check(lib().mlease_session_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self._cb = None
+
+    def close(self):
+        if self._h is not None:
+            lib().mlease_session_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- data ----
+    def add_partition_dense(self, partition_id, X, response, weight=None, offset=None):
+        X = _keep(X, np.float32)
+        n, d = X.shape
+        ld = X.stride(0) if hasattr(X, "data_ptr") else d
+        r, w, o = _keep(response, np.int32), _keep(weight, np.float32), _keep(offset, np.float32)
+        check(lib().mlease_add_partition_dense(self._h, int(partition_id), n, ptr(X), ld, ptr(r), ptr(w), ptr(o)))
+
+    def add_partition_csr(self, partition_id, rowptr, colidx, vals, response, weight=None, offset=None):
+        rp, ci, v = _keep(rowptr, np.int64), _keep(colidx, np.int32), _keep(vals, np.float32)
+        r, w, o = _keep(response, np.int32), _keep(weight, np.float32), _keep(offset, np.float32)
+        check(lib().mlease_add_partition_csr(self._h, int(partition_id), len(r), ptr(rp), ptr(ci), ptr(v), ptr(r), ptr(w), ptr(o)))
+
+    # ---- ADMM ----
+    def begin(self):
+        check(lib().mlease_admm_begin(self._h))
+
+    def local_step(self, exchange_dev_ptr):
+        check(lib().mlease_admm_local_step(self._h, ptr(exchange_dev_ptr)))
+
+    def consensus(self, exchange_sum_dev_ptr):
+        md, stop = C.c_double(0), C.c_int32(0)
+        check(lib().mlease_admm_consensus(self._h, ptr(exchange_sum_dev_ptr), C.byref(md), C.byref(stop)))
+        return md.value, bool(stop.value)
+
+    def run(self, num_iters, allreduce=None):
+        """Single-process job (allreduce None) or with a Python all-reduce callable(buf_ptr, count, stream_ptr)."""
+        done = C.c_int32(0)
+        cb = None
+        if allreduce is not None:
+            def _cb(ctx, buf, count, stream):
+                try:
+                    allreduce(buf, count, stream)
+                    return 0
+                except Exception:  # pragma: no cover
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            cb = ALLREDUCE_FN(_cb)
+            self._cb = cb
+        check(lib().mlease_admm_run(self._h, int(num_iters), C.cast(cb, C.c_void_p) if cb else None, None, C.byref(done)))
+        return done.value
+
+    # ---- state ----
+    def z(self, lambda_idx=0):
+        out = np.zeros(self.Dt, np.float64)
+        check(lib().mlease_get_z(self._h, lambda_idx, ptr(out)))
+        return out
+
+    def final_model(self, lambda_idx=0):
+        out = np.zeros(self.Dt, np.float32)
+        check(lib().mlease_get_final_model(self._h, lambda_idx, ptr(out)))
+        return out
+
+    def x(self, partition_id, lambda_idx=0):
+        out = np.zeros(self.Dt, np.float64)
+        check(lib().mlease_get_x(self._h, partition_id, lambda_idx, ptr(out)))
+        return out
+
+    def u(self, partition_id, lambda_idx=0):
+        out = np.zeros(self.Dt, np.float32)
+        check(lib().mlease_get_u(self._h, partition_id, lambda_idx, ptr(out)))
+        return out
+
+    def uplusx(self, partition_id, lambda_idx=0):
+        out = np.zeros(self.Dt, np.float32)
+        check(lib().mlease_get_uplusx(self._h, partition_id, lambda_idx, ptr(out)))
+        return out
+
+    def stats(self):
+        s = StatsC()
+        check(lib().mlease_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in StatsC._fields_}
+
+    # ---- function-level entry points ----
+    def objective(self, partition_id, w, prior_mean, prior_precision, want_grad=True, want_hessian=False, tensor=True):
+        w, m, q = (np.ascontiguousarray(a, np.float64) for a in (w, prior_mean, prior_precision))
+        f = C.c_double(0)
+        g = np.zeros(self.Dt, np.float64) if want_grad else None
+        H = np.zeros((self.Dt, self.Dt), np.float64) if want_hessian else None
+        check(lib().mlease_objective(self._h, partition_id, ptr(w), ptr(m), ptr(q), C.byref(f), ptr(g), ptr(H), int(tensor)))
+        return f.value, g, H
+
+    def fit_partition(self, partition_id, init, prior_mean, prior_precision):
+        x = np.array(init, np.float64, copy=True)
+        m, q = (np.ascontiguousarray(a, np.float64) for a in (prior_mean, prior_precision))
+        steps = C.c_int32(0)
+        check(lib().mlease_fit_partition(self._h, partition_id, ptr(x), ptr(m), ptr(q), C.byref(steps)))
+        return x, steps.value
+
+    def time_kernel(self, partition_id, which, reps=5, emit_scaled=False):
+        ms = C.c_float(0)
+        check(lib().mlease_time_kernel(self._h, partition_id, {"k1": 1, "gram": 2, "cholesky": 3}[which], reps, int(emit_scaled), C.byref(ms)))
+        return ms.value
+
+
+def score(vals, model, *, rowptr=None, colidx=None, offset=None, num_features=None, device=0, stream=None,
+          num_click_replicates=1, binary_feature=False, out=None):
+    """RegressionTest scoring (models/LinearModel.java:241-257; jobs/RegressionTest.java:163). Dense if colidx is None."""
+    model = _keep(model, np.float64)
+    Dg = int(num_features if num_features is not None else len(model) - 1)
+    if colidx is None:
+        vals = _keep(vals, np.float32)
+        n, ld = vals.shape[0], (vals.stride(0) if hasattr(vals, "data_ptr") else vals.shape[1])
+        rp = ci = None
+    else:
+        rp, ci, vals = _keep(rowptr, np.int64), _keep(colidx, np.int32), _keep(vals, np.float32)
+        n, ld = len(rp) - 1, 0
+    o = _keep(offset, np.float32)
+    pred = np.zeros(n, np.float32) if out is None else out
+    check(lib().mlease_score(device, stream, Dg, n, ptr(rp), ptr(ci), ptr(vals), ld, ptr(o), ptr(model), int(num_click_replicates),
+                             int(binary_feature), ptr(pred)))
+    return pred
+
+
+def test_loglik(response, pred, weight=None, combiner_block=0, device=0, stream=None):
+    """RegressionTestLoglik (jobs/RegressionTestLoglik.java:124-200) -> (float32 avg loglik, count)."""
+    r, p, w = _keep(response, np.int32), _keep(pred, np.float32), _keep(weight, np.float32)
+    ll, cnt = C.c_float(0), C.c_double(0)
+    check(lib().mlease_test_loglik(device, stream, len(r), ptr(r), ptr(p), ptr(w), int(combiner_block), C.byref(ll), C.byref(cnt)))
+    return np.float32(ll.value), cnt.value
+
+
+test_loglik.__test__ = False
+
+
+def naive_train_dense(X, key_rowstart, response, lam, weight=None, offset=None, lambda_map=None, prior_mean=0.0,
+                      penalize_intercept=False, has_intercept=True, data_size_threshold=0, device=0, stream=None):
+    """RegressionNaiveTrain reducer for K keys (jobs/RegressionNaiveTrain.java:302-415) -> (models [K,D+1], skipped[K])."""
+    X = _keep(X, np.float32)
+    krs = np.ascontiguousarray(key_rowstart, np.int64)
+    K, D = len(krs) - 1, X.shape[1]
+    ld = X.stride(0) if hasattr(X, "data_ptr") else D
+    r, w, o, lm = _keep(response, np.int32), _keep(weight, np.float32), _keep(offset, np.float32), _keep(lambda_map, np.float32)
+    out = np.zeros((K, D + 1), np.float64)
+    skipped = np.zeros(K, np.int32)
+    check(lib().mlease_naive_train_dense(device, stream, K, D, ptr(krs), ptr(X), ld, ptr(r), ptr(w), ptr(o), float(lam), ptr(lm),
+                                         float(prior_mean), int(penalize_intercept), int(has_intercept), int(data_size_threshold),
+                                         ptr(out), ptr(skipped)))
+    return out, skipped.astype(bool)

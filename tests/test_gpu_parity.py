@@ -1,0 +1,220 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Tolerances: objective/gradient 1e-5 relative (fp32 data path, fp64 reductions); Gram (bf16
+tensor-core operands) 2e-2 vs the fp64 Hessian and 1e-3 vs the fp32 SIMT kernel on the same bf16 operand;
+coefficients / z: 1e-5 relative (north star)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(n, d, seed, sparse=False, density=0.3):
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(n, d)).astype(np.float32)
+    if sparse:
+        X *= rng.random((n, d)) < density
+    beta = rng.normal(size=d) / np.sqrt(d)
+    y = (rng.random(n) < 1 / (1 + np.exp(-(X @ beta - 0.5)))).astype(np.int32)
+    w = rng.uniform(0.5, 2.0, n).astype(np.float32)
+    o = rng.normal(0, 0.1, n).astype(np.float32)
+    return X, y, w, o
+
+
+def _csr_of(X):
+    rp, ci, v = [0], [], []
+    for i in range(X.shape[0]):
+        nz = np.nonzero(X[i])[0]
+        ci += list(nz); v += list(X[i, nz]); rp.append(len(ci))
+    return np.array(rp, np.int64), np.array(ci, np.int32), np.array(v, np.float32)
+
+
+def _session(mb, D, lambdas=(1.0,), P=1, **kw):
+    return mb.AdmmSession(P, D, list(lambdas), **kw)
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import mlease_b200
+    return mlease_b200
+
+
+@pytest.mark.parametrize("n,d,sparse", [(1000, 37, False), (777, 100, False), (300, 1100, False), (500, 2500, False), (1000, 50, True)])
+def test_k1_objective_and_gradient(mb, n, d, sparse):
+    X, y, w, o = _mk(n, d, seed=n + d, sparse=sparse)
+    rng = np.random.default_rng(1)
+    wv = rng.normal(0, 0.3, d + 1); pm = rng.normal(0, 0.3, d + 1); pv = rng.uniform(0.2, 2.0, d + 1)
+    with _session(mb, d) as s:
+        if sparse:
+            rp, ci, v = _csr_of(X)
+            s.add_partition_csr(0, rp, ci, v, y, w, o)
+            data = orc.Csr(rp, ci, v, y, w, o, d)
+        else:
+            s.add_partition_dense(0, X, y, w, o)
+            data = orc.Csr.from_dense(X, y, w, o)
+        f, g, _ = s.objective(0, wv, pm, 1.0 / pv)
+    f_ref, g_ref = orc.objective("grad", data, wv, pm, pv)
+    assert abs(f - f_ref) <= 1e-5 * abs(f_ref), (f, f_ref)
+    assert np.abs(g - g_ref).max() <= 1e-5 * np.abs(g_ref).max(), np.abs(g - g_ref).max() / np.abs(g_ref).max()
+
+
+@pytest.mark.parametrize("n,d,sparse", [(1000, 37, False), (2000, 100, False), (700, 300, False), (1000, 50, True)])
+def test_gram_tcgen05_vs_oracle_hessian(mb, n, d, sparse):
+    X, y, w, o = _mk(n, d, seed=3 * n + d, sparse=sparse)
+    rng = np.random.default_rng(2)
+    wv = rng.normal(0, 0.3, d + 1); pm = np.zeros(d + 1); pv = np.full(d + 1, 0.5)
+    with _session(mb, d) as s:
+        if sparse:
+            rp, ci, v = _csr_of(X)
+            s.add_partition_csr(0, rp, ci, v, y, w, o)
+            data = orc.Csr(rp, ci, v, y, w, o, d)
+        else:
+            s.add_partition_dense(0, X, y, w, o)
+            data = orc.Csr.from_dense(X, y, w, o)
+        _, _, H_tc = s.objective(0, wv, pm, 1.0 / pv, want_hessian=True, tensor=True)
+        _, _, H_simt = s.objective(0, wv, pm, 1.0 / pv, want_hessian=True, tensor=False)
+    H_ref = orc.objective("hessian", data, wv, pm, pv)
+    scale = np.abs(H_ref).max()
+    e_simt = np.abs(H_simt - H_ref).max() / scale
+    e_tc = np.abs(H_tc - H_ref).max() / scale
+    e_x = np.abs(H_tc - H_simt).max() / scale
+    assert e_simt < 2e-2, ("simt vs oracle", e_simt)
+    assert e_tc < 2e-2, ("tcgen05 vs oracle", e_tc, e_simt, e_x)
+    assert e_x < 1e-3, ("tcgen05 vs simt", e_x)
+
+
+@pytest.mark.parametrize("n,d", [(1500, 20), (3000, 100), (800, 300)])
+def test_fit_partition_matches_exact_tron(mb, n, d):
+    X, y, w, o = _mk(n, d, seed=11 * n + d)
+    rng = np.random.default_rng(3)
+    pm = rng.normal(0, 0.2, d + 1); pv = np.full(d + 1, 1.0); init = rng.normal(0, 0.1, d + 1)
+    with _session(mb, d) as s:
+        s.add_partition_dense(0, X, y, w, o)
+        x, steps = s.fit_partition(0, init, pm, 1.0 / pv)
+        st = s.stats()
+    x_ref, _ = orc.liblinear_train(orc.Csr.from_dense(X, y, w, o), init, pm, pv, 1e-14, 100000)
+    err = np.abs(x - x_ref).max() / np.abs(x_ref).max()
+    assert err < 1e-6, (err, steps, st)
+    assert 1 <= steps <= 30 and st["not_converged"] == 0
+
+
+def _run_gpu_admm(mb, parts, D, lambdas, niters, csr, **kw):
+    P = len(parts)
+    with mb.AdmmSession(P, D, lambdas, **kw) as s:
+        for p, part in enumerate(parts):
+            (s.add_partition_csr if csr else s.add_partition_dense)(p, *part)
+        done = s.run(niters)
+        z = np.stack([s.z(l) for l in range(len(lambdas))])
+        xs = np.stack([[s.x(p, l) for l in range(len(lambdas))] for p in range(P)])
+        us = np.stack([[s.u(p, l) for l in range(len(lambdas))] for p in range(P)])
+        st = s.stats()
+    return done, z, xs, us, st
+
+
+def test_admm_fixture_csr_matches_oracle_exact(mb, fixture_data, frozen):
+    d = fixture_data
+    prs = frozen["part_rowstart"]
+    parts = []
+    for p in range(len(prs) - 1):
+        r0, r1 = prs[p], prs[p + 1]
+        rp = d.rowptr[r0:r1 + 1] - d.rowptr[r0]
+        sl = slice(d.rowptr[r0], d.rowptr[r1])
+        parts.append((rp, d.colidx[sl], d.val[sl], d.response[r0:r1], d.weight[r0:r1], d.offset[r0:r1]))
+    lambdas = [1.0, 10.0, 100.0]
+    for niters in (1, 2, 20):
+        done, z, xs, us, st = _run_gpu_admm(mb, parts, d.n_features, lambdas, niters, csr=True, epsilon=0.0)
+        ref = frozen["exact_z_hist"][niters - 1]
+        for l in range(3):
+            err = np.abs(z[l] - ref[l]).max() / np.abs(ref[l]).max()
+            assert err < 1e-5, (niters, l, err, st)
+    # last-iteration reducer outputs (x double, u float) vs the oracle
+    assert np.abs(xs - frozen["exact_x_last"]).max() / np.abs(frozen["exact_x_last"]).max() < 1e-5
+    assert np.abs(us - frozen["exact_u_last"]).max() / max(1e-12, np.abs(frozen["exact_u_last"]).max()) < 2e-5
+    assert st["not_converged"] == 0
+
+
+def test_admm_dense_config1_shape_matches_oracle_exact(mb):
+    # BASELINE config 0: 2 partitions x 10k x 100 dense, lambda = 1
+    P, n, D = 2, 10000, 100
+    parts, Xs, ys = [], [], []
+    rng = np.random.default_rng(1000)
+    beta = rng.normal(size=D) / np.sqrt(D)
+    for p in range(P):
+        r = np.random.default_rng(1000 + p)
+        X = r.normal(size=(n, D)).astype(np.float32)
+        y = (r.random(n) < 1 / (1 + np.exp(-(X @ beta - 1.0)))).astype(np.int32)
+        parts.append((X, y)); Xs.append(X); ys.append(y)
+    data = orc.Csr.from_dense(np.vstack(Xs), np.concatenate(ys))
+    ref = orc.admm_run(data, [0, n, 2 * n], [1.0], niters=10, mode="exact", nthreads=4, epsilon=0.0)
+    done, z, xs, us, st = _run_gpu_admm(mb, parts, D, [1.0], 10, csr=False, epsilon=0.0)
+    err = np.abs(z[0] - ref["z_hist"][-1, 0]).max() / np.abs(ref["z_hist"][-1, 0]).max()
+    assert done == 10 and err < 1e-5, (err, st)
+    fa = orc.admm_run(data, [0, n, 2 * n], [1.0], niters=10, mode="faithful", nthreads=4, epsilon=0.0)
+    gap = np.abs(z[0] - fa["z_hist"][-1, 0]).max() / np.abs(z[0]).max()
+    assert gap < 5e-2   # informational bound vs the loose-tolerance reference schedule (SURVEY 8c iii)
+
+
+def test_admm_stop_rule_and_options(mb):
+    X, y, w, o = _mk(600, 8, seed=5)
+    parts = [(X[:300], y[:300], w[:300], o[:300]), (X[300:], y[300:], w[300:], o[300:])]
+    data = orc.Csr.from_dense(X, y, w, o)
+    for kw, okw in ((dict(penalize_intercept=True), dict(penalize_intercept=True)),
+                    (dict(rho_adapt_coefficient=0.3), dict(rho_adapt_coefficient=0.3)),
+                    (dict(rhos=[2.0]), dict(rhos=[2.0]))):
+        rhos = kw.pop("rhos", None)
+        ref = orc.admm_run(data, [0, 300, 600], [10.0], rhos=okw.pop("rhos", None), niters=6, mode="exact", epsilon=0.0, **okw)
+        done, z, _, _, st = _run_gpu_admm(mb, parts, 8, [10.0], 6, csr=False, epsilon=0.0, rhos=rhos, **kw)
+        err = np.abs(z[0] - ref["z_hist"][-1, 0]).max() / np.abs(ref["z_hist"][-1, 0]).max()
+        assert err < 1e-5, (kw, err)
+    ref = orc.admm_run(data, [0, 300, 600], [10.0], niters=300, mode="faithful", epsilon=1e-3)
+    done, z, _, _, st = _run_gpu_admm(mb, parts, 8, [10.0], 300, csr=False, epsilon=1e-3)
+    assert abs(done - ref["iters_done"]) <= 2, (done, ref["iters_done"])
+
+
+def test_score_and_loglik_match_oracle(mb, fixture_data, frozen):
+    d = fixture_data
+    model = frozen["exact_z_hist"][-1, 0]
+    pred = mb.score(d.val, model, rowptr=d.rowptr, colidx=d.colidx, offset=d.offset)
+    ref = frozen["score_pred"]
+    assert np.abs(pred - ref).max() <= 2e-6 * np.abs(ref).max()
+    ll, cnt = mb.test_loglik(d.response, ref, d.weight, combiner_block=128)
+    assert abs(float(ll) - float(frozen["loglik"])) <= 1e-6 * abs(float(frozen["loglik"])) and cnt == 1000
+    X, y, w, o = _mk(500, 33, seed=9)
+    m = np.random.default_rng(0).normal(size=34)
+    p2 = mb.score(X, m, offset=o, num_click_replicates=3)
+    r2 = orc.score(orc.Csr.from_dense(X, y, w, o), m, num_click_replicates=3)
+    assert np.abs(p2 - r2).max() <= 2e-6 * np.abs(r2).max()
+    with pytest.raises(mb.MleaseError):
+        mb.test_loglik([5], [0.0])
+
+
+def test_naive_train_matches_oracle(mb):
+    X, y, w, o = _mk(1200, 16, seed=21)
+    krs = [0, 400, 800, 1200]
+    ref, _, _ = orc.naive_train(orc.Csr.from_dense(X, y, w, o), krs, 2.0, mode="exact")
+    got, skipped = mb.naive_train_dense(X, krs, y, 2.0, weight=w, offset=o)
+    assert not skipped.any()
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5
+    got2, sk2 = mb.naive_train_dense(X, krs, y, 2.0, weight=w, offset=o, data_size_threshold=500)
+    assert sk2.all() and not got2.any()
+    ref3, _, _ = orc.naive_train(orc.Csr.from_dense(X, y, w, o), krs, 2.0, has_intercept=False, penalize_intercept=True, mode="exact")
+    got3, _ = mb.naive_train_dense(X, krs, y, 2.0, weight=w, offset=o, has_intercept=False, penalize_intercept=True)
+    assert np.abs(got3 - ref3).max() / np.abs(ref3).max() < 1e-5
+
+
+def test_errors_follow_reference_conventions(mb):
+    X, y, w, o = _mk(50, 4, seed=1)
+    with pytest.raises(mb.MleaseError, match="Only L1 and L2"):
+        mb.AdmmSession(1, 4, [1.0], regularizer=3)
+    with _session(mb, 4) as s:
+        with pytest.raises(mb.MleaseError, match="response"):
+            s.add_partition_dense(0, X, np.full(50, 2, np.int32))
+        with pytest.raises(mb.MleaseError, match="weight"):
+            s.add_partition_dense(0, X, y, -w)
+        with pytest.raises(mb.MleaseError, match="Map key is wrong"):
+            s.add_partition_dense(3, X, y)
+    with mb.AdmmSession(2, 4, [1.0]) as s:
+        s.add_partition_dense(0, X, y)
+        with pytest.raises(mb.MleaseError, match="Some models failed"):
+            s.run(2)

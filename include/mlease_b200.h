@@ -59,10 +59,10 @@ typedef struct {
   int32_t penalize_intercept;  /* default 0 */
   int32_t aggressive_decay;    /* default 0 */
   int32_t binary_feature;      /* binary.feature: ignore values, use 1 (regression/liblinearfunc/LibLinearBinaryDataset.java) */
-  double epsilon;              /* outer stop, default 1e-4 (:473) */
+  double epsilon;              /* outer stop (:473); < 0 -> default 1e-4, 0 = never stop early */
   float rho_adapt_coefficient; /* default 0 (:323-327) */
   /* solver knobs (no reference equivalent: the inner solve is exact Newton, not TRON) */
-  double newton_xtol;          /* stop when |dir|_inf <= xtol*max(|beta|_inf,1e-2); 0 -> 1e-8 */
+  double newton_xtol;          /* stop when |dir|_inf <= xtol*max(|beta|_inf,1e-2); 0 -> 2e-7 (float32 lattice of the data path) */
   int32_t max_newton;          /* max accepted Newton steps per x-update; 0 -> 50 */
   int32_t hessian_policy;      /* 0 adaptive chord (refresh when contraction is poor), 1 every step */
   void* stream;                /* cudaStream_t to run on (NULL = legacy default stream) */
@@ -101,8 +101,9 @@ int mlease_admm_consensus(mlease_session* s, const double* exchange_sum_dev, dou
 int mlease_admm_run(mlease_session* s, int32_t num_iters, mlease_allreduce_fn allreduce, void* ctx, int32_t* iters_done);
 
 /* State readback (host buffers).  z: driver-side double z (:365-404); final model = float(z)
- * (models/LinearModel.java:697-720 toAvro).  x / u / uplusx: the reducer outputs of the last iteration
- * (:706-711) for iter-<i>/{model,u} files.  Length num_features+1, intercept last. */
+ * (models/LinearModel.java:697-720 toAvro).  After consensus of iteration i: x = the double x_p of iteration i
+ * (float(x) is iter-<i>/model), uplusx = float(u+x) of iteration i (:706-711), u = float(uplusx - z), i.e. the
+ * iter-<i+1>/u file computeU (:736-765) writes.  Length num_features+1, intercept last. */
 int mlease_get_z(mlease_session* s, int32_t lambda_idx, double* out);
 int mlease_get_final_model(mlease_session* s, int32_t lambda_idx, float* out);
 int mlease_get_x(mlease_session* s, int32_t partition_id, int32_t lambda_idx, double* out);

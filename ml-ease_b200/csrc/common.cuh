@@ -32,6 +32,7 @@ struct Ctrl {
   double gnorm;      // |g_acc|_inf
   double gnorm_prev;
   double dirnorm;    // |dir|_inf
+  double dirnorm_prev;
   double xtol;
   int max_newton;
   int hess_policy;   // 0 adaptive chord, 1 every step
@@ -78,6 +79,7 @@ struct Problem {
   float* u_f;              // u used by this iteration
   float* uplusx_f;         // float(u + x)
   float* x_f;              // float(x)
+  double* x_d;             // x of the last x-update (the ADMM consensus overwrites beta with the next init)
   int lambda_idx;
   int part_local;
 };

@@ -19,7 +19,7 @@ __global__ void admm_reset_kernel(const Problem* __restrict__ probs, int L, doub
   const Problem& pb = probs[blockIdx.x];
   const int l = pb.lambda_idx;
   for (int k = threadIdx.x; k < ldv; k += blockDim.x) {
-    pb.u_f[k] = 0.f; pb.uplusx_f[k] = 0.f; pb.x_f[k] = 0.f;
+    pb.u_f[k] = 0.f; pb.uplusx_f[k] = 0.f; pb.x_f[k] = 0.f; pb.x_d[k] = 0.0;
     pb.m[k] = 0.0;                       // z - u with both maps empty (:155-185, :312)
     pb.beta[k] = 0.0;                    // init = z = {}
     pb.q[k] = k < pb.Dt ? rho_eff[l] : 1.0;
@@ -39,6 +39,7 @@ __global__ void admm_pack_kernel(const Problem* __restrict__ probs, int nparts, 
     const float xf = (float)x;
     const float uf = pb.u_f[k];
     pb.x_f[k] = xf;
+    pb.x_d[k] = x;
     pb.uplusx_f[k] = (float)(1.0 * (double)uf + 1.0 * x);
     s += (double)xf + (double)uf;
   }

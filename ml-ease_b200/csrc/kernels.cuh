@@ -14,7 +14,6 @@ cudaError_t newton_begin(const Problem* d_probs, int nprob, double xtol, int max
                          int invalidate_hess, cudaStream_t st, int* launches);
 cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, cudaStream_t st, int* launches);
 cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches);
-cudaError_t newton_poll(const Problem* d_probs, int nprob, int* d_flag, cudaStream_t st, int* launches);
 
 // K2 (k2_gram.cu)
 int gram_make_tensor_map(void* out_map_host, const void* xt, long long n, int Dp);

@@ -42,16 +42,20 @@ __global__ void newton_begin_kernel(const Problem* __restrict__ probs, double xt
   Ctrl* c = pb.ctrl;
   for (int k = threadIdx.x; k < pb.ldx; k += blockDim.x) {
     const double b = k < pb.Dt ? pb.beta[k] : 0.0;
-    pb.beta[k] = b;
-    pb.beta_t[k] = b;
-    pb.beta_tf[k] = (float)b;
+    // Trial points live on the float lattice: K1 reads beta as fp32, so the gradient it returns is the
+    // gradient AT float(beta_t).  Keeping beta_t == (double)float(beta_t) makes the iteration consistent;
+    // only the final (unevaluated) Newton correction is applied in double.
+    const float bf = (float)b;
+    pb.beta[k] = (double)bf;
+    pb.beta_t[k] = (double)bf;
+    pb.beta_tf[k] = bf;
     pb.dir[k] = 0.0;
   }
   if (threadIdx.x == 0) {
     if (invalidate_hess) c->hess_valid = 0;
     c->done = 0; c->have_dir = 0; c->need_solve = 0; c->need_hess = 0; c->fail = 0;
     c->newton_steps = 0; c->evals = 0; c->rejects = 0; c->hess_builds = 0; c->stall = 0;
-    c->alpha = 1.0; c->phi0 = 0.0; c->f_acc = 0.0; c->f_t = 0.0; c->gnorm = 0.0; c->gnorm_prev = 0.0; c->dirnorm = 0.0;
+    c->alpha = 1.0; c->phi0 = 0.0; c->f_acc = 0.0; c->f_t = 0.0; c->gnorm = 0.0; c->gnorm_prev = 0.0; c->dirnorm = 0.0; c->dirnorm_prev = 0.0;
     c->xtol = xtol; c->max_newton = max_newton; c->hess_policy = hess_policy;
     c->emit = (hess_policy == 1 || !c->hess_valid) ? 1 : 0;
   }
@@ -144,9 +148,9 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
   } else {
     const double a = s_alpha;
     for (int k = threadIdx.x; k < ldx; k += NT) {
-      const double bt = k < Dt ? pb.beta[k] + a * pb.dir[k] : 0.0;
-      pb.beta_t[k] = bt;
-      pb.beta_tf[k] = (float)bt;
+      const float btf = k < Dt ? (float)(pb.beta[k] + a * pb.dir[k]) : 0.f;
+      pb.beta_t[k] = (double)btf;
+      pb.beta_tf[k] = btf;
     }
   }
 }
@@ -229,6 +233,7 @@ __global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restr
   phi0 = block_sum(phi0, sc);
   __shared__ int s_final;
   if (tid == 0) {
+    c->dirnorm_prev = c->dirnorm;
     c->dirnorm = dinf;
     c->phi0 = phi0;
     c->alpha = 1.0;
@@ -238,6 +243,13 @@ __global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restr
     int fin = 0;
     if (!(phi0 < 0.0) || !(dinf == dinf)) { c->fail = 1; c->done = 1; fin = 2; }  // factor unusable
     else if (dinf <= c->xtol * fmax(binf, 1e-2)) { c->done = 1; fin = 1; }
+    else if (c->newton_steps >= 2 && dinf <= 1e-5 * fmax(binf, 1e-2) && dinf > 0.5 * c->dirnorm_prev) {
+      // rounding floor of the fp32 data path: the step no longer shrinks -> take it and stop
+      if (++c->stall >= 2) { c->done = 1; fin = 1; }
+    } else {
+      c->stall = 0;
+    }
+    c->need_hess = 0;
     s_final = fin;
   }
   __syncthreads();
@@ -245,18 +257,11 @@ __global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restr
   const bool fin = s_final == 1;
   for (int k = tid; k < pb.ldx; k += NT) {
     const double bt = k < Dt ? pb.beta[k] + rhs[k] : 0.0;
-    pb.beta_t[k] = bt;
-    pb.beta_tf[k] = (float)bt;
-    if (fin) pb.beta[k] = bt;  // final tiny step taken without another pass
+    const float btf = (float)bt;
+    pb.beta_t[k] = (double)btf;
+    pb.beta_tf[k] = btf;
+    if (fin) pb.beta[k] = bt;  // final tiny step taken in double, without another pass
   }
-}
-
-// any problem still running? (host polls a pinned flag between slots)
-__global__ void newton_poll_kernel(const Problem* __restrict__ probs, int nprob, int* flag_out) {
-  int running = 0;
-  for (int b = threadIdx.x; b < nprob; b += blockDim.x) running |= (probs[b].ctrl->done == 0);
-  running = __syncthreads_or(running);
-  if (threadIdx.x == 0) *flag_out = running;
 }
 
 cudaError_t newton_begin(const Problem* d_probs, int nprob, double xtol, int max_newton, int hess_policy,
@@ -282,10 +287,4 @@ cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_
   if (launches) *launches += 1;
   return cudaGetLastError();
 }
-cudaError_t newton_poll(const Problem* d_probs, int nprob, int* d_flag, cudaStream_t st, int* launches) {
-  newton_poll_kernel<<<1, 256, 0, st>>>(d_probs, nprob, d_flag);
-  if (launches) *launches += 1;
-  return cudaGetLastError();
-}
-
 }  // namespace mlease

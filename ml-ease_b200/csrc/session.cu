@@ -156,7 +156,7 @@ int batch_alloc(Batch& B, int num_sms) {
     while (best > 1 && (double)best * B.Dp * B.Dp * 4.0 * nprob > 1024.0 * 1024 * 1024) best--;
     B.gram_slices = best;
   }
-  const size_t nd = (size_t)nprob * (7 * (size_t)ldx + (size_t)(B.csr ? 1 : B.k1_grid) * ldx + (size_t)B.k1_grid + 8);
+  const size_t nd = (size_t)nprob * (8 * (size_t)ldx + (size_t)(B.csr ? 1 : B.k1_grid) * ldx + (size_t)B.k1_grid + 8);
   const size_t nf = (size_t)nprob * 4 * ldx;
   double* dd; float* ff; float* hp; double* lc; double* ld;
   if (int rc = dev_alloc(B, (void**)&dd, nd * sizeof(double))) return rc;
@@ -177,7 +177,7 @@ int batch_alloc(Batch& B, int num_sms) {
     p.gram_slices = B.gram_slices;
     double* q = dd;
     p.beta = q; q += ldx; p.beta_t = q; q += ldx; p.m = q; q += ldx; p.q = q; q += ldx;
-    p.g_t = q; q += ldx; p.g_acc = q; q += ldx; p.dir = q; q += ldx;
+    p.g_t = q; q += ldx; p.g_acc = q; q += ldx; p.dir = q; q += ldx; p.x_d = q; q += ldx;
     p.gpart = q; q += (size_t)p.k1_ctas * ldx;
     p.fpart = q; q += B.k1_grid + 8;
     dd = q;
@@ -439,7 +439,7 @@ int mlease_session_create(const mlease_admm_config* cfg, mlease_session** out) {
   s->cfg.lambdas = nullptr; s->cfg.rhos = nullptr; s->cfg.lambda_map = nullptr;
   s->stream = reinterpret_cast<cudaStream_t>(cfg->stream);
   s->num_sms = prop.multiProcessorCount;
-  s->xtol = cfg->newton_xtol > 0 ? cfg->newton_xtol : 1e-8;
+  s->xtol = cfg->newton_xtol > 0 ? cfg->newton_xtol : 2e-7;
   s->max_newton = cfg->max_newton > 0 ? cfg->max_newton : 50;
   if (cudaMallocHost((void**)&s->h_flag, 64) != cudaSuccess || cudaMallocHost((void**)&s->h_small, (size_t)(8 * s->L + 8) * sizeof(double)) != cudaSuccess) {
     delete s;
@@ -598,7 +598,7 @@ int mlease_admm_consensus(mlease_session* s, const double* exchange_sum_dev, dou
   for (int l = 0; l < s->L; l++) { mx = std::max(mx, hd[l]); mn = std::min(mn, hd[l]); }
   s->mindiff = mn; s->last_maxdiff = mx;
   if (maxdiff) *maxdiff = mx;
-  const double eps = s->cfg.epsilon > 0 ? s->cfg.epsilon : 0.0001;
+  const double eps = s->cfg.epsilon >= 0 ? s->cfg.epsilon : 0.0001;   // default 1e-4 (:473); 0 = never stop early
   if (stop) *stop = (mx < eps && s->liblinear_eps <= 0.00001) ? 1 : 0;   // :493-496
   return 0;
 }
@@ -644,7 +644,7 @@ static int get_vec(mlease_session* s, int pid, int l, int which, void* out) {
   if (pi < 0) return fail(MLEASE_ERR_INVALID, "partition not resident in this session");
   CK(cudaSetDevice(s->cfg.device));
   const Problem& p = s->batch->h[pi * s->L + l];
-  const void* src = which == 0 ? (const void*)p.beta : which == 1 ? (const void*)p.u_f : (const void*)p.uplusx_f;
+  const void* src = which == 0 ? (const void*)p.x_d : which == 1 ? (const void*)p.u_f : (const void*)p.uplusx_f;
   CK(cudaMemcpyAsync(out, src, s->Dt * (which == 0 ? 8 : 4), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   return 0;
@@ -952,7 +952,7 @@ int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg
       CK(cudaMemcpyAsync(dm, m.data(), ldx * 8, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(dq, q.data(), ldx * 8, cudaMemcpyHostToDevice, st));
       naive_init_kernel<<<B.nprob, 128, 0, st>>>(B.d, dm, dq);   // init = 0 (null initParam), prior mean / precision
-      if (int rc = batch_xupdate(B, st, 1e-8, 100, 0, 1, hflag, dflag, cnt)) return rc;
+      if (int rc = batch_xupdate(B, st, 2e-7, 100, 0, 1, hflag, dflag, cnt)) return rc;
       gather_beta_kernel<<<B.nprob, 128, 0, st>>>(B.d, Dt, dout);
       std::vector<double> xs((size_t)B.nprob * Dt);
       CK(cudaMemcpyAsync(xs.data(), dout, xs.size() * 8, cudaMemcpyDeviceToHost, st));

@@ -122,6 +122,13 @@ typedef struct {
   float liblinear_epsilon;  /* schedule variable (:279,338-346), control only */
 } mlease_stats;
 int mlease_get_stats(mlease_session* s, mlease_stats* out);
+/* Per-kernel device timing for roofline reporting (CUDA events on the session stream around every launch of
+ * the Newton slot; categories: 0 = K1 fused pass, 1 = small kernels (reduce/decide, solve, poll), 2 = Gram (tcgen05),
+ * 3 = Cholesky).  enable: 1 on, 0 off, 2 on + reset accumulators, -1 read only.  Outputs (any may be NULL) are the
+ * accumulators BEFORE this call's reset: ms4[4], count4[4], and the algorithmic work done by the session so far:
+ * k1_bytes (dense n*(4*ldx+9) per pass), k1_emit_bytes (bf16 operand writes), gram_flops (n*D'*(D'+1)). */
+int mlease_profile(mlease_session* s, int32_t enable, double* ms4, int64_t* count4, double* k1_bytes, double* k1_emit_bytes,
+                   double* gram_flops);
 
 /* ---------------------------------------------------------------------------------------
  * Function-level entry points (parity tests against the oracle's fun/grad/hessian):

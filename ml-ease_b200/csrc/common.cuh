@@ -55,6 +55,7 @@ struct Problem {
   const long long* rowptr; // CSR (bias NOT stored; handled by the kernels)
   const int* colidx;
   const float* vals;
+  long long nnz_hint;      // CSR nnz (host-side accounting only)
   __nv_bfloat16* Xt;       // [n][Dp] bf16 = sqrt(d_i) * x_ij  (Gram operand), zero in [ldx, Dp)
   int Dp;                  // multiple of 128
   // solver state

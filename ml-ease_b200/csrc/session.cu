@@ -110,6 +110,42 @@ struct Batch {
 struct Counters {
   long long k1_passes = 0, gram_builds = 0, newton_steps = 0, rejected = 0, launches = 0;
   int not_converged = 0, last_slots = 0;
+  double k1_bytes = 0;     // algorithmic bytes of all K1 passes: dense n*(4*ldx+9), CSR 8*nnz+8*n+9*n
+  double k1_emit_bytes = 0;// extra bytes written by passes that emitted the scaled bf16 copy (n*Dp*2)
+  double gram_flops = 0;   // algorithmic flops of all Gram builds: n*Dt*(Dt+1) (lower triangle, 2 flop/MAC)
+};
+
+// Optional per-kernel device timing (CUDA events on the launching stream) for bench.py's roofline.
+struct Profiler {
+  bool on = false;
+  struct Rec { int cat; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  double ms[4] = {0, 0, 0, 0};
+  long long n[4] = {0, 0, 0, 0};
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void begin(int cat, cudaStream_t st) {
+    if (!on) return;
+    Rec r; r.cat = cat; r.a = get(); r.b = get();
+    cudaEventRecord(r.a, st);
+    recs.push_back(r);
+  }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(recs.back().b, st);
+  }
+  void resolve() {   // call after a stream synchronize
+    for (auto& r : recs) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cat] += t; n[r.cat]++; }
+      pool.push_back(r.a); pool.push_back(r.b);
+    }
+    recs.clear();
+  }
+  ~Profiler() { for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } for (auto e : pool) cudaEventDestroy(e); }
 };
 
 int dev_alloc(Batch& B, void** p, size_t bytes, bool zero = true) {
@@ -202,7 +238,9 @@ int batch_alloc(Batch& B, int num_sms) {
 
 // One x-update for every problem of the batch: beta (init), m, q must already be on the device.
 int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int policy, int invalidate, int* h_flag, int* d_flag,
-                  Counters& cnt) {
+                  Counters& cnt, Profiler* prof = nullptr) {
+  Profiler nop;
+  Profiler& pf = prof ? *prof : nop;
   int launches = 0;
   CK(newton_begin(B.d, B.nprob, xtol, max_newton, policy, invalidate, st, &launches));
   poll2_kernel<<<1, 256, 0, st>>>(B.d, B.nprob, d_flag);
@@ -212,15 +250,25 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
   int flag = *h_flag;
   int slots = 0;
   while ((flag & 1) && slots < 400) {
+    pf.begin(0, st);
     CK(k1_launch(B.d, B.nprob, B.csr, B.ldx, B.has_bias, B.k1_grid, -1, st, &launches));
+    pf.end(st);
+    pf.begin(1, st);
     CK(k1_reduce_decide(B.d, B.nprob, st, &launches));
+    pf.end(st);
     if (flag & 2) {
+      pf.begin(2, st);
       CK(gram_launch_tcgen05(B.d, B.nprob, B.d_tmaps, B.d_tiles, B.ntiles, B.gram_slices, 0, st, &launches));
+      pf.end(st);
+      pf.begin(3, st);
       CK(cholesky_launch(B.d, B.nprob, B.ldh, st, &launches));
+      pf.end(st);
     }
+    pf.begin(1, st);
     CK(newton_solve(B.d, B.nprob, B.ldh, st, &launches));
     poll2_kernel<<<1, 256, 0, st>>>(B.d, B.nprob, d_flag);
     launches++;
+    pf.end(st);
     CK(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     flag = *h_flag;
@@ -232,6 +280,15 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
   cnt.launches += launches;
   cnt.last_slots = slots;
   int bad_spd = 0, bad_ls = 0;
+  pf.resolve();
+  for (int b = 0; b < B.nprob; b++) {
+    const Ctrl& c = hc[b];
+    const Problem& p = B.h[b];
+    const double rowbytes = B.csr ? 17.0 : (4.0 * B.ldx + 9.0);
+    cnt.k1_bytes += (double)c.evals * ((double)p.n * rowbytes + (B.csr ? 8.0 * (double)p.nnz_hint : 0.0));
+    cnt.gram_flops += (double)c.hess_builds * (double)p.n * (double)B.Dt * (double)(B.Dt + 1);
+    cnt.k1_emit_bytes += (double)c.hess_builds * (double)p.n * (double)B.Dp * 2.0;
+  }
   for (auto& c : hc) {
     cnt.k1_passes += c.evals; cnt.newton_steps += c.newton_steps; cnt.rejected += c.rejects; cnt.gram_builds += c.hess_builds;
     if (c.fail == 3 || !c.done) cnt.not_converged++;
@@ -273,6 +330,7 @@ struct mlease_session {
   double last_maxdiff = 0;
   bool begun = false;
   Counters cnt;
+  Profiler prof;
   double xtol = 1e-8;
   int max_newton = 50;
   ~mlease_session() {
@@ -302,7 +360,7 @@ int find_part(mlease_session* s, int pid) {
 void fill_problem_data(Problem& p, const PartData& pd) {
   std::memset(&p, 0, sizeof(Problem));
   p.X = pd.X; p.n = pd.n; p.y = pd.y; p.w = pd.w; p.o = pd.o;
-  p.rowptr = pd.rowptr; p.colidx = pd.colidx; p.vals = pd.vals;
+  p.rowptr = pd.rowptr; p.colidx = pd.colidx; p.vals = pd.vals; p.nnz_hint = pd.nnz;
 }
 
 int finalize(mlease_session* s) {
@@ -575,7 +633,7 @@ int mlease_admm_local_step(mlease_session* s, double* exchange_dev) {
     if (r != s->rho_fact[l]) invalidate = 1;   // prior precision changed -> stale factors are for another H
     s->rho_fact[l] = r;
   }
-  if (int rc = batch_xupdate(*s->batch, s->stream, s->xtol, s->max_newton, s->cfg.hessian_policy, invalidate, s->h_flag, s->d_flag, s->cnt)) return rc;
+  if (int rc = batch_xupdate(*s->batch, s->stream, s->xtol, s->max_newton, s->cfg.hessian_policy, invalidate, s->h_flag, s->d_flag, s->cnt, &s->prof)) return rc;
   int launches = 0;
   CK(admm_pack(s->batch->d, (int)s->parts.size(), s->L, s->Dt, exchange_dev, s->stream, &launches));
   s->cnt.launches += launches;
@@ -652,6 +710,20 @@ static int get_vec(mlease_session* s, int pid, int l, int which, void* out) {
 int mlease_get_x(mlease_session* s, int32_t pid, int32_t l, double* out) { return get_vec(s, pid, l, 0, out); }
 int mlease_get_u(mlease_session* s, int32_t pid, int32_t l, float* out) { return get_vec(s, pid, l, 1, out); }
 int mlease_get_uplusx(mlease_session* s, int32_t pid, int32_t l, float* out) { return get_vec(s, pid, l, 2, out); }
+
+int mlease_profile(mlease_session* s, int32_t enable, double* ms4, int64_t* count4, double* k1_bytes, double* k1_emit_bytes, double* gram_flops) {
+  if (!s) return fail(MLEASE_ERR_INVALID, "null session");
+  if (ms4) for (int i = 0; i < 4; i++) ms4[i] = s->prof.ms[i];
+  if (count4) for (int i = 0; i < 4; i++) count4[i] = s->prof.n[i];
+  if (k1_bytes) *k1_bytes = s->cnt.k1_bytes;
+  if (k1_emit_bytes) *k1_emit_bytes = s->cnt.k1_emit_bytes;
+  if (gram_flops) *gram_flops = s->cnt.gram_flops;
+  if (enable >= 0) {
+    s->prof.on = enable != 0;
+    if (enable == 2) { for (int i = 0; i < 4; i++) { s->prof.ms[i] = 0; s->prof.n[i] = 0; } s->cnt.k1_bytes = s->cnt.k1_emit_bytes = s->cnt.gram_flops = 0; }
+  }
+  return 0;
+}
 
 int mlease_get_stats(mlease_session* s, mlease_stats* out) {
   if (!s || !out) return fail(MLEASE_ERR_INVALID, "null argument");

@@ -70,6 +70,7 @@ def lib():
             "mlease_score": [i32, vp, i32, i64, vp, vp, vp, i64, vp, vp, i32, i32, vp],
             "mlease_test_loglik": [i32, vp, i64, vp, vp, vp, i64, C.POINTER(f32), C.POINTER(f64)],
             "mlease_time_kernel": [vp, i32, i32, i32, i32, C.POINTER(f32)],
+            "mlease_profile": [vp, i32, vp, vp, C.POINTER(f64), C.POINTER(f64), C.POINTER(f64)],
         }
         for name, args in sig.items():
             fn = getattr(_lib, name)
@@ -83,7 +84,7 @@ EXPORTED = ["mlease_last_error", "mlease_abi_version", "mlease_session_create", 
             "mlease_add_partition_dense", "mlease_add_partition_csr", "mlease_admm_begin", "mlease_admm_local_step",
             "mlease_admm_consensus", "mlease_admm_run", "mlease_get_z", "mlease_get_final_model", "mlease_get_x", "mlease_get_u",
             "mlease_get_uplusx", "mlease_get_stats", "mlease_objective", "mlease_fit_partition", "mlease_naive_train_dense",
-            "mlease_score", "mlease_test_loglik", "mlease_time_kernel"]
+            "mlease_score", "mlease_test_loglik", "mlease_time_kernel", "mlease_profile"]
 
 
 def check(rc):

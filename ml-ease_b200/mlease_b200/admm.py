@@ -167,6 +167,15 @@ class AdmmSession:
         check(lib().mlease_fit_partition(self._h, partition_id, ptr(x), ptr(m), ptr(q), C.byref(steps)))
         return x, steps.value
 
+    def profile(self, enable=-1):
+        """Per-kernel CUDA-event timing accumulators; enable: 1 on, 0 off, 2 on+reset, -1 read only."""
+        ms = np.zeros(4, np.float64); cnt = np.zeros(4, np.int64)
+        kb, eb, gf = C.c_double(0), C.c_double(0), C.c_double(0)
+        check(lib().mlease_profile(self._h, int(enable), ptr(ms), ptr(cnt), C.byref(kb), C.byref(eb), C.byref(gf)))
+        names = ("k1", "small", "gram", "cholesky")
+        return dict(ms=dict(zip(names, ms.tolist())), launches=dict(zip(names, cnt.tolist())), k1_bytes=kb.value,
+                    k1_emit_bytes=eb.value, gram_flops=gf.value)
+
     def time_kernel(self, partition_id, which, reps=5, emit_scaled=False):
         ms = C.c_float(0)
         check(lib().mlease_time_kernel(self._h, partition_id, {"k1": 1, "gram": 2, "cholesky": 3}[which], reps, int(emit_scaled), C.byref(ms)))

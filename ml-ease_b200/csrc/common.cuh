@@ -7,6 +7,8 @@
 
 namespace mlease {
 
+constexpr int BFGS_M = 6;   // secant pairs kept on top of the (possibly stale) explicit inverse Hessian
+
 // ------------------------------------------------------------------------------------------
 // Per-problem control block, device resident.  A "problem" is one (local partition, lambda)
 // x-update = one AdmmReducer.reduce call (jobs/RegressionAdmmTrain.java:642-718).
@@ -26,6 +28,9 @@ struct Ctrl {
   int rejects;       // rejected trial points in this x-update
   int hess_builds;   // Gram+Cholesky rebuilds in this x-update
   int stall;         // consecutive poor contractions
+  int bfgs_count;    // secant pairs stored so far (ring of BFGS_M), reset when the Hessian is rebuilt
+  int refresh_next;  // rebuild the Hessian at the first point of the NEXT x-update (chord steps contracted slowly)
+  double worst_ratio;// largest |g_new|/|g_old| seen over the chord steps of this x-update
   double alpha;      // current step length along dir
   double phi0;       // g_acc . dir  (< 0)
   double f_acc, f_t; // objective at accepted / trial point
@@ -74,12 +79,19 @@ struct Problem {
   int gram_slices;
   double* Lc;              // [ldh][ldh] Cholesky factor (lower), ldh multiple of 32
   double* Ldiag;           // [ldh][32] factorised diagonal blocks (side buffer, see k3_cholesky.cu)
+  double* Ldinv;           // [ldh][32] inverses of the diagonal blocks (lower triangular)
+  double* Yinv;            // [ldh][ldh] L^-1 (lower)
+  double* Hinv;            // [ldh][ldh] (L L^T)^-1, full symmetric: a Newton direction is one GEMV
   int ldh;
   Ctrl* ctrl;
   // ADMM per-problem vectors (float, as the reference's avro files hold them)
   float* u_f;              // u used by this iteration
   float* uplusx_f;         // float(u + x)
   float* x_f;              // float(x)
+  double* bfgs_S;          // [BFGS_M][ldx] steps  s_k = beta_{k+1} - beta_k
+  double* bfgs_Y;          // [BFGS_M][ldx] gradient differences y_k
+  double* bfgs_rho;        // [BFGS_M] 1/(s.y)
+  double* bfgs_alpha;      // [BFGS_M] two-loop scratch
   double* x_d;             // x of the last x-update (the ADMM consensus overwrites beta with the next init)
   int lambda_idx;
   int part_local;

@@ -93,33 +93,46 @@ k1_dense_kernel(const Problem* __restrict__ probs, int R, int S, int force_emit)
     const long long row0 = (blockIdx.x + k * (long long)gridDim.x) * R;
     const int rows = (int)min((long long)R, n - row0);
 
-    // ---- phase A: row dots --------------------------------------------------------------
-    for (int r = warp; r < rows; r += K1_WARPS) {
-      const float4* xr = reinterpret_cast<const float4*>(tile + (size_t)r * ldx);
-      float a0 = 0.f, a1 = 0.f;
+    // ---- phase A: row dots, two rows per warp per step (beta float4 shared by both rows) ---------------
+    // lanes 0/1 own the per-row scalars of rows r/r+1: their y,w,o loads are issued BEFORE the dot loop so the
+    // global-load latency hides behind it; the sigmoid/loss math then runs on two lanes at once.
+    for (int r = 2 * warp; r < rows; r += 2 * K1_WARPS) {
+      const bool two = (r + 1) < rows;
+      const int myr = r + (lane & 1);
+      float yy = 0.f, ww = 0.f, oo = 0.f;
+      if (lane < 2 && myr < rows) {
+        const long long i = row0 + myr;
+        yy = (float)pb.y[i]; ww = pb.w[i]; oo = pb.o[i];
+      }
+      const float4* x0p = reinterpret_cast<const float4*>(tile + (size_t)r * ldx);
+      const float4* x1p = reinterpret_cast<const float4*>(tile + (size_t)(two ? r + 1 : r) * ldx);
+      float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
       int c = lane;
       for (; c + 32 < ncg; c += 64) {
-        float4 x0 = xr[c], b0 = beta4[c], x1 = xr[c + 32], b1 = beta4[c + 32];
+        const float4 b0 = beta4[c], b1 = beta4[c + 32];
+        const float4 x0 = x0p[c], x1 = x1p[c], x2 = x0p[c + 32], x3 = x1p[c + 32];
         a0 = fmaf(x0.x, b0.x, a0); a0 = fmaf(x0.y, b0.y, a0); a0 = fmaf(x0.z, b0.z, a0); a0 = fmaf(x0.w, b0.w, a0);
-        a1 = fmaf(x1.x, b1.x, a1); a1 = fmaf(x1.y, b1.y, a1); a1 = fmaf(x1.z, b1.z, a1); a1 = fmaf(x1.w, b1.w, a1);
+        a1 = fmaf(x1.x, b0.x, a1); a1 = fmaf(x1.y, b0.y, a1); a1 = fmaf(x1.z, b0.z, a1); a1 = fmaf(x1.w, b0.w, a1);
+        c0 = fmaf(x2.x, b1.x, c0); c0 = fmaf(x2.y, b1.y, c0); c0 = fmaf(x2.z, b1.z, c0); c0 = fmaf(x2.w, b1.w, c0);
+        c1 = fmaf(x3.x, b1.x, c1); c1 = fmaf(x3.y, b1.y, c1); c1 = fmaf(x3.z, b1.z, c1); c1 = fmaf(x3.w, b1.w, c1);
       }
       if (c < ncg) {
-        float4 x0 = xr[c], b0 = beta4[c];
+        const float4 b0 = beta4[c];
+        const float4 x0 = x0p[c], x1 = x1p[c];
         a0 = fmaf(x0.x, b0.x, a0); a0 = fmaf(x0.y, b0.y, a0); a0 = fmaf(x0.z, b0.z, a0); a0 = fmaf(x0.w, b0.w, a0);
+        a1 = fmaf(x1.x, b0.x, a1); a1 = fmaf(x1.y, b0.y, a1); a1 = fmaf(x1.z, b0.z, a1); a1 = fmaf(x1.w, b0.w, a1);
       }
-      float acc = warp_sum(a0 + a1);
-      if (lane == 0) {
-        const long long i = row0 + r;
-        const float yy = (float)pb.y[i];
-        const float ww = pb.w[i];
-        const float t = yy * (acc + pb.o[i]);
-        const float e = expf(-fabsf(t));
-        const float inv = 1.f / (1.f + e);
-        const float p = t >= 0.f ? inv : e * inv;        // sigmoid(y s)
-        const float qq = t >= 0.f ? e * inv : inv;       // 1 - p, no cancellation
-        loss64 += (double)(ww * ((t >= 0.f ? 0.f : -t) + log1pf(e)));
-        r_s[r] = -ww * yy * qq;                          // w (p-1) y
-        sd_s[r] = sqrtf(ww * p * qq);                    // sqrt(d_i)
+      const float s0 = warp_sum(a0 + c0), s1 = warp_sum(a1 + c1);
+      if (lane < 2 && myr < rows) {
+        const float t = yy * ((lane ? s1 : s0) + oo);
+        const float e = __expf(-fabsf(t));                 // in (0,1]; ex2.approx path
+        const float inv = __frcp_rn(1.f + e);
+        const float p = t >= 0.f ? inv : e * inv;          // sigmoid(y s)
+        const float qq = t >= 0.f ? e * inv : inv;         // 1 - p, no cancellation
+        // log1p(e) = -log(1/(1+e)); absolute error ~1e-7 per row is far below the objective's use (line search only)
+        loss64 += (double)(ww * ((t >= 0.f ? 0.f : -t) - __logf(inv)));
+        r_s[myr] = -ww * yy * qq;                          // w (p-1) y
+        sd_s[myr] = sqrtf(ww * p * qq);                    // sqrt(d_i)
       }
     }
     __syncthreads();
@@ -146,11 +159,23 @@ k1_dense_kernel(const Problem* __restrict__ probs, int R, int S, int force_emit)
               *reinterpret_cast<uint2*>(xt + (size_t)r * pb.Dp) = pk;
             }
           } else {
-            for (int r = sl; r < rows; r += nsl) {
+            float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1, a3 = a1;
+            int r = sl;
+            for (; r + 3 * nsl < rows; r += 4 * nsl) {
+              const float4 x0 = t4[(size_t)r * ncg], x1 = t4[(size_t)(r + nsl) * ncg], x2 = t4[(size_t)(r + 2 * nsl) * ncg],
+                           x3 = t4[(size_t)(r + 3 * nsl) * ncg];
+              const float r0 = r_s[r], r1 = r_s[r + nsl], r2 = r_s[r + 2 * nsl], r3 = r_s[r + 3 * nsl];
+              a.x = fmaf(x0.x, r0, a.x); a.y = fmaf(x0.y, r0, a.y); a.z = fmaf(x0.z, r0, a.z); a.w = fmaf(x0.w, r0, a.w);
+              a1.x = fmaf(x1.x, r1, a1.x); a1.y = fmaf(x1.y, r1, a1.y); a1.z = fmaf(x1.z, r1, a1.z); a1.w = fmaf(x1.w, r1, a1.w);
+              a2.x = fmaf(x2.x, r2, a2.x); a2.y = fmaf(x2.y, r2, a2.y); a2.z = fmaf(x2.z, r2, a2.z); a2.w = fmaf(x2.w, r2, a2.w);
+              a3.x = fmaf(x3.x, r3, a3.x); a3.y = fmaf(x3.y, r3, a3.y); a3.z = fmaf(x3.z, r3, a3.z); a3.w = fmaf(x3.w, r3, a3.w);
+            }
+            for (; r < rows; r += nsl) {
               const float4 x = t4[(size_t)r * ncg];
               const float rr = r_s[r];
               a.x = fmaf(x.x, rr, a.x); a.y = fmaf(x.y, rr, a.y); a.z = fmaf(x.z, rr, a.z); a.w = fmaf(x.w, rr, a.w);
             }
+            a.x += (a1.x + a2.x) + a3.x; a.y += (a1.y + a2.y) + a3.y; a.z += (a1.z + a2.z) + a3.z; a.w += (a1.w + a2.w) + a3.w;
           }
           acc64[g][0] += (double)a.x; acc64[g][1] += (double)a.y; acc64[g][2] += (double)a.z; acc64[g][3] += (double)a.w;
         }
@@ -183,6 +208,7 @@ k1_dense_kernel(const Problem* __restrict__ probs, int R, int S, int force_emit)
       }
     }
   }
+  loss64 += __shfl_down_sync(0xffffffffu, loss64, 1);   // lanes 0 and 1 carry the per-row losses
   if (lane == 0) red_s[warp] = loss64;
   __syncthreads();
   if (tid == 0) {

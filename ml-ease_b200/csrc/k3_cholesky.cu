@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(const Problem* __restri
     for (int e = tid; e < NB * NB; e += 256) {
       const int i = e / NB, j = e % NB;
       pb.Ldiag[(size_t)(c0 + i) * NB + j] = (j <= i) ? A[i][j] : 0.0;
+      pb.Ldinv[(size_t)(c0 + i) * NB + j] = (j <= i) ? Li[i][j] : 0.0;
     }
     if (tid == 0 && s_bad) { c->fail = 1; }
   }
@@ -168,8 +169,121 @@ __global__ void chol_finish_kernel(const Problem* __restrict__ probs) {
   }
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (c->fail == 1) { c->done = 1; c->hess_valid = 0; }
-    else { c->hess_valid = 1; c->hess_builds++; c->tot_hess++; }
+    else { c->hess_valid = 1; c->hess_builds++; c->tot_hess++; c->bfgs_count = 0; }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Explicit inverse, built once per factorisation so that every chord-Newton direction afterwards is a
+// single multi-CTA GEMV instead of two latency-bound triangular solves:
+//   Y = L^-1    : forward substitution with NR right-hand sides (columns of I) per CTA, 32x32 L tiles staged
+//                 through shared memory, diagonal blocks applied through their stored inverses
+//   Hinv = Y^T Y: 64x64 tiles, both triangles written
+// ------------------------------------------------------------------------------------------
+template <int NR>
+__global__ void __launch_bounds__(256) trinv_kernel(const Problem* __restrict__ probs) {
+  const Problem& pb = probs[blockIdx.y];
+  Ctrl* c = pb.ctrl;
+  if (c->done || !c->need_hess) return;
+  extern __shared__ double ysm[];            // Y columns [ldh][NR]
+  __shared__ double Lt[NB][NB + 1];
+  __shared__ double Rb[NB][NR + 1];
+  const int ldh = pb.ldh, nb = ldh / NB;
+  const int c0 = blockIdx.x * NR;            // first RHS column of this CTA
+  if (c0 >= ldh) return;
+  const int kb0 = c0 / NB;
+  const int tid = threadIdx.x;
+  const double* L = pb.Lc;
+  constexpr int CPT = (NB * NR) / 256 > 0 ? (NB * NR) / 256 : 1;   // outputs per thread
+  for (int kb = kb0; kb < nb; kb++) {
+    const int r0 = kb * NB;
+    // rhs block = I block
+    for (int e = tid; e < NB * NR; e += 256) {
+      const int i = e / NR, j = e % NR;
+      Rb[i][j] = (r0 + i == c0 + j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int jb = kb0; jb < kb; jb++) {
+      for (int e = tid; e < NB * NB; e += 256) Lt[e / NB][e % NB] = L[(size_t)(r0 + e / NB) * ldh + jb * NB + (e % NB)];
+      __syncthreads();
+      for (int q = 0; q < CPT; q++) {
+        const int e = tid + q * 256;
+        if (e < NB * NR) {
+          const int i = e / NR, j = e % NR;
+          double a = 0.0;
+#pragma unroll 8
+          for (int kk = 0; kk < NB; kk++) a += Lt[i][kk] * ysm[(size_t)(jb * NB + kk) * NR + j];
+          Rb[i][j] -= a;
+        }
+      }
+      __syncthreads();
+    }
+    // Y block = Ldinv[kb] * rhs block
+    for (int e = tid; e < NB * NB; e += 256) Lt[e / NB][e % NB] = pb.Ldinv[(size_t)(r0 + e / NB) * NB + (e % NB)];
+    __syncthreads();
+    for (int q = 0; q < CPT; q++) {
+      const int e = tid + q * 256;
+      if (e < NB * NR) {
+        const int i = e / NR, j = e % NR;
+        double a = 0.0;
+        for (int kk = 0; kk <= i; kk++) a += Lt[i][kk] * Rb[kk][j];
+        ysm[(size_t)(r0 + i) * NR + j] = a;
+        pb.Yinv[(size_t)(r0 + i) * ldh + c0 + j] = a;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) hinv_syrk_kernel(const Problem* __restrict__ probs) {
+  const Problem& pb = probs[blockIdx.z];
+  Ctrl* c = pb.ctrl;
+  if (c->done || !c->need_hess) return;
+  if (blockIdx.x > blockIdx.y) return;
+  const int ldh = pb.ldh;
+  const int i0 = blockIdx.y * TB, j0 = blockIdx.x * TB;   // i0 >= j0
+  if (i0 >= ldh) return;
+  __shared__ double Yi[NB][TB + 1];
+  __shared__ double Yj[NB][TB + 1];
+  const double* Y = pb.Yinv;
+  const int tid = threadIdx.x;
+  const int ti = (tid / 16) * 4, tj = (tid % 16) * 4;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+  // Y is lower triangular: Y[k][i] != 0 only for k >= i, so start at the row block of i0 (>= j0)
+  for (int k0 = (i0 / NB) * NB; k0 < ldh; k0 += NB) {
+    for (int e = tid; e < NB * TB; e += 256) {
+      const int kk = e / TB, cc = e % TB;
+      const int k = k0 + kk;
+      Yi[kk][cc] = (i0 + cc < ldh && i0 + cc <= k) ? Y[(size_t)k * ldh + i0 + cc] : 0.0;
+      Yj[kk][cc] = (j0 + cc < ldh && j0 + cc <= k) ? Y[(size_t)k * ldh + j0 + cc] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int kk = 0; kk < NB; kk++) {
+      double x[4], y[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) { x[a] = Yi[kk][ti + a]; y[a] = Yj[kk][tj + a]; }
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] += x[a] * y[b];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int i = i0 + ti + a, j = j0 + tj + b;
+      if (i < ldh && j < ldh) {
+        pb.Hinv[(size_t)i * ldh + j] = acc[a][b];
+        pb.Hinv[(size_t)j * ldh + i] = acc[a][b];
+      }
+    }
 }
 
 cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches) {
@@ -190,6 +304,28 @@ cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStre
       chol_update_kernel<<<dim3(T, T, nprob), 256, 0, st>>>(d_probs, k);
       if (launches) *launches += 1;
     }
+  }
+  // explicit inverse (reads the panel blocks below the diagonal from Lc and the diagonal inverses from Ldinv)
+  {
+    const int NR = ldh <= 1024 ? 16 : (ldh <= 2048 ? 8 : 4);
+    const size_t smem = (size_t)ldh * NR * sizeof(double);
+    const int gx = (ldh + NR - 1) / NR;
+    cudaError_t e = cudaSuccess;
+    if (NR == 16) {
+      e = cudaFuncSetAttribute(trinv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess) trinv_kernel<16><<<dim3(gx, nprob), 256, smem, st>>>(d_probs);
+    } else if (NR == 8) {
+      e = cudaFuncSetAttribute(trinv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess) trinv_kernel<8><<<dim3(gx, nprob), 256, smem, st>>>(d_probs);
+    } else {
+      e = cudaFuncSetAttribute(trinv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess) trinv_kernel<4><<<dim3(gx, nprob), 256, smem, st>>>(d_probs);
+    }
+    if (e != cudaSuccess) return e;
+    if (launches) *launches += 1;
+    const int T = (ldh + TB - 1) / TB;
+    hinv_syrk_kernel<<<dim3(T, T, nprob), 256, 0, st>>>(d_probs);
+    if (launches) *launches += 1;
   }
   chol_finish_kernel<<<dim3(nb, nprob), 256, 0, st>>>(d_probs);
   if (launches) *launches += 1;

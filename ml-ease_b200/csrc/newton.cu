@@ -57,7 +57,12 @@ __global__ void newton_begin_kernel(const Problem* __restrict__ probs, double xt
     c->newton_steps = 0; c->evals = 0; c->rejects = 0; c->hess_builds = 0; c->stall = 0;
     c->alpha = 1.0; c->phi0 = 0.0; c->f_acc = 0.0; c->f_t = 0.0; c->gnorm = 0.0; c->gnorm_prev = 0.0; c->dirnorm = 0.0; c->dirnorm_prev = 0.0;
     c->xtol = xtol; c->max_newton = max_newton; c->hess_policy = hess_policy;
-    c->emit = (hess_policy == 1 || !c->hess_valid) ? 1 : 0;
+    // Rebuild at the start point when there is no factor, when the policy says always, or when the previous
+    // x-update's chord steps contracted slowly: a factor taken at a (nearly) converged point makes every later
+    // x-update of the ADMM run a 2-3 pass affair, and costs about as much as 2.5 K1 passes.
+    c->emit = (hess_policy == 1 || !c->hess_valid || c->refresh_next) ? 1 : 0;
+    c->refresh_next = 0;
+    c->worst_ratio = 0.0;
   }
 }
 
@@ -86,6 +91,18 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
   }
   double lossp = 0.0;
   for (int t = threadIdx.x; t < nct; t += NT) lossp += pb.fpart[t];
+  // secant pair of this step (used only if the step is accepted): s = beta_t - beta, y = g_t - g_acc
+  double sy = 0.0, ss = 0.0, yy2 = 0.0;
+  if (have_dir) {
+    for (int k = threadIdx.x; k < Dt; k += NT) {
+      const double sk = pb.beta_t[k] - pb.beta[k], yk = pb.g_t[k] - pb.g_acc[k];
+      sy += sk * yk; ss += sk * sk; yy2 += yk * yk;
+    }
+  }
+  sy = block_sum(sy, sc);
+  ss = block_sum(ss, sc);
+  yy2 = block_sum(yy2, sc);
+  __shared__ int s_slot;
   prior2 = block_sum(prior2, sc);
   phi = block_sum(phi, sc);
   lossp = block_sum(lossp, sc);
@@ -114,7 +131,10 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
       c->gnorm_prev = c->gnorm;
       c->gnorm = ginf;
       c->f_acc = f_t;
-      if (have_dir) { c->newton_steps++; c->tot_newton++; }
+      if (have_dir) {
+        c->newton_steps++; c->tot_newton++;
+        if (c->gnorm_prev > 0.0) c->worst_ratio = fmax(c->worst_ratio, ginf / c->gnorm_prev);
+      }
       if (ginf == 0.0) {
         c->done = 1; c->need_solve = 0; c->need_hess = 0;
       } else if (c->newton_steps >= c->max_newton) {
@@ -138,9 +158,23 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
     c->alpha = alpha;
     s_action = action;
     s_alpha = alpha;
+    s_slot = -1;
+    if (action == 1 && have_dir && sy > 1e-10 * sqrt(ss * yy2) && sy > 0.0) {   // strictly convex => s.y > 0 up to rounding
+      s_slot = c->bfgs_count % BFGS_M;
+      pb.bfgs_rho[s_slot] = 1.0 / sy;
+      c->bfgs_count++;
+    }
   }
   __syncthreads();
   if (s_action == 1) {
+    if (s_slot >= 0) {
+      double* S = pb.bfgs_S + (size_t)s_slot * ldx;
+      double* Y = pb.bfgs_Y + (size_t)s_slot * ldx;
+      for (int k = threadIdx.x; k < ldx; k += NT) {
+        S[k] = k < Dt ? pb.beta_t[k] - pb.beta[k] : 0.0;
+        Y[k] = k < Dt ? pb.g_t[k] - pb.g_acc[k] : 0.0;
+      }
+    }
     for (int k = threadIdx.x; k < ldx; k += NT) {
       pb.beta[k] = pb.beta_t[k];
       pb.g_acc[k] = k < Dt ? pb.g_t[k] : 0.0;
@@ -155,75 +189,79 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
   }
 }
 
-// dir = -(L L^T)^-1 g_acc with the (possibly stale) Cholesky factor; then either terminate
-// (|dir| tiny: take the step, done) or set the next trial point beta + dir.
-// Blocked forward/backward substitution, one CTA per problem, NB = 32.
+// Quasi-Newton direction: the explicit inverse of the last Hessian rebuild is the initial matrix H0^-1 of an
+// L-BFGS two-loop recursion over the last BFGS_M secant pairs (exact gradients => s.y > 0), so chord steps
+// converge superlinearly instead of at the linear rate |I - H0^-1 H|.
+//   pre  (1 CTA/problem): q = g_acc; for newest..oldest: a_i = rho_i s_i.q ; q -= a_i y_i        -> g_t (scratch)
+//   gemv (multi-CTA)    : r = Hinv q                                                                -> dir
+//   post (in newton_solve_kernel): for oldest..newest: b = rho_i y_i.r ; r += s_i (a_i - b) ; dir = -r
+__global__ void __launch_bounds__(NT) newton_pre_kernel(const Problem* __restrict__ probs) {
+  const Problem& pb = probs[blockIdx.x];
+  Ctrl* c = pb.ctrl;
+  if (c->done || !c->need_solve) return;
+  __shared__ double sc[NT / 32];
+  const int Dt = pb.Dt, ldx = pb.ldx;
+  const int npairs = min(c->bfgs_count, BFGS_M);
+  double* q = pb.g_t;   // free scratch between the decide kernel and the next K1 reduce
+  for (int k = threadIdx.x; k < Dt; k += NT) q[k] = pb.g_acc[k];
+  __syncthreads();
+  for (int j = 0; j < npairs; j++) {
+    const int slot = (c->bfgs_count - 1 - j) % BFGS_M;
+    const double* S = pb.bfgs_S + (size_t)slot * ldx;
+    const double* Y = pb.bfgs_Y + (size_t)slot * ldx;
+    double d = 0.0;
+    for (int k = threadIdx.x; k < Dt; k += NT) d += S[k] * q[k];
+    d = block_sum(d, sc);
+    const double a = pb.bfgs_rho[slot] * d;
+    if (threadIdx.x == 0) pb.bfgs_alpha[slot] = a;
+    for (int k = threadIdx.x; k < Dt; k += NT) q[k] -= a * Y[k];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(NT) newton_gemv_kernel(const Problem* __restrict__ probs) {
+  const Problem& pb = probs[blockIdx.y];
+  Ctrl* c = pb.ctrl;
+  if (c->done || !c->need_solve) return;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  if (r >= pb.Dt) return;
+  const double* Hr = pb.Hinv + (size_t)r * pb.ldh;
+  const double* q = pb.g_t;
+  double a = 0.0;
+  for (int k = lane; k < pb.Dt; k += 32) a += Hr[k] * q[k];
+  a = warp_sum(a);
+  if (lane == 0) pb.dir[r] = a;   // r = Hinv q (sign applied after the second loop)
+}
+
+// Direction bookkeeping: norms, termination test, next trial point.  One CTA per problem.
 __global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restrict__ probs) {
   const Problem& pb = probs[blockIdx.x];
   Ctrl* c = pb.ctrl;
   if (c->done || !c->need_solve) return;
-  extern __shared__ double sm[];
-  const int ldh = pb.ldh, Dt = pb.Dt, nb = ldh / 32;
-  double* rhs = sm;                  // [ldh]
-  double* blk = rhs + ldh;           // [32][33] diagonal block
-  double* part = blk + 32 * 33;      // [8][32] cross-warp partials
   __shared__ double sc[NT / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double* L = pb.Lc;
-  for (int k = tid; k < ldh; k += NT) rhs[k] = k < Dt ? -pb.g_acc[k] : 0.0;
-  __syncthreads();
-  // forward: L y = rhs
-  for (int kb = 0; kb < nb; kb++) {
-    const int r0 = kb * 32;
-    // rhs[r0..r0+31] -= L[r0+r][0..r0) . y[0..r0)   (warp w owns rows 4w..4w+3, lanes stride columns)
-    for (int rr = 0; rr < 4; rr++) {
-      const int r = warp * 4 + rr;
-      const double* Lr = L + (size_t)(r0 + r) * ldh;
-      double a = 0.0;
-      for (int j = lane; j < r0; j += 32) a += Lr[j] * rhs[j];
-      a = warp_sum(a);
-      if (lane == 0) part[r] = a;
+  const int tid = threadIdx.x;
+  const int Dt = pb.Dt, ldx = pb.ldx;
+  double* rhs = pb.dir;
+  {
+    const int npairs = min(c->bfgs_count, BFGS_M);
+    for (int j = npairs - 1; j >= 0; j--) {
+      const int slot = (c->bfgs_count - 1 - j) % BFGS_M;
+      const double* S = pb.bfgs_S + (size_t)slot * ldx;
+      const double* Y = pb.bfgs_Y + (size_t)slot * ldx;
+      double d = 0.0;
+      for (int k = tid; k < Dt; k += NT) d += Y[k] * rhs[k];
+      d = block_sum(d, sc);
+      const double coef = pb.bfgs_alpha[slot] - pb.bfgs_rho[slot] * d;
+      for (int k = tid; k < Dt; k += NT) rhs[k] += coef * S[k];
+      __syncthreads();
     }
-    for (int e = tid; e < 32 * 32; e += NT) blk[(e >> 5) * 33 + (e & 31)] = L[(size_t)(r0 + (e >> 5)) * ldh + r0 + (e & 31)];
-    __syncthreads();
-    if (warp == 0) {
-      double v = rhs[r0 + lane] - part[lane];
-      for (int j = 0; j < 32; j++) {
-        const double yj = __shfl_sync(0xffffffffu, v, j) / blk[j * 33 + j];
-        if (lane == j) v = yj;
-        else if (lane > j) v -= blk[lane * 33 + j] * yj;
-      }
-      rhs[r0 + lane] = v;
-    }
+    for (int k = tid; k < Dt; k += NT) rhs[k] = -rhs[k];
     __syncthreads();
   }
-  // backward: L^T x = y
-  for (int kb = nb - 1; kb >= 0; kb--) {
-    const int r0 = kb * 32;
-    // acc[c] = sum_{r >= r0+32} L[r][r0+c] * x[r]    (lanes = 32 consecutive columns, warps stride rows)
-    double a = 0.0;
-    for (int r = r0 + 32 + warp; r < ldh; r += NT / 32) a += L[(size_t)r * ldh + r0 + lane] * rhs[r];
-    part[warp * 32 + lane] = a;
-    for (int e = tid; e < 32 * 32; e += NT) blk[(e >> 5) * 33 + (e & 31)] = L[(size_t)(r0 + (e >> 5)) * ldh + r0 + (e & 31)];
-    __syncthreads();
-    if (warp == 0) {
-      double s = 0.0;
-      for (int w = 0; w < NT / 32; w++) s += part[w * 32 + lane];
-      double v = rhs[r0 + lane] - s;
-      for (int j = 31; j >= 0; j--) {
-        const double xj = __shfl_sync(0xffffffffu, v, j) / blk[j * 33 + j];
-        if (lane == j) v = xj;
-        else if (lane < j) v -= blk[j * 33 + lane] * xj;
-      }
-      rhs[r0 + lane] = v;
-    }
-    __syncthreads();
-  }
-  // rhs now holds dir
   double dinf = 0.0, binf = 0.0, phi0 = 0.0;
   for (int k = tid; k < Dt; k += NT) {
     const double d = rhs[k];
-    pb.dir[k] = d;
     dinf = fmax(dinf, fabs(d));
     binf = fmax(binf, fabs(pb.beta[k]));
     phi0 += d * pb.g_acc[k];
@@ -250,6 +288,7 @@ __global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restr
       c->stall = 0;
     }
     c->need_hess = 0;
+    if (fin && c->hess_policy == 0 && c->newton_steps >= 6) c->refresh_next = 1;   // the quasi-Newton model is ageing
     s_final = fin;
   }
   __syncthreads();
@@ -276,15 +315,10 @@ cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, cudaStream_t st,
   return cudaGetLastError();
 }
 cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches) {
-  const size_t smem = ((size_t)ldh + 32 * 33 + 8 * 32) * sizeof(double);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(newton_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
-  newton_solve_kernel<<<nprob, NT, smem, st>>>(d_probs);
-  if (launches) *launches += 1;
+  newton_pre_kernel<<<nprob, NT, 0, st>>>(d_probs);
+  newton_gemv_kernel<<<dim3((ldh + NT / 32 - 1) / (NT / 32), nprob), NT, 0, st>>>(d_probs);
+  newton_solve_kernel<<<nprob, NT, 0, st>>>(d_probs);
+  if (launches) *launches += 3;
   return cudaGetLastError();
 }
 }  // namespace mlease

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -63,6 +64,14 @@ __global__ void check_csr_kernel(long long nnz, const int* colidx, float* vals, 
     const int c = colidx[j];
     if (c < 0 || c >= Dg) atomicOr(bad, 4);
     if (binary) vals[j] = 1.0f;
+  }
+}
+__global__ void repack_rows_kernel(float* dst, int ldx, const float* src, long long ld_in, long long rows, int Dg) {
+  const long long total = rows * Dg;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / Dg;
+    const int c = (int)(e - i * Dg);
+    dst[i * ldx + c] = src[i * ld_in + c];
   }
 }
 __global__ void poll2_kernel(const Problem* probs, int nprob, int* flag_out) {
@@ -192,14 +201,17 @@ int batch_alloc(Batch& B, int num_sms) {
     while (best > 1 && (double)best * B.Dp * B.Dp * 4.0 * nprob > 1024.0 * 1024 * 1024) best--;
     B.gram_slices = best;
   }
-  const size_t nd = (size_t)nprob * (8 * (size_t)ldx + (size_t)(B.csr ? 1 : B.k1_grid) * ldx + (size_t)B.k1_grid + 8);
+  const size_t nd = (size_t)nprob * ((8 + 2 * BFGS_M) * (size_t)ldx + 2 * BFGS_M + (size_t)(B.csr ? 1 : B.k1_grid) * ldx + (size_t)B.k1_grid + 8);
   const size_t nf = (size_t)nprob * 4 * ldx;
-  double* dd; float* ff; float* hp; double* lc; double* ld;
+  double* dd; float* ff; float* hp; double* lc; double* ld; double* ldi; double* yi; double* hi;
   if (int rc = dev_alloc(B, (void**)&dd, nd * sizeof(double))) return rc;
   if (int rc = dev_alloc(B, (void**)&ff, nf * sizeof(float))) return rc;
   if (int rc = dev_alloc(B, (void**)&hp, (size_t)nprob * B.gram_slices * B.Dp * B.Dp * sizeof(float))) return rc;
   if (int rc = dev_alloc(B, (void**)&lc, (size_t)nprob * B.ldh * B.ldh * sizeof(double))) return rc;
   if (int rc = dev_alloc(B, (void**)&ld, (size_t)nprob * B.ldh * 32 * sizeof(double))) return rc;
+  if (int rc = dev_alloc(B, (void**)&ldi, (size_t)nprob * B.ldh * 32 * sizeof(double))) return rc;
+  if (int rc = dev_alloc(B, (void**)&yi, (size_t)nprob * B.ldh * B.ldh * sizeof(double))) return rc;
+  if (int rc = dev_alloc(B, (void**)&hi, (size_t)nprob * B.ldh * B.ldh * sizeof(double))) return rc;
   if (int rc = dev_alloc(B, (void**)&B.d_ctrl, (size_t)nprob * sizeof(Ctrl))) return rc;
   if (int rc = dev_alloc(B, (void**)&B.d, (size_t)nprob * sizeof(Problem))) return rc;
   if (int rc = dev_alloc(B, &B.d_tmaps, (size_t)nprob * sizeof(CUtensorMap))) return rc;
@@ -214,6 +226,7 @@ int batch_alloc(Batch& B, int num_sms) {
     double* q = dd;
     p.beta = q; q += ldx; p.beta_t = q; q += ldx; p.m = q; q += ldx; p.q = q; q += ldx;
     p.g_t = q; q += ldx; p.g_acc = q; q += ldx; p.dir = q; q += ldx; p.x_d = q; q += ldx;
+    p.bfgs_S = q; q += (size_t)BFGS_M * ldx; p.bfgs_Y = q; q += (size_t)BFGS_M * ldx; p.bfgs_rho = q; q += BFGS_M; p.bfgs_alpha = q; q += BFGS_M;
     p.gpart = q; q += (size_t)p.k1_ctas * ldx;
     p.fpart = q; q += B.k1_grid + 8;
     dd = q;
@@ -223,6 +236,9 @@ int batch_alloc(Batch& B, int num_sms) {
     p.Hpart = hp + (size_t)b * B.gram_slices * B.Dp * B.Dp;
     p.Lc = lc + (size_t)b * B.ldh * B.ldh;
     p.Ldiag = ld + (size_t)b * B.ldh * 32;
+    p.Ldinv = ldi + (size_t)b * B.ldh * 32;
+    p.Yinv = yi + (size_t)b * B.ldh * B.ldh;
+    p.Hinv = hi + (size_t)b * B.ldh * B.ldh;
     p.ctrl = B.d_ctrl + b;
     if (!p.Xt) {
       void* xt;
@@ -273,6 +289,12 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
     CK(cudaStreamSynchronize(st));
     flag = *h_flag;
     slots++;
+    if (getenv("MLEASE_DEBUG") && atoi(getenv("MLEASE_DEBUG")) >= 2) {
+      Ctrl c0;
+      cudaMemcpy(&c0, B.d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[mlease]   slot %d p0: done %d steps %d hb %d emit %d f %.10e |g| %.3e |dir| %.3e phi0 %.3e alpha %.2f wr %.3f\n", slots, c0.done,
+              c0.newton_steps, c0.hess_builds, c0.emit, c0.f_acc, c0.gnorm, c0.dirnorm, c0.phi0, c0.alpha, c0.worst_ratio);
+    }
   }
   std::vector<Ctrl> hc(B.nprob);
   CK(cudaMemcpyAsync(hc.data(), B.d_ctrl, (size_t)B.nprob * sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
@@ -281,6 +303,13 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
   cnt.last_slots = slots;
   int bad_spd = 0, bad_ls = 0;
   pf.resolve();
+  if (getenv("MLEASE_DEBUG")) {
+    fprintf(stderr, "[mlease] x-update: %d problems, %d slots;", B.nprob, slots);
+    for (int b = 0; b < B.nprob && b < 4; b++)
+      fprintf(stderr, " p%d{ev %d st %d rej %d hb %d fail %d stall %d |g| %.2e |dir| %.2e}", b, hc[b].evals, hc[b].newton_steps, hc[b].rejects,
+              hc[b].hess_builds, hc[b].fail, hc[b].stall, hc[b].gnorm, hc[b].dirnorm);
+    fprintf(stderr, "\n");
+  }
   for (int b = 0; b < B.nprob; b++) {
     const Ctrl& c = hc[b];
     const Problem& p = B.h[b];
@@ -557,7 +586,43 @@ int mlease_add_partition_dense(mlease_session* s, int32_t pid, int64_t nrows, co
   CK(cudaMalloc(&x, (size_t)nrows * s->ldx * sizeof(float)));
   s->owned.push_back(x);
   pd.X = (float*)x;
-  CK(cudaMemcpy2DAsync(pd.X, (size_t)s->ldx * 4, X, (size_t)ldx_in * 4, (size_t)s->Dg * 4, (size_t)nrows, cudaMemcpyDefault, s->stream));
+  {
+    cudaPointerAttributes pa;
+    const bool on_device = cudaPointerGetAttributes(&pa, X) == cudaSuccess && (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    if (on_device) {
+      CK(cudaMemcpy2DAsync(pd.X, (size_t)s->ldx * 4, X, (size_t)ldx_in * 4, (size_t)s->Dg * 4, (size_t)nrows, cudaMemcpyDeviceToDevice, s->stream));
+    } else {
+      // Host source: a pitched 2-D DMA of 4 KB rows runs far below PCIe speed, so stream contiguous chunks into two
+      // staging buffers on a copy stream and repack them into the padded layout on the compute stream.
+      const long long chunk_rows = std::max<long long>(1, (128LL << 20) / (ldx_in * 4));
+      float* stage[2] = {nullptr, nullptr};
+      cudaEvent_t h2d_done[2], repack_done[2];
+      cudaStream_t cs;
+      CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; b++) {
+        CK(cudaMalloc((void**)&stage[b], (size_t)chunk_rows * ldx_in * 4));
+        CK(cudaEventCreateWithFlags(&h2d_done[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&repack_done[b], cudaEventDisableTiming));
+      }
+      int ci = 0;
+      for (long long r0 = 0; r0 < nrows; r0 += chunk_rows, ci++) {
+        const int b = ci & 1;
+        const long long rows = std::min(chunk_rows, (long long)nrows - r0);
+        if (ci >= 2) CK(cudaStreamWaitEvent(cs, repack_done[b], 0));
+        const size_t bytes = ((size_t)(rows - 1) * ldx_in + s->Dg) * 4;
+        CK(cudaMemcpyAsync(stage[b], X + r0 * ldx_in, bytes, cudaMemcpyHostToDevice, cs));
+        CK(cudaEventRecord(h2d_done[b], cs));
+        CK(cudaStreamWaitEvent(s->stream, h2d_done[b], 0));
+        repack_rows_kernel<<<2048, 256, 0, s->stream>>>(pd.X + r0 * s->ldx, s->ldx, stage[b], ldx_in, rows, s->Dg);
+        CK(cudaEventRecord(repack_done[b], s->stream));
+      }
+      CK(cudaStreamSynchronize(cs));
+      CK(cudaStreamSynchronize(s->stream));
+      for (int b = 0; b < 2; b++) { cudaFree(stage[b]); cudaEventDestroy(h2d_done[b]); cudaEventDestroy(repack_done[b]); }
+      cudaStreamDestroy(cs);
+    }
+  }
   fill_bias_pad_kernel<<<1024, 256, 0, s->stream>>>(pd.X, nrows, s->ldx, s->Dg, 1);
   if (int rc = add_common(s, pd, response, weight, offset)) return rc;
   s->parts.push_back(pd);
@@ -1000,7 +1065,7 @@ int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg
     size_t end = pos;
     while (end < todo.size() && end - pos < 16384) {
       const long long nk = krs[todo[end] + 1] - krs[todo[end]];
-      const size_t need = (size_t)nk * Dp * 2 + (size_t)Dp * Dp * 4 + (size_t)ldh * ldh * 8 + (size_t)ldh * 32 * 8 + 64 * (size_t)ldx;
+      const size_t need = (size_t)nk * Dp * 2 + (size_t)Dp * Dp * 4 + 3 * (size_t)ldh * ldh * 8 + 2 * (size_t)ldh * 32 * 8 + 64 * (size_t)ldx;
       if (end > pos && bytes + need > free_b / 2) break;
       bytes += need;
       end++;

@@ -8,11 +8,9 @@
 // Dense layout: X row-major [n][ldx] fp32, ldx % 4 == 0, bias column physical.  A CTA streams
 // row tiles of R rows (R*ldx*4 contiguous bytes) through an S-stage shared-memory ring with
 // 1-D bulk TMA copies (cp.async.bulk, mbarrier complete_tx), then
-//   phase A: one warp per row, float4 smem reads, s_i = x_i.beta + o_i, p = sigmoid(y s),
-//            r_i = w (p-1) y, d_i = w p (1-p), loss_i                      (row-dot)
-//   phase B: one thread per float4 column group, g += r_i * x_i  over the tile's rows, and
-//            (optionally) Xt[i][:] = bf16(sqrt(d_i) * x_i[:])            (column-sum + emit)
-// so every element of X is read from HBM exactly once and from shared memory twice.
+//   phase A: s_i = x_i.beta + o_i, p = sigmoid(y s), r_i = w (p-1) y, d_i = w p (1-p), loss_i      (row dots)
+//   phase B: g += r_i * x_i over the tile's rows, and (optionally) Xt[i][:] = bf16(sqrt(d_i) * x_i[:])
+// so every element of X is read from HBM exactly once and from shared memory exactly once (into registers).
 // Per-CTA partial gradients are accumulated in fp64 registers and written to gpart; a fixed
 // order reduction (k1_reduce_decide in newton.cu) makes the result run-to-run deterministic.
 #include "kernels.cuh"
@@ -22,9 +20,18 @@ namespace mlease {
 constexpr int K1_THREADS = 256;
 constexpr int K1_WARPS = K1_THREADS / 32;
 
-template <int G>
-__global__ void __launch_bounds__(K1_THREADS, 1)
-k1_dense_kernel(const Problem* __restrict__ probs, int R, int S, int force_emit) {
+// Thread t owns float4 column group(s) cg = t (+256 g) and RT rows of every tile (rows sl*RT .. sl*RT+RT-1 when
+// several row slices share the 256 threads for narrow matrices).  The tile is read from shared memory ONCE, into
+// registers, and serves both the row dots (phase A) and the column sums / bf16 emit (phase B):
+//   A  : x[j] <- tile, p[j] = x[j].beta (beta float4 lives in registers for the whole kernel), p -> smem pd[row][t]
+//   -- barrier 1 (all of the stage is in registers: the producer thread refills it immediately) --
+//   A' : warp w sums pd rows w, w+8, ..; lanes 0..k do the sigmoid / loss / IRLS weight of those rows in parallel
+//   -- barrier 2 --
+//   B  : g += r[row] * x[j];  optionally Xt[row] = bf16(sqrt(d[row]) * x[j])
+// pd / r / sqrt(d) are double buffered by tile parity, so two barriers per tile are enough.
+template <int G, int RT>
+__global__ void __launch_bounds__(K1_THREADS, (G == 1 ? 2 : 1))
+k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emit) {
   const Problem& pb = probs[blockIdx.y];
   Ctrl* ctrl = pb.ctrl;
   if (ctrl->done) return;
@@ -33,188 +40,191 @@ k1_dense_kernel(const Problem* __restrict__ probs, int R, int S, int force_emit)
   const int ldx = pb.ldx;
   const int ncg = ldx >> 2;  // float4 column groups
   const long long n = pb.n;
+  const int Rt = RT * nsl;   // rows per tile
+  const int pdw = (G == 1) ? ncg : K1_THREADS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* __restrict__ Xg = pb.X;
+  const signed char* __restrict__ yg = pb.y;
+  const float* __restrict__ wg = pb.w;
+  const float* __restrict__ og = pb.o;
+  __nv_bfloat16* __restrict__ Xt = pb.Xt;
+  const int Dp = pb.Dp;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const size_t stage_bytes = (size_t)R * ldx * sizeof(float);
-  float* stage0 = reinterpret_cast<float*>(smem_raw);
-  float* beta_s = reinterpret_cast<float*>(smem_raw + (size_t)S * stage_bytes);
-  float* r_s = beta_s + ldx;
-  float* sd_s = r_s + R;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sd_s + R) + 15) & ~uintptr_t(15));
-  double* red_s = reinterpret_cast<double*>(full_bar + 8);  // 8 warps of scratch
+  const size_t stage_bytes = (size_t)Rt * ldx * sizeof(float);
+  float* pd_s = reinterpret_cast<float*>(smem_raw + (size_t)S * stage_bytes);   // [2][Rt][pdw]
+  float* r_s = pd_s + 2 * (size_t)Rt * pdw;                                     // [2][Rt]
+  float* sd_s = r_s + 2 * Rt;                                                   // [2][Rt]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sd_s + 2 * Rt) + 15) & ~uintptr_t(15));
+  double* red_s = reinterpret_cast<double*>(full_bar + 8);
 
-  const long long ntiles = (n + R - 1) / R;
-  // tiles handled by this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const long long ntiles = (n + Rt - 1) / Rt;
   const long long my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) mbar_init(&full_bar[s], 1);
     fence_mbar_init();
   }
-  for (int c = tid; c < ldx; c += K1_THREADS) beta_s[c] = pb.beta_tf[c];
   __syncthreads();
 
-  auto issue = [&](long long k) {  // tile index within this CTA's sequence -> stage k % S
+  auto issue = [&](long long k) {
     const long long t = blockIdx.x + k * (long long)gridDim.x;
-    const long long row0 = t * R;
-    const int rows = (int)min((long long)R, n - row0);
+    const long long row0 = t * Rt;
+    const int rows = (int)min((long long)Rt, n - row0);
     const uint32_t bytes = (uint32_t)((size_t)rows * ldx * sizeof(float));
     uint64_t* bar = &full_bar[k % S];
     mbar_arrive_expect_tx(bar, bytes);
-    bulk_g2s(reinterpret_cast<unsigned char*>(stage0) + (k % S) * stage_bytes, pb.X + row0 * ldx, bytes, bar);
+    bulk_g2s(smem_raw + (k % S) * stage_bytes, Xg + row0 * ldx, bytes, bar);
   };
   if (tid == 0) {
-    for (int k = 0; k < S - 1 && k < my_tiles; k++) issue(k);
+    for (int k = 0; k < S && k < my_tiles; k++) issue(k);
   }
 
-  // thread -> column-group mapping for phase B
-  int nsl = 1, sl = 0, cg0 = tid;
-  bool activeB = true;
-  if (G == 1) {
-    nsl = K1_THREADS / ncg;
-    if (nsl < 1) nsl = 1;
-    sl = tid / ncg;
-    cg0 = tid - sl * ncg;
-    activeB = sl < nsl;
+  // column / row-slice ownership
+  int sl = 0, cg0 = tid;
+  if (G == 1) { sl = tid / ncg; cg0 = tid - sl * ncg; }
+  const bool act = (G == 1) ? (sl < nsl) : true;
+  float4 b4[G];
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    const int cg = cg0 + g * K1_THREADS;
+    b4[g] = (act && cg < ncg) ? reinterpret_cast<const float4*>(pb.beta_tf)[cg] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   double acc64[G][4];
 #pragma unroll
   for (int g = 0; g < G; g++) acc64[g][0] = acc64[g][1] = acc64[g][2] = acc64[g][3] = 0.0;
   double loss64 = 0.0;
-
-  const float4* beta4 = reinterpret_cast<const float4*>(beta_s);
+  const int myrow = warp + K1_WARPS * lane;   // the row of the tile whose scalars this lane owns
 
   for (long long k = 0; k < my_tiles; k++) {
     const int st = (int)(k % S);
-    if (tid == 0 && k + S - 1 < my_tiles) issue(k + S - 1);
-    mbar_wait(&full_bar[st], (uint32_t)((k / S) & 1));
-    const float* tile = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(stage0) + st * stage_bytes);
-    const long long row0 = (blockIdx.x + k * (long long)gridDim.x) * R;
-    const int rows = (int)min((long long)R, n - row0);
+    const int buf = (int)(k & 1);
+    const long long row0 = (blockIdx.x + k * (long long)gridDim.x) * Rt;
+    const int rows = (int)min((long long)Rt, n - row0);
+    // row scalars first: their global-load latency hides behind the wait + phase A
+    float yy = 0.f, ww = 0.f, oo = 0.f;
+    const bool has = myrow < rows;
+    if (has) { const long long i = row0 + myrow; yy = (float)yg[i]; ww = wg[i]; oo = og[i]; }
 
-    // ---- phase A: row dots, two rows per warp per step (beta float4 shared by both rows) ---------------
-    // lanes 0/1 own the per-row scalars of rows r/r+1: their y,w,o loads are issued BEFORE the dot loop so the
-    // global-load latency hides behind it; the sigmoid/loss math then runs on two lanes at once.
-    for (int r = 2 * warp; r < rows; r += 2 * K1_WARPS) {
-      const bool two = (r + 1) < rows;
-      const int myr = r + (lane & 1);
-      float yy = 0.f, ww = 0.f, oo = 0.f;
-      if (lane < 2 && myr < rows) {
-        const long long i = row0 + myr;
-        yy = (float)pb.y[i]; ww = pb.w[i]; oo = pb.o[i];
+    mbar_wait(&full_bar[st], (uint32_t)((k / S) & 1));
+    const float4* tile4 = reinterpret_cast<const float4*>(smem_raw + st * stage_bytes);
+    float* pd = pd_s + (size_t)buf * Rt * pdw;
+
+    // ---- phase A -----------------------------------------------------------------------------------
+    float4 x[G][RT];
+    if (act) {
+#pragma unroll
+      for (int j = 0; j < RT; j++) {
+        const int row = sl * RT + j;
+        float p = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          const int cg = cg0 + g * K1_THREADS;
+          x[g][j] = (row < rows && cg < ncg) ? tile4[(size_t)row * ncg + cg] : make_float4(0.f, 0.f, 0.f, 0.f);
+          p = fmaf(x[g][j].x, b4[g].x, p); p = fmaf(x[g][j].y, b4[g].y, p);
+          p = fmaf(x[g][j].z, b4[g].z, p); p = fmaf(x[g][j].w, b4[g].w, p);
+        }
+        if (row < rows) pd[(size_t)row * pdw + ((G == 1) ? cg0 : tid)] = p;
       }
-      const float4* x0p = reinterpret_cast<const float4*>(tile + (size_t)r * ldx);
-      const float4* x1p = reinterpret_cast<const float4*>(tile + (size_t)(two ? r + 1 : r) * ldx);
-      float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
-      int c = lane;
-      for (; c + 32 < ncg; c += 64) {
-        const float4 b0 = beta4[c], b1 = beta4[c + 32];
-        const float4 x0 = x0p[c], x1 = x1p[c], x2 = x0p[c + 32], x3 = x1p[c + 32];
-        a0 = fmaf(x0.x, b0.x, a0); a0 = fmaf(x0.y, b0.y, a0); a0 = fmaf(x0.z, b0.z, a0); a0 = fmaf(x0.w, b0.w, a0);
-        a1 = fmaf(x1.x, b0.x, a1); a1 = fmaf(x1.y, b0.y, a1); a1 = fmaf(x1.z, b0.z, a1); a1 = fmaf(x1.w, b0.w, a1);
-        c0 = fmaf(x2.x, b1.x, c0); c0 = fmaf(x2.y, b1.y, c0); c0 = fmaf(x2.z, b1.z, c0); c0 = fmaf(x2.w, b1.w, c0);
-        c1 = fmaf(x3.x, b1.x, c1); c1 = fmaf(x3.y, b1.y, c1); c1 = fmaf(x3.z, b1.z, c1); c1 = fmaf(x3.w, b1.w, c1);
+    }
+    __syncthreads();   // barrier 1: the stage is fully in registers
+    if (tid == 0 && k + S < my_tiles) issue(k + S);
+
+    // ---- phase A': row sums + per-row scalar math ------------------------------------------------------
+    {
+      float mysum = 0.f;
+      int jj = 0;
+      for (int row = warp; row < rows; row += K1_WARPS, jj++) {
+        const float* pr = pd + (size_t)row * pdw;
+        float a = 0.f;
+        for (int c = lane; c < pdw; c += 32) a += pr[c];
+        a = warp_sum(a);
+        if (lane == jj) mysum = a;
       }
-      if (c < ncg) {
-        const float4 b0 = beta4[c];
-        const float4 x0 = x0p[c], x1 = x1p[c];
-        a0 = fmaf(x0.x, b0.x, a0); a0 = fmaf(x0.y, b0.y, a0); a0 = fmaf(x0.z, b0.z, a0); a0 = fmaf(x0.w, b0.w, a0);
-        a1 = fmaf(x1.x, b0.x, a1); a1 = fmaf(x1.y, b0.y, a1); a1 = fmaf(x1.z, b0.z, a1); a1 = fmaf(x1.w, b0.w, a1);
-      }
-      const float s0 = warp_sum(a0 + c0), s1 = warp_sum(a1 + c1);
-      if (lane < 2 && myr < rows) {
-        const float t = yy * ((lane ? s1 : s0) + oo);
-        const float e = __expf(-fabsf(t));                 // in (0,1]; ex2.approx path
+      if (has) {
+        const float t = yy * (mysum + oo);
+        const float e = __expf(-fabsf(t));                 // in (0,1]
         const float inv = __frcp_rn(1.f + e);
         const float p = t >= 0.f ? inv : e * inv;          // sigmoid(y s)
         const float qq = t >= 0.f ? e * inv : inv;         // 1 - p, no cancellation
-        // log1p(e) = -log(1/(1+e)); absolute error ~1e-7 per row is far below the objective's use (line search only)
+        // log1p(e) = -log(1/(1+e)); absolute error ~1e-7 per row, the objective only steers the line search
         loss64 += (double)(ww * ((t >= 0.f ? 0.f : -t) - __logf(inv)));
-        r_s[myr] = -ww * yy * qq;                          // w (p-1) y
-        sd_s[myr] = sqrtf(ww * p * qq);                    // sqrt(d_i)
+        r_s[buf * Rt + myrow] = -ww * yy * qq;             // w (p-1) y
+        sd_s[buf * Rt + myrow] = sqrtf(ww * p * qq);       // sqrt(d_i)
       }
     }
-    __syncthreads();
+    __syncthreads();   // barrier 2
 
-    // ---- phase B: column sums (+ emit scaled bf16 copy) ------------------------------------
-    if (activeB) {
+    // ---- phase B -----------------------------------------------------------------------------------
+    if (act) {
+      const float* rb = r_s + buf * Rt + sl * RT;
+      const float* sb = sd_s + buf * Rt + sl * RT;
 #pragma unroll
       for (int g = 0; g < G; g++) {
         const int cg = cg0 + g * K1_THREADS;
         if (cg < ncg) {
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4* t4 = reinterpret_cast<const float4*>(tile) + cg;
-          if (emit) {
-            __nv_bfloat16* xt = pb.Xt + (size_t)row0 * pb.Dp + 4 * cg;
-            for (int r = sl; r < rows; r += nsl) {
-              const float4 x = t4[(size_t)r * ncg];
-              const float rr = r_s[r], sd = sd_s[r];
-              a.x = fmaf(x.x, rr, a.x); a.y = fmaf(x.y, rr, a.y); a.z = fmaf(x.z, rr, a.z); a.w = fmaf(x.w, rr, a.w);
-              __nv_bfloat162 lo = __floats2bfloat162_rn(x.x * sd, x.y * sd);
-              __nv_bfloat162 hi = __floats2bfloat162_rn(x.z * sd, x.w * sd);
-              uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&lo);
-              pk.y = *reinterpret_cast<uint32_t*>(&hi);
-              *reinterpret_cast<uint2*>(xt + (size_t)r * pb.Dp) = pk;
+#pragma unroll
+          for (int j = 0; j < RT; j++) {
+            if (sl * RT + j < rows) {
+              const float rr = rb[j];
+              a.x = fmaf(x[g][j].x, rr, a.x); a.y = fmaf(x[g][j].y, rr, a.y);
+              a.z = fmaf(x[g][j].z, rr, a.z); a.w = fmaf(x[g][j].w, rr, a.w);
             }
-          } else {
-            float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1, a3 = a1;
-            int r = sl;
-            for (; r + 3 * nsl < rows; r += 4 * nsl) {
-              const float4 x0 = t4[(size_t)r * ncg], x1 = t4[(size_t)(r + nsl) * ncg], x2 = t4[(size_t)(r + 2 * nsl) * ncg],
-                           x3 = t4[(size_t)(r + 3 * nsl) * ncg];
-              const float r0 = r_s[r], r1 = r_s[r + nsl], r2 = r_s[r + 2 * nsl], r3 = r_s[r + 3 * nsl];
-              a.x = fmaf(x0.x, r0, a.x); a.y = fmaf(x0.y, r0, a.y); a.z = fmaf(x0.z, r0, a.z); a.w = fmaf(x0.w, r0, a.w);
-              a1.x = fmaf(x1.x, r1, a1.x); a1.y = fmaf(x1.y, r1, a1.y); a1.z = fmaf(x1.z, r1, a1.z); a1.w = fmaf(x1.w, r1, a1.w);
-              a2.x = fmaf(x2.x, r2, a2.x); a2.y = fmaf(x2.y, r2, a2.y); a2.z = fmaf(x2.z, r2, a2.z); a2.w = fmaf(x2.w, r2, a2.w);
-              a3.x = fmaf(x3.x, r3, a3.x); a3.y = fmaf(x3.y, r3, a3.y); a3.z = fmaf(x3.z, r3, a3.z); a3.w = fmaf(x3.w, r3, a3.w);
-            }
-            for (; r < rows; r += nsl) {
-              const float4 x = t4[(size_t)r * ncg];
-              const float rr = r_s[r];
-              a.x = fmaf(x.x, rr, a.x); a.y = fmaf(x.y, rr, a.y); a.z = fmaf(x.z, rr, a.z); a.w = fmaf(x.w, rr, a.w);
-            }
-            a.x += (a1.x + a2.x) + a3.x; a.y += (a1.y + a2.y) + a3.y; a.z += (a1.z + a2.z) + a3.z; a.w += (a1.w + a2.w) + a3.w;
           }
           acc64[g][0] += (double)a.x; acc64[g][1] += (double)a.y; acc64[g][2] += (double)a.z; acc64[g][3] += (double)a.w;
+          if (emit) {
+            __nv_bfloat16* xt = Xt + (size_t)(row0 + sl * RT) * Dp + 4 * cg;
+#pragma unroll
+            for (int j = 0; j < RT; j++) {
+              if (sl * RT + j < rows) {
+                const float sd = sb[j];
+                __nv_bfloat162 lo = __floats2bfloat162_rn(x[g][j].x * sd, x[g][j].y * sd);
+                __nv_bfloat162 hi = __floats2bfloat162_rn(x[g][j].z * sd, x[g][j].w * sd);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(xt + (size_t)j * Dp) = pk;
+              }
+            }
+          }
         }
       }
     }
-    __syncthreads();  // all reads of this stage (and of r_s/sd_s) done -> stage may be refilled
   }
 
-  // ---- CTA epilogue: reduce slices, write partials -------------------------------------------
+  // ---- CTA epilogue: reduce row slices, write partials ---------------------------------------------------
+  __syncthreads();
   double* gp = pb.gpart + (size_t)blockIdx.x * ldx;
   if (G == 1 && nsl > 1) {
-    double* sc = reinterpret_cast<double*>(smem_raw);  // all bulk copies have completed and been consumed
-    if (activeB) {
+    double* sc = reinterpret_cast<double*>(smem_raw);  // every bulk copy has completed and been consumed
+    if (act) {
       double* d = sc + ((size_t)sl * ncg + cg0) * 4;
       d[0] = acc64[0][0]; d[1] = acc64[0][1]; d[2] = acc64[0][2]; d[3] = acc64[0][3];
     }
     __syncthreads();
     for (int c = tid; c < ldx; c += K1_THREADS) {
-      double s = 0.0;
-      for (int q = 0; q < nsl; q++) s += sc[(size_t)q * ldx + c];
-      gp[c] = s;
+      double sacc = 0.0;
+      for (int q = 0; q < nsl; q++) sacc += sc[(size_t)q * ldx + c];
+      gp[c] = sacc;
     }
   } else {
 #pragma unroll
     for (int g = 0; g < G; g++) {
       const int cg = cg0 + g * K1_THREADS;
-      if (activeB && cg < ncg) {
+      if (act && cg < ncg) {
         gp[4 * cg + 0] = acc64[g][0]; gp[4 * cg + 1] = acc64[g][1];
         gp[4 * cg + 2] = acc64[g][2]; gp[4 * cg + 3] = acc64[g][3];
       }
     }
   }
-  loss64 += __shfl_down_sync(0xffffffffu, loss64, 1);   // lanes 0 and 1 carry the per-row losses
+  loss64 = warp_sum(loss64);
   if (lane == 0) red_s[warp] = loss64;
   __syncthreads();
   if (tid == 0) {
-    double s = 0.0;
-    for (int wq = 0; wq < K1_WARPS; wq++) s += red_s[wq];
-    pb.fpart[blockIdx.x] = s;
+    double sacc = 0.0;
+    for (int wq = 0; wq < K1_WARPS; wq++) sacc += red_s[wq];
+    pb.fpart[blockIdx.x] = sacc;
   }
 }
 
@@ -284,22 +294,42 @@ k1_csr_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit) {
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-static size_t k1_smem_bytes(int ldx, int R, int S) {
-  return (size_t)S * R * ldx * 4 + (size_t)ldx * 4 + (size_t)2 * R * 4 + 16 + 8 * 8 + 8 * 8 + 64;
+struct K1Plan { int G, RT, nsl, S, rows_per_tile, ctas_per_sm; size_t smem; };
+
+static size_t k1_smem_bytes(int ldx, int Rt, int S, int pdw) {
+  return (size_t)S * Rt * ldx * 4 + (size_t)2 * Rt * pdw * 4 + (size_t)4 * Rt * 4 + 16 + 8 * 8 + 8 * 8 + 64;
 }
 
-// Picks the tile height R and stage count S for a given ldx (device smem budget 227 KB).
-bool k1_dense_plan(int ldx, int* R_out, int* S_out, int* G_out, size_t* smem_out) {
-  const size_t budget = 220 * 1024;
-  int G = (ldx / 4 + K1_THREADS - 1) / K1_THREADS;
-  if (G > 4) return false;
-  if (G == 3) G = 4;
-  int S = 3;
-  int R = (int)((budget - (size_t)ldx * 4 - 1024) / ((size_t)S * ldx * 4));
-  if (R > 64) R = 64;
-  if (R >= 8) R &= ~7;
-  if (R < 2) return false;
-  *R_out = R; *S_out = S; *G_out = G; *smem_out = k1_smem_bytes(ldx, R, S);
+// Tile shape for a given ldx.  G==1 (ldx <= 1024): RT=8 rows in registers, nsl row slices share the 256 threads,
+// two CTAs per SM; wider matrices: G column groups per thread, one CTA per SM.
+static bool k1_plan(int ldx, K1Plan* p) {
+  const int ncg = ldx / 4;
+  p->G = (ncg + K1_THREADS - 1) / K1_THREADS;
+  if (p->G > 4) return false;
+  if (p->G == 3) p->G = 4;
+  p->RT = p->G == 4 ? 4 : 8;
+  p->nsl = 1;
+  if (p->G == 1) {
+    p->nsl = K1_THREADS / ncg;
+    if (p->nsl < 1) p->nsl = 1;
+    if (p->nsl > 16) p->nsl = 16;   // rows per tile <= 128 keeps the per-warp row loop short
+  }
+  p->rows_per_tile = p->RT * p->nsl;
+  const int pdw = p->G == 1 ? ncg : K1_THREADS;
+  p->ctas_per_sm = p->G == 1 ? 2 : 1;
+  const size_t budget = p->ctas_per_sm == 2 ? (size_t)113 * 1024 : (size_t)225 * 1024;
+  for (int S = 4; S >= 2; S--) {
+    const size_t b = k1_smem_bytes(ldx, p->rows_per_tile, S, pdw);
+    if (b <= budget) { p->S = S; p->smem = b; return true; }
+  }
+  return false;
+}
+
+bool k1_dense_plan(int ldx, int* R_out, int* S_out, int* G_out, size_t* smem_out, int* ctas_per_sm) {
+  K1Plan p;
+  if (!k1_plan(ldx, &p)) return false;
+  *R_out = p.rows_per_tile; *S_out = p.S; *G_out = p.G; *smem_out = p.smem;
+  if (ctas_per_sm) *ctas_per_sm = p.ctas_per_sm;
   return true;
 }
 
@@ -311,16 +341,15 @@ cudaError_t k1_launch(const Problem* d_probs, int nprob, bool csr, int ldx, int 
     if (launches) *launches += 2;
     return cudaGetLastError();
   }
-  int R, S, G;
-  size_t smem;
-  if (!k1_dense_plan(ldx, &R, &S, &G, &smem)) return cudaErrorInvalidValue;
+  K1Plan p;
+  if (!k1_plan(ldx, &p)) return cudaErrorInvalidValue;
   dim3 grid(ctas_per_problem, nprob);
   cudaError_t e;
-#define K1_LAUNCH(GG)                                                                                         \
-  e = cudaFuncSetAttribute(k1_dense_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-  if (e != cudaSuccess) return e;                                                                              \
-  k1_dense_kernel<GG><<<grid, K1_THREADS, smem, stream>>>(d_probs, R, S, force_emit);
-  if (G == 1) { K1_LAUNCH(1) } else if (G == 2) { K1_LAUNCH(2) } else { K1_LAUNCH(4) }
+#define K1_LAUNCH(GG, RR)                                                                                          \
+  e = cudaFuncSetAttribute(k1_dense_kernel<GG, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);      \
+  if (e != cudaSuccess) return e;                                                                                   \
+  k1_dense_kernel<GG, RR><<<grid, K1_THREADS, p.smem, stream>>>(d_probs, p.S, p.nsl, force_emit);
+  if (p.G == 1) { K1_LAUNCH(1, 8) } else if (p.G == 2) { K1_LAUNCH(2, 8) } else { K1_LAUNCH(4, 4) }
 #undef K1_LAUNCH
   if (launches) *launches += 1;
   return cudaGetLastError();

@@ -174,12 +174,12 @@ int batch_alloc(Batch& B, int num_sms) {
   if (B.csr) {
     B.k1_grid = std::max(1, std::min((int)((maxn + 7) / 8), (num_sms * 8) / std::max(1, nprob)));
   } else {
-    int R, S, G;
+    int R, S, G, cps = 1;
     size_t smem;
-    if (!k1_dense_plan(ldx, &R, &S, &G, &smem))
+    if (!k1_dense_plan(ldx, &R, &S, &G, &smem, &cps))
       return fail(MLEASE_ERR_INVALID, "dense partitions support at most 4095 features (+intercept); use CSR input beyond that");
     const long long row_tiles = (maxn + R - 1) / R;
-    B.k1_grid = (int)std::max(1LL, std::min(row_tiles, (long long)std::max(1, num_sms / std::max(1, nprob))));
+    B.k1_grid = (int)std::max(1LL, std::min(row_tiles, (long long)std::max(1, (num_sms * cps) / std::max(1, nprob))));
   }
   // Gram decomposition
   std::vector<short> tiles(2 * 8192);

@@ -20,6 +20,26 @@ namespace mlease {
 constexpr int K1_THREADS = 256;
 constexpr int K1_WARPS = K1_THREADS / 32;
 
+
+// tile -> registers + partial dots (FULL: every row of the tile exists, no guards)
+template <int G, int RT, bool FULL>
+__device__ __forceinline__ void k1_phase_a(float4 (&x)[G][RT], const float4* __restrict__ tile4, const float4 (&b4)[G], float* __restrict__ pw,
+                                           int ncg, int pdw, int cg0, int myrows0, int rows) {
+#pragma unroll
+  for (int j = 0; j < RT; j++) {
+    const bool ok = FULL || (myrows0 + j < rows);
+    float p = 0.f;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      const bool okc = ok && (G == 1 || cg0 + g * K1_THREADS < ncg);
+      x[g][j] = okc ? tile4[(uint32_t)(j * ncg + g * K1_THREADS)] : make_float4(0.f, 0.f, 0.f, 0.f);
+      p = fmaf(x[g][j].x, b4[g].x, p); p = fmaf(x[g][j].y, b4[g].y, p);
+      p = fmaf(x[g][j].z, b4[g].z, p); p = fmaf(x[g][j].w, b4[g].w, p);
+    }
+    pw[(uint32_t)(j * pdw)] = p;   // rows beyond `rows` get 0: harmless, never read
+  }
+}
+
 // Thread t owns float4 column group(s) cg = t (+256 g) and RT rows of every tile (rows sl*RT .. sl*RT+RT-1 when
 // several row slices share the 256 threads for narrow matrices).  The tile is read from shared memory ONCE, into
 // registers, and serves both the row dots (phase A) and the column sums / bf16 emit (phase B):
@@ -55,11 +75,11 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
   float* pd_s = reinterpret_cast<float*>(smem_raw + (size_t)S * stage_bytes);   // [2][Rt][pdw]
   float* r_s = pd_s + 2 * (size_t)Rt * pdw;                                     // [2][Rt]
   float* sd_s = r_s + 2 * Rt;                                                   // [2][Rt]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sd_s + 2 * Rt) + 15) & ~uintptr_t(15));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sd_s + 3 * Rt) + 15) & ~uintptr_t(15));
   double* red_s = reinterpret_cast<double*>(full_bar + 8);
 
-  const long long ntiles = (n + Rt - 1) / Rt;
-  const long long my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int ntiles = (int)((n + Rt - 1) / Rt);
+  const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) mbar_init(&full_bar[s], 1);
@@ -67,17 +87,17 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
   }
   __syncthreads();
 
-  auto issue = [&](long long k) {
-    const long long t = blockIdx.x + k * (long long)gridDim.x;
-    const long long row0 = t * Rt;
+  // producer (thread 0): bulk-copy tile number `t` of the matrix into stage `stg`
+  auto issue = [&](int t, int stg) {
+    const long long row0 = (long long)t * Rt;
     const int rows = (int)min((long long)Rt, n - row0);
-    const uint32_t bytes = (uint32_t)((size_t)rows * ldx * sizeof(float));
-    uint64_t* bar = &full_bar[k % S];
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)ldx * 4u;
+    uint64_t* bar = &full_bar[stg];
     mbar_arrive_expect_tx(bar, bytes);
-    bulk_g2s(smem_raw + (k % S) * stage_bytes, Xg + row0 * ldx, bytes, bar);
+    bulk_g2s(smem_raw + (size_t)stg * stage_bytes, Xg + row0 * ldx, bytes, bar);
   };
   if (tid == 0) {
-    for (int k = 0; k < S && k < my_tiles; k++) issue(k);
+    for (int k = 0; k < S && k < my_tiles; k++) issue((int)blockIdx.x + k * (int)gridDim.x, k);
   }
 
   // column / row-slice ownership
@@ -94,90 +114,98 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
 #pragma unroll
   for (int g = 0; g < G; g++) acc64[g][0] = acc64[g][1] = acc64[g][2] = acc64[g][3] = 0.0;
   double loss64 = 0.0;
-  const int myrow = warp + K1_WARPS * lane;   // the row of the tile whose scalars this lane owns
+  float* s_s = sd_s + 2 * Rt;                       // [Rt] row scores (x_i . beta)
+  const uint32_t xoff = (uint32_t)(sl * RT * ncg + cg0);   // float4 index of this thread's first element in a tile
+  const uint32_t poff = (uint32_t)(sl * RT * pdw + ((G == 1) ? cg0 : tid));
+  const int myrows0 = sl * RT;
 
-  for (long long k = 0; k < my_tiles; k++) {
-    const int st = (int)(k % S);
-    const int buf = (int)(k & 1);
-    const long long row0 = (blockIdx.x + k * (long long)gridDim.x) * Rt;
+  int st = 0;
+  uint32_t par = 0;
+  int tile_no = (int)blockIdx.x;
+  const int tile_step = (int)gridDim.x;
+  for (int k = 0; k < my_tiles; k++, tile_no += tile_step) {
+    const int buf = k & 1;
+    const long long row0 = (long long)tile_no * Rt;
     const int rows = (int)min((long long)Rt, n - row0);
-    // row scalars first: their global-load latency hides behind the wait + phase A
+    const bool full = rows == Rt;
+    // per-row scalars (thread t < rows owns row t): issued before the wait so their latency is hidden
     float yy = 0.f, ww = 0.f, oo = 0.f;
-    const bool has = myrow < rows;
-    if (has) { const long long i = row0 + myrow; yy = (float)yg[i]; ww = wg[i]; oo = og[i]; }
+    const bool has = tid < rows;
+    if (has) { const long long i = row0 + tid; yy = (float)yg[i]; ww = wg[i]; oo = og[i]; }
 
-    mbar_wait(&full_bar[st], (uint32_t)((k / S) & 1));
-    const float4* tile4 = reinterpret_cast<const float4*>(smem_raw + st * stage_bytes);
+    mbar_wait(&full_bar[st], par);
+    const float4* tile4 = reinterpret_cast<const float4*>(smem_raw + (size_t)st * stage_bytes) + xoff;
     float* pd = pd_s + (size_t)buf * Rt * pdw;
 
-    // ---- phase A -----------------------------------------------------------------------------------
+    // ---- phase A: tile -> registers, partial dots -> pd -------------------------------------------------
     float4 x[G][RT];
     if (act) {
+      float* pw = pd + poff;
+      if (full) k1_phase_a<G, RT, true>(x, tile4, b4, pw, ncg, pdw, cg0, myrows0, rows);
+      else k1_phase_a<G, RT, false>(x, tile4, b4, pw, ncg, pdw, cg0, myrows0, rows);
+    }
+    __syncthreads();   // barrier 1: the stage is fully in registers
+    if (tid == 0 && k + S < my_tiles) issue(tile_no + S * tile_step, st);
+    if (++st == S) { st = 0; par ^= 1u; }
+
+    // ---- phase A': row sums (warp w: rows w, w+8, ...) -> s_s -------------------------------------------
+    for (int row = warp; row < rows; row += K1_WARPS) {
+      const float* pr = pd + (uint32_t)(row * pdw);
+      float a = 0.f;
+      for (int c = lane; c < pdw; c += 32) a += pr[c];
+      a = warp_sum(a);
+      if (lane == 0) s_s[row] = a;
+    }
+    __syncthreads();   // barrier 2
+    // ---- per-row scalar math, one thread per row (only the first warps of the CTA take this branch) -------
+    if (has) {
+      const float t = yy * (s_s[tid] + oo);
+      const float e = __expf(-fabsf(t));                 // in (0,1]
+      const float inv = __frcp_rn(1.f + e);
+      const float p = t >= 0.f ? inv : e * inv;          // sigmoid(y s)
+      const float qq = t >= 0.f ? e * inv : inv;         // 1 - p, no cancellation
+      // log1p(e) = -log(1/(1+e)); absolute error ~1e-7 per row, the objective only steers the line search
+      loss64 += (double)(ww * ((t >= 0.f ? 0.f : -t) - __logf(inv)));
+      r_s[buf * Rt + tid] = -ww * yy * qq;               // w (p-1) y
+      sd_s[buf * Rt + tid] = sqrtf(ww * p * qq);         // sqrt(d_i)
+    }
+    __syncthreads();   // barrier 3
+
+    // ---- phase B: column sums from registers (+ bf16 emit) ------------------------------------------------
+    if (act) {
+      float rr[RT];
+      {
+        const float4* rb4 = reinterpret_cast<const float4*>(r_s + buf * Rt + myrows0);
 #pragma unroll
-      for (int j = 0; j < RT; j++) {
-        const int row = sl * RT + j;
-        float p = 0.f;
+        for (int j4 = 0; j4 < RT / 4; j4++) {
+          const float4 v = rb4[j4];
+          rr[4 * j4] = v.x; rr[4 * j4 + 1] = v.y; rr[4 * j4 + 2] = v.z; rr[4 * j4 + 3] = v.w;
+        }
+      }
+      if (!full) {
+#pragma unroll
+        for (int j = 0; j < RT; j++) if (myrows0 + j >= rows) rr[j] = 0.f;   // x is 0 there too; avoid 0*NaN from stale smem
+      }
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < RT; j++) {
+          a.x = fmaf(x[g][j].x, rr[j], a.x); a.y = fmaf(x[g][j].y, rr[j], a.y);
+          a.z = fmaf(x[g][j].z, rr[j], a.z); a.w = fmaf(x[g][j].w, rr[j], a.w);
+        }
+        acc64[g][0] += (double)a.x; acc64[g][1] += (double)a.y; acc64[g][2] += (double)a.z; acc64[g][3] += (double)a.w;
+      }
+      if (emit) {
+        const float* sb = sd_s + buf * Rt + myrows0;
 #pragma unroll
         for (int g = 0; g < G; g++) {
           const int cg = cg0 + g * K1_THREADS;
-          x[g][j] = (row < rows && cg < ncg) ? tile4[(size_t)row * ncg + cg] : make_float4(0.f, 0.f, 0.f, 0.f);
-          p = fmaf(x[g][j].x, b4[g].x, p); p = fmaf(x[g][j].y, b4[g].y, p);
-          p = fmaf(x[g][j].z, b4[g].z, p); p = fmaf(x[g][j].w, b4[g].w, p);
-        }
-        if (row < rows) pd[(size_t)row * pdw + ((G == 1) ? cg0 : tid)] = p;
-      }
-    }
-    __syncthreads();   // barrier 1: the stage is fully in registers
-    if (tid == 0 && k + S < my_tiles) issue(k + S);
-
-    // ---- phase A': row sums + per-row scalar math ------------------------------------------------------
-    {
-      float mysum = 0.f;
-      int jj = 0;
-      for (int row = warp; row < rows; row += K1_WARPS, jj++) {
-        const float* pr = pd + (size_t)row * pdw;
-        float a = 0.f;
-        for (int c = lane; c < pdw; c += 32) a += pr[c];
-        a = warp_sum(a);
-        if (lane == jj) mysum = a;
-      }
-      if (has) {
-        const float t = yy * (mysum + oo);
-        const float e = __expf(-fabsf(t));                 // in (0,1]
-        const float inv = __frcp_rn(1.f + e);
-        const float p = t >= 0.f ? inv : e * inv;          // sigmoid(y s)
-        const float qq = t >= 0.f ? e * inv : inv;         // 1 - p, no cancellation
-        // log1p(e) = -log(1/(1+e)); absolute error ~1e-7 per row, the objective only steers the line search
-        loss64 += (double)(ww * ((t >= 0.f ? 0.f : -t) - __logf(inv)));
-        r_s[buf * Rt + myrow] = -ww * yy * qq;             // w (p-1) y
-        sd_s[buf * Rt + myrow] = sqrtf(ww * p * qq);       // sqrt(d_i)
-      }
-    }
-    __syncthreads();   // barrier 2
-
-    // ---- phase B -----------------------------------------------------------------------------------
-    if (act) {
-      const float* rb = r_s + buf * Rt + sl * RT;
-      const float* sb = sd_s + buf * Rt + sl * RT;
-#pragma unroll
-      for (int g = 0; g < G; g++) {
-        const int cg = cg0 + g * K1_THREADS;
-        if (cg < ncg) {
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int j = 0; j < RT; j++) {
-            if (sl * RT + j < rows) {
-              const float rr = rb[j];
-              a.x = fmaf(x[g][j].x, rr, a.x); a.y = fmaf(x[g][j].y, rr, a.y);
-              a.z = fmaf(x[g][j].z, rr, a.z); a.w = fmaf(x[g][j].w, rr, a.w);
-            }
-          }
-          acc64[g][0] += (double)a.x; acc64[g][1] += (double)a.y; acc64[g][2] += (double)a.z; acc64[g][3] += (double)a.w;
-          if (emit) {
-            __nv_bfloat16* xt = Xt + (size_t)(row0 + sl * RT) * Dp + 4 * cg;
+          if (G == 1 || cg < ncg) {
+            __nv_bfloat16* xt = Xt + (size_t)(row0 + myrows0) * Dp + 4 * cg;
 #pragma unroll
             for (int j = 0; j < RT; j++) {
-              if (sl * RT + j < rows) {
+              if (full || myrows0 + j < rows) {
                 const float sd = sb[j];
                 __nv_bfloat162 lo = __floats2bfloat162_rn(x[g][j].x * sd, x[g][j].y * sd);
                 __nv_bfloat162 hi = __floats2bfloat162_rn(x[g][j].z * sd, x[g][j].w * sd);
@@ -297,7 +325,7 @@ k1_csr_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit) {
 struct K1Plan { int G, RT, nsl, S, rows_per_tile, ctas_per_sm; size_t smem; };
 
 static size_t k1_smem_bytes(int ldx, int Rt, int S, int pdw) {
-  return (size_t)S * Rt * ldx * 4 + (size_t)2 * Rt * pdw * 4 + (size_t)4 * Rt * 4 + 16 + 8 * 8 + 8 * 8 + 64;
+  return (size_t)S * Rt * ldx * 4 + (size_t)2 * Rt * pdw * 4 + (size_t)5 * Rt * 4 + 16 + 8 * 8 + 8 * 8 + 64;
 }
 
 // Tile shape for a given ldx.  G==1 (ldx <= 1024): RT=8 rows in registers, nsl row slices share the 256 threads,

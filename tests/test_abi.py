@@ -1,0 +1,60 @@
+"""CPU checks of the C-ABI boundary: the library loads, exports every symbol include/mlease_b200.h declares,
+and every compute entry point fails loudly without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_header_symbols_are_exported():
+    import mlease_b200
+    from mlease_b200._native import EXPORTED, SO_PATH
+    hdr = open(os.path.join(ROOT, "include", "mlease_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(mlease_[a-z_0-9]+)\s*\(", hdr)) - {"mlease_allreduce_fn"})
+    lib = C.CDLL(SO_PATH)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(EXPORTED) == declared, (sorted(set(declared) ^ set(EXPORTED)))
+    assert mlease_b200.lib().mlease_abi_version() == 1
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    import mlease_b200 as mb
+    with pytest.raises(mb.MleaseError, match="no CPU fallback"):
+        mb.AdmmSession(2, 10, [1.0])
+    with pytest.raises(mb.MleaseError, match="no CPU fallback"):
+        mb.score(np.zeros((2, 3), np.float32), np.zeros(4))
+    with pytest.raises(mb.MleaseError, match="no CPU fallback"):
+        mb.test_loglik([1, 0], [0.1, 0.2])
+    with pytest.raises(mb.MleaseError, match="no CPU fallback"):
+        mb.naive_train_dense(np.zeros((4, 3), np.float32), [0, 4], [1, 0, 1, 0], 1.0)
+
+
+def test_config_validation_happens_before_device_use():
+    import mlease_b200 as mb
+    with pytest.raises(mb.MleaseError, match="Only L1 and L2"):
+        mb.AdmmSession(2, 10, [1.0], regularizer=7)
+    with pytest.raises(mb.MleaseError, match="L1"):
+        mb.AdmmSession(2, 10, [1.0], regularizer=1)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ml-ease_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in txt.lower() or f == "build.py", os.path.join(dp, f)

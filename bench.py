@@ -186,6 +186,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = "cuda:%d" % local_rank
     if world > 1:
+        # keep stdout to the single JSON line: NCCL's version banner / debug lines go to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device(dev))
     P, n, D, L = args.partitions, args.rows, args.features, 1
     my_parts = shard_partitions(P, world, rank)

@@ -158,6 +158,42 @@ def test_admm_dense_config1_shape_matches_oracle_exact(mb):
     assert gap < 5e-2   # informational bound vs the loose-tolerance reference schedule (SURVEY 8c iii)
 
 
+def test_admm_sparse_config3_shape_multi_lambda(mb):
+    # BASELINE config 2 shape in small: sparse rows (1% nnz), multi-lambda {0.1,1,10} in one run, 2 partitions
+    P, n, D, nnz = 2, 6000, 1500, 15
+    rng = np.random.default_rng(77)
+    beta = rng.normal(size=D) / np.sqrt(nnz)
+    parts, rp_all, ci_all, v_all, y_all = [], [0], [], [], []
+    for p in range(P):
+        r = np.random.default_rng(1000 + p)
+        ci = np.stack([np.sort(r.choice(D, nnz, replace=False)) for _ in range(n)]).astype(np.int32)
+        v = r.normal(size=(n, nnz)).astype(np.float32)
+        s = (v * beta[ci]).sum(1) - 0.5
+        y = (r.random(n) < 1 / (1 + np.exp(-s))).astype(np.int32)
+        rp = np.arange(n + 1, dtype=np.int64) * nnz
+        parts.append((rp, ci.reshape(-1), v.reshape(-1), y))
+        ci_all.append(ci.reshape(-1)); v_all.append(v.reshape(-1)); y_all.append(y)
+    data = orc.Csr(np.arange(P * n + 1, dtype=np.int64) * nnz, np.concatenate(ci_all), np.concatenate(v_all), np.concatenate(y_all), n_features=D)
+    lambdas = [0.1, 1.0, 10.0]
+    ref = orc.admm_run(data, [0, n, 2 * n], lambdas, niters=6, mode="exact", nthreads=8, epsilon=0.0)
+    done, z, xs, us, st = _run_gpu_admm(mb, parts, D, lambdas, 6, csr=True, epsilon=0.0)
+    for l in range(3):
+        err = np.abs(z[l] - ref["z_hist"][-1, l]).max() / np.abs(ref["z_hist"][-1, l]).max()
+        assert err < 1e-5, (l, err, st)
+    assert st["not_converged"] == 0
+
+
+def test_naive_train_many_keys(mb):
+    # BASELINE config 4 shape in small: many independent per-key fits in lock-step batches
+    K, n, D = 300, 120, 24
+    X, y, w, o = _mk(K * n, D, seed=31)
+    krs = np.arange(K + 1) * n
+    ref, _, _ = orc.naive_train(orc.Csr.from_dense(X, y, w, o), krs, 1.0, mode="exact", nthreads=8)
+    got, skipped = mb.naive_train_dense(X, krs, y, 1.0, weight=w, offset=o)
+    assert not skipped.any()
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5
+
+
 def test_admm_stop_rule_and_options(mb):
     X, y, w, o = _mk(600, 8, seed=5)
     parts = [(X[:300], y[:300], w[:300], o[:300]), (X[300:], y[300:], w[300:], o[300:])]

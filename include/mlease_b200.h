@@ -99,6 +99,9 @@ int mlease_admm_begin(mlease_session* s);
 int mlease_admm_local_step(mlease_session* s, double* exchange_dev);
 int mlease_admm_consensus(mlease_session* s, const double* exchange_sum_dev, double* maxdiff, int32_t* stop);
 int mlease_admm_run(mlease_session* s, int32_t num_iters, mlease_allreduce_fn allreduce, void* ctx, int32_t* iters_done);
+/* One iteration of a single-process job (all num_blocks partitions resident): local_step + consensus on the session's own
+ * exchange buffer.  Lets a host job write the reference's iter-<i>/ files between iterations. */
+int mlease_admm_iterate(mlease_session* s, double* maxdiff, int32_t* stop);
 
 /* State readback (host buffers).  z: driver-side double z (:365-404); final model = float(z)
  * (models/LinearModel.java:697-720 toAvro).  After consensus of iteration i: x = the double x_p of iteration i

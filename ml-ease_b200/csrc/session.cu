@@ -748,6 +748,15 @@ int mlease_admm_run(mlease_session* s, int32_t num_iters, mlease_allreduce_fn al
   return 0;
 }
 
+int mlease_admm_iterate(mlease_session* s, double* maxdiff, int32_t* stop) {
+  if (!s) return fail(MLEASE_ERR_INVALID, "null session");
+  if (!s->begun) return fail(MLEASE_ERR_STATE, "mlease_admm_begin was not called");
+  if ((int)s->parts.size() != s->P)
+    return fail(MLEASE_ERR_STATE, "Some models failed! (" + std::to_string(s->parts.size()) + " of " + std::to_string(s->P) + " partitions present)");
+  if (int rc = mlease_admm_local_step(s, s->d_exch)) return rc;
+  return mlease_admm_consensus(s, s->d_exch, maxdiff, stop);
+}
+
 int mlease_get_z(mlease_session* s, int32_t l, double* out) {
   if (!s || !out || l < 0 || l >= s->L || !s->batch) return fail(MLEASE_ERR_INVALID, "bad argument");
   CK(cudaSetDevice(s->cfg.device));

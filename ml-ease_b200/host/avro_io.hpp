@@ -1,0 +1,107 @@
+// avro_io.hpp -- minimal Avro object-container codec for the job layer (null + deflate codecs, zig-zag varints,
+// schema-driven generic decode/encode incl. Pig-style ["null", T] unions).  Replaces the reference's use of
+// avro 1.7.6 + AvroHdfsFileReader/Writer (com/linkedin/mapred/Avro*.java) for local files.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace mlease_host {
+
+// ---------------------------------------------------------------- tiny JSON (schemas only)
+struct Json {
+  enum Kind { Null, Bool, Num, Str, Arr, Obj } kind = Null;
+  bool b = false;
+  double num = 0;
+  std::string str;
+  std::vector<Json> arr;
+  std::vector<std::pair<std::string, Json>> obj;
+  const Json* get(const std::string& k) const {
+    for (auto& kv : obj) if (kv.first == k) return &kv.second;
+    return nullptr;
+  }
+};
+Json json_parse(const std::string& text);
+std::string json_dump(const Json& j);
+
+// ---------------------------------------------------------------- schema + generic values
+struct Schema;
+using SchemaP = std::shared_ptr<Schema>;
+struct Schema {
+  enum Type { Null, Boolean, Int, Long, Float, Double, String, Bytes, Record, Array, Union, Map, Enum, Fixed } type = Null;
+  std::string name;                                   // records / enums / fixed
+  std::vector<std::pair<std::string, SchemaP>> fields;  // records
+  SchemaP items;                                      // arrays / map values
+  std::vector<SchemaP> branches;                      // unions
+  std::vector<std::string> symbols;                   // enums
+  int fixed_size = 0;
+  int field_index(const std::string& n) const {
+    for (size_t i = 0; i < fields.size(); i++) if (fields[i].first == n) return (int)i;
+    return -1;
+  }
+};
+SchemaP schema_from_json(const Json& j, std::map<std::string, SchemaP>& named);
+SchemaP schema_parse(const std::string& json_text);
+Json schema_to_json(const SchemaP& s, std::map<std::string, bool>& emitted);
+SchemaP schema_remove_union(const SchemaP& s);   // utils/Util.java:377-417 (Util.removeUnion)
+
+struct Value {
+  Schema::Type type = Schema::Null;
+  int64_t i = 0;       // boolean / int / long / enum index
+  double d = 0;        // float / double
+  std::string s;       // string / bytes / fixed
+  std::vector<Value> items;   // array elements, record fields (by index), map values (s = key in each item)
+  bool is_null() const { return type == Schema::Null; }
+  static Value null() { return Value(); }
+  static Value of_int(int64_t v) { Value x; x.type = Schema::Int; x.i = v; return x; }
+  static Value of_float(float v) { Value x; x.type = Schema::Float; x.d = v; return x; }
+  static Value of_double(double v) { Value x; x.type = Schema::Double; x.d = v; return x; }
+  static Value of_string(const std::string& v) { Value x; x.type = Schema::String; x.s = v; return x; }
+};
+
+// ---------------------------------------------------------------- container files
+class AvroReader {
+ public:
+  explicit AvroReader(const std::string& path);
+  const SchemaP& schema() const { return schema_; }
+  const std::string& schema_json() const { return schema_json_; }
+  bool next(Value& out);          // false at end of file
+  int64_t blocks_read() const { return blocks_; }
+ private:
+  bool load_block();
+  std::string data_;
+  size_t pos_ = 0;
+  std::string block_;
+  size_t bpos_ = 0;
+  int64_t remaining_ = 0, blocks_ = 0;
+  std::string sync_, codec_, schema_json_;
+  SchemaP schema_;
+};
+
+class AvroWriter {
+ public:
+  // codec: "null" or "deflate" (the reference's jobs write deflate, com/linkedin/mapred/AbstractAvroJob.java)
+  AvroWriter(const std::string& path, const std::string& schema_json, const std::string& codec = "deflate");
+  ~AvroWriter();
+  void append(const Value& v);
+  void close();
+  const SchemaP& schema() const { return schema_; }
+ private:
+  void flush_block();
+  std::string path_, codec_, buf_, out_;
+  SchemaP schema_;
+  std::string sync_;
+  int64_t count_ = 0;
+  bool closed_ = false;
+};
+
+// helpers
+std::vector<std::string> list_avro_files(const std::string& path);   // file, or *.avro / part-* files of a directory (sorted)
+void make_dirs(const std::string& path);
+bool path_exists(const std::string& path);
+void remove_tree(const std::string& path);
+
+}  // namespace mlease_host

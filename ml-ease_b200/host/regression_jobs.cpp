@@ -1,0 +1,779 @@
+// regression_jobs.cpp -- host-side mirror of the reference's job layer for the accelerated path, in C++ because
+// the reference's host language (Java) has no toolchain in this image.  Same job classes, same config keys, same
+// output directory layout and avro schemas; the arithmetic goes through the C ABI of include/mlease_b200.h.
+//
+//   Regression            jobs/Regression.java:37-80         Prepare -> AdmmTrain -> Test -> TestLoglik
+//   RegressionPrepare     jobs/RegressionPrepare.java:58-191
+//   RegressionAdmmTrain   jobs/RegressionAdmmTrain.java:130-522 (L2 branch)
+//   RegressionTest        jobs/RegressionTest.java:65-170
+//   RegressionTestLoglik  jobs/RegressionTestLoglik.java:57-201
+//   RegressionNaiveTrain  jobs/RegressionNaiveTrain.java:99-415 (+ jobs/PartitionIdAssigner.java:41-101)
+//   JobConfig             com/linkedin/mapred/JobConfig.java:50-224 (java .properties file)
+// Not mirrored: Hadoop job submission, HDFS, DistributedCache (local files only; is.local is implied).
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <unordered_map>
+
+#include "../../include/mlease_b200.h"
+#include "avro_io.hpp"
+
+using namespace mlease_host;
+
+namespace {
+
+thread_local std::string g_job_err;
+
+struct JobError : std::runtime_error { using std::runtime_error::runtime_error; };
+[[noreturn]] void io_error(const std::string& m) { throw JobError(m); }
+void ck(int rc) { if (rc != 0) io_error(std::string(mlease_last_error())); }
+
+// ------------------------------------------------------------------------------------------ JobConfig
+struct JobConfig {
+  std::map<std::string, std::string> kv;
+  static std::string trim(const std::string& s) {
+    size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? "" : s.substr(a, b - a + 1);
+  }
+  // java.util.Properties subset: key=value | key:value | key value, '#'/'!' comments, trailing '\' continuation
+  static JobConfig load(const std::string& file) {
+    std::ifstream f(file);
+    if (!f) io_error("cannot open job config " + file);
+    JobConfig c;
+    std::string line, acc;
+    while (std::getline(f, line)) {
+      std::string t = trim(line);
+      if (acc.empty() && (t.empty() || t[0] == '#' || t[0] == '!')) continue;
+      if (!t.empty() && t.back() == '\\') { acc += t.substr(0, t.size() - 1); continue; }
+      acc += t;
+      size_t p = acc.find_first_of("=: \t");
+      std::string k = p == std::string::npos ? acc : acc.substr(0, p);
+      std::string v = p == std::string::npos ? "" : acc.substr(p);
+      size_t q = v.find_first_not_of(" \t");
+      if (q != std::string::npos && (v[q] == '=' || v[q] == ':')) v = v.substr(q + 1);
+      c.kv[trim(k)] = trim(v);
+      acc.clear();
+    }
+    return c;
+  }
+  bool has(const std::string& k) const { return kv.count(k) > 0; }
+  std::string get(const std::string& k) const {
+    auto it = kv.find(k);
+    if (it == kv.end()) io_error("Key " + k + " is not in the job config");   // JobConfig.getString(key) on a missing key
+    return it->second;
+  }
+  std::string get(const std::string& k, const std::string& d) const { auto it = kv.find(k); return it == kv.end() ? d : it->second; }
+  int get_int(const std::string& k) const { return std::stoi(get(k)); }
+  int get_int(const std::string& k, int d) const { return has(k) ? std::stoi(get(k)) : d; }
+  double get_double(const std::string& k, double d) const { return has(k) ? std::stod(get(k)) : d; }
+  float get_float(const std::string& k, float d) const { return has(k) ? std::stof(get(k)) : d; }
+  bool get_bool(const std::string& k, bool d) const {
+    if (!has(k)) return d;
+    std::string v = get(k);
+    std::transform(v.begin(), v.end(), v.begin(), ::tolower);
+    return v == "true" || v == "1";
+  }
+  std::vector<std::string> get_list(const std::string& k, const std::string& sep = ",") const {
+    std::vector<std::string> out;
+    std::string v = get(k);
+    size_t st = 0;
+    while (true) {
+      size_t p = v.find(sep, st);
+      std::string tok = trim(v.substr(st, p == std::string::npos ? std::string::npos : p - st));
+      if (!tok.empty()) out.push_back(tok);
+      if (p == std::string::npos) break;
+      st = p + sep.size();
+    }
+    return out;
+  }
+};
+
+// ------------------------------------------------------------------------------------------ Java string semantics
+// Float.toString / String.valueOf(float): model keys "1.0", "1.0#3" (jobs/RegressionAdmmTrain.java:184,650)
+std::string java_float_to_string(float f) {
+  if (std::isnan(f)) return "NaN";
+  if (std::isinf(f)) return f > 0 ? "Infinity" : "-Infinity";
+  if (f == 0) return std::signbit(f) ? "-0.0" : "0.0";
+  char buf[64];
+  auto res = std::to_chars(buf, buf + sizeof(buf), f, std::chars_format::scientific);
+  std::string s(buf, res.ptr);
+  bool neg = s[0] == '-';
+  if (neg) s = s.substr(1);
+  size_t e = s.find('e');
+  std::string digits;
+  for (char c : s.substr(0, e)) if (c != '.') digits.push_back(c);
+  int ex = std::atoi(s.c_str() + e + 1);
+  std::string out;
+  if (ex >= -3 && ex < 7) {
+    if (ex >= 0) {
+      std::string ip = digits.substr(0, std::min<size_t>(digits.size(), ex + 1));
+      while ((int)ip.size() < ex + 1) ip.push_back('0');
+      out = ip + "." + (digits.size() > (size_t)ex + 1 ? digits.substr(ex + 1) : "0");
+    } else out = "0." + std::string(-ex - 1, '0') + digits;
+  } else out = digits.substr(0, 1) + "." + (digits.size() > 1 ? digits.substr(1) : "0") + "E" + std::to_string(ex);
+  return neg ? "-" + out : out;
+}
+int32_t java_string_hash(const std::string& s) { uint32_t h = 0; for (unsigned char c : s) h = 31u * h + c; return (int32_t)h; }
+
+// ------------------------------------------------------------------------------------------ schemas (src/main/avro/*.avsc)
+const char* FEATURE_FIELDS = "[{\"name\":\"name\",\"type\":\"string\"},{\"name\":\"term\",\"type\":\"string\"},{\"name\":\"value\",\"type\":\"float\"}]";
+std::string schema_prepare_output() {
+  return std::string("{\"type\":\"record\",\"name\":\"RegressionPrepareOutput\",\"namespace\":\"com.linkedin.mlease.regression.avro\",\"fields\":["
+                     "{\"name\":\"key\",\"type\":\"string\"},{\"name\":\"response\",\"type\":\"int\"},{\"name\":\"features\",\"type\":{\"type\":\"array\",\"items\":"
+                     "{\"type\":\"record\",\"name\":\"feature\",\"fields\":") + FEATURE_FIELDS + "}}},{\"name\":\"weight\",\"type\":\"float\"},{\"name\":\"offset\",\"type\":\"float\"}]}";
+}
+std::string schema_linear_model() {
+  return std::string("{\"type\":\"record\",\"name\":\"LinearModelAvro\",\"namespace\":\"com.linkedin.mlease.avro\",\"fields\":[{\"name\":\"key\",\"type\":\"string\"},"
+                     "{\"name\":\"model\",\"type\":{\"type\":\"array\",\"items\":{\"type\":\"record\",\"name\":\"feature\",\"fields\":") + FEATURE_FIELDS + "}}}]}";
+}
+std::string schema_train_output() {
+  return std::string("{\"type\":\"record\",\"name\":\"RegressionTrainOutput\",\"namespace\":\"com.linkedin.mlease.regression.avro\",\"fields\":[{\"name\":\"key\",\"type\":\"string\"},"
+                     "{\"name\":\"model\",\"type\":{\"type\":\"array\",\"items\":{\"type\":\"record\",\"name\":\"feature\",\"fields\":") + FEATURE_FIELDS + "}}},"
+                     "{\"name\":\"uplusx\",\"type\":{\"type\":\"array\",\"items\":{\"type\":\"record\",\"name\":\"feature1\",\"fields\":" + FEATURE_FIELDS + "}}}]}";
+}
+const char* SCHEMA_LAMBDA_RHO = "{\"type\":\"record\",\"name\":\"LambdaRhoMap\",\"namespace\":\"com.linkedin.mlease.regression.avro\",\"fields\":[{\"name\":\"lambda\",\"type\":\"float\"},{\"name\":\"rho\",\"type\":\"float\"}]}";
+const char* SCHEMA_SAMPLE_LOGLIK = "{\"type\":\"record\",\"name\":\"SampleTestLoglik\",\"namespace\":\"com.linkedin.mlease.regression.avro\",\"fields\":[{\"name\":\"lambda\",\"type\":\"string\"},{\"name\":\"iter\",\"type\":\"int\"},{\"name\":\"testLoglik\",\"type\":\"float\"}]}";
+const char* SCHEMA_TEST_LOGLIK = "{\"type\":\"record\",\"name\":\"RegressionTestLoglikOutput\",\"namespace\":\"com.linkedin.mlease.regression.avro\",\"fields\":[{\"name\":\"key\",\"type\":\"string\"},{\"name\":\"testLoglik\",\"type\":\"float\"},{\"name\":\"count\",\"type\":\"double\"}]}";
+const char* SCHEMA_PARTITION_ID = "{\"type\":\"record\",\"name\":\"Pair\",\"namespace\":\"org.apache.avro.mapred\",\"fields\":[{\"name\":\"key\",\"type\":\"string\"},{\"name\":\"value\",\"type\":\"int\"}]}";
+const std::string INTERCEPT = "(INTERCEPT)";
+
+// ------------------------------------------------------------------------------------------ generic record access
+double num_of(const Value& v) { return (v.type == Schema::Float || v.type == Schema::Double) ? v.d : (double)v.i; }
+const Value* field(const Value& rec, const Schema& s, const std::string& name) {
+  int i = s.field_index(name);
+  if (i < 0 || rec.items[i].is_null()) return nullptr;
+  return &rec.items[i];
+}
+// resolves the record schema behind unions
+const Schema& rec_schema(const SchemaP& s) {
+  const Schema* p = s.get();
+  while (p->type == Schema::Union) { const Schema* nx = nullptr; for (auto& b : p->branches) if (b->type != Schema::Null) { nx = b.get(); break; } p = nx; }
+  return *p;
+}
+const Schema& items_schema(const Schema& arr_field) {
+  const Schema* p = &arr_field;
+  while (p->type == Schema::Union) { const Schema* nx = nullptr; for (auto& b : p->branches) if (b->type != Schema::Null) { nx = b.get(); break; } p = nx; }
+  if (p->type != Schema::Array) io_error("features is not a list");
+  return rec_schema(p->items);
+}
+// utils/Util.java:309-337 getResponseAvro: click, then response, then label override; Boolean or Integer only
+int get_response(const Value& rec, const Schema& s) {
+  const Value* r = nullptr;
+  if (auto v = field(rec, s, "click")) r = v;
+  if (auto v = field(rec, s, "response")) r = v;
+  if (auto v = field(rec, s, "label")) r = v;
+  if (!r) io_error("Data should contain one field of the three: response, click or label!");
+  if (r->type == Schema::Boolean) return r->i ? 1 : 0;
+  if (r->type == Schema::Int) return (int)r->i;
+  io_error("Response/Click/Label column should be either boolean or int32!");
+}
+std::string feature_key(const std::string& name, const std::string& term) { return term.empty() ? name : name + "\x01" + term; }
+
+struct Dictionary {
+  std::unordered_map<std::string, int> idx;
+  std::vector<std::string> names;
+  int add(const std::string& n) { auto it = idx.find(n); if (it != idx.end()) return it->second; int i = (int)names.size(); idx.emplace(n, i); names.push_back(n); return i; }
+  int find(const std::string& n) const { auto it = idx.find(n); return it == idx.end() ? -1 : it->second; }
+};
+
+// one prepared record stream in CSR form (global dictionary ids)
+struct Rows {
+  std::vector<std::string> key;
+  std::vector<int32_t> response;
+  std::vector<float> weight, offset;
+  std::vector<int64_t> rowptr{0};
+  std::vector<int32_t> colidx;
+  std::vector<float> vals;
+  size_t n() const { return response.size(); }
+};
+
+void read_prepared(const std::string& path, Dictionary& dict, Rows& rows, bool binary_feature) {
+  auto files = list_avro_files(path);
+  if (files.empty()) io_error("no input files under " + path);
+  for (auto& f : files) {
+    AvroReader rd(f);
+    const Schema& s = rec_schema(rd.schema());
+    int fi = s.field_index("features");
+    if (fi < 0) io_error("features is null");
+    const Schema& fs = items_schema(*s.fields[fi].second);
+    int ni = fs.field_index("name"), ti = fs.field_index("term"), vi = fs.field_index("value");
+    Value rec;
+    while (rd.next(rec)) {
+      const Value* k = field(rec, s, "key");
+      rows.key.push_back(k ? (k->type == Schema::String ? k->s : std::to_string(k->i)) : "");
+      int resp = get_response(rec, s);
+      if (resp != 1 && resp != 0 && resp != -1) io_error("response = " + std::to_string(resp) + " (only 1, 0, -1 are allowed)");
+      rows.response.push_back(resp);
+      const Value* w = field(rec, s, "weight"); const Value* o = field(rec, s, "offset");
+      rows.weight.push_back(w ? (float)num_of(*w) : 1.0f);
+      rows.offset.push_back(o ? (float)num_of(*o) : 0.0f);
+      const Value& feats = rec.items[fi];
+      for (auto& fv : feats.items) {
+        const std::string& nm = fv.items[ni].s;
+        std::string tm = (ti >= 0 && !fv.items[ti].is_null()) ? fv.items[ti].s : "";
+        if (nm == INTERCEPT && tm.empty()) io_error("feature name cannot be (INTERCEPT)");
+        rows.colidx.push_back(dict.add(feature_key(nm, tm)));
+        rows.vals.push_back(binary_feature ? 1.0f : (float)num_of(fv.items[vi]));
+      }
+      rows.rowptr.push_back((int64_t)rows.colidx.size());
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ model files
+Value feature_value(const std::string& key, float v) {
+  Value r; r.type = Schema::Record; r.items.resize(3);
+  size_t p = key.find('\x01');
+  r.items[0] = Value::of_string(p == std::string::npos ? key : key.substr(0, p));
+  r.items[1] = Value::of_string(p == std::string::npos ? "" : key.substr(p + 1));
+  r.items[2] = Value::of_float(v);
+  return r;
+}
+// models/LinearModel.java:697-720 toAvro: intercept first, every value cast to float
+Value model_list(const Dictionary& dict, const float* coef /*[D+1], intercept last*/) {
+  Value a; a.type = Schema::Array;
+  const int D = (int)dict.names.size();
+  a.items.push_back(feature_value(INTERCEPT, coef[D]));
+  for (int k = 0; k < D; k++) a.items.push_back(feature_value(dict.names[k], coef[k]));
+  return a;
+}
+void write_linear_models(const std::string& path, const Dictionary& dict, const std::vector<std::pair<std::string, std::vector<float>>>& models) {
+  AvroWriter w(path, schema_linear_model());
+  for (auto& m : models) {
+    Value r; r.type = Schema::Record; r.items.resize(2);
+    r.items[0] = Value::of_string(m.first);
+    r.items[1] = model_list(dict, m.second.data());
+    w.append(r);
+  }
+  w.close();
+}
+// reads LinearModelAvro files -> key -> (feature key -> value), intercept under INTERCEPT
+std::map<std::string, std::unordered_map<std::string, double>> read_linear_models(const std::string& path) {
+  std::map<std::string, std::unordered_map<std::string, double>> out;
+  for (auto& f : list_avro_files(path)) {
+    AvroReader rd(f);
+    const Schema& s = rec_schema(rd.schema());
+    int ki = s.field_index("key"), mi = s.field_index("model");
+    Value rec;
+    while (rd.next(rec)) {
+      auto& m = out[rec.items[ki].s];
+      for (auto& fv : rec.items[mi].items) m[feature_key(fv.items[0].s, fv.items[1].s)] = fv.items[2].d;
+    }
+  }
+  return out;
+}
+
+struct Session {
+  mlease_session* s = nullptr;
+  ~Session() { if (s) mlease_session_destroy(s); }
+};
+
+std::vector<float> parse_lambdas(const JobConfig& c) {
+  std::vector<float> l;
+  for (auto& t : c.get_list("lambda")) l.push_back(std::stof(t));   // Float.parseFloat (:166)
+  return l;
+}
+
+// driver-side per-iteration test log-likelihood (jobs/RegressionAdmmTrain.java:766-811): double throughout,
+// first test file only, at most 1e6 records, divides by sum of weights
+double sample_test_loglik(const Rows& t, const Dictionary& dict, const std::vector<int>& test2model, const std::vector<double>& z) {
+  const int D = (int)dict.names.size();
+  double ll = 0, n = 0;
+  size_t lim = std::min<size_t>(t.n(), 1000000);
+  for (size_t i = 0; i < lim; i++) {
+    double xb = -std::log(1 - 1 + 1 * std::exp(-z[D]));
+    for (int64_t j = t.rowptr[i]; j < t.rowptr[i + 1]; j++) { int m = test2model[t.colidx[j]]; if (m >= 0) xb += z[m] * (double)t.vals[j]; }
+    xb += (double)t.offset[i];
+    ll += (t.response[i] == 1) ? -std::log1p(std::exp(-xb)) * t.weight[i] : -std::log1p(std::exp(xb)) * t.weight[i];
+    n += t.weight[i];
+  }
+  return ll / n;
+}
+
+// raw (unprepared) records -> Rows; used by Test and by the per-iteration loglik
+void read_raw(const std::string& file, Dictionary& dict, Rows& rows, bool binary_feature) {
+  AvroReader rd(file);
+  const Schema& s = rec_schema(rd.schema());
+  int fi = s.field_index("features");
+  if (fi < 0) io_error("features is null");
+  const Schema& fs = items_schema(*s.fields[fi].second);
+  int ni = fs.field_index("name"), ti = fs.field_index("term"), vi = fs.field_index("value");
+  Value rec;
+  while (rd.next(rec)) {
+    int resp = get_response(rec, s);
+    if (resp != 1 && resp != 0 && resp != -1) io_error("response = " + std::to_string(resp));
+    rows.key.push_back("");
+    rows.response.push_back(resp);
+    const Value* w = field(rec, s, "weight"); const Value* o = field(rec, s, "offset");
+    rows.weight.push_back(w ? (float)num_of(*w) : 1.0f);
+    rows.offset.push_back(o ? (float)num_of(*o) : 0.0f);
+    if (rec.items[fi].is_null()) io_error("features is null");
+    for (auto& fv : rec.items[fi].items) {
+      if (fv.items[ni].is_null()) io_error("name is null");
+      std::string tm = (ti >= 0 && !fv.items[ti].is_null()) ? fv.items[ti].s : "";
+      rows.colidx.push_back(dict.add(feature_key(fv.items[ni].s, tm)));
+      rows.vals.push_back(binary_feature ? 1.0f : (float)num_of(fv.items[vi]));
+    }
+    rows.rowptr.push_back((int64_t)rows.colidx.size());
+  }
+}
+
+// ============================================================================================ RegressionPrepare
+// jobs/RegressionPrepare.java:95-191.  map.key set -> key = data[map.key].toString() (bit-exact); otherwise the reference
+// draws floor(Math.random()*nblocks) from an UNSEEDED generator (:112) which cannot be reproduced: here a splitmix64 stream
+// seeded by `random.seed` (default 0) plays that role, and positives are replicated onto consecutive partitions (:172-186).
+struct SplitMix { uint64_t s; double next() { uint64_t z = (s += 0x9E3779B97F4A7C15ULL); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; z ^= z >> 31; return (z >> 11) * (1.0 / 9007199254740992.0); } };
+
+void run_prepare(const JobConfig& c) {
+  const std::string mapkey = c.get("map.key", "");
+  const int nblocks = c.get_int("num.blocks", 0);
+  const int reps = c.get_int("num.click.replicates", 1);
+  const bool ignore_value = c.get_bool("binary.feature", false);
+  const std::string out = c.get("output.path");
+  SplitMix rng{(uint64_t)c.get_double("random.seed", 0)};
+  auto files = list_avro_files(c.get("input.paths"));
+  if (files.empty()) io_error("no input under " + c.get("input.paths"));
+  AvroWriter w(out + "/part-00000.avro", schema_prepare_output());
+  for (auto& f : files) {
+    AvroReader rd(f);
+    const Schema& s = rec_schema(rd.schema());
+    int fi = s.field_index("features");
+    Value rec;
+    while (rd.next(rec)) {
+      std::string key;
+      if (!mapkey.empty()) {
+        const Value* k = field(rec, s, mapkey);
+        if (!k) io_error("map.key is wrongly specified! No such key exists in some lines of the data!");
+        key = k->type == Schema::String ? k->s : (k->type == Schema::Float || k->type == Schema::Double) ? std::to_string(k->d) : std::to_string(k->i);
+      } else {
+        key = std::to_string((int)std::floor(rng.next() * nblocks));
+      }
+      const int response = get_response(rec, s);
+      if (fi < 0 || rec.items[fi].is_null()) io_error("features is null");
+      const Schema& fs = items_schema(*s.fields[fi].second);
+      int ni = fs.field_index("name"), ti = fs.field_index("term"), vi = fs.field_index("value");
+      Value feats; feats.type = Schema::Array;
+      for (auto& fv : rec.items[fi].items) {
+        if (ni < 0 || fv.items[ni].is_null()) io_error("name is null");
+        Value r; r.type = Schema::Record; r.items.resize(3);
+        r.items[0] = Value::of_string(fv.items[ni].s);
+        r.items[1] = Value::of_string((ti >= 0 && !fv.items[ti].is_null()) ? fv.items[ti].s : "");
+        r.items[2] = Value::of_float(ignore_value ? 1.0f : (float)num_of(fv.items[vi]));   // :142-146
+        feats.items.push_back(r);
+      }
+      double weight = 1.0;
+      if (auto wv = field(rec, s, "weight")) weight = num_of(*wv);
+      if (auto rv = field(rec, s, "response")) { if (num_of(*rv) == 1) weight = weight / reps; }   // tests field `response` (:159)
+      double offset = 0.0;
+      if (auto ov = field(rec, s, "offset")) offset = num_of(*ov);
+      Value o; o.type = Schema::Record; o.items.resize(5);
+      o.items[1] = Value::of_int(response); o.items[2] = feats;
+      o.items[3] = Value::of_float((float)weight); o.items[4] = Value::of_float((float)offset);
+      if (mapkey.empty() && response == 1) {
+        int pid = std::stoi(key);
+        for (int i = 0; i < reps; i++) {
+          if (pid >= nblocks) pid -= nblocks;
+          o.items[0] = Value::of_string(std::to_string(pid));
+          w.append(o);
+          pid++;
+        }
+      } else {
+        o.items[0] = Value::of_string(key);
+        w.append(o);
+      }
+    }
+  }
+  w.close();
+}
+
+// ============================================================================================ RegressionAdmmTrain
+void run_admm_train(const JobConfig& c) {
+  const std::string out = c.get("output.base.path");
+  const int nblocks = c.get_int("num.blocks");
+  const int niter = c.get_int("num.iters", 10);
+  const int reg = c.get_int("regularizer");
+  if (reg != 1 && reg != 2) io_error("Only L1 and L2 regularization supported!");
+  const bool ignore_value = c.get_bool("binary.feature", false);
+  std::vector<float> lambdas = parse_lambdas(c);
+  const int L = (int)lambdas.size();
+  std::vector<float> rhos;
+  if (c.has("rho")) {
+    for (auto& t : c.get_list("rho")) rhos.push_back(std::stof(t));
+    if ((int)rhos.size() != L) io_error("The number of rho's should be exactly the same as the number of lambda's. OR: don't claim rho!");
+  } else for (float l : lambdas) rhos.push_back(l <= 100 ? 1.0f : 10.0f);
+  if (c.get_float("initialize.boost.rate", 0) > 0) io_error("initialize.boost.rate > 0 is not on the accelerated path yet (SURVEY 8f-2)");
+  if (!c.get("lambda.map", "").empty()) io_error("lambda.map files are not wired into the host job yet (the C ABI accepts a per-feature lambda_map)");
+
+  Dictionary dict;
+  Rows rows;
+  read_prepared(c.get("input.paths", out + "/tmp-data"), dict, rows, ignore_value);
+  const int D = (int)dict.names.size(), Dt = D + 1;
+
+  // group rows by partition id (AdmmMapper: Integer.parseInt(key), :558; AdmmPartitioner range check :585-588)
+  std::vector<std::vector<size_t>> by_part(nblocks);
+  for (size_t i = 0; i < rows.n(); i++) {
+    int p;
+    try { p = std::stoi(rows.key[i]); } catch (...) { io_error("For input string: \"" + rows.key[i] + "\" (partition key must be an int)"); }
+    if (p < 0 || p >= nblocks) io_error("Map key is wrong! key has to be in the range of [0,numPartitions-1].");
+    by_part[p].push_back(i);
+  }
+  for (int p = 0; p < nblocks; p++) if (by_part[p].empty()) io_error("Some models failed!");   // an empty reducer emits no model (utils/LinearModelUtils.java:77-83)
+
+  mlease_admm_config cfg; std::memset(&cfg, 0, sizeof(cfg));
+  cfg.device = c.get_int("gpu.device", 0); cfg.num_blocks = nblocks; cfg.num_features = D; cfg.num_lambdas = L;
+  cfg.lambdas = lambdas.data(); cfg.rhos = rhos.data(); cfg.regularizer = reg;
+  cfg.penalize_intercept = c.get_bool("penalize.intercept", false);
+  cfg.aggressive_decay = c.get_bool("aggressive.liblinear.epsilon.decay", false);
+  cfg.binary_feature = ignore_value;
+  cfg.epsilon = c.get_double("epsilon", 0.0001);
+  cfg.rho_adapt_coefficient = c.get_float("rho.adapt.coefficient", 0);
+  Session S;
+  ck(mlease_session_create(&cfg, &S.s));
+  for (int p = 0; p < nblocks; p++) {
+    std::vector<int64_t> rp{0}; std::vector<int32_t> ci; std::vector<float> vv, ww, oo; std::vector<int32_t> rr;
+    for (size_t i : by_part[p]) {
+      for (int64_t j = rows.rowptr[i]; j < rows.rowptr[i + 1]; j++) { ci.push_back(rows.colidx[j]); vv.push_back(rows.vals[j]); }
+      rp.push_back((int64_t)ci.size()); rr.push_back(rows.response[i]); ww.push_back(rows.weight[i]); oo.push_back(rows.offset[i]);
+    }
+    ck(mlease_add_partition_csr(S.s, p, (int64_t)rr.size(), rp.data(), ci.data(), vv.data(), rr.data(), ww.data(), oo.data()));
+  }
+
+  // lambda-rho map (:200-201, :721-734)
+  {
+    AvroWriter w(out + "/lambda-rho/part-r-00000.avro", SCHEMA_LAMBDA_RHO);
+    for (int l = 0; l < L; l++) { Value r; r.type = Schema::Record; r.items = {Value::of_float(lambdas[l]), Value::of_float(rhos[l])}; w.append(r); }
+    w.close();
+  }
+  // optional per-iteration test loglik on the first file under test.path (:204-232)
+  Rows test; std::vector<int> test2model; bool test_per_iter = false;
+  {
+    std::string tp = c.get("test.path", "");
+    auto tf = tp.empty() ? std::vector<std::string>() : list_avro_files(tp);
+    if (!tf.empty()) {
+      Dictionary td; read_raw(tf[0], td, test, ignore_value);
+      test2model.resize(td.names.size());
+      for (size_t k = 0; k < td.names.size(); k++) test2model[k] = dict.find(td.names[k]);
+      test_per_iter = test.n() > 0;
+    }
+  }
+  float best_loglik = -9999999.0f;
+  auto models_z = [&](bool as_float) {
+    std::vector<std::pair<std::string, std::vector<float>>> m;
+    for (int l = 0; l < L; l++) {
+      std::vector<double> z(Dt); ck(mlease_get_z(S.s, l, z.data()));
+      std::vector<float> zf(Dt); for (int k = 0; k < Dt; k++) zf[k] = (float)z[k];
+      m.emplace_back(java_float_to_string(lambdas[l]), zf);
+    }
+    (void)as_float;
+    return m;
+  };
+  ck(mlease_admm_begin(S.s));
+  int i;
+  for (i = 1; i <= niter; i++) {
+    const std::string it = out + "/iter-" + std::to_string(i);
+    // u of this iteration (empty file at i == 1, :310-313) and z as the reducers see it (:330-331)
+    {
+      std::vector<std::pair<std::string, std::vector<float>>> us;
+      if (i > 1)
+        for (int p = 0; p < nblocks; p++) for (int l = 0; l < L; l++) {
+          std::vector<float> u(Dt); ck(mlease_get_u(S.s, p, l, u.data()));
+          us.emplace_back(java_float_to_string(lambdas[l]) + "#" + std::to_string(p), u);
+        }
+      write_linear_models(it + "/u/part-r-00000.avro", dict, us);
+      if (i > 1) write_linear_models(it + "/init-value/part-r-00000.avro", dict, models_z(true));
+      else {   // z = {lambda -> new LinearModel()} (:184): one record per lambda holding only the zero intercept
+        Dictionary none; std::vector<std::pair<std::string, std::vector<float>>> z0;
+        for (int l = 0; l < L; l++) z0.emplace_back(java_float_to_string(lambdas[l]), std::vector<float>(1, 0.f));
+        write_linear_models(it + "/init-value/part-r-00000.avro", none, z0);
+      }
+    }
+    double maxdiff = 0; int32_t stop = 0;
+    ck(mlease_admm_iterate(S.s, &maxdiff, &stop));
+    // reducer outputs (:706-711)
+    {
+      AvroWriter w(it + "/model/part-r-00000.avro", schema_train_output());
+      for (int p = 0; p < nblocks; p++) for (int l = 0; l < L; l++) {
+        std::vector<double> x(Dt); std::vector<float> xf(Dt), ux(Dt);
+        ck(mlease_get_x(S.s, p, l, x.data())); ck(mlease_get_uplusx(S.s, p, l, ux.data()));
+        for (int k = 0; k < Dt; k++) xf[k] = (float)x[k];
+        Value r; r.type = Schema::Record; r.items.resize(3);
+        r.items[0] = Value::of_string(java_float_to_string(lambdas[l]) + "#" + std::to_string(p));
+        r.items[1] = model_list(dict, xf.data()); r.items[2] = model_list(dict, ux.data());
+        w.append(r);
+      }
+      w.close();
+    }
+    fprintf(stderr, "[RegressionAdmmTrain] iteration %d: max |z - z_prev| = %.6g\n", i, maxdiff);
+    if (c.get_bool("remove.tmp.dir", false) && i >= 2) remove_tree(out + "/iter-" + std::to_string(i - 1));
+    if (test_per_iter) {   // updateLogLikBestModel (:812-845)
+      AvroWriter w(out + "/sample-test-loglik/iteration-" + std::to_string(i) + ".avro", SCHEMA_SAMPLE_LOGLIK);
+      for (int l = 0; l < L; l++) {
+        std::vector<double> z(Dt); ck(mlease_get_z(S.s, l, z.data()));
+        double ll = sample_test_loglik(test, dict, test2model, z);
+        Value r; r.type = Schema::Record; r.items = {Value::of_string(java_float_to_string(lambdas[l])), Value::of_int(i), Value::of_float((float)ll)};
+        w.append(r);
+        if (ll > best_loglik) {
+          remove_tree(out + "/best-model");
+          std::vector<float> zf(Dt); for (int k = 0; k < Dt; k++) zf[k] = (float)z[k];
+          write_linear_models(out + "/best-model/best-iteration-" + std::to_string(i) + ".avro", dict, {{java_float_to_string(lambdas[l]), zf}});
+          best_loglik = (float)ll;
+        }
+      }
+      w.close();
+    }
+    if (stop) break;
+  }
+  write_linear_models(out + "/final-model/part-r-00000.avro", dict, models_z(true));
+  if (c.get_bool("remove.tmp.dir", false)) {
+    for (int j = std::min(i, niter) - 2; j <= std::min(i, niter); j++) remove_tree(out + "/iter-" + std::to_string(j));
+    remove_tree(out + "/tmp-data");
+  }
+}
+
+// ============================================================================================ RegressionTest
+void run_test(const JobConfig& c) {
+  const std::string in = c.get("input.paths", "");
+  if (in.empty()) return;   // "test.input.paths is empty! So no test will be done!"
+  const std::string outBase = c.get("output.base.path");
+  const bool ignore_value = c.get_bool("binary.feature", false);
+  const std::string modelBase = c.get("model.base.path");
+  auto test_one = [&](const std::string& modelPath, const std::string& modelKey, const std::string& outPath) {
+    auto models = read_linear_models(modelPath);
+    const std::unordered_map<std::string, double>* m = nullptr;
+    if (!modelKey.empty()) { auto it = models.find(modelKey); if (it == models.end()) io_error("no model for lambda " + modelKey + " under " + modelPath); m = &it->second; }
+    else { if (models.empty()) io_error("no best-model"); m = &models.begin()->second; }
+    int part = 0;
+    for (auto& f : list_avro_files(in)) {
+      Dictionary td; Rows rows;
+      read_raw(f, td, rows, ignore_value);
+      const int D = (int)td.names.size();
+      std::vector<double> coef(D + 1, 0.0);
+      for (int k = 0; k < D; k++) { auto it = m->find(td.names[k]); if (it != m->end()) coef[k] = it->second; }
+      { auto it = m->find(INTERCEPT); coef[D] = it == m->end() ? 0.0 : it->second; }
+      std::vector<float> pred(rows.n());
+      if (rows.n())
+        ck(mlease_score(c.get_int("gpu.device", 0), nullptr, D, (int64_t)rows.n(), rows.rowptr.data(), rows.colidx.data(), rows.vals.data(), 0,
+                        rows.offset.data(), coef.data(), 1, ignore_value ? 1 : 0, pred.data()));
+      // output = input fields (unions removed, utils/Util.java:377-417) + pred (jobs/RegressionTest.java:198-236)
+      AvroReader rd(f);
+      SchemaP os = std::make_shared<Schema>(*schema_remove_union(rd.schema()));
+      os->name = "AdmmTestOutput";
+      auto pf = std::make_shared<Schema>(); pf->type = Schema::Float;
+      os->fields.emplace_back("pred", pf);
+      std::map<std::string, bool> em;
+      char nm[64]; snprintf(nm, sizeof nm, "/part-r-%05d.avro", part++);
+      AvroWriter w(outPath + nm, json_dump(schema_to_json(os, em)));
+      Value rec; size_t i = 0;
+      while (rd.next(rec)) { rec.items.push_back(Value::of_float(pred[i++])); w.append(rec); }
+      w.close();
+    }
+  };
+  for (auto& lam : c.get_list("lambda"))
+    test_one(modelBase + "/final-model", java_float_to_string(std::stof(lam)), outBase + "/lambda-" + lam);
+  if (path_exists(modelBase + "/best-model")) test_one(modelBase + "/best-model", "", outBase + "/best-model");
+}
+
+// ============================================================================================ RegressionTestLoglik
+void run_test_loglik(const JobConfig& c) {
+  if (!c.get_bool("get.test.loglik", true)) return;
+  const std::string inBase = c.get("input.base.paths"), outBase = c.get("output.base.path");
+  auto one = [&](const std::string& inPath, const std::string& outPath) {
+    if (!path_exists(inPath)) return;
+    std::vector<int32_t> resp; std::vector<float> pred, weight;
+    for (auto& f : list_avro_files(inPath)) {
+      AvroReader rd(f);
+      const Schema& s = rec_schema(rd.schema());
+      Value rec;
+      while (rd.next(rec)) {
+        const Value* r = field(rec, s, "response"); const Value* p = field(rec, s, "pred"); const Value* w = field(rec, s, "weight");
+        if (!r || !p) io_error("response/pred is null");
+        resp.push_back((int)num_of(*r)); pred.push_back((float)num_of(*p)); weight.push_back(w ? (float)num_of(*w) : 1.0f);
+      }
+    }
+    if (resp.empty()) return;
+    float ll; double cnt;
+    // one combiner call per map task; local runs have one split per file -> combiner_block = everything
+    ck(mlease_test_loglik(c.get_int("gpu.device", 0), nullptr, (int64_t)resp.size(), resp.data(), pred.data(), weight.data(), (int64_t)resp.size(), &ll, &cnt));
+    AvroWriter w(outPath + "/part-r-00000.avro", SCHEMA_TEST_LOGLIK);
+    Value r; r.type = Schema::Record; r.items = {Value::of_string("averageTestLoglik"), Value::of_float(ll), Value::of_double(cnt)};
+    w.append(r); w.close();
+  };
+  if (c.has("lambda"))
+    for (auto& lam : c.get_list("lambda")) one(inBase + "/lambda-" + lam, outBase + "/lambda-" + lam + "/_loglik");
+  one(inBase + "/best-model", outBase + "/best-model/_loglik");
+}
+
+// ============================================================================================ RegressionNaiveTrain
+// deterministic partition ids: sorted Utf8 order of "<lambda>#<key>" (single reducer), jobs/PartitionIdAssigner.java:79-88
+std::map<std::string, int> assign_partition_ids(const std::set<std::string>& keys, const std::vector<float>& lambdas) {
+  std::map<std::string, int> ids;
+  for (float l : lambdas) for (auto& k : keys) ids[java_float_to_string(l) + "#" + k] = 0;
+  int n = 0; for (auto& kv : ids) kv.second = n++;
+  return ids;
+}
+
+void run_naive_train(const JobConfig& c) {
+  const std::string out = c.get("output.base.path");
+  const bool heavy = c.get_bool("heavy.per.item.train", false);
+  const bool mean = c.get_bool("compute.model.mean", true);
+  const int nblocks = mean ? c.get_int("num.blocks") : -1;
+  const bool ignore_value = c.get_bool("binary.feature", false);
+  if (ignore_value) io_error("binary.feature needs CSR input; the dense NaiveTrain path does not support it");
+  if (!c.get("lambda.map", "").empty()) io_error("lambda.map files are not wired into the host job yet");
+  std::set<float> lambda_set; for (auto& t : c.get_list("lambda")) lambda_set.insert(std::stof(t));
+  std::vector<float> lambdas(lambda_set.begin(), lambda_set.end());
+  Dictionary dict; Rows rows;
+  read_prepared(c.get("input.paths", out + "/tmp-data"), dict, rows, false);
+  const int D = (int)dict.names.size(), Dt = D + 1;
+  std::map<std::string, std::vector<size_t>> by_key;
+  for (size_t i = 0; i < rows.n(); i++) by_key[rows.key[i]].push_back(i);
+  if (heavy) {
+    std::set<std::string> ks; for (auto& kv : by_key) ks.insert(kv.first);
+    AvroWriter w(out + "/partitionIds/part-r-00000.avro", SCHEMA_PARTITION_ID);
+    for (auto& kv : assign_partition_ids(ks, lambdas)) { Value r; r.type = Schema::Record; r.items = {Value::of_string(kv.first), Value::of_int(kv.second)}; w.append(r); }
+    w.close();
+  }
+  // dense gather (features absent from a row are 0; a feature absent from a key is an all-zero column -> coefficient = prior mean)
+  const int K = (int)by_key.size();
+  std::vector<int64_t> krs{0}; std::vector<std::string> knames;
+  std::vector<float> X((size_t)rows.n() * D, 0.f), ww, oo; std::vector<int32_t> rr;
+  size_t r = 0;
+  for (auto& kv : by_key) {
+    knames.push_back(kv.first);
+    for (size_t i : kv.second) {
+      for (int64_t j = rows.rowptr[i]; j < rows.rowptr[i + 1]; j++) X[r * D + rows.colidx[j]] += rows.vals[j];
+      rr.push_back(rows.response[i]); ww.push_back(rows.weight[i]); oo.push_back(rows.offset[i]); r++;
+    }
+    krs.push_back((int64_t)r);
+  }
+  std::vector<std::pair<std::string, std::vector<float>>> models;
+  std::map<std::string, std::pair<int, std::vector<double>>> sums;
+  for (float lam : lambdas) {
+    std::vector<double> m((size_t)K * Dt); std::vector<int32_t> skipped(K);
+    ck(mlease_naive_train_dense(c.get_int("gpu.device", 0), nullptr, K, D, krs.data(), X.data(), D, rr.data(), ww.data(), oo.data(), lam, nullptr,
+                                c.get_float("prior.mean", 0.0f), c.get_bool("penalize.intercept", false), c.get_bool("has.intercept", true),
+                                c.get_int("data.size.threshold", 0), m.data(), skipped.data()));
+    const std::string ls = java_float_to_string(lam);
+    auto& acc = sums[ls]; acc.second.assign(Dt, 0.0);
+    for (int k = 0; k < K; k++) {
+      if (skipped[k]) continue;
+      std::vector<float> mf(Dt); for (int j = 0; j < Dt; j++) mf[j] = (float)m[(size_t)k * Dt + j];
+      models.emplace_back(ls + "#" + knames[k], mf);
+      acc.first++;
+      if (mean) for (int j = 0; j < Dt; j++) acc.second[j] = 1.0 * acc.second[j] + (1.0 / nblocks) * (double)mf[j];   // cons/MeanLinearModelConsumer.java:59-63
+    }
+  }
+  write_linear_models(out + "/models/part-r-00000.avro", dict, models);
+  if (mean) {
+    int total = 0; for (auto& kv : sums) total += kv.second.first;
+    if (total != (int)lambdas.size() * nblocks) throw std::runtime_error("Some models failed!");
+    std::vector<std::pair<std::string, std::vector<float>>> fin;
+    for (auto& kv : sums) { std::vector<float> f(Dt); for (int j = 0; j < Dt; j++) f[j] = (float)kv.second.second[j]; fin.emplace_back(kv.first, f); }
+    write_linear_models(out + "/final-model/part-r-00000.avro", dict, fin);
+  }
+  if (c.get_bool("remove.tmp.dir", true)) remove_tree(out + "/tmp-data");
+}
+
+// ============================================================================================ Regression (chain)
+void run_regression(const JobConfig& c) {
+  const std::string out = c.get("output.base.path");
+  if (c.get_bool("force.output.overwrite", false)) remove_tree(out);
+  JobConfig cp = c; cp.kv["output.path"] = out + "/tmp-data";
+  run_prepare(cp);
+  JobConfig ct = c; ct.kv["input.paths"] = out + "/tmp-data";
+  run_admm_train(ct);
+  if (c.has("test.path")) {
+    JobConfig cte = c; cte.kv["input.paths"] = c.get("test.path"); cte.kv["model.base.path"] = out; cte.kv["output.base.path"] = out + "/test";
+    run_test(cte);
+    JobConfig cl = c; cl.kv["input.base.paths"] = out + "/test"; cl.kv["output.base.path"] = out + "/test";
+    run_test_loglik(cl);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+const char* mlease_job_last_error(void) { return g_job_err.c_str(); }
+
+// job_class: Regression | RegressionPrepare | RegressionAdmmTrain | RegressionTest | RegressionTestLoglik | RegressionNaiveTrain
+// (the README's names AdmmPrepare / AdmmTrain / AdmmTest / AdmmTestLoglik / NaiveTrain are accepted as aliases).
+int mlease_job_run(const char* job_class, const char* config_path) {
+  try {
+    JobConfig c = JobConfig::load(config_path);
+    std::string j = job_class;
+    if (j == "Regression") run_regression(c);
+    else if (j == "RegressionPrepare" || j == "AdmmPrepare") run_prepare(c);
+    else if (j == "RegressionAdmmTrain" || j == "AdmmTrain") run_admm_train(c);
+    else if (j == "RegressionTest" || j == "AdmmTest") run_test(c);
+    else if (j == "RegressionTestLoglik" || j == "AdmmTestLoglik") run_test_loglik(c);
+    else if (j == "RegressionNaiveTrain" || j == "NaiveTrain") run_naive_train(c);
+    else { g_job_err = "unknown job class " + j; return 1; }
+    return 0;
+  } catch (const std::exception& e) {
+    g_job_err = e.what();
+    return 2;
+  }
+}
+
+// deterministic host logic exposed for bit-exact tests against the oracle -----------------------------------------
+// RegressionPrepare key/weight rule for one record stream (jobs/RegressionPrepare.java:154-186); base_key is either the
+// map.key value or the externally drawn floor(random*nblocks).
+int mlease_prepare_keys(int64_t nrows, const int32_t* base_key, const int32_t* response, const double* weight_in, int32_t nblocks,
+                        int32_t num_click_replicates, int32_t random_key_mode, int32_t* out_keys, int32_t* out_nkeys, float* out_weight) {
+  for (int64_t i = 0; i < nrows; i++) {
+    double w = weight_in ? weight_in[i] : 1.0;
+    if (response[i] == 1) w = w / num_click_replicates;
+    out_weight[i] = (float)w;
+    int32_t* ok = out_keys + i * num_click_replicates;
+    if (random_key_mode && response[i] == 1) {
+      int pid = base_key[i];
+      for (int c = 0; c < num_click_replicates; c++) { if (pid >= nblocks) pid -= nblocks; ok[c] = pid; pid++; }
+      out_nkeys[i] = num_click_replicates;
+    } else { ok[0] = base_key[i]; out_nkeys[i] = 1; }
+  }
+  return 0;
+}
+// PartitionIdAssigner ids + NaivePartitioner partitions (jobs/PartitionIdAssigner.java:79-88; jobs/RegressionNaiveTrain.java:269-283)
+int mlease_partition_ids(int32_t nkeys, const char* keys_packed, const float* lambdas, int32_t L, int32_t num_reducers, int32_t* out_ids,
+                         int32_t* out_partition, int32_t* out_hash_partition) {
+  std::vector<std::string> keys; const char* p = keys_packed;
+  for (int i = 0; i < nkeys; i++) { keys.emplace_back(p); p += keys.back().size() + 1; }
+  std::set<std::string> ks(keys.begin(), keys.end());
+  std::vector<float> ls(lambdas, lambdas + L);
+  auto ids = assign_partition_ids(ks, ls);
+  for (int l = 0; l < L; l++)
+    for (int i = 0; i < nkeys; i++) {
+      std::string full = java_float_to_string(lambdas[l]) + "#" + keys[i];
+      int id = ids[full];
+      out_ids[(size_t)l * nkeys + i] = id;
+      if (out_partition) out_partition[(size_t)l * nkeys + i] = id % num_reducers;
+      if (out_hash_partition) { int32_t h = java_string_hash(full); int32_t a = h == INT32_MIN ? h : std::abs(h); out_hash_partition[(size_t)l * nkeys + i] = a % num_reducers; }
+    }
+  return 0;
+}
+int mlease_java_float_to_string(float f, char* buf, int32_t buflen) {
+  std::string s = java_float_to_string(f);
+  if ((int)s.size() + 1 > buflen) return 1;
+  std::memcpy(buf, s.c_str(), s.size() + 1);
+  return 0;
+}
+// avro helpers for tests: decode a container file into CSR arrays is done in Python; here: count + re-encode round trip
+int mlease_avro_copy(const char* in_path, const char* out_path, const char* codec, int64_t* nrecords, int64_t* nblocks) {
+  try {
+    AvroReader rd(in_path);
+    AvroWriter w(out_path, rd.schema_json(), codec);
+    Value v; int64_t n = 0;
+    while (rd.next(v)) { w.append(v); n++; }
+    w.close();
+    if (nrecords) *nrecords = n;
+    if (nblocks) *nblocks = rd.blocks_read();
+    return 0;
+  } catch (const std::exception& e) { g_job_err = e.what(); return 2; }
+}
+}  // extern "C"

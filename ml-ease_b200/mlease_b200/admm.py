@@ -102,6 +102,12 @@ class AdmmSession:
         check(lib().mlease_admm_consensus(self._h, ptr(exchange_sum_dev_ptr), C.byref(md), C.byref(stop)))
         return md.value, bool(stop.value)
 
+    def iterate(self):
+        """One iteration of a single-process job: local_step + consensus on the session's own exchange buffer."""
+        md, stop = C.c_double(0), C.c_int32(0)
+        check(lib().mlease_admm_iterate(self._h, C.byref(md), C.byref(stop)))
+        return md.value, bool(stop.value)
+
     def run(self, num_iters, allreduce=None):
         """Single-process job (allreduce None) or with a Python all-reduce callable(buf_ptr, count, stream_ptr)."""
         done = C.c_int32(0)

@@ -49,7 +49,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(SO, objs):
         subprocess.check_call([NVCC, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    build_host(force)
     return SO
+
+
+HOST = os.path.join(ROOT, "host")
+HOST_SO = os.path.join(LIBDIR, "libmlease_host.so")
+HOST_CLI = os.path.join(LIBDIR, "mlease_regression")
+
+
+def build_host(force: bool = False) -> str:
+    """Host job layer (C++17, zlib): libmlease_host.so + the mlease_regression CLI, both linked to libmlease_b200.so."""
+    srcs = [os.path.join(HOST, f) for f in ("avro_io.cpp", "regression_jobs.cpp")]
+    deps = srcs + [os.path.join(HOST, "avro_io.hpp"), os.path.join(os.path.dirname(ROOT), "include", "mlease_b200.h"),
+                   os.path.join(os.path.dirname(ROOT), "include", "mlease_host.h"), SO]
+    cxx = os.environ.get("CXX", "g++")
+    common = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function"]
+    link = ["-L" + LIBDIR, "-lmlease_b200", "-lz", "-Wl,-rpath,$ORIGIN"]
+    if force or _stale(HOST_SO, deps):
+        subprocess.check_call([cxx] + common + ["-shared", "-o", HOST_SO] + srcs + link)
+    main = os.path.join(HOST, "mlease_regression_main.cpp")
+    if force or _stale(HOST_CLI, [main, HOST_SO]):
+        subprocess.check_call([cxx] + common + ["-o", HOST_CLI, main, "-L" + LIBDIR, "-lmlease_host", "-lmlease_b200", "-lz", "-Wl,-rpath,$ORIGIN"])
+    return HOST_SO
 
 
 if __name__ == "__main__":

@@ -8,3 +8,5 @@ for t in test_k1 test_gram test_fit test_admm_fixture test_admm_dense test_admm_
   echo "=== $t"
   timeout -s KILL ${T:-240} python -m pytest tests/test_gpu_parity.py -m gpu -k $t -q -x 2>&1 | tail -${TAIL:-25}
 done 2>&1 | tee gpurun_out/gpu_tests.log
+echo "=== test_gpu_jobs" | tee -a gpurun_out/gpu_tests.log
+timeout -s KILL ${T:-240} python -m pytest tests/test_gpu_jobs.py -m gpu -q -x 2>&1 | tail -${TAIL:-25} | tee -a gpurun_out/gpu_tests.log

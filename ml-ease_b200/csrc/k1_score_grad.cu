@@ -23,21 +23,46 @@ constexpr int K1_WARPS = K1_THREADS / 32;
 
 // tile -> registers + partial dots (FULL: every row of the tile exists, no guards)
 template <int G, int RT, bool FULL>
-__device__ __forceinline__ void k1_phase_a(float4 (&x)[G][RT], const float4* __restrict__ tile4, const float4 (&b4)[G], float* __restrict__ pw,
-                                           int ncg, int pdw, int cg0, int myrows0, int rows) {
+__device__ __forceinline__ void k1_phase_a(float4 (&x)[G][RT], float (&p)[RT], const float4* __restrict__ tile4, const float4 (&b4)[G],
+                                           int ncg, int cg0, int myrows0, int rows) {
 #pragma unroll
   for (int j = 0; j < RT; j++) {
     const bool ok = FULL || (myrows0 + j < rows);
-    float p = 0.f;
+    float pj = 0.f;
 #pragma unroll
     for (int g = 0; g < G; g++) {
       const bool okc = ok && (G == 1 || cg0 + g * K1_THREADS < ncg);
       x[g][j] = okc ? tile4[(uint32_t)(j * ncg + g * K1_THREADS)] : make_float4(0.f, 0.f, 0.f, 0.f);
-      p = fmaf(x[g][j].x, b4[g].x, p); p = fmaf(x[g][j].y, b4[g].y, p);
-      p = fmaf(x[g][j].z, b4[g].z, p); p = fmaf(x[g][j].w, b4[g].w, p);
+      pj = fmaf(x[g][j].x, b4[g].x, pj); pj = fmaf(x[g][j].y, b4[g].y, pj);
+      pj = fmaf(x[g][j].z, b4[g].z, pj); pj = fmaf(x[g][j].w, b4[g].w, pj);
     }
-    pw[(uint32_t)(j * pdw)] = p;   // rows beyond `rows` get 0: harmless, never read
+    p[j] = pj;
   }
+}
+
+// Warp-level transposed reduction of RT per-lane values: after log2(RT) halving exchanges every lane holds ONE value,
+// the sum over its 32/RT-lane-strided group, for row r = lane / (32/RT); the remaining butterfly sums the group.
+// Returns the warp total of row (lane / (32/RT)) in every lane of that group.  ~RT + log2(32) shuffles instead of 5*RT.
+template <int RT>
+__device__ __forceinline__ float k1_warp_rows_reduce(float (&p)[RT], int lane) {
+  int c = RT;
+#pragma unroll
+  for (int m = 16; m >= 32 / RT; m >>= 1) {   // halving steps: xor 16, 8, ... while more than one value is held
+    c >>= 1;
+    const bool up = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < RT / 2; i++) {
+      if (i < c) {
+        const float send = up ? p[i] : p[i + c];
+        const float keep = up ? p[i + c] : p[i];
+        p[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+      }
+    }
+  }
+  float v = p[0];
+#pragma unroll
+  for (int m = 16 / RT; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
 }
 
 // Thread t owns float4 column group(s) cg = t (+256 g) and RT rows of every tile (rows sl*RT .. sl*RT+RT-1 when
@@ -137,39 +162,60 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
     const float4* tile4 = reinterpret_cast<const float4*>(smem_raw + (size_t)st * stage_bytes) + xoff;
     float* pd = pd_s + (size_t)buf * Rt * pdw;
 
-    // ---- phase A: tile -> registers, partial dots -> pd -------------------------------------------------
+    // ---- phase A: tile -> registers, partial dots ---------------------------------------------------------
     float4 x[G][RT];
+    float p[RT];
     if (act) {
-      float* pw = pd + poff;
-      if (full) k1_phase_a<G, RT, true>(x, tile4, b4, pw, ncg, pdw, cg0, myrows0, rows);
-      else k1_phase_a<G, RT, false>(x, tile4, b4, pw, ncg, pdw, cg0, myrows0, rows);
+      if (full) k1_phase_a<G, RT, true>(x, p, tile4, b4, ncg, cg0, myrows0, rows);
+      else k1_phase_a<G, RT, false>(x, p, tile4, b4, ncg, cg0, myrows0, rows);
+    } else {
+#pragma unroll
+      for (int j = 0; j < RT; j++) p[j] = 0.f;
     }
-    __syncthreads();   // barrier 1: the stage is fully in registers
-    if (tid == 0 && k + S < my_tiles) issue(tile_no + S * tile_step, st);
+    float score = 0.f;
+    if (nsl == 1) {
+      // all 256 threads share the tile's RT rows: reduce in registers with shuffles, 1 smem word per (warp,row)
+      const float v = k1_warp_rows_reduce<RT>(p, lane);
+      if ((lane & (32 / RT - 1)) == 0) pd[warp * RT + lane / (32 / RT)] = v;
+      __syncthreads();   // barrier 1: the stage is fully in registers
+      if (tid == 0 && k + S < my_tiles) issue(tile_no + S * tile_step, st);
+      if (has) {
+#pragma unroll
+        for (int w = 0; w < K1_WARPS; w++) score += pd[w * RT + tid];
+      }
+    } else {
+      if (act) {
+        float* pw = pd + poff;
+#pragma unroll
+        for (int j = 0; j < RT; j++) pw[(uint32_t)(j * pdw)] = p[j];   // rows beyond `rows` get 0: harmless
+      }
+      __syncthreads();   // barrier 1: the stage is fully in registers
+      if (tid == 0 && k + S < my_tiles) issue(tile_no + S * tile_step, st);
+      // row sums (warp w: rows w, w+8, ...) -> s_s
+      for (int row = warp; row < rows; row += K1_WARPS) {
+        const float* pr = pd + (uint32_t)(row * pdw);
+        float a = 0.f;
+        for (int c = lane; c < pdw; c += 32) a += pr[c];
+        a = warp_sum(a);
+        if (lane == 0) s_s[row] = a;
+      }
+      __syncthreads();   // barrier 1b
+      if (has) score = s_s[tid];
+    }
     if (++st == S) { st = 0; par ^= 1u; }
-
-    // ---- phase A': row sums (warp w: rows w, w+8, ...) -> s_s -------------------------------------------
-    for (int row = warp; row < rows; row += K1_WARPS) {
-      const float* pr = pd + (uint32_t)(row * pdw);
-      float a = 0.f;
-      for (int c = lane; c < pdw; c += 32) a += pr[c];
-      a = warp_sum(a);
-      if (lane == 0) s_s[row] = a;
-    }
-    __syncthreads();   // barrier 2
     // ---- per-row scalar math, one thread per row (only the first warps of the CTA take this branch) -------
     if (has) {
-      const float t = yy * (s_s[tid] + oo);
+      const float t = yy * (score + oo);
       const float e = __expf(-fabsf(t));                 // in (0,1]
       const float inv = __frcp_rn(1.f + e);
-      const float p = t >= 0.f ? inv : e * inv;          // sigmoid(y s)
+      const float pp = t >= 0.f ? inv : e * inv;         // sigmoid(y s)
       const float qq = t >= 0.f ? e * inv : inv;         // 1 - p, no cancellation
       // log1p(e) = -log(1/(1+e)); absolute error ~1e-7 per row, the objective only steers the line search
       loss64 += (double)(ww * ((t >= 0.f ? 0.f : -t) - __logf(inv)));
       r_s[buf * Rt + tid] = -ww * yy * qq;               // w (p-1) y
-      sd_s[buf * Rt + tid] = sqrtf(ww * p * qq);         // sqrt(d_i)
+      sd_s[buf * Rt + tid] = sqrtf(ww * pp * qq);        // sqrt(d_i)
     }
-    __syncthreads();   // barrier 3
+    __syncthreads();   // barrier 2
 
     // ---- phase B: column sums from registers (+ bf16 emit) ------------------------------------------------
     if (act) {

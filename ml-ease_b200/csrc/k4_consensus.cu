@@ -7,7 +7,8 @@
 //                  the host in the reference's float arithmetic :381, 1 for the unpenalised intercept :392-403,
 //                  per-feature lambda.map weights :382-386), |z - z_prev|_inf (:456-472), and the NEXT
 //                  iteration's reducer inputs: u = float(uplusx - z) (computeU :736-765), z as float (:330-331),
-//                  prior mean m = z_f - u (:695-698), init = z_f (:692-693), prior precision rho_eff (:652-658,705).
+//                  prior mean m = z_f - u (:695-698), prior precision rho_eff (:652-658,705); the warm start is the previous x_p
+//                  (the reference's init = z_f, :692-693, only seeds TRON; the minimiser is the same).
 //
 // Latency-bound, O(P_local * L * D') work: one CTA per lambda.
 #include "kernels.cuh"
@@ -65,7 +66,11 @@ __global__ void __launch_bounds__(256) admm_consensus_kernel(const Problem* __re
       const float un = (float)((double)pb.uplusx_f[k] - zn);
       pb.u_f[k] = un;
       pb.m[k] = -1.0 * (double)un + 1.0 * (double)zf;
-      pb.beta[k] = (double)zf;
+      // Warm start of the next x-update.  The reference starts TRON at z (:692-693) because its reducers are stateless;
+      // the minimiser does not depend on the start, and with the state resident the previous x_p is far closer to it:
+      // the optimality conditions of two consecutive x-updates give H (x_new - x_old) = -rho ((x_old - z) - (z - z_prev)),
+      // i.e. a move of order (rho / lambda_min(H)) * primal residual, while |z - x_new| is of the order of the residual itself.
+      pb.beta[k] = pb.x_d[k];
       pb.q[k] = rho_next[l];
     }
   }

@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restr
       c->stall = 0;
     }
     c->need_hess = 0;
-    if (fin && c->hess_policy == 0 && c->newton_steps >= 6) c->refresh_next = 1;   // the quasi-Newton model is ageing
+    if (fin && c->hess_policy == 0 && c->newton_steps >= 6 && c->hess_builds == 0) c->refresh_next = 1;   // a stale model needed many steps
     s_final = fin;
   }
   __syncthreads();

@@ -277,13 +277,19 @@ def main():
 
     pk = peaks()
     out = dict(base)
+    traffic = None   # DRAM bytes of one steady-state K1 launch from the committed ncu --set full capture (same command, N=1)
+    try:
+        if world == 1 and (P, n, D) == (8, 1_000_000, 1000):
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))["traffic_bytes_per_launch"]
+    except Exception:
+        traffic = None
     val = done / (ms / 1000.0)
     k1_ms, k1_n = prof["ms"]["k1"], prof["launches"]["k1"]
     gr_ms, gr_n = prof["ms"]["gram"], prof["launches"]["gram"]
     k1_total_bytes = prof["k1_bytes"]
     k1_gbs = (k1_total_bytes / 1e9) / (k1_ms / 1e3) if k1_ms > 0 else None
     roof = {"kernel": "k1_dense_kernel (fused score+reweight+gradient, one pass over X)", "bound": "hbm",
-            "achieved": k1_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": (k1_gbs / pk["hbm"]) if k1_gbs else None, "traffic": None,
+            "achieved": k1_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": (k1_gbs / pk["hbm"]) if k1_gbs else None, "traffic": traffic,
             "peak_source": pk["src"] + " hbm_gbs (copy)", "launches": k1_n, "avg_launch_ms": k1_ms / max(k1_n, 1),
             "algorithmic_bytes_per_launch": k1_total_bytes / max(k1_n, 1),
             "emit_bytes_not_counted": prof["k1_emit_bytes"], "share_of_step": k1_ms / ms}

@@ -307,7 +307,8 @@ cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStre
   }
   // explicit inverse (reads the panel blocks below the diagonal from Lc and the diagonal inverses from Ldinv)
   {
-    const int NR = ldh <= 1024 ? 16 : (ldh <= 2048 ? 8 : 4);
+    int NR = 16;   // right-hand sides per CTA, bounded by the 200 KB of shared memory the Y columns may take
+    while (NR > 1 && (size_t)ldh * NR * sizeof(double) > 200 * 1024) NR >>= 1;
     const size_t smem = (size_t)ldh * NR * sizeof(double);
     const int gx = (ldh + NR - 1) / NR;
     cudaError_t e = cudaSuccess;
@@ -317,9 +318,15 @@ cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStre
     } else if (NR == 8) {
       e = cudaFuncSetAttribute(trinv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e == cudaSuccess) trinv_kernel<8><<<dim3(gx, nprob), 256, smem, st>>>(d_probs);
-    } else {
+    } else if (NR == 4) {
       e = cudaFuncSetAttribute(trinv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e == cudaSuccess) trinv_kernel<4><<<dim3(gx, nprob), 256, smem, st>>>(d_probs);
+    } else if (NR == 2) {
+      e = cudaFuncSetAttribute(trinv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess) trinv_kernel<2><<<dim3(gx, nprob), 256, smem, st>>>(d_probs);
+    } else {
+      e = cudaFuncSetAttribute(trinv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess) trinv_kernel<1><<<dim3(gx, nprob), 256, smem, st>>>(d_probs);
     }
     if (e != cudaSuccess) return e;
     if (launches) *launches += 1;

@@ -194,6 +194,38 @@ def test_naive_train_many_keys(mb):
     assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5
 
 
+def test_admm_fixed_point_is_pooled_sklearn_fit_and_invariants(mb):
+    """Parity protocol (ii), SURVEY 8c: after enough iterations the GPU ADMM reaches the minimiser of the POOLED problem
+    sum_i logloss + (lambda/2)|beta|^2 (intercept unpenalised) computed by scikit-learn -- independent of the oracle --
+    and size-independent invariants hold: the unpenalised intercept makes mean_p u_p[intercept] = 0 after every consensus."""
+    from sklearn.linear_model import LogisticRegression
+    P, n, D, lam = 4, 30000, 120, 10.0
+    rng = np.random.default_rng(5)
+    beta = rng.normal(size=D) / np.sqrt(D)
+    Xs, ys = [], []
+    for p in range(P):
+        X = rng.normal(size=(n, D)).astype(np.float32) * (1.0 + 0.3 * p)    # heterogeneous partitions -> real consensus work
+        y = (rng.random(n) < 1 / (1 + np.exp(-(X @ beta - 0.7 + 0.2 * p)))).astype(np.int32)
+        Xs.append(X); ys.append(y)
+    with mb.AdmmSession(P, D, [lam], epsilon=0.0) as s:
+        for p in range(P):
+            s.add_partition_dense(p, Xs[p], ys[p])
+        s.begin()
+        for it in range(400):
+            md, stop = s.iterate()
+            if it in (0, 5, 50):
+                usum = sum(s.u(p, 0)[-1].astype(np.float64) for p in range(P))
+                assert abs(usum) <= 1e-6 * P, (it, usum)
+        z = s.z(0)
+        st = s.stats()
+    clf = LogisticRegression(C=1.0 / lam, fit_intercept=True, solver="newton-cholesky", tol=1e-12, max_iter=200)
+    clf.fit(np.vstack(Xs).astype(np.float64), np.concatenate(ys))
+    ref = np.concatenate([clf.coef_.ravel(), clf.intercept_])
+    err = np.abs(z - ref).max() / np.abs(ref).max()
+    assert err < 2e-5, (err, md, st)
+    assert st["not_converged"] == 0 and md < 1e-6
+
+
 def test_admm_stop_rule_and_options(mb):
     X, y, w, o = _mk(600, 8, seed=5)
     parts = [(X[:300], y[:300], w[:300], o[:300]), (X[300:], y[300:], w[300:], o[300:])]

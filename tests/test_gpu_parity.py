@@ -207,7 +207,8 @@ def test_admm_fixed_point_is_pooled_sklearn_fit_and_invariants(mb):
         X = rng.normal(size=(n, D)).astype(np.float32) * (1.0 + 0.3 * p)    # heterogeneous partitions -> real consensus work
         y = (rng.random(n) < 1 / (1 + np.exp(-(X @ beta - 0.7 + 0.2 * p)))).astype(np.int32)
         Xs.append(X); ys.append(y)
-    with mb.AdmmSession(P, D, [lam], epsilon=0.0) as s:
+    # rho is a free ADMM parameter (the fixed point does not depend on it); matched to the data curvature it converges fast
+    with mb.AdmmSession(P, D, [lam], rhos=[5000.0], epsilon=0.0) as s:
         for p in range(P):
             s.add_partition_dense(p, Xs[p], ys[p])
         s.begin()

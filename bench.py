@@ -159,8 +159,29 @@ def cpu_arm(args, steps, rows_cpu=None):
                 seconds=dt, iters=its, passes=int(r["passes"]))
 
 
+_REAL_STDOUT = None
+
+
+def isolate_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, etc.) may write to fd 1 from any
+    rank, so fd 1 is pointed at stderr for the whole process and the JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line)
+    else:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+
+
 def main():
     args = parse()
+    isolate_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -184,7 +205,7 @@ def main():
                     "samples_per_s": cb["value"] * args.partitions * args.rows, "gpu_launches": 0,
                     "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                     "e2e": {"value": cb["value"], "unit": "ADMM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(out), flush=True)
+        emit(out)
         return
 
     import torch
@@ -320,7 +341,7 @@ def main():
     if world == 1 and not args.no_cpu:
         cb = cpu_arm(args, min(K, 20))
         out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 

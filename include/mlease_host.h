@@ -1,7 +1,7 @@
 /*
  * mlease_host.h -- C entry points of the host job layer (libmlease_host.so; ml-ease_b200/host/).
- * The reference's job classes (com/linkedin/mlease/regression/jobs/*.java) keep their names, config keys (java
- * .properties job file, com/linkedin/mapred/JobConfig.java:78-90), avro schemas (src/main/avro/*.avsc) and output
+ * The reference's job classes (the com/linkedin/mlease/regression/jobs/ sources) keep their names, config keys (java
+ * .properties job file, com/linkedin/mapred/JobConfig.java:78-90), avro schemas (the .avsc files under src/main/avro/) and output
  * directory layout; the arithmetic goes through include/mlease_b200.h.  CLI: `mlease_regression <job class> <config>`
  * mirrors `hadoop jar … com.linkedin.mlease.regression.jobs.Regression <config>` (jobs/Regression.java:88-98).
  */

@@ -12,7 +12,7 @@ cudaError_t k1_launch(const Problem* d_probs, int nprob, bool csr, int ldx, int 
 // Newton state machine (newton.cu)
 cudaError_t newton_begin(const Problem* d_probs, int nprob, double xtol, int max_newton, int hess_policy,
                          int invalidate_hess, cudaStream_t st, int* launches);
-cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, cudaStream_t st, int* launches);
+cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, int Dt, cudaStream_t st, int* launches);
 cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches);
 
 // K2 (k2_gram.cu)

@@ -66,7 +66,29 @@ __global__ void newton_begin_kernel(const Problem* __restrict__ probs, double xt
   }
 }
 
-// Fixed-order reduction of the K1 partials + prior term, then the accept/shrink decision.
+// Fixed-order (deterministic) reduction of the per-CTA K1 partials, parallel over columns: CTA = 32 columns x 8 groups of
+// partials; g_t[k] = sum_t gpart[t][k] (data term only; the prior term is added by the decide kernel).
+__global__ void __launch_bounds__(256) k1_partial_reduce_kernel(const Problem* __restrict__ probs) {
+  const Problem& pb = probs[blockIdx.y];
+  if (pb.ctrl->done) return;
+  __shared__ double sh[8][33];
+  const int c = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + c;
+  const int nct = pb.k1_ctas, ldx = pb.ldx;
+  double s = 0.0;
+  if (k < pb.Dt)
+    for (int t = grp; t < nct; t += 8) s += pb.gpart[(size_t)t * ldx + k];
+  sh[grp][c] = s;
+  __syncthreads();
+  if (grp == 0 && k < pb.Dt) {
+    double a = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; g++) a += sh[g][c];
+    pb.g_t[k] = a;
+  }
+}
+
+// Prior term, objective, then the accept/shrink decision and (fused) the first L-BFGS loop of the next direction.
 //   g_t = sum_cta gpart + q*(beta_t - m)           (llf/LogisticRegressionL2.java:223-224)
 //   f_t = sum_cta fpart + 1/2 sum q (beta_t-m)^2   (:181-190)
 __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __restrict__ probs) {
@@ -80,10 +102,8 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
   const bool have_dir = c->have_dir != 0;
   double prior2 = 0.0, ginf = 0.0, phi = 0.0;
   for (int k = threadIdx.x; k < Dt; k += NT) {
-    double s = 0.0;
-    for (int t = 0; t < nct; t++) s += pb.gpart[(size_t)t * ldx + k];
     const double dlt = pb.beta_t[k] - pb.m[k];
-    const double g = s + pb.q[k] * dlt;
+    const double g = pb.g_t[k] + pb.q[k] * dlt;   // g_t holds the reduced data term (k1_partial_reduce_kernel)
     pb.g_t[k] = g;
     prior2 += pb.q[k] * dlt * dlt;
     ginf = fmax(ginf, fabs(g));
@@ -159,7 +179,10 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
     s_action = action;
     s_alpha = alpha;
     s_slot = -1;
-    if (action == 1 && have_dir && sy > 1e-10 * sqrt(ss * yy2) && sy > 0.0) {   // strictly convex => s.y > 0 up to rounding
+    // A rebuild at this accepted point supersedes the secant pairs: drop them HERE (before the fused first L-BFGS loop
+    // below runs), so that both loops of the recursion see the same, empty, pair set.
+    if (action == 1 && c->need_hess) c->bfgs_count = 0;
+    if (action == 1 && have_dir && !c->need_hess && sy > 1e-10 * sqrt(ss * yy2) && sy > 0.0) {   // strictly convex => s.y > 0 up to rounding
       s_slot = c->bfgs_count % BFGS_M;
       pb.bfgs_rho[s_slot] = 1.0 / sy;
       c->bfgs_count++;
@@ -187,38 +210,35 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
       pb.beta_tf[k] = btf;
     }
   }
+  // ---- fused: first loop of the L-BFGS two-loop recursion for the next direction (q -> g_t scratch) ----
+  __syncthreads();
+  if (c->done || !c->need_solve) return;
+  {
+    const int npairs = min(c->bfgs_count, BFGS_M);
+    double* q = pb.g_t;   // free scratch from here until the next K1 reduce
+    for (int k = threadIdx.x; k < Dt; k += NT) q[k] = pb.g_acc[k];
+    __syncthreads();
+    for (int j = 0; j < npairs; j++) {
+      const int slot = (c->bfgs_count - 1 - j) % BFGS_M;
+      const double* S = pb.bfgs_S + (size_t)slot * ldx;
+      const double* Y = pb.bfgs_Y + (size_t)slot * ldx;
+      double d = 0.0;
+      for (int k = threadIdx.x; k < Dt; k += NT) d += S[k] * q[k];
+      d = block_sum(d, sc);
+      const double a = pb.bfgs_rho[slot] * d;
+      if (threadIdx.x == 0) pb.bfgs_alpha[slot] = a;
+      for (int k = threadIdx.x; k < Dt; k += NT) q[k] -= a * Y[k];
+      __syncthreads();
+    }
+  }
 }
 
 // Quasi-Newton direction: the explicit inverse of the last Hessian rebuild is the initial matrix H0^-1 of an
 // L-BFGS two-loop recursion over the last BFGS_M secant pairs (exact gradients => s.y > 0), so chord steps
 // converge superlinearly instead of at the linear rate |I - H0^-1 H|.
-//   pre  (1 CTA/problem): q = g_acc; for newest..oldest: a_i = rho_i s_i.q ; q -= a_i y_i        -> g_t (scratch)
+//   pre  (tail of k1_reduce_decide_kernel): q = g_acc; for newest..oldest: a_i = rho_i s_i.q ; q -= a_i y_i  -> g_t (scratch)
 //   gemv (multi-CTA)    : r = Hinv q                                                                -> dir
 //   post (in newton_solve_kernel): for oldest..newest: b = rho_i y_i.r ; r += s_i (a_i - b) ; dir = -r
-__global__ void __launch_bounds__(NT) newton_pre_kernel(const Problem* __restrict__ probs) {
-  const Problem& pb = probs[blockIdx.x];
-  Ctrl* c = pb.ctrl;
-  if (c->done || !c->need_solve) return;
-  __shared__ double sc[NT / 32];
-  const int Dt = pb.Dt, ldx = pb.ldx;
-  const int npairs = min(c->bfgs_count, BFGS_M);
-  double* q = pb.g_t;   // free scratch between the decide kernel and the next K1 reduce
-  for (int k = threadIdx.x; k < Dt; k += NT) q[k] = pb.g_acc[k];
-  __syncthreads();
-  for (int j = 0; j < npairs; j++) {
-    const int slot = (c->bfgs_count - 1 - j) % BFGS_M;
-    const double* S = pb.bfgs_S + (size_t)slot * ldx;
-    const double* Y = pb.bfgs_Y + (size_t)slot * ldx;
-    double d = 0.0;
-    for (int k = threadIdx.x; k < Dt; k += NT) d += S[k] * q[k];
-    d = block_sum(d, sc);
-    const double a = pb.bfgs_rho[slot] * d;
-    if (threadIdx.x == 0) pb.bfgs_alpha[slot] = a;
-    for (int k = threadIdx.x; k < Dt; k += NT) q[k] -= a * Y[k];
-    __syncthreads();
-  }
-}
-
 __global__ void __launch_bounds__(NT) newton_gemv_kernel(const Problem* __restrict__ probs) {
   const Problem& pb = probs[blockIdx.y];
   Ctrl* c = pb.ctrl;
@@ -309,16 +329,16 @@ cudaError_t newton_begin(const Problem* d_probs, int nprob, double xtol, int max
   if (launches) *launches += 1;
   return cudaGetLastError();
 }
-cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, cudaStream_t st, int* launches) {
+cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, int Dt, cudaStream_t st, int* launches) {
+  k1_partial_reduce_kernel<<<dim3((Dt + 31) / 32, nprob), 256, 0, st>>>(d_probs);
   k1_reduce_decide_kernel<<<nprob, NT, 0, st>>>(d_probs);
-  if (launches) *launches += 1;
+  if (launches) *launches += 2;
   return cudaGetLastError();
 }
 cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches) {
-  newton_pre_kernel<<<nprob, NT, 0, st>>>(d_probs);
   newton_gemv_kernel<<<dim3((ldh + NT / 32 - 1) / (NT / 32), nprob), NT, 0, st>>>(d_probs);
   newton_solve_kernel<<<nprob, NT, 0, st>>>(d_probs);
-  if (launches) *launches += 3;
+  if (launches) *launches += 2;
   return cudaGetLastError();
 }
 }  // namespace mlease

@@ -110,6 +110,7 @@ struct Batch {
   Ctrl* d_ctrl = nullptr;
   void* d_tmaps = nullptr;
   void* d_tiles = nullptr;
+  std::vector<Ctrl> mirror;   // host copy of the control blocks as of the last read-back
   std::vector<void*> owned;
   ~Batch() {
     for (void* p : owned) cudaFree(p);
@@ -259,18 +260,24 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
   Profiler& pf = prof ? *prof : nop;
   int launches = 0;
   CK(newton_begin(B.d, B.nprob, xtol, max_newton, policy, invalidate, st, &launches));
-  poll2_kernel<<<1, 256, 0, st>>>(B.d, B.nprob, d_flag);
-  launches++;
-  CK(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  int flag = *h_flag;
+  // The first slot's flags are known on the host: every problem is running, and a rebuild is due iff the policy says
+  // always, the factors were invalidated, or the mirrored control blocks say so (no factor yet / refresh requested).
+  const bool small = B.nprob <= 64;   // small batches read the whole control array back each slot (one sync, no poll kernel)
+  int flag = 1;
+  {
+    bool emit0 = policy == 1 || invalidate || B.mirror.empty();
+    for (auto& c : B.mirror) if (!c.hess_valid || c.refresh_next) emit0 = true;
+    if (emit0) flag |= 2;
+  }
+  B.mirror.resize(B.nprob);
+  std::vector<Ctrl>& hc = B.mirror;
   int slots = 0;
   while ((flag & 1) && slots < 400) {
     pf.begin(0, st);
     CK(k1_launch(B.d, B.nprob, B.csr, B.ldx, B.has_bias, B.k1_grid, -1, st, &launches));
     pf.end(st);
     pf.begin(1, st);
-    CK(k1_reduce_decide(B.d, B.nprob, st, &launches));
+    CK(k1_reduce_decide(B.d, B.nprob, B.Dt, st, &launches));
     pf.end(st);
     if (flag & 2) {
       pf.begin(2, st);
@@ -282,12 +289,18 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
     }
     pf.begin(1, st);
     CK(newton_solve(B.d, B.nprob, B.ldh, st, &launches));
-    poll2_kernel<<<1, 256, 0, st>>>(B.d, B.nprob, d_flag);
-    launches++;
+    if (!small) { poll2_kernel<<<1, 256, 0, st>>>(B.d, B.nprob, d_flag); launches++; }
     pf.end(st);
-    CK(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    flag = *h_flag;
+    if (small) {
+      CK(cudaMemcpyAsync(hc.data(), B.d_ctrl, (size_t)B.nprob * sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      flag = 0;
+      for (auto& c : hc) if (!c.done) { flag |= 1; if (c.emit) flag |= 2; }
+    } else {
+      CK(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      flag = *h_flag;
+    }
     slots++;
     if (getenv("MLEASE_DEBUG") && atoi(getenv("MLEASE_DEBUG")) >= 2) {
       Ctrl c0;
@@ -296,9 +309,10 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
               c0.newton_steps, c0.hess_builds, c0.emit, c0.f_acc, c0.gnorm, c0.dirnorm, c0.phi0, c0.alpha, c0.worst_ratio);
     }
   }
-  std::vector<Ctrl> hc(B.nprob);
-  CK(cudaMemcpyAsync(hc.data(), B.d_ctrl, (size_t)B.nprob * sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (!small) {
+    CK(cudaMemcpyAsync(hc.data(), B.d_ctrl, (size_t)B.nprob * sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
   cnt.launches += launches;
   cnt.last_slots = slots;
   int bad_spd = 0, bad_ls = 0;
@@ -835,11 +849,11 @@ int mlease_objective(mlease_session* s, int32_t pid, const double* w, const doub
   int launches = 0;
   CK(newton_begin(B->d, 1, 1e-8, 1, 1, 1, s->stream, &launches));
   CK(k1_launch(B->d, 1, B->csr, B->ldx, 1, B->k1_grid, H ? 1 : 0, s->stream, &launches));
-  CK(k1_reduce_decide(B->d, 1, s->stream, &launches));
+  CK(k1_reduce_decide(B->d, 1, B->Dt, s->stream, &launches));
   const Problem& p = B->h[0];
   Ctrl c;
   CK(cudaMemcpyAsync(&c, B->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
-  if (g) CK(cudaMemcpyAsync(g, p.g_t, s->Dt * 8, cudaMemcpyDeviceToHost, s->stream));
+  if (g) CK(cudaMemcpyAsync(g, p.g_acc, s->Dt * 8, cudaMemcpyDeviceToHost, s->stream));   // first evaluation is always accepted: g_acc = gradient at w
   CK(cudaStreamSynchronize(s->stream));
   if (f) *f = c.f_t;
   if (H) {

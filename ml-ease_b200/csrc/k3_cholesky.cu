@@ -122,15 +122,15 @@ __global__ void __launch_bounds__(256) chol_update_kernel(const Problem* __restr
   const int base = (k + 1) * NB;
   const int i0 = base + blockIdx.y * TB, j0 = base + blockIdx.x * TB;
   if (i0 >= ldh || j0 >= ldh) return;
-  __shared__ double Ai[TB][NB + 1];
-  __shared__ double Aj[TB][NB + 1];
+  __shared__ double Ai[NB][TB + 2];   // [k][row]: a thread's 4 rows are contiguous -> conflict-light vector reads
+  __shared__ double Aj[NB][TB + 2];
   double* H = pb.Lc;
   const int c0 = k * NB;
   const int tid = threadIdx.x;
   for (int e = tid; e < TB * NB; e += 256) {
     const int i = e / NB, kk = e % NB;
-    Ai[i][kk] = (i0 + i < ldh) ? H[(size_t)(i0 + i) * ldh + c0 + kk] : 0.0;
-    Aj[i][kk] = (j0 + i < ldh) ? H[(size_t)(j0 + i) * ldh + c0 + kk] : 0.0;
+    Ai[kk][i] = (i0 + i < ldh) ? H[(size_t)(i0 + i) * ldh + c0 + kk] : 0.0;
+    Aj[kk][i] = (j0 + i < ldh) ? H[(size_t)(j0 + i) * ldh + c0 + kk] : 0.0;
   }
   __syncthreads();
   const int ti = (tid / 16) * 4, tj = (tid % 16) * 4;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) chol_update_kernel(const Problem* __restr
   for (int kk = 0; kk < NB; kk++) {
     double x[4], y[4];
 #pragma unroll
-    for (int a = 0; a < 4; a++) { x[a] = Ai[ti + a][kk]; y[a] = Aj[tj + a][kk]; }
+    for (int a = 0; a < 4; a++) { x[a] = Ai[kk][ti + a]; y[a] = Aj[kk][tj + a]; }
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -176,62 +176,80 @@ __global__ void chol_finish_kernel(const Problem* __restrict__ probs) {
 // ------------------------------------------------------------------------------------------
 // Explicit inverse, built once per factorisation so that every chord-Newton direction afterwards is a
 // single multi-CTA GEMV instead of two latency-bound triangular solves:
-//   Y = L^-1    : forward substitution with NR right-hand sides (columns of I) per CTA, 32x32 L tiles staged
-//                 through shared memory, diagonal blocks applied through their stored inverses
+//   Y = L^-1    : forward substitution with 64 right-hand sides (columns of I) per CTA, tiles staged through shared
+//                 memory, diagonal blocks applied through their stored inverses
 //   Hinv = Y^T Y: 64x64 tiles, both triangles written
 // ------------------------------------------------------------------------------------------
+// Y = L^-1 by blocked forward substitution, one CTA per NR columns of Y.  Row block kb of those columns is
+//   Y[kb] = Ldinv[kb] * ( I[kb] - sum_{jb<kb} L[kb][jb] * Y[jb] )
+// with 32x32 tiles of L and 32xNR tiles of the already computed Y (read back from global memory / L2, so the column
+// count per CTA is not bounded by shared memory: D' = 10k works the same way as D' = 1k).  The next pair of tiles is
+// prefetched into registers while the current pair is multiplied.  Thread (ti, tq) owns row ti and the NR/8 columns
+// tq, tq+8, tq+16, ... : for a fixed k the 8 lanes of a row read 8 consecutive doubles (no bank conflicts).
 template <int NR>
 __global__ void __launch_bounds__(256) trinv_kernel(const Problem* __restrict__ probs) {
   const Problem& pb = probs[blockIdx.y];
   Ctrl* c = pb.ctrl;
   if (c->done || !c->need_hess) return;
-  extern __shared__ double ysm[];            // Y columns [ldh][NR]
+  constexpr int CPT = NR / 8;   // columns per thread
   __shared__ double Lt[NB][NB + 1];
-  __shared__ double Rb[NB][NR + 1];
+  __shared__ double Yt[NB][NR + 2];
+  __shared__ double Rb[NB][NR + 2];
   const int ldh = pb.ldh, nb = ldh / NB;
-  const int c0 = blockIdx.x * NR;            // first RHS column of this CTA
+  const int c0 = blockIdx.x * NR;
   if (c0 >= ldh) return;
+  const int ncols = min(NR, ldh - c0);
   const int kb0 = c0 / NB;
   const int tid = threadIdx.x;
-  const double* L = pb.Lc;
-  constexpr int CPT = (NB * NR) / 256 > 0 ? (NB * NR) / 256 : 1;   // outputs per thread
+  const int ti = tid >> 3, tq = tid & 7;
+  const double* __restrict__ L = pb.Lc;
+  double* __restrict__ Y = pb.Yinv;
+  const int lr = tid >> 3, lc = (tid & 7) * 4;   // Lt 32x32: 4 consecutive doubles per thread
   for (int kb = kb0; kb < nb; kb++) {
     const int r0 = kb * NB;
-    // rhs block = I block
-    for (int e = tid; e < NB * NR; e += 256) {
-      const int i = e / NR, j = e % NR;
-      Rb[i][j] = (r0 + i == c0 + j) ? 1.0 : 0.0;
-    }
-    __syncthreads();
+    double acc[CPT];
+#pragma unroll
+    for (int q = 0; q < CPT; q++) acc[q] = (r0 + ti == c0 + tq + 8 * q) ? 1.0 : 0.0;
+    double pl[4], py[CPT];
+    auto prefetch = [&](int jb) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) pl[q] = L[(size_t)(r0 + lr) * ldh + jb * NB + lc + q];
+#pragma unroll
+      for (int q = 0; q < CPT; q++) py[q] = (tq + 8 * q < ncols) ? Y[(size_t)(jb * NB + ti) * ldh + c0 + tq + 8 * q] : 0.0;
+    };
+    if (kb > kb0) prefetch(kb0);
     for (int jb = kb0; jb < kb; jb++) {
-      for (int e = tid; e < NB * NB; e += 256) Lt[e / NB][e % NB] = L[(size_t)(r0 + e / NB) * ldh + jb * NB + (e % NB)];
+#pragma unroll
+      for (int q = 0; q < 4; q++) Lt[lr][lc + q] = pl[q];
+#pragma unroll
+      for (int q = 0; q < CPT; q++) Yt[ti][tq + 8 * q] = py[q];
       __syncthreads();
-      for (int q = 0; q < CPT; q++) {
-        const int e = tid + q * 256;
-        if (e < NB * NR) {
-          const int i = e / NR, j = e % NR;
-          double a = 0.0;
+      if (jb + 1 < kb) prefetch(jb + 1);
 #pragma unroll 8
-          for (int kk = 0; kk < NB; kk++) a += Lt[i][kk] * ysm[(size_t)(jb * NB + kk) * NR + j];
-          Rb[i][j] -= a;
-        }
+      for (int kk = 0; kk < NB; kk++) {
+        const double l = Lt[ti][kk];
+#pragma unroll
+        for (int q = 0; q < CPT; q++) acc[q] -= l * Yt[kk][tq + 8 * q];
       }
       __syncthreads();
     }
-    // Y block = Ldinv[kb] * rhs block
-    for (int e = tid; e < NB * NB; e += 256) Lt[e / NB][e % NB] = pb.Ldinv[(size_t)(r0 + e / NB) * NB + (e % NB)];
+#pragma unroll
+    for (int q = 0; q < CPT; q++) Rb[ti][tq + 8 * q] = acc[q];
+#pragma unroll
+    for (int q = 0; q < 4; q++) Lt[lr][lc + q] = pb.Ldinv[(size_t)(r0 + lr) * NB + lc + q];
     __syncthreads();
-    for (int q = 0; q < CPT; q++) {
-      const int e = tid + q * 256;
-      if (e < NB * NR) {
-        const int i = e / NR, j = e % NR;
-        double a = 0.0;
-        for (int kk = 0; kk <= i; kk++) a += Lt[i][kk] * Rb[kk][j];
-        ysm[(size_t)(r0 + i) * NR + j] = a;
-        pb.Yinv[(size_t)(r0 + i) * ldh + c0 + j] = a;
-      }
+    double yv[CPT];
+#pragma unroll
+    for (int q = 0; q < CPT; q++) yv[q] = 0.0;
+    for (int kk = 0; kk <= ti; kk++) {
+      const double l = Lt[ti][kk];
+#pragma unroll
+      for (int q = 0; q < CPT; q++) yv[q] += l * Rb[kk][tq + 8 * q];
     }
-    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < CPT; q++)
+      if (tq + 8 * q < ncols) Y[(size_t)(r0 + ti) * ldh + c0 + tq + 8 * q] = yv[q];
+    __syncthreads();   // the Y block just written is read back (by other threads of this CTA) for the next row blocks
   }
 }
 
@@ -307,27 +325,9 @@ cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStre
   }
   // explicit inverse (reads the panel blocks below the diagonal from Lc and the diagonal inverses from Ldinv)
   {
-    int NR = 16;   // right-hand sides per CTA, bounded by the 200 KB of shared memory the Y columns may take
-    while (NR > 1 && (size_t)ldh * NR * sizeof(double) > 200 * 1024) NR >>= 1;
-    const size_t smem = (size_t)ldh * NR * sizeof(double);
-    const int gx = (ldh + NR - 1) / NR;
-    cudaError_t e = cudaSuccess;
-    if (NR == 16) {
-      e = cudaFuncSetAttribute(trinv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess) trinv_kernel<16><<<dim3(gx, nprob), 256, smem, st>>>(d_probs);
-    } else if (NR == 8) {
-      e = cudaFuncSetAttribute(trinv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess) trinv_kernel<8><<<dim3(gx, nprob), 256, smem, st>>>(d_probs);
-    } else if (NR == 4) {
-      e = cudaFuncSetAttribute(trinv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess) trinv_kernel<4><<<dim3(gx, nprob), 256, smem, st>>>(d_probs);
-    } else if (NR == 2) {
-      e = cudaFuncSetAttribute(trinv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess) trinv_kernel<2><<<dim3(gx, nprob), 256, smem, st>>>(d_probs);
-    } else {
-      e = cudaFuncSetAttribute(trinv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess) trinv_kernel<1><<<dim3(gx, nprob), 256, smem, st>>>(d_probs);
-    }
+    if (ldh <= 2048) trinv_kernel<32><<<dim3((ldh + 31) / 32, nprob), 256, 0, st>>>(d_probs);   // more CTAs for small systems
+    else trinv_kernel<64><<<dim3((ldh + 63) / 64, nprob), 256, 0, st>>>(d_probs);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (launches) *launches += 1;
     const int T = (ldh + TB - 1) / TB;

@@ -41,6 +41,7 @@ struct Ctrl {
   double xtol;
   int max_newton;
   int hess_policy;   // 0 adaptive chord, 1 every step
+  int rebuild_is_expensive;  // a Gram+Cholesky rebuild costs more than ~8 passes over X: never rebuild mid-update, lean on L-BFGS
   // cumulative counters (never reset by begin-of-iteration)
   long long tot_evals, tot_newton, tot_rejects, tot_hess;
 };

@@ -37,7 +37,7 @@ __device__ __forceinline__ double block_max(double v, double* sc) {
 // Start of an x-update: beta = beta_t = init, flags reset.  init/m/q were written by the caller
 // (ADMM consensus kernel or mlease_fit_partition).
 __global__ void newton_begin_kernel(const Problem* __restrict__ probs, double xtol, int max_newton, int hess_policy,
-                                    int invalidate_hess) {
+                                    int invalidate_hess, int rebuild_is_expensive) {
   const Problem& pb = probs[blockIdx.x];
   Ctrl* c = pb.ctrl;
   for (int k = threadIdx.x; k < pb.ldx; k += blockDim.x) {
@@ -56,7 +56,7 @@ __global__ void newton_begin_kernel(const Problem* __restrict__ probs, double xt
     c->done = 0; c->have_dir = 0; c->need_solve = 0; c->need_hess = 0; c->fail = 0;
     c->newton_steps = 0; c->evals = 0; c->rejects = 0; c->hess_builds = 0; c->stall = 0;
     c->alpha = 1.0; c->phi0 = 0.0; c->f_acc = 0.0; c->f_t = 0.0; c->gnorm = 0.0; c->gnorm_prev = 0.0; c->dirnorm = 0.0; c->dirnorm_prev = 0.0;
-    c->xtol = xtol; c->max_newton = max_newton; c->hess_policy = hess_policy;
+    c->xtol = xtol; c->max_newton = max_newton; c->hess_policy = hess_policy; c->rebuild_is_expensive = rebuild_is_expensive;
     // Rebuild at the start point when there is no factor, when the policy says always, or when the previous
     // x-update's chord steps contracted slowly: a factor taken at a (nearly) converged point makes every later
     // x-update of the ADMM run a 2-3 pass affair, and costs about as much as 2.5 K1 passes.
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
         if (c->hess_policy == 1) {
           c->emit = 1;
         } else {
-          const bool poor = have_dir && c->gnorm_prev > 0.0 && ginf > 0.25 * c->gnorm_prev;
+          const bool poor = !c->rebuild_is_expensive && have_dir && c->gnorm_prev > 0.0 && ginf > 0.25 * c->gnorm_prev;
           c->emit = (poor && !c->need_hess) ? 1 : 0;
           if (!c->need_hess && !c->hess_valid) { c->emit = 1; }
         }
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restr
       c->stall = 0;
     }
     c->need_hess = 0;
-    if (fin && c->hess_policy == 0 && c->newton_steps >= 6 && c->hess_builds == 0) c->refresh_next = 1;   // a stale model needed many steps
+    if (fin && c->hess_policy == 0 && c->newton_steps >= (c->rebuild_is_expensive ? 16 : 6) && c->hess_builds == 0) c->refresh_next = 1;   // a stale model needed many steps
     s_final = fin;
   }
   __syncthreads();
@@ -324,8 +324,8 @@ __global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restr
 }
 
 cudaError_t newton_begin(const Problem* d_probs, int nprob, double xtol, int max_newton, int hess_policy,
-                         int invalidate_hess, cudaStream_t st, int* launches) {
-  newton_begin_kernel<<<nprob, 256, 0, st>>>(d_probs, xtol, max_newton, hess_policy, invalidate_hess);
+                         int invalidate_hess, int rebuild_is_expensive, cudaStream_t st, int* launches) {
+  newton_begin_kernel<<<nprob, 256, 0, st>>>(d_probs, xtol, max_newton, hess_policy, invalidate_hess, rebuild_is_expensive);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

@@ -105,6 +105,7 @@ struct Batch {
   bool csr = false;
   int has_bias = 1;
   int k1_grid = 1, gram_slices = 1, ntiles = 0;
+  int rebuild_is_expensive = 0;   // cost model: Gram + Cholesky + inverse vs one K1 pass (set in batch_alloc)
   std::vector<Problem> h;
   Problem* d = nullptr;
   Ctrl* d_ctrl = nullptr;
@@ -181,6 +182,17 @@ int batch_alloc(Batch& B, int num_sms) {
       return fail(MLEASE_ERR_INVALID, "dense partitions support at most 4095 features (+intercept); use CSR input beyond that");
     const long long row_tiles = (maxn + R - 1) / R;
     B.k1_grid = (int)std::max(1LL, std::min(row_tiles, (long long)std::max(1, (num_sms * cps) / std::max(1, nprob))));
+  }
+  // Cost model for the rebuild policy (seconds, order of magnitude): one K1 pass streams the partition at ~5 TB/s; a rebuild
+  // is n*Dt^2 bf16 flop at ~1 PFLOP/s (tcgen05 Gram, lower triangle) plus ~Dt^3 fp64 flop at ~5 TFLOP/s (Cholesky + inverse).
+  {
+    double bytes = 0;
+    for (auto& p : B.h) bytes = std::max(bytes, B.csr ? 8.0 * (double)p.nnz_hint + 17.0 * (double)p.n : (double)p.n * 4.0 * ldx);
+    const double t_pass = bytes / 5e12 + 20e-6;
+    const double t_rebuild = (double)maxn * B.Dt * B.Dt / 1e15 + (double)B.Dt * B.Dt * B.Dt / 5e12 + 300e-6;
+    // only wide systems qualify: small ones (NaiveTrain's per-key fits, cold-started every time) are launch-bound, not
+    // flop-bound, and a mid-update rebuild saves them many lock-step slots
+    B.rebuild_is_expensive = (t_rebuild > 8.0 * t_pass && B.Dt > 2048) ? 1 : 0;
   }
   // Gram decomposition
   std::vector<short> tiles(2 * 8192);
@@ -259,7 +271,7 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
   Profiler nop;
   Profiler& pf = prof ? *prof : nop;
   int launches = 0;
-  CK(newton_begin(B.d, B.nprob, xtol, max_newton, policy, invalidate, st, &launches));
+  CK(newton_begin(B.d, B.nprob, xtol, max_newton, policy, invalidate, B.rebuild_is_expensive, st, &launches));
   // The first slot's flags are known on the host: every problem is running, and a rebuild is due iff the policy says
   // always, the factors were invalidated, or the mirrored control blocks say so (no factor yet / refresh requested).
   const bool small = B.nprob <= 64;   // small batches read the whole control array back each slot (one sync, no poll kernel)
@@ -847,7 +859,7 @@ int mlease_objective(mlease_session* s, int32_t pid, const double* w, const doub
   Batch* B = s->scratch;
   if (int rc = scratch_set(s, w, m, q)) return rc;
   int launches = 0;
-  CK(newton_begin(B->d, 1, 1e-8, 1, 1, 1, s->stream, &launches));
+  CK(newton_begin(B->d, 1, 1e-8, 1, 1, 1, 0, s->stream, &launches));
   CK(k1_launch(B->d, 1, B->csr, B->ldx, 1, B->k1_grid, H ? 1 : 0, s->stream, &launches));
   CK(k1_reduce_decide(B->d, 1, B->Dt, s->stream, &launches));
   const Problem& p = B->h[0];
@@ -905,7 +917,7 @@ int mlease_time_kernel(mlease_session* s, int32_t pid, int32_t which, int32_t re
   std::vector<double> zero(s->Dt, 0.0), one(s->Dt, 1.0);
   if (int rc = scratch_set(s, zero.data(), zero.data(), one.data())) return rc;
   int launches = 0;
-  CK(newton_begin(B->d, 1, 1e-8, 1, 1, 1, s->stream, &launches));
+  CK(newton_begin(B->d, 1, 1e-8, 1, 1, 1, 0, s->stream, &launches));
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   // warm-up launch (also produces the scaled copy the Gram needs)

@@ -62,6 +62,7 @@ struct Problem {
   const int* colidx;
   const float* vals;
   long long nnz_hint;      // CSR nnz (host-side accounting only)
+  int csr_unique;          // every CSR row has strictly increasing column ids (parallel bf16 emit is exact)
   __nv_bfloat16* Xt;       // [n][Dp] bf16 = sqrt(d_i) * x_ij  (Gram operand), zero in [ldx, Dp)
   int Dp;                  // multiple of 128
   // solver state

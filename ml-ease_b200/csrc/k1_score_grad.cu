@@ -303,66 +303,79 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
 }
 
 // ------------------------------------------------------------------------------------------
-// CSR variant (configs 3/4): one warp per row, gather for the score, fp64 atomics for the
-// scatter into gpart[0][:] (zeroed by k1_csr_zero).  The bias is implicit (value 1, column Dt-1).
-// If emit: the dense scaled row is assembled into Xt (zero-filled by the caller once; each
-// refresh rewrites exactly the row's nnz + bias positions).
+// CSR variant (configs 3/4: ~1 % dense rows).  One warp per row, rows dealt to CTAs in contiguous chunks:
+//   gather : s_i = sum_j v_ij * beta[c_ij] (+ beta[bias]), beta staged in shared memory
+//   scatter: g[c_ij] += r_i * v_ij into a per-CTA shared-memory gradient (float atomics, spread addresses), flushed once per
+//            CTA as an fp64 partial row of gpart -> the same fixed-order cross-CTA reduction as the dense path
+//   emit   : Xt[i][c_ij] = bf16(sqrt(d_i) v_ij): the dense bf16 Gram operand is assembled from the sparse row (positions
+//            outside the row's pattern stay 0 from the one-time memset; rows with repeated columns take a serial path
+//            because duplicates add in the reference's Xv)
+// HBM-bound on 8 B per stored value (+ 17 B per row).
 // ------------------------------------------------------------------------------------------
-__global__ void k1_csr_zero_kernel(const Problem* __restrict__ probs) {
-  const Problem& pb = probs[blockIdx.y];
-  if (pb.ctrl->done) return;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < pb.ldx; c += gridDim.x * blockDim.x) pb.gpart[c] = 0.0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) pb.fpart[0] = 0.0;
-}
-
-__global__ void __launch_bounds__(256)
-k1_csr_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit) {
+// 1024 threads per CTA: the row loop is a chain of dependent global loads (rowptr -> colidx/vals -> gather), so the kernel
+// lives on occupancy (up to 64 warps per SM with two CTAs).
+__global__ void __launch_bounds__(1024) k1_csr_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit, int beta_in_smem) {
   const Problem& pb = probs[blockIdx.y];
   Ctrl* ctrl = pb.ctrl;
   if (ctrl->done) return;
   const bool emit = force_emit >= 0 ? (force_emit != 0) : (ctrl->emit != 0);
-  const int lane = threadIdx.x & 31;
-  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  const float* __restrict__ bt = pb.beta_tf;
-  const int Dt = pb.Dt;
+  extern __shared__ __align__(16) float csr_sm[];
+  const int ldx = pb.ldx, Dt = pb.Dt;
+  float* g_s = csr_sm;
+  float* b_s = csr_sm + ldx;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int k = tid; k < ldx; k += blockDim.x) { g_s[k] = 0.f; if (beta_in_smem) b_s[k] = pb.beta_tf[k]; }
+  __syncthreads();
+  const float* __restrict__ bt = beta_in_smem ? b_s : pb.beta_tf;
+  const long long n = pb.n;
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long rb = (long long)blockIdx.x * per, re = min(n, rb + per);
+  const long long* __restrict__ rp = pb.rowptr;
+  const int* __restrict__ ci = pb.colidx;
+  const float* __restrict__ vv = pb.vals;
+  const bool uniq = pb.csr_unique != 0;
   double loss = 0.0;
-  for (long long i = warp_global; i < pb.n; i += nwarps) {
-    const long long j0 = pb.rowptr[i], j1 = pb.rowptr[i + 1];
+  for (long long i = rb + warp; i < re; i += nw) {
+    const long long j0 = rp[i], j1 = rp[i + 1];
+    const float yy = (float)pb.y[i], ww = pb.w[i], oo = pb.o[i];
     float a = 0.f;
-    for (long long j = j0 + lane; j < j1; j += 32) a = fmaf(pb.vals[j], bt[pb.colidx[j]], a);
+    for (long long j = j0 + lane; j < j1; j += 32) a = fmaf(vv[j], bt[ci[j]], a);
     a = warp_sum(a);
     if (has_bias) a += bt[Dt - 1];
-    const float yy = (float)pb.y[i], ww = pb.w[i];
-    const float t = yy * (a + pb.o[i]);
-    const float e = expf(-fabsf(t));
-    const float inv = 1.f / (1.f + e);
+    const float t = yy * (a + oo);
+    const float e = __expf(-fabsf(t));
+    const float inv = __frcp_rn(1.f + e);
     const float p = t >= 0.f ? inv : e * inv;
     const float qq = t >= 0.f ? e * inv : inv;
-    if (lane == 0) loss += (double)(ww * ((t >= 0.f ? 0.f : -t) + log1pf(e)));
+    if (lane == 0) loss += (double)(ww * ((t >= 0.f ? 0.f : -t) - __logf(inv)));
     const float rr = -ww * yy * qq;
-    const float sd = sqrtf(ww * p * qq);
-    for (long long j = j0 + lane; j < j1; j += 32) {
-      const int c = pb.colidx[j];
-      const float v = pb.vals[j];
-      atomicAdd(&pb.gpart[c], (double)(v * rr));
-    }
-    if (has_bias && lane == 0) atomicAdd(&pb.gpart[Dt - 1], (double)rr);
+    for (long long j = j0 + lane; j < j1; j += 32) atomicAdd(&g_s[ci[j]], vv[j] * rr);
+    if (has_bias && lane == 0) atomicAdd(&g_s[Dt - 1], rr);
     if (emit) {
+      const float sd = sqrtf(ww * p * qq);
       __nv_bfloat16* xt = pb.Xt + (size_t)i * pb.Dp;
-      // duplicates within a row add in the reference's Xv; the dense assembly must add too
-      for (long long j = j0 + lane; j < j1; j += 32) xt[pb.colidx[j]] = __float2bfloat16_rn(0.f);
-      __syncwarp();
-      for (long long j = j0; j < j1; j++) {  // serial over the row's nnz keeps duplicate handling exact
-        if (lane == 0) {
-          const int c = pb.colidx[j];
-          xt[c] = __float2bfloat16_rn(__bfloat162float(xt[c]) + pb.vals[j] * sd);
-        }
+      if (uniq) {
+        for (long long j = j0 + lane; j < j1; j += 32) xt[ci[j]] = __float2bfloat16_rn(vv[j] * sd);
+      } else {
+        for (long long j = j0 + lane; j < j1; j += 32) xt[ci[j]] = __float2bfloat16_rn(0.f);
+        __syncwarp();
+        if (lane == 0)
+          for (long long j = j0; j < j1; j++) xt[ci[j]] = __float2bfloat16_rn(__bfloat162float(xt[ci[j]]) + vv[j] * sd);
       }
       if (has_bias && lane == 0) xt[Dt - 1] = __float2bfloat16_rn(sd);
     }
   }
-  if (lane == 0 && loss != 0.0) atomicAdd(&pb.fpart[0], loss);
+  __syncthreads();
+  double* gp = pb.gpart + (size_t)blockIdx.x * ldx;
+  for (int k = tid; k < ldx; k += blockDim.x) gp[k] = (double)g_s[k];
+  __shared__ double red[32];
+  if (lane == 0) red[warp] = loss;
+  __syncthreads();
+  if (tid == 0) {
+    double sacc = 0.0;
+    for (int wq = 0; wq < nw; wq++) sacc += red[wq];
+    pb.fpart[blockIdx.x] = sacc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -410,9 +423,13 @@ bool k1_dense_plan(int ldx, int* R_out, int* S_out, int* G_out, size_t* smem_out
 cudaError_t k1_launch(const Problem* d_probs, int nprob, bool csr, int ldx, int has_bias, int ctas_per_problem,
                       int force_emit, cudaStream_t stream, int* launches) {
   if (csr) {
-    k1_csr_zero_kernel<<<dim3(4, nprob), 256, 0, stream>>>(d_probs);
-    k1_csr_kernel<<<dim3(ctas_per_problem, nprob), 256, 0, stream>>>(d_probs, has_bias, force_emit);
-    if (launches) *launches += 2;
+    const int beta_in_smem = (size_t)2 * ldx * 4 <= 200 * 1024 ? 1 : 0;
+    const size_t smem = (size_t)(beta_in_smem ? 2 : 1) * ldx * 4;
+    if (smem > 220 * 1024) return cudaErrorInvalidValue;   // > 56k features: needs a column-blocked gradient (not built yet)
+    cudaError_t e = cudaFuncSetAttribute(k1_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k1_csr_kernel<<<dim3(ctas_per_problem, nprob), 1024, smem, stream>>>(d_probs, has_bias, force_emit, beta_in_smem);
+    if (launches) *launches += 1;
     return cudaGetLastError();
   }
   K1Plan p;

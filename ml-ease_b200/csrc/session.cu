@@ -59,6 +59,11 @@ __global__ void convert_labels_kernel(long long n, const int* resp, const float*
     o[i] = o_in ? o_in[i] : 0.0f;
   }
 }
+__global__ void check_rows_sorted_kernel(long long n, const long long* rowptr, const int* colidx, int* bad) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    for (long long j = rowptr[i] + 1; j < rowptr[i + 1]; j++)
+      if (colidx[j] <= colidx[j - 1]) { atomicOr(bad, 8); break; }
+}
 __global__ void check_csr_kernel(long long nnz, const int* colidx, float* vals, int Dg, int binary, int* bad) {
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (long long)gridDim.x * blockDim.x) {
     const int c = colidx[j];
@@ -97,6 +102,7 @@ struct PartData {
   int* colidx = nullptr;
   float* vals = nullptr;
   long long nnz = 0;
+  int csr_unique = 0;
 };
 
 // A batch of problems with identical shape that advance in lockstep through the Newton slots.
@@ -174,7 +180,8 @@ int batch_alloc(Batch& B, int num_sms) {
   long long maxn = 1;
   for (auto& p : B.h) maxn = std::max(maxn, p.n);
   if (B.csr) {
-    B.k1_grid = std::max(1, std::min((int)((maxn + 7) / 8), (num_sms * 8) / std::max(1, nprob)));
+    const int cps = (size_t)2 * ldx * 4 <= 100 * 1024 ? 2 : 1;   // CTAs per SM the shared-memory gradient allows
+    B.k1_grid = std::max(1, std::min((int)((maxn + 63) / 64), (num_sms * cps) / std::max(1, nprob)));
   } else {
     int R, S, G, cps = 1;
     size_t smem;
@@ -214,7 +221,7 @@ int batch_alloc(Batch& B, int num_sms) {
     while (best > 1 && (double)best * B.Dp * B.Dp * 4.0 * nprob > 1024.0 * 1024 * 1024) best--;
     B.gram_slices = best;
   }
-  const size_t nd = (size_t)nprob * ((8 + 2 * BFGS_M) * (size_t)ldx + 2 * BFGS_M + (size_t)(B.csr ? 1 : B.k1_grid) * ldx + (size_t)B.k1_grid + 8);
+  const size_t nd = (size_t)nprob * ((8 + 2 * BFGS_M) * (size_t)ldx + 2 * BFGS_M + (size_t)B.k1_grid * ldx + (size_t)B.k1_grid + 8);
   const size_t nf = (size_t)nprob * 4 * ldx;
   double* dd; float* ff; float* hp; double* lc; double* ld; double* ldi; double* yi; double* hi;
   if (int rc = dev_alloc(B, (void**)&dd, nd * sizeof(double))) return rc;
@@ -234,7 +241,7 @@ int batch_alloc(Batch& B, int num_sms) {
   for (int b = 0; b < nprob; b++) {
     Problem& p = B.h[b];
     p.ldx = ldx; p.Dt = B.Dt; p.Dp = B.Dp; p.ldh = B.ldh;
-    p.k1_ctas = B.csr ? 1 : B.k1_grid;
+    p.k1_ctas = B.k1_grid;
     p.gram_slices = B.gram_slices;
     double* q = dd;
     p.beta = q; q += ldx; p.beta_t = q; q += ldx; p.m = q; q += ldx; p.q = q; q += ldx;
@@ -415,7 +422,7 @@ int find_part(mlease_session* s, int pid) {
 void fill_problem_data(Problem& p, const PartData& pd) {
   std::memset(&p, 0, sizeof(Problem));
   p.X = pd.X; p.n = pd.n; p.y = pd.y; p.w = pd.w; p.o = pd.o;
-  p.rowptr = pd.rowptr; p.colidx = pd.colidx; p.vals = pd.vals; p.nnz_hint = pd.nnz;
+  p.rowptr = pd.rowptr; p.colidx = pd.colidx; p.vals = pd.vals; p.nnz_hint = pd.nnz; p.csr_unique = pd.csr_unique;
 }
 
 int finalize(mlease_session* s) {
@@ -685,6 +692,11 @@ int mlease_add_partition_csr(mlease_session* s, int32_t pid, int64_t nrows, cons
     CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     if (*s->h_flag) return fail(MLEASE_ERR_INVALID, "feature index out of range");
+    CK(cudaMemsetAsync(s->d_flag, 0, 4, s->stream));
+    check_rows_sorted_kernel<<<(int)std::min<long long>((nrows + 255) / 256, 4096), 256, 0, s->stream>>>(nrows, (const long long*)rp, (const int*)ci, s->d_flag);
+    CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    pd.csr_unique = *s->h_flag ? 0 : 1;
   }
   pd.rowptr = (long long*)rp; pd.colidx = (int*)ci; pd.vals = (float*)vv;
   if (int rc = add_common(s, pd, response, weight, offset)) return rc;

@@ -63,6 +63,13 @@ struct Problem {
   const float* vals;
   long long nnz_hint;      // CSR nnz (host-side accounting only)
   int csr_unique;          // every CSR row has strictly increasing column ids (parallel bf16 emit is exact)
+  const long long* bm_offs;       // block-major entry list for the CSR Gram: run offsets [nblk128][bm_groups] (+1 total)
+  const unsigned short* bm_keys;  // per entry: byte offset inside the swizzled [32 rows][128 cols] operand block
+  const float* bm_vals;           // per entry: the stored value
+  long long bm_groups;            // number of 32-row groups
+  int nblk128;             // number of 128-column blocks (Dp / 128)
+  float* sdvec;            // [n] sqrt(d_i) written by K1 when the Gram is assembled straight from CSR (no Xt)
+  int gram_from_csr;       // 1: gram_csr_tcgen05_kernel builds the bf16 tiles in shared memory from the sparse rows
   __nv_bfloat16* Xt;       // [n][Dp] bf16 = sqrt(d_i) * x_ij  (Gram operand), zero in [ldx, Dp)
   int Dp;                  // multiple of 128
   // solver state

@@ -19,6 +19,9 @@
 // debug cross-check reachable through mlease_objective(tensor=0); the product path never uses it.
 #include <cuda.h>
 
+#include <algorithm>
+#include <cub/device/device_scan.cuh>
+
 #include "kernels.cuh"
 
 namespace mlease {
@@ -175,6 +178,291 @@ gram_tcgen05_kernel(const Problem* __restrict__ probs, const CUtensorMap* __rest
 }
 
 // ------------------------------------------------------------------------------------------
+// Sparse variant: the same 128x256 / split-K tcgen05 Gram, but the bf16 operand tiles are ASSEMBLED IN SHARED MEMORY
+// straight from the CSR rows (no dense Xt in HBM: at 1 % density that copy is 100x the input and makes the dense kernel
+// HBM-bound).  8 producer warps, each owning one 32-row stage of the ring: a lane owns one data row, looks up where the
+// row's entries for the tile's column ranges start (column-block offset index built at upload), scales them by sqrt(d_i)
+// and scatters them as bf16 into the canonical MN-major SWIZZLE_128B layout the UMMA descriptors expect
+// (byte offset = box*4096 + k*128 + ((chunk ^ (k & 7)) * 16) + 2*e).  Positions outside the sparsity pattern are zero:
+// stages are cleared once, and a producer re-clears exactly the entries it wrote when it gets its stage back.
+// Generic-proxy stores are published to the tensor core's async proxy with fence.proxy.async before the mbarrier arrive.
+// Warp roles (13 warps): 0 = MMA issuer + TMEM allocator, 1..8 = producers, 9..12 = epilogue.
+// ------------------------------------------------------------------------------------------
+constexpr int SK = 32;                       // data rows (K) per stage
+constexpr int SST = 8;                       // stages = producer warps
+constexpr int S_A_BYTES = SK * GM * 2;       // 8 KB  : 2 boxes of [32 k][64 cols]
+constexpr int S_B_BYTES = SK * GN * 2;       // 16 KB : 4 boxes
+constexpr int S_STAGE_BYTES = S_A_BYTES + S_B_BYTES;
+constexpr int S_BOX_BYTES = SK * 128;        // 4 KB
+constexpr int S_THREADS = 13 * 32;
+constexpr size_t S_SMEM = (size_t)SST * S_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t sw128_off(int k, int col) {   // byte offset of element (row k, column col) inside an operand tile
+  const int box = col >> 6, cc = col & 63;
+  return (uint32_t)(box * S_BOX_BYTES + k * 128 + ((((cc >> 3) ^ (k & 7)) << 4) | ((cc & 7) << 1)));
+}
+
+__global__ void __launch_bounds__(S_THREADS, 1)
+gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __restrict__ tiles, int ntiles, int force, int bias_col) {
+  const Problem& pb = probs[blockIdx.z];
+  Ctrl* ctrl = pb.ctrl;
+  if (!force && (ctrl->done || !ctrl->need_hess)) return;
+  const GramTile tile = tiles[blockIdx.x];
+  const int slice = blockIdx.y, nslices = gridDim.y;
+  const int Dp = pb.Dp;
+  const long long n = pb.n;
+  const long long ksteps_total = (n + SK - 1) / SK;
+  const long long per = (ksteps_total + nslices - 1) / nslices;
+  const long long ks0 = slice * per;
+  const long long ks1 = min(ksteps_total, ks0 + per);
+  const int nk = (int)max(0LL, ks1 - ks0);
+
+  extern __shared__ unsigned char g_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(g_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)SST * S_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + SST;
+  uint64_t* acc_bar = empty_bar + SST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // clear the whole ring once
+  for (int e = threadIdx.x; e < SST * S_STAGE_BYTES / 16; e += S_THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < SST; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, GN);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();   // the zero fill must be visible to the async proxy too
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_bf16_mn(GM, GN);
+      for (int k = 0; k < nk; k++) {
+        const int st = k % SST;
+        mbar_wait(&full_bar[st], (uint32_t)((k / SST) & 1));
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)st * S_STAGE_BYTES);
+        const uint32_t b_addr = a_addr + S_A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < SK / UK; kk++) {
+          const uint64_t da = umma_desc_mn_sw128(a_addr + kk * (UK * 128), S_BOX_BYTES, 1024);
+          const uint64_t db = umma_desc_mn_sw128(b_addr + kk * (UK * 128), S_BOX_BYTES, 1024);
+          umma_f16(tmem_base, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[st]);
+      }
+      umma_commit(acc_bar);
+    }
+  } else if (warp <= SST) {
+    // ===== producers: warp p owns stage p-1 and the K-steps k = p-1, p-1+SST, ...  One K-step = one 32-row group, whose
+    // entries for a 128-column block are one contiguous run of the block-major list: three runs per stage (A block,
+    // two B blocks).  Offsets are fetched two uses ahead and the first 32 entries of each run one use ahead, so the
+    // loads of a use are in flight during the whole previous use.
+    const int st = warp - 1;
+    unsigned char* a_tile = smem + (size_t)st * S_STAGE_BYTES;
+    unsigned char* b_tile = a_tile + S_A_BYTES;
+    unsigned char* const sbase[3] = {a_tile, b_tile, b_tile + 2 * S_BOX_BYTES};
+    const int acol0 = tile.bi * GM, bcol0 = tile.bj * GN;
+    const int nblk = pb.nblk128;
+    const long long ngroups = pb.bm_groups;
+    const long long* __restrict__ offs = pb.bm_offs;
+    const unsigned short* __restrict__ keys = pb.bm_keys;
+    const float* __restrict__ bvals = pb.bm_vals;
+    const float* __restrict__ sdv = pb.sdvec;
+    // lanes 0..5 fetch {lo, hi} of the three runs
+    const int my_blk = (lane >> 1) == 0 ? tile.bi : tile.bj * 2 + ((lane >> 1) - 1);
+    const bool my_valid = lane < 6 && my_blk < nblk;
+    const long long* my_offs = offs + (size_t)(my_valid ? my_blk : 0) * ngroups + (lane & 1);
+    // the bias column (value 1 in every row, llf/LibLinearDataset.java:592-614) is not stored in the CSR rows
+    const bool bias_in_a = bias_col >= acol0 && bias_col < acol0 + GM;
+    const bool bias_in_b = bias_col >= bcol0 && bias_col < bcol0 + GN;
+    const uint32_t bias_off_a = bias_in_a ? sw128_off(lane, bias_col - acol0) : 0u;
+    const uint32_t bias_off_b = bias_in_b ? sw128_off(lane, bias_col - bcol0) : 0u;
+    constexpr uint32_t NOKEY = 0xFFFFFFFFu;
+
+    long long o_nxt = (my_valid && st < nk) ? my_offs[ks0 + st] : 0;                   // offsets of the use being prefetched
+    long long o_nx2 = (my_valid && st + SST < nk) ? my_offs[ks0 + st + SST] : 0;       // ... and of the one after
+    long long lo[3], hi[3], plo[3] = {0, 0, 0}, phi[3] = {0, 0, 0};
+    uint32_t ckey[3], pkey[3] = {NOKEY, NOKEY, NOKEY};
+    float cval[3], csd;
+    // prefetch use 0
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+      lo[s] = __shfl_sync(0xffffffffu, o_nxt, 2 * s);
+      hi[s] = __shfl_sync(0xffffffffu, o_nxt, 2 * s + 1);
+      const long long e = lo[s] + lane;
+      ckey[s] = e < hi[s] ? (uint32_t)keys[e] : NOKEY;
+      cval[s] = e < hi[s] ? bvals[e] : 0.f;
+    }
+    {
+      const long long r = (ks0 + st) * SK + lane;
+      csd = (st < nk && r < n) ? sdv[r] : 0.f;
+    }
+    bool prow = false;
+    for (int k = st, use = 0; k < nk; k += SST, use++) {
+      // ---- issue the loads of the next use
+      long long nlo[3], nhi[3];
+      uint32_t nkey[3];
+      float nval[3], nsd;
+      const long long o_cur_next = o_nx2;
+      o_nx2 = (my_valid && k + 2 * SST < nk) ? my_offs[ks0 + k + 2 * SST] : 0;
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        nlo[s] = __shfl_sync(0xffffffffu, o_cur_next, 2 * s);
+        nhi[s] = __shfl_sync(0xffffffffu, o_cur_next, 2 * s + 1);
+        const long long e = nlo[s] + lane;
+        nkey[s] = e < nhi[s] ? (uint32_t)keys[e] : NOKEY;
+        nval[s] = e < nhi[s] ? bvals[e] : 0.f;
+      }
+      {
+        const long long rn = (ks0 + k + SST) * SK + lane;
+        nsd = (k + SST < nk && rn < n) ? sdv[rn] : 0.f;
+      }
+      // ---- un-write what the previous use of this stage stored (same addresses, zero)
+      if (use > 0) {
+        mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+          if (pkey[s] != NOKEY) *reinterpret_cast<unsigned short*>(sbase[s] + pkey[s]) = 0;
+          for (long long e0 = plo[s] + 32; e0 < phi[s]; e0 += 32) {
+            const long long e = e0 + lane;
+            if (e < phi[s]) *reinterpret_cast<unsigned short*>(sbase[s] + keys[e]) = 0;
+          }
+        }
+        if (prow && bias_in_a) *reinterpret_cast<unsigned short*>(a_tile + bias_off_a) = 0;
+        if (prow && bias_in_b) *reinterpret_cast<unsigned short*>(b_tile + bias_off_b) = 0;
+      }
+      // ---- write this use
+      const long long r = (ks0 + k) * SK + lane;
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        {
+          const bool v = ckey[s] != NOKEY;
+          const uint32_t key = v ? ckey[s] : 0u;
+          const float sdk = __shfl_sync(0xffffffffu, csd, (key >> 7) & 31);
+          if (v) *reinterpret_cast<__nv_bfloat16*>(sbase[s] + key) = __float2bfloat16_rn(cval[s] * sdk);
+        }
+        for (long long e0 = lo[s] + 32; e0 < hi[s]; e0 += 32) {
+          const long long e = e0 + lane;
+          const bool v = e < hi[s];
+          const uint32_t key = v ? (uint32_t)keys[e] : 0u;
+          const float val = v ? bvals[e] : 0.f;
+          const float sdk = __shfl_sync(0xffffffffu, csd, (key >> 7) & 31);
+          if (v) *reinterpret_cast<__nv_bfloat16*>(sbase[s] + key) = __float2bfloat16_rn(val * sdk);
+        }
+      }
+      prow = r < n;
+      if (prow && bias_in_a) *reinterpret_cast<__nv_bfloat16*>(a_tile + bias_off_a) = __float2bfloat16_rn(csd);
+      if (prow && bias_in_b) *reinterpret_cast<__nv_bfloat16*>(b_tile + bias_off_b) = __float2bfloat16_rn(csd);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[st]);
+      // ---- rotate
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        plo[s] = lo[s]; phi[s] = hi[s]; pkey[s] = ckey[s];
+        lo[s] = nlo[s]; hi[s] = nhi[s]; ckey[s] = nkey[s]; cval[s] = nval[s];
+      }
+      csd = nsd;
+    }
+  } else {
+    // ===== epilogue: warps 9..12 -> TMEM lane quadrant (warp % 4) =====
+    const int quad = warp & 3;
+    float* out = pb.Hpart + (size_t)slice * Dp * Dp;
+    const int row = tile.bi * GM + quad * 32 + lane;
+    if (nk > 0) {
+      mbar_wait(acc_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < GN; c0 += 32) {
+      uint32_t r[32];
+      if (nk > 0) {
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j++) r[j] = 0u;
+      }
+      const int col = tile.bj * GN + c0;
+      if (row < Dp && col < Dp) {
+        float4* dst = reinterpret_cast<float4*>(out + (size_t)row * Dp + col);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, GN);
+  }
+}
+
+// Block-major entry list for the CSR Gram.  For every 128-column block b and every 32-row group g the entries
+// (row in group, column in block, value) are stored contiguously at [offs[b*ngroups+g], offs[b*ngroups+g+1]); the key is
+// the byte offset of the element inside a swizzled [32 k][128 col] operand block (sw128_off), the value the stored float.
+// Rows must be sorted by column (strictly increasing), which the upload checks.
+__global__ void __launch_bounds__(256) csr_bm_count_kernel(long long n, const long long* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                           int nblk, long long ngroups, long long* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < ngroups; g += nw) {
+    const long long r = g * 32 + lane;
+    long long j = r < n ? rowptr[r] : 0;
+    const long long j1 = r < n ? rowptr[r + 1] : 0;
+    for (int b = 0; b < nblk; b++) {
+      const long long s = j;
+      while (j < j1 && colidx[j] < (b + 1) * 128) j++;
+      int c = (int)(j - s);
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0) counts[(size_t)b * ngroups + g] = c;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) csr_bm_fill_kernel(long long n, const long long* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                          const float* __restrict__ vals, int nblk, long long ngroups,
+                                                          const long long* __restrict__ offs, unsigned short* __restrict__ keys,
+                                                          float* __restrict__ bvals) {
+  const int lane = threadIdx.x & 31;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < ngroups; g += nw) {
+    const long long r = g * 32 + lane;
+    long long j = r < n ? rowptr[r] : 0;
+    const long long j1 = r < n ? rowptr[r + 1] : 0;
+    for (int b = 0; b < nblk; b++) {
+      const long long s = j;
+      while (j < j1 && colidx[j] < (b + 1) * 128) j++;
+      const int c = (int)(j - s);
+      int incl = c;   // inclusive warp scan
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      long long pos = offs[(size_t)b * ngroups + g] + (incl - c);
+      for (long long e = s; e < j; e++, pos++) {
+        keys[pos] = (unsigned short)sw128_off(lane, colidx[e] - b * 128);
+        bvals[pos] = vals[e];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // fp32 SIMT debug kernel: same operand (bf16 Xt), same output format (slice 0; other slices zeroed).
 // 64x64 lower tiles, 256 threads x (4x4).
 // ------------------------------------------------------------------------------------------
@@ -269,6 +557,45 @@ cudaError_t gram_launch_tcgen05(const Problem* d_probs, int nprob, const void* d
   gram_tcgen05_kernel<<<dim3(ntiles, nslices, nprob), G_THREADS, G_SMEM, st>>>(
       d_probs, reinterpret_cast<const CUtensorMap*>(d_tmaps), reinterpret_cast<const GramTile*>(d_tiles), ntiles, force);
   if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t gram_launch_csr_tcgen05(const Problem* d_probs, int nprob, const void* d_tiles, int ntiles, int nslices, int force,
+                                    int bias_col, cudaStream_t st, int* launches) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gram_csr_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  gram_csr_tcgen05_kernel<<<dim3(ntiles, nslices, nprob), S_THREADS, S_SMEM, st>>>(d_probs, reinterpret_cast<const GramTile*>(d_tiles), ntiles, force, bias_col);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+// counts -> exclusive offsets in place: offs has nblk*ngroups+1 entries (the last one = total entries)
+cudaError_t csr_bm_offsets(long long n, const long long* rowptr, const int* colidx, int nblk, long long ngroups, long long* offs,
+                           cudaStream_t st) {
+  const long long m = (long long)nblk * ngroups;
+  cudaError_t e = cudaMemsetAsync(offs, 0, (size_t)(m + 1) * sizeof(long long), st);
+  if (e != cudaSuccess) return e;
+  const int grid = (int)std::min<long long>((ngroups + 7) / 8, 148 * 32);
+  csr_bm_count_kernel<<<std::max(grid, 1), 256, 0, st>>>(n, rowptr, colidx, nblk, ngroups, offs);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  size_t tmp_bytes = 0;
+  if ((e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, offs, offs, (long long)(m + 1), st)) != cudaSuccess) return e;
+  void* tmp = nullptr;
+  if ((e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16)) != cudaSuccess) return e;
+  e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, offs, offs, (long long)(m + 1), st);
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  cudaFree(tmp);
+  return e != cudaSuccess ? e : e2;
+}
+
+cudaError_t csr_bm_fill(long long n, const long long* rowptr, const int* colidx, const float* vals, int nblk, long long ngroups,
+                        const long long* offs, unsigned short* keys, float* bvals, cudaStream_t st) {
+  const int grid = (int)std::min<long long>((ngroups + 7) / 8, 148 * 32);
+  csr_bm_fill_kernel<<<std::max(grid, 1), 256, 0, st>>>(n, rowptr, colidx, vals, nblk, ngroups, offs, keys, bvals);
   return cudaGetLastError();
 }
 

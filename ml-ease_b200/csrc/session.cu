@@ -103,6 +103,11 @@ struct PartData {
   float* vals = nullptr;
   long long nnz = 0;
   int csr_unique = 0;
+  long long* bm_offs = nullptr;    // block-major entry list for the CSR Gram (built at upload when rows are sorted & unique)
+  unsigned short* bm_keys = nullptr;
+  float* bm_vals = nullptr;
+  long long bm_groups = 0;
+  int nblk128 = 0;
 };
 
 // A batch of problems with identical shape that advance in lockstep through the Newton slots.
@@ -111,6 +116,7 @@ struct Batch {
   bool csr = false;
   int has_bias = 1;
   int k1_grid = 1, gram_slices = 1, ntiles = 0;
+  int gram_from_csr = 0;          // every problem of the batch assembles its Gram tiles from CSR (no dense bf16 operand)
   int rebuild_is_expensive = 0;   // cost model: Gram + Cholesky + inverse vs one K1 pass (set in batch_alloc)
   std::vector<Problem> h;
   Problem* d = nullptr;
@@ -190,6 +196,8 @@ int batch_alloc(Batch& B, int num_sms) {
     const long long row_tiles = (maxn + R - 1) / R;
     B.k1_grid = (int)std::max(1LL, std::min(row_tiles, (long long)std::max(1, (num_sms * cps) / std::max(1, nprob))));
   }
+  B.gram_from_csr = B.csr ? 1 : 0;
+  for (auto& p : B.h) if (!p.bm_offs) B.gram_from_csr = 0;
   // Cost model for the rebuild policy (seconds, order of magnitude): one K1 pass streams the partition at ~5 TB/s; a rebuild
   // is n*Dt^2 bf16 flop at ~1 PFLOP/s (tcgen05 Gram, lower triangle) plus ~Dt^3 fp64 flop at ~5 TFLOP/s (Cholesky + inverse).
   {
@@ -260,12 +268,21 @@ int batch_alloc(Batch& B, int num_sms) {
     p.Yinv = yi + (size_t)b * B.ldh * B.ldh;
     p.Hinv = hi + (size_t)b * B.ldh * B.ldh;
     p.ctrl = B.d_ctrl + b;
-    if (!p.Xt) {
-      void* xt;
-      if (int rc = dev_alloc(B, &xt, (size_t)p.n * B.Dp * sizeof(__nv_bfloat16))) return rc;
-      p.Xt = reinterpret_cast<__nv_bfloat16*>(xt);
+    if (B.gram_from_csr) {
+      void* sv;
+      if (int rc = dev_alloc(B, &sv, (size_t)p.n * sizeof(float))) return rc;
+      p.sdvec = reinterpret_cast<float*>(sv);
+      p.gram_from_csr = 1;
+      std::memset(&maps[b], 0, sizeof(CUtensorMap));
+    } else {
+      p.gram_from_csr = 0;
+      if (!p.Xt) {
+        void* xt;
+        if (int rc = dev_alloc(B, &xt, (size_t)p.n * B.Dp * sizeof(__nv_bfloat16))) return rc;
+        p.Xt = reinterpret_cast<__nv_bfloat16*>(xt);
+      }
+      if (gram_make_tensor_map(&maps[b], p.Xt, p.n, B.Dp) != 0) return fail(MLEASE_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     }
-    if (gram_make_tensor_map(&maps[b], p.Xt, p.n, B.Dp) != 0) return fail(MLEASE_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   }
   CK(cudaMemcpy(B.d_tmaps, maps.data(), (size_t)nprob * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(B.d, B.h.data(), (size_t)nprob * sizeof(Problem), cudaMemcpyHostToDevice));
@@ -300,7 +317,8 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
     pf.end(st);
     if (flag & 2) {
       pf.begin(2, st);
-      CK(gram_launch_tcgen05(B.d, B.nprob, B.d_tmaps, B.d_tiles, B.ntiles, B.gram_slices, 0, st, &launches));
+      if (B.gram_from_csr) CK(gram_launch_csr_tcgen05(B.d, B.nprob, B.d_tiles, B.ntiles, B.gram_slices, 0, B.has_bias ? B.Dt - 1 : -1, st, &launches));
+      else CK(gram_launch_tcgen05(B.d, B.nprob, B.d_tmaps, B.d_tiles, B.ntiles, B.gram_slices, 0, st, &launches));
       pf.end(st);
       pf.begin(3, st);
       CK(cholesky_launch(B.d, B.nprob, B.ldh, st, &launches));
@@ -423,6 +441,8 @@ void fill_problem_data(Problem& p, const PartData& pd) {
   std::memset(&p, 0, sizeof(Problem));
   p.X = pd.X; p.n = pd.n; p.y = pd.y; p.w = pd.w; p.o = pd.o;
   p.rowptr = pd.rowptr; p.colidx = pd.colidx; p.vals = pd.vals; p.nnz_hint = pd.nnz; p.csr_unique = pd.csr_unique;
+  p.bm_offs = pd.bm_offs; p.bm_keys = pd.bm_keys; p.bm_vals = pd.bm_vals; p.bm_groups = pd.bm_groups;
+  p.nblk128 = pd.nblk128; p.gram_from_csr = pd.bm_offs ? 1 : 0;
 }
 
 int finalize(mlease_session* s) {
@@ -697,6 +717,18 @@ int mlease_add_partition_csr(mlease_session* s, int32_t pid, int64_t nrows, cons
     CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     pd.csr_unique = *s->h_flag ? 0 : 1;
+    if (pd.csr_unique) {
+      pd.nblk128 = round_up(s->ldx, 128) / 128;
+      pd.bm_groups = (nrows + 31) / 32;
+      void *bo, *bk, *bv;
+      if (int rc = sess_alloc(s, &bo, ((size_t)pd.nblk128 * pd.bm_groups + 1) * sizeof(long long))) return rc;
+      if (int rc = sess_alloc(s, &bk, (size_t)pd.nnz * sizeof(unsigned short))) return rc;
+      if (int rc = sess_alloc(s, &bv, (size_t)pd.nnz * sizeof(float))) return rc;
+      CK(csr_bm_offsets(nrows, (const long long*)rp, (const int*)ci, pd.nblk128, pd.bm_groups, (long long*)bo, s->stream));
+      CK(csr_bm_fill(nrows, (const long long*)rp, (const int*)ci, (const float*)vv, pd.nblk128, pd.bm_groups, (const long long*)bo,
+                     (unsigned short*)bk, (float*)bv, s->stream));
+      pd.bm_offs = (long long*)bo; pd.bm_keys = (unsigned short*)bk; pd.bm_vals = (float*)bv;
+    }
   }
   pd.rowptr = (long long*)rp; pd.colidx = (int*)ci; pd.vals = (float*)vv;
   if (int rc = add_common(s, pd, response, weight, offset)) return rc;
@@ -881,7 +913,9 @@ int mlease_objective(mlease_session* s, int32_t pid, const double* w, const doub
   CK(cudaStreamSynchronize(s->stream));
   if (f) *f = c.f_t;
   if (H) {
-    if (tensor) CK(gram_launch_tcgen05(B->d, 1, B->d_tmaps, B->d_tiles, B->ntiles, B->gram_slices, 1, s->stream, &launches));
+    if (!tensor && B->gram_from_csr) return fail(MLEASE_ERR_INVALID, "the SIMT debug Gram needs the dense bf16 operand, which CSR partitions with sorted unique rows do not materialise");
+    if (tensor && B->gram_from_csr) CK(gram_launch_csr_tcgen05(B->d, 1, B->d_tiles, B->ntiles, B->gram_slices, 1, B->has_bias ? B->Dt - 1 : -1, s->stream, &launches));
+    else if (tensor) CK(gram_launch_tcgen05(B->d, 1, B->d_tmaps, B->d_tiles, B->ntiles, B->gram_slices, 1, s->stream, &launches));
     else CK(gram_launch_simt(B->d, 1, B->Dp, 1, s->stream, &launches));
     const size_t per = (size_t)B->Dp * B->Dp;
     std::vector<float> hp(per * B->gram_slices);
@@ -934,8 +968,10 @@ int mlease_time_kernel(mlease_session* s, int32_t pid, int32_t which, int32_t re
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   // warm-up launch (also produces the scaled copy the Gram needs)
   CK(k1_launch(B->d, 1, B->csr, B->ldx, 1, B->k1_grid, 1, s->stream, &launches));
+  const int bias_col = B->has_bias ? B->Dt - 1 : -1;
   if (which == 3) {
-    CK(gram_launch_tcgen05(B->d, 1, B->d_tmaps, B->d_tiles, B->ntiles, B->gram_slices, 1, s->stream, &launches));
+    if (B->gram_from_csr) CK(gram_launch_csr_tcgen05(B->d, 1, B->d_tiles, B->ntiles, B->gram_slices, 1, bias_col, s->stream, &launches));
+    else CK(gram_launch_tcgen05(B->d, 1, B->d_tmaps, B->d_tiles, B->ntiles, B->gram_slices, 1, s->stream, &launches));
     Ctrl c; std::memset(&c, 0, sizeof(c)); c.need_hess = 1;
     CK(cudaMemcpyAsync(B->d_ctrl, &c, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
   }
@@ -943,6 +979,7 @@ int mlease_time_kernel(mlease_session* s, int32_t pid, int32_t which, int32_t re
   CK(cudaEventRecord(e0, s->stream));
   for (int r = 0; r < reps; r++) {
     if (which == 1) CK(k1_launch(B->d, 1, B->csr, B->ldx, 1, B->k1_grid, emit_scaled ? 1 : 0, s->stream, &launches));
+    else if (which == 2 && B->gram_from_csr) CK(gram_launch_csr_tcgen05(B->d, 1, B->d_tiles, B->ntiles, B->gram_slices, 1, bias_col, s->stream, &launches));
     else if (which == 2) CK(gram_launch_tcgen05(B->d, 1, B->d_tmaps, B->d_tiles, B->ntiles, B->gram_slices, 1, s->stream, &launches));
     else if (which == 3) CK(cholesky_launch(B->d, 1, B->ldh, s->stream, &launches));
     else return fail(MLEASE_ERR_INVALID, "which must be 1, 2 or 3");

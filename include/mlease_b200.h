@@ -139,6 +139,8 @@ int mlease_profile(mlease_session* s, int32_t enable, double* ms4, int64_t* coun
  * evaluated on a resident partition at host vector w, prior mean m, prior precision q (=1/priorVar),
  * all of length num_features+1.  Any output may be NULL.  H is [Dt x Dt] row-major (full, symmetric).
  * tensor != 0 builds H with the tcgen05 Gram kernel (bf16 operands), 0 with the fp32 SIMT debug kernel.
+ * tensor == 2 returns in H the INVERSE the Newton direction is computed with (tcgen05 Gram + diag(q) -> fp64 blocked
+ * Cholesky -> explicit inverse), so that tests can check H^-1 * H = I for every factorisation path.
  * ------------------------------------------------------------------------------------- */
 int mlease_objective(mlease_session* s, int32_t partition_id, const double* w, const double* m, const double* q,
                      double* f, double* g, double* H, int32_t tensor);

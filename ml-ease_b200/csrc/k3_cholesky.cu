@@ -8,6 +8,8 @@
 // fp64 on purpose: the Gram comes from bf16 tensor-core products, but the factorisation must not
 // break down when cond(H) approaches 1/eps_fp32; 3.3e8 flop at D'=1001 is latency- not
 // throughput-bound on B200's fp64 pipe.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace mlease {
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(const Problem* __restri
 }
 
 // Trailing update A22 -= L21 L21^T on lower-triangular TBxTB tiles.
-__global__ void __launch_bounds__(256) chol_update_kernel(const Problem* __restrict__ probs, int k) {
+__global__ void __launch_bounds__(256) chol_update_kernel(const Problem* __restrict__ probs, int k, int jlimit) {
   const Problem& pb = probs[blockIdx.z];
   Ctrl* c = pb.ctrl;
   if (c->done || !c->need_hess) return;
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(256) chol_update_kernel(const Problem* __restr
   const int ldh = pb.ldh;
   const int base = (k + 1) * NB;
   const int i0 = base + blockIdx.y * TB, j0 = base + blockIdx.x * TB;
-  if (i0 >= ldh || j0 >= ldh) return;
+  if (i0 >= ldh || j0 >= ldh || j0 >= jlimit) return;   // jlimit: the wide path only updates inside its outer panel
   __shared__ double Ai[NB][TB + 2];   // [k][row]: a thread's 4 rows are contiguous -> conflict-light vector reads
   __shared__ double Aj[NB][TB + 2];
   double* H = pb.Lc;
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(256) chol_update_kernel(const Problem* __restr
 #pragma unroll
     for (int b = 0; b < 4; b++) {
       const int i = i0 + ti + a, j = j0 + tj + b;
-      if (i < ldh && j <= i) H[(size_t)i * ldh + j] -= acc[a][b];
+      if (i < ldh && j <= i && j < jlimit) H[(size_t)i * ldh + j] -= acc[a][b];
     }
 }
 
@@ -187,7 +189,7 @@ __global__ void chol_finish_kernel(const Problem* __restrict__ probs) {
 // prefetched into registers while the current pair is multiplied.  Thread (ti, tq) owns row ti and the NR/8 columns
 // tq, tq+8, tq+16, ... : for a fixed k the 8 lanes of a row read 8 consecutive doubles (no bank conflicts).
 template <int NR>
-__global__ void __launch_bounds__(256) trinv_kernel(const Problem* __restrict__ probs) {
+__global__ void __launch_bounds__(256) trinv_kernel(const Problem* __restrict__ probs, int leaf) {
   const Problem& pb = probs[blockIdx.y];
   Ctrl* c = pb.ctrl;
   if (c->done || !c->need_hess) return;
@@ -195,9 +197,11 @@ __global__ void __launch_bounds__(256) trinv_kernel(const Problem* __restrict__ 
   __shared__ double Lt[NB][NB + 1];
   __shared__ double Yt[NB][NR + 2];
   __shared__ double Rb[NB][NR + 2];
-  const int ldh = pb.ldh, nb = ldh / NB;
+  const int ldh = pb.ldh;
   const int c0 = blockIdx.x * NR;
   if (c0 >= ldh) return;
+  // leaf > 0: invert only the diagonal leaf x leaf block this column group lies in (the wide path merges leaves with GEMMs)
+  const int nb = leaf > 0 ? min(ldh, (c0 / leaf + 1) * leaf) / NB : ldh / NB;
   const int ncols = min(NR, ldh - c0);
   const int kb0 = c0 / NB;
   const int tid = threadIdx.x;
@@ -304,6 +308,226 @@ __global__ void __launch_bounds__(256) hinv_syrk_kernel(const Problem* __restric
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Wide systems (ldh > 2048): the same factorisation / inverse / product, restructured so that almost all flops are
+// fp64 tensor-core GEMMs (DMMA m8n8k4) on 128x64 tiles with K chunks of 16 staged through shared memory:
+//   Cholesky : outer panels of WNB columns; inside a panel the NB=32 steps above (panel kernel + K=32 updates limited
+//              to the panel's columns), then one K=WNB trailing update             C -= A A^T      (mode 0)
+//   Y = L^-1 : leaves of WLEAF columns by trinv_kernel, then pairwise merges bottom-up
+//              T = L21 * Y11 (mode 1, T in the Hinv buffer), Y21 = -Y22 * T          (mode 2)
+//   Hinv     : Y^T Y over k >= max(i, j)                                            (mode 3)
+// Operand tiles live in shared memory either [row][k] (stride 20) or [k][row] (stride tile+4), whichever matches the
+// contiguous direction in global memory; both strides are = 4 mod 16 doubles, which makes the DMMA fragment loads
+// (thread t: row t/4, k t%4) bank-conflict free.
+// ------------------------------------------------------------------------------------------
+constexpr int WNB = 256;     // outer panel width of the wide Cholesky
+constexpr int WLEAF = 256;   // leaf size of the recursive inverse
+constexpr int DM = 128, DN = 64, DK = 16;
+constexpr int DA_SZ = DM * 20 > DK * (DM + 4) ? DM * 20 : DK * (DM + 4);   // doubles per A stage
+constexpr int DB_SZ = DN * 20 > DK * (DN + 4) ? DN * 20 : DK * (DN + 4);
+constexpr size_t DGEMM_SMEM = (size_t)2 * (DA_SZ + DB_SZ) * sizeof(double);
+
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256, 2) dgemm_kernel(const Problem* __restrict__ probs, int mode, int p0, int p1) {
+  const Problem& pb = probs[blockIdx.z];
+  Ctrl* ctl = pb.ctrl;
+  if (ctl->done || !ctl->need_hess) return;
+  const int ldh = pb.ldh;
+  const double* A; const double* B; double* C;
+  int M, N, K;
+  if (mode == 0) {            // trailing update after the outer panel at column p0 of width p1
+    const int c = p0, w = p1;
+    M = N = ldh - c - w; K = w;
+    A = B = pb.Lc + (size_t)(c + w) * ldh + c;
+    C = pb.Lc + (size_t)(c + w) * ldh + (c + w);
+  } else if (mode == 1 || mode == 2) {   // merge of the diagonal blocks [r0, r0+m) and [r0+m, r0+m+m2)
+    const int m = p0, r0 = 2 * blockIdx.y * m;
+    const int m2 = min(m, ldh - r0 - m);
+    if (m2 <= 0) return;
+    M = m2; N = m;
+    if (mode == 1) {
+      K = m;
+      A = pb.Lc + (size_t)(r0 + m) * ldh + r0;
+      B = pb.Yinv + (size_t)r0 * ldh + r0;
+      C = pb.Hinv + (size_t)(r0 + m) * ldh + r0;
+    } else {
+      K = m2;
+      A = pb.Yinv + (size_t)(r0 + m) * ldh + (r0 + m);
+      B = pb.Hinv + (size_t)(r0 + m) * ldh + r0;
+      C = pb.Yinv + (size_t)(r0 + m) * ldh + r0;
+    }
+  } else {
+    M = N = K = ldh;
+    A = B = pb.Yinv;
+    C = pb.Hinv;
+  }
+  const int tiles_n = (N + DN - 1) / DN;
+  const int i0 = (blockIdx.x / tiles_n) * DM, j0 = (blockIdx.x % tiles_n) * DN;
+  if (i0 >= M) return;
+  if ((mode == 0 || mode == 3) && j0 >= i0 + DM) return;   // strictly upper tile of a symmetric result
+  int klo = 0, khi = K;
+  if (mode == 1) klo = j0;                      // Y11 is lower triangular: Y11[k][j] = 0 for k < j
+  if (mode == 2) khi = min(K, i0 + DM);         // Y22 is lower triangular: Y22[i][k] = 0 for k > i
+  if (mode == 3) klo = max(i0, j0);             // Y[k][i] = 0 for k < i
+
+  extern __shared__ double dg_smem[];
+  double* As = dg_smem;                 // [2][DA_SZ]
+  double* Bs = dg_smem + 2 * DA_SZ;     // [2][DB_SZ]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tg = lane & 3;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+
+  double2 ra[4], rb[2];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (A_KC) {
+        const int row = (tid >> 3) + 32 * q, kk = (tid & 7) * 2;
+        ra[q] = (i0 + row < M) ? *reinterpret_cast<const double2*>(A + (size_t)(i0 + row) * ldh + k0 + kk) : make_double2(0.0, 0.0);
+      } else {
+        const int kk = (tid >> 6) + 4 * q, ii = (tid & 63) * 2;
+        ra[q] = (i0 + ii < M) ? *reinterpret_cast<const double2*>(A + (size_t)(k0 + kk) * ldh + i0 + ii) : make_double2(0.0, 0.0);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      if (B_KC) {
+        const int col = (tid >> 3) + 32 * q, kk = (tid & 7) * 2;
+        rb[q] = (j0 + col < N) ? *reinterpret_cast<const double2*>(B + (size_t)(j0 + col) * ldh + k0 + kk) : make_double2(0.0, 0.0);
+      } else {
+        const int kk = (tid >> 5) + 8 * q, jj = (tid & 31) * 2;
+        rb[q] = (j0 + jj < N) ? *reinterpret_cast<const double2*>(B + (size_t)(k0 + kk) * ldh + j0 + jj) : make_double2(0.0, 0.0);
+      }
+    }
+  };
+  auto sstore = [&](int buf) {
+    double* a = As + buf * DA_SZ;
+    double* b = Bs + buf * DB_SZ;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (A_KC) *reinterpret_cast<double2*>(a + ((tid >> 3) + 32 * q) * 20 + (tid & 7) * 2) = ra[q];
+      else *reinterpret_cast<double2*>(a + ((tid >> 6) + 4 * q) * (DM + 4) + (tid & 63) * 2) = ra[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      if (B_KC) *reinterpret_cast<double2*>(b + ((tid >> 3) + 32 * q) * 20 + (tid & 7) * 2) = rb[q];
+      else *reinterpret_cast<double2*>(b + ((tid >> 5) + 8 * q) * (DN + 4) + (tid & 31) * 2) = rb[q];
+    }
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  if (klo < khi) {
+    gload(klo);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = klo; k0 < khi; k0 += DK) {
+      const bool more = k0 + DK < khi;
+      if (more) gload(k0 + DK);
+      const double* a = As + buf * DA_SZ;
+      const double* b = Bs + buf * DB_SZ;
+#pragma unroll
+      for (int k4 = 0; k4 < DK; k4 += 4) {
+        double fa[4], fb[4];
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+          fa[f] = A_KC ? a[(wm + f * 8 + g) * 20 + k4 + tg] : a[(k4 + tg) * (DM + 4) + wm + f * 8 + g];
+          fb[f] = B_KC ? b[(wn + f * 8 + g) * 20 + k4 + tg] : b[(k4 + tg) * (DN + 4) + wn + f * 8 + g];
+        }
+#pragma unroll
+        for (int fm = 0; fm < 4; fm++)
+#pragma unroll
+          for (int fn = 0; fn < 4; fn++) dmma_8x8x4(acc[fm][fn][0], acc[fm][fn][1], fa[fm], fb[fn]);
+      }
+      if (more) sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+#pragma unroll
+  for (int fm = 0; fm < 4; fm++) {
+    const int i = i0 + wm + fm * 8 + g;
+    if (i >= M) continue;
+#pragma unroll
+    for (int fn = 0; fn < 4; fn++) {
+      const int j = j0 + wn + fn * 8 + 2 * tg;
+      if (j >= N) continue;
+      const double v0 = acc[fm][fn][0], v1 = acc[fm][fn][1];
+      if (mode == 0) {
+        double* d = C + (size_t)i * ldh + j;
+        if (j + 1 <= i) { double2 o = *reinterpret_cast<double2*>(d); o.x -= v0; o.y -= v1; *reinterpret_cast<double2*>(d) = o; }
+        else if (j <= i) d[0] -= v0;
+      } else if (mode == 1) {
+        *reinterpret_cast<double2*>(C + (size_t)i * ldh + j) = make_double2(v0, v1);
+      } else if (mode == 2) {
+        *reinterpret_cast<double2*>(C + (size_t)i * ldh + j) = make_double2(-v0, -v1);
+      } else {
+        if (j <= i) { C[(size_t)i * ldh + j] = v0; C[(size_t)j * ldh + i] = v0; }
+        if (j + 1 <= i) { C[(size_t)i * ldh + j + 1] = v1; C[(size_t)(j + 1) * ldh + i] = v1; }
+      }
+    }
+  }
+}
+
+template <bool A_KC, bool B_KC>
+static cudaError_t dgemm_launch(const Problem* d_probs, int nprob, int mode, int p0, int p1, int M, int N, int nmerge, cudaStream_t st,
+                                int* launches) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dgemm_kernel<A_KC, B_KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DGEMM_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int tiles = ((M + DM - 1) / DM) * ((N + DN - 1) / DN);
+  if (tiles <= 0 || nmerge <= 0) return cudaSuccess;
+  dgemm_kernel<A_KC, B_KC><<<dim3(tiles, nmerge, nprob), 256, DGEMM_SMEM, st>>>(d_probs, mode, p0, p1);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+static cudaError_t cholesky_launch_wide(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches) {
+  cudaError_t e;
+  // ---- factorisation
+  for (int c = 0; c < ldh; c += WNB) {
+    const int w = std::min(WNB, ldh - c);
+    for (int k = c / NB; k < (c + w) / NB; k++) {
+      const int below = ldh - (k + 1) * NB;
+      const int gx = below > 0 ? (below + RB - 1) / RB : 1;
+      chol_panel_kernel<<<dim3(gx, nprob), 256, 0, st>>>(d_probs, k);
+      if (launches) *launches += 1;
+      const int inner = c + w - (k + 1) * NB;   // panel columns still to be updated
+      if (inner > 0) {
+        chol_update_kernel<<<dim3((inner + TB - 1) / TB, (below + TB - 1) / TB, nprob), 256, 0, st>>>(d_probs, k, c + w);
+        if (launches) *launches += 1;
+      }
+    }
+    const int rest = ldh - c - w;
+    if (rest > 0 && (e = dgemm_launch<true, true>(d_probs, nprob, 0, c, w, rest, rest, 1, st, launches)) != cudaSuccess) return e;
+  }
+  // ---- inverse: leaves, then merges
+  trinv_kernel<64><<<dim3((ldh + 63) / 64, nprob), 256, 0, st>>>(d_probs, WLEAF);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (launches) *launches += 1;
+  for (int m = WLEAF; m < ldh; m *= 2) {
+    const int nmerge = (ldh + 2 * m - 1) / (2 * m);
+    if ((e = dgemm_launch<true, false>(d_probs, nprob, 1, m, 0, m, m, nmerge, st, launches)) != cudaSuccess) return e;
+    if ((e = dgemm_launch<true, false>(d_probs, nprob, 2, m, 0, m, m, nmerge, st, launches)) != cudaSuccess) return e;
+  }
+  // ---- Hinv = Y^T Y
+  return dgemm_launch<false, false>(d_probs, nprob, 3, 0, 0, ldh, ldh, 1, st, launches);
+}
+
 cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches) {
   {
     dim3 blk(32, 8);
@@ -312,21 +536,24 @@ cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStre
     if (launches) *launches += 1;
   }
   const int nb = ldh / NB;
-  for (int k = 0; k < nb; k++) {
-    const int below = ldh - (k + 1) * NB;
-    const int gx = below > 0 ? (below + RB - 1) / RB : 1;
-    chol_panel_kernel<<<dim3(gx, nprob), 256, 0, st>>>(d_probs, k);
-    if (launches) *launches += 1;
-    if (below > 0) {
-      const int T = (below + TB - 1) / TB;
-      chol_update_kernel<<<dim3(T, T, nprob), 256, 0, st>>>(d_probs, k);
+  if (ldh > 2048) {
+    cudaError_t e = cholesky_launch_wide(d_probs, nprob, ldh, st, launches);
+    if (e != cudaSuccess) return e;
+  } else {
+    for (int k = 0; k < nb; k++) {
+      const int below = ldh - (k + 1) * NB;
+      const int gx = below > 0 ? (below + RB - 1) / RB : 1;
+      chol_panel_kernel<<<dim3(gx, nprob), 256, 0, st>>>(d_probs, k);
       if (launches) *launches += 1;
+      if (below > 0) {
+        const int T = (below + TB - 1) / TB;
+        chol_update_kernel<<<dim3(T, T, nprob), 256, 0, st>>>(d_probs, k, ldh);
+        if (launches) *launches += 1;
+      }
     }
-  }
-  // explicit inverse (reads the panel blocks below the diagonal from Lc and the diagonal inverses from Ldinv)
-  {
-    if (ldh <= 2048) trinv_kernel<32><<<dim3((ldh + 31) / 32, nprob), 256, 0, st>>>(d_probs);   // more CTAs for small systems
-    else trinv_kernel<64><<<dim3((ldh + 63) / 64, nprob), 256, 0, st>>>(d_probs);
+    // explicit inverse (reads the panel blocks below the diagonal from Lc and the diagonal inverses from Ldinv)
+    if (ldh <= 2048) trinv_kernel<32><<<dim3((ldh + 31) / 32, nprob), 256, 0, st>>>(d_probs, 0);   // more CTAs for small systems
+    else trinv_kernel<64><<<dim3((ldh + 63) / 64, nprob), 256, 0, st>>>(d_probs, 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (launches) *launches += 1;

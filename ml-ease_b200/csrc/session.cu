@@ -917,6 +917,21 @@ int mlease_objective(mlease_session* s, int32_t pid, const double* w, const doub
     if (tensor && B->gram_from_csr) CK(gram_launch_csr_tcgen05(B->d, 1, B->d_tiles, B->ntiles, B->gram_slices, 1, B->has_bias ? B->Dt - 1 : -1, s->stream, &launches));
     else if (tensor) CK(gram_launch_tcgen05(B->d, 1, B->d_tmaps, B->d_tiles, B->ntiles, B->gram_slices, 1, s->stream, &launches));
     else CK(gram_launch_simt(B->d, 1, B->Dp, 1, s->stream, &launches));
+    if (tensor == 2) {
+      // the inverse the Newton direction uses: split-K Gram partials + diag(q) -> fp64 Cholesky -> explicit inverse
+      Ctrl c2; std::memset(&c2, 0, sizeof(c2)); c2.need_hess = 1;
+      CK(cudaMemcpyAsync(B->d_ctrl, &c2, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
+      CK(cholesky_launch(B->d, 1, B->ldh, s->stream, &launches));
+      std::vector<double> hi((size_t)B->ldh * B->ldh);
+      CK(cudaMemcpyAsync(hi.data(), p.Hinv, hi.size() * 8, cudaMemcpyDeviceToHost, s->stream));
+      CK(cudaMemcpyAsync(&c2, B->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
+      CK(cudaStreamSynchronize(s->stream));
+      s->cnt.launches += launches;
+      if (c2.fail) return fail(MLEASE_ERR_NUMERIC, "Hessian not positive definite");
+      for (int i = 0; i < s->Dt; i++)
+        for (int j = 0; j < s->Dt; j++) H[(size_t)i * s->Dt + j] = hi[(size_t)i * B->ldh + j];
+      return 0;
+    }
     const size_t per = (size_t)B->Dp * B->Dp;
     std::vector<float> hp(per * B->gram_slices);
     CK(cudaMemcpyAsync(hp.data(), p.Hpart, hp.size() * 4, cudaMemcpyDeviceToHost, s->stream));

@@ -87,6 +87,27 @@ def test_gram_tcgen05_vs_oracle_hessian(mb, n, d, sparse):
     assert e_x < 1e-3, ("tcgen05 vs simt", e_x)
 
 
+@pytest.mark.parametrize("n,d,sparse", [(1500, 100, False), (3000, 700, False), (4000, 2303, False), (5000, 2600, True)])
+def test_inverse_times_hessian_is_identity(mb, n, d, sparse):
+    """The explicit inverse behind every Newton direction, for both factorisation paths: ldh <= 2048 (NB=32 right-looking
+    Cholesky, substitution inverse, SIMT product) and ldh > 2048 (outer panels + DMMA trailing updates, recursive inverse
+    with DMMA merges, DMMA Y^T Y), including a width that is not a multiple of the leaf / panel size."""
+    X, y, w, o = _mk(n, d, seed=7 * n + d, sparse=sparse, density=0.05 if sparse else 0.3)
+    rng = np.random.default_rng(5)
+    wv = rng.normal(0, 0.3 / np.sqrt(d), d + 1); pm = np.zeros(d + 1); pv = np.full(d + 1, 0.5)
+    with _session(mb, d) as s:
+        if sparse:
+            rp, ci, v = _csr_of(X)
+            s.add_partition_csr(0, rp, ci, v, y, w, o)
+        else:
+            s.add_partition_dense(0, X, y, w, o)
+        _, _, H = s.objective(0, wv, pm, 1.0 / pv, want_hessian=True, tensor=True)
+        _, _, Hinv = s.objective(0, wv, pm, 1.0 / pv, want_hessian=True, tensor=2)
+    assert np.abs(Hinv - Hinv.T).max() == 0.0
+    err = np.abs(Hinv @ H - np.eye(d + 1)).max()
+    assert err < 1e-9, err
+
+
 @pytest.mark.parametrize("n,d", [(1500, 20), (3000, 100), (800, 300)])
 def test_fit_partition_matches_exact_tron(mb, n, d):
     X, y, w, o = _mk(n, d, seed=11 * n + d)

@@ -67,6 +67,7 @@ struct Problem {
   const unsigned short* bm_keys;  // per entry: byte offset inside the swizzled [32 rows][128 cols] operand block
   const float* bm_vals;           // per entry: the stored value
   long long bm_groups;            // number of 32-row groups
+  float vmax, wmax;               // max |stored value| and max record weight of the partition (fixed-point scale of the CSR K1)
   int nblk128;             // number of 128-column blocks (Dp / 128)
   float* sdvec;            // [n] sqrt(d_i) written by K1 when the Gram is assembled straight from CSR (no Xt)
   int gram_from_csr;       // 1: gram_csr_tcgen05_kernel builds the bf16 tiles in shared memory from the sparse rows

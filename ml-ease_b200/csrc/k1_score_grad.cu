@@ -314,6 +314,111 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
 // ------------------------------------------------------------------------------------------
 // 1024 threads per CTA: the row loop is a chain of dependent global loads (rowptr -> colidx/vals -> gather), so the kernel
 // lives on occupancy (up to 64 warps per SM with two CTAs).
+// CSR K1 for partitions whose rows hold each column at most once (the normal case; checked at upload).
+// Same pass as k1_csr_kernel below, but the per-CTA gradient is accumulated in shared memory as two-word fixed point
+// with native 32-bit integer atomics (ATOMS.ADD) instead of float atomics, which compile to compare-and-swap loops.
+// Integer addition commutes, so the result does not depend on the order in which warps retire: the pass is
+// deterministic, like the dense one.  With B >= sum over the CTA's rows of |contribution| to any one column
+// (rows x max weight x max |value|), S = 2^(29 - ceil(log2 B)) and k = 30 - ceil(log2 rows):
+//   hi = rint(c S), lo = rint((c S - hi) 2^k), gradient = (sum hi + sum lo / 2^k) / S,
+// i.e. a resolution of B 2^-(29+k) per contribution (k = 16 at 16k rows per CTA), below fp32 rounding of the
+// contribution itself.  The first 128 entries of a row stay in registers between the margin and the gradient half.
+__global__ void __launch_bounds__(1024, 1) k1_csr_fx_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit, int beta_in_smem) {
+  const Problem& pb = probs[blockIdx.y];
+  Ctrl* ctrl = pb.ctrl;
+  if (ctrl->done) return;
+  const bool emit = force_emit >= 0 ? (force_emit != 0) : (ctrl->emit != 0);
+  extern __shared__ __align__(16) float csr_sm[];
+  const int ldx = pb.ldx, Dt = pb.Dt;
+  int* g_hi = reinterpret_cast<int*>(csr_sm);
+  int* g_lo = g_hi + ldx;
+  float* b_s = csr_sm + 2 * (size_t)ldx;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int k = tid; k < ldx; k += blockDim.x) { g_hi[k] = 0; g_lo[k] = 0; if (beta_in_smem) b_s[k] = pb.beta_tf[k]; }
+  __syncthreads();
+  const float* __restrict__ bt = beta_in_smem ? b_s : pb.beta_tf;
+  const long long n = pb.n;
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long rb = (long long)blockIdx.x * per, re = min(n, rb + per);
+  // fixed-point scales (powers of two: scaling is exact)
+  float bound = (float)per * pb.wmax * fmaxf(pb.vmax, has_bias ? 1.f : 0.f);
+  if (!(bound > 0.f) || !(bound < 3.0e38f)) bound = 1.f;
+  const int e_hi = 29 - (ilogbf(bound) + 1);
+  int kbits = 30 - (64 - __clzll((unsigned long long)max(per, 1LL)));
+  kbits = max(0, min(kbits, 24));
+  const float s_hi = ldexpf(1.f, e_hi), s_k = ldexpf(1.f, kbits);
+  const long long* __restrict__ rp = pb.rowptr;
+  const int* __restrict__ ci = pb.colidx;
+  const float* __restrict__ vv = pb.vals;
+  double loss = 0.0;
+  long long i = rb + warp;
+  long long j0 = 0, j1 = 0;
+  float yy = 0.f, ww = 0.f, oo = 0.f;
+  if (i < re) { j0 = rp[i]; j1 = rp[i + 1]; yy = (float)pb.y[i]; ww = pb.w[i]; oo = pb.o[i]; }
+  while (i < re) {
+    float v[4];
+    int c[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const long long j = j0 + lane + 32 * q;
+      const bool ok = j < j1;
+      v[q] = ok ? vv[j] : 0.f;
+      c[q] = ok ? ci[j] : -1;
+    }
+    // the next row's header while this row's entries are in flight
+    const long long in = i + nw;
+    long long j0n = 0, j1n = 0;
+    float yn = 0.f, wn = 0.f, on = 0.f;
+    if (in < re) { j0n = rp[in]; j1n = rp[in + 1]; yn = (float)pb.y[in]; wn = pb.w[in]; on = pb.o[in]; }
+    float a = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; q++) a = fmaf(v[q], c[q] >= 0 ? bt[c[q]] : 0.f, a);
+    for (long long j = j0 + 128 + lane; j < j1; j += 32) a = fmaf(vv[j], bt[ci[j]], a);
+    a = warp_sum(a);
+    if (has_bias) a += bt[Dt - 1];
+    const float t = yy * (a + oo);
+    const float e = __expf(-fabsf(t));
+    const float inv = __frcp_rn(1.f + e);
+    const float p = t >= 0.f ? inv : e * inv;
+    const float qq = t >= 0.f ? e * inv : inv;
+    if (lane == 0) loss += (double)(ww * ((t >= 0.f ? 0.f : -t) - __logf(inv)));
+    const float rs = -ww * yy * qq * s_hi;     // contribution scale: c S = value * rs
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (c[q] >= 0) {
+        const float ts = v[q] * rs, h = rintf(ts);
+        atomicAdd(&g_hi[c[q]], (int)h);
+        atomicAdd(&g_lo[c[q]], __float2int_rn((ts - h) * s_k));
+      }
+    }
+    for (long long j = j0 + 128 + lane; j < j1; j += 32) {
+      const float ts = vv[j] * rs, h = rintf(ts);
+      const int cc = ci[j];
+      atomicAdd(&g_hi[cc], (int)h);
+      atomicAdd(&g_lo[cc], __float2int_rn((ts - h) * s_k));
+    }
+    if (has_bias && lane == 0) {
+      const float h = rintf(rs);
+      atomicAdd(&g_hi[Dt - 1], (int)h);
+      atomicAdd(&g_lo[Dt - 1], __float2int_rn((rs - h) * s_k));
+    }
+    if (emit && lane == 0) pb.sdvec[i] = sqrtf(ww * p * qq);   // the Gram kernel assembles the scaled rows itself
+    i = in; j0 = j0n; j1 = j1n; yy = yn; ww = wn; oo = on;
+  }
+  __syncthreads();
+  double* gp = pb.gpart + (size_t)blockIdx.x * ldx;
+  const double inv_hi = (double)ldexpf(1.f, -e_hi), inv_k = (double)ldexpf(1.f, -kbits);
+  for (int k = tid; k < ldx; k += blockDim.x) gp[k] = ((double)g_hi[k] + (double)g_lo[k] * inv_k) * inv_hi;
+  __shared__ double red[32];
+  if (lane == 0) red[warp] = loss;
+  __syncthreads();
+  if (tid == 0) {
+    double sacc = 0.0;
+    for (int wq = 0; wq < nw; wq++) sacc += red[wq];
+    pb.fpart[blockIdx.x] = sacc;
+  }
+}
+
 __global__ void __launch_bounds__(1024) k1_csr_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit, int beta_in_smem) {
   const Problem& pb = probs[blockIdx.y];
   Ctrl* ctrl = pb.ctrl;
@@ -423,7 +528,17 @@ bool k1_dense_plan(int ldx, int* R_out, int* S_out, int* G_out, size_t* smem_out
 }
 
 cudaError_t k1_launch(const Problem* d_probs, int nprob, bool csr, int ldx, int has_bias, int ctas_per_problem,
-                      int force_emit, cudaStream_t stream, int* launches) {
+                      int force_emit, cudaStream_t stream, int* launches, int csr_fx) {
+  if (csr && csr_fx) {
+    const int beta_in_smem = (size_t)3 * ldx * 4 <= 220 * 1024 ? 1 : 0;
+    const size_t smem = (size_t)(beta_in_smem ? 3 : 2) * ldx * 4;
+    if (smem > 220 * 1024) return cudaErrorInvalidValue;   // > 28k features: needs a column-blocked gradient (not built yet)
+    cudaError_t e = cudaFuncSetAttribute(k1_csr_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k1_csr_fx_kernel<<<dim3(ctas_per_problem, nprob), 1024, smem, stream>>>(d_probs, has_bias, force_emit, beta_in_smem);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+  }
   if (csr) {
     const int beta_in_smem = (size_t)2 * ldx * 4 <= 200 * 1024 ? 1 : 0;
     const size_t smem = (size_t)(beta_in_smem ? 2 : 1) * ldx * 4;

@@ -64,7 +64,10 @@ struct GramTile { short bi, bj; };   // 128-row block index, 256-col block index
 
 __global__ void __launch_bounds__(G_THREADS, 1)
 gram_tcgen05_kernel(const Problem* __restrict__ probs, const CUtensorMap* __restrict__ tmaps, const GramTile* __restrict__ tiles,
-                    int ntiles, int force) {
+                    int ntiles, int force, int share) {
+  // share = L > 1: the L problems of one partition are at the same iterate (cold start), so their Grams are identical;
+  // only the first of each group is built and chol_prep_kernel reads it for the whole group
+  if (share > 1 && blockIdx.z % share != 0) return;
   const int pidx = blockIdx.z;
   const Problem& pb = probs[pidx];
   Ctrl* ctrl = pb.ctrl;
@@ -194,7 +197,8 @@ constexpr int S_A_BYTES = SK * GM * 2;       // 8 KB  : 2 boxes of [32 k][64 col
 constexpr int S_B_BYTES = SK * GN * 2;       // 16 KB : 4 boxes
 constexpr int S_STAGE_BYTES = S_A_BYTES + S_B_BYTES;
 constexpr int S_BOX_BYTES = SK * 128;        // 4 KB
-constexpr int S_THREADS = 13 * 32;
+constexpr int SPW = 3;                       // producer warps per stage: one per 128-column operand block
+constexpr int S_THREADS = (1 + SPW * SST + 4) * 32;   // MMA warp, producers, 4 epilogue warps
 constexpr size_t S_SMEM = (size_t)SST * S_STAGE_BYTES + 1024 + 256;
 
 __device__ __forceinline__ uint32_t sw128_off(int k, int col) {   // byte offset of element (row k, column col) inside an operand tile
@@ -203,7 +207,8 @@ __device__ __forceinline__ uint32_t sw128_off(int k, int col) {   // byte offset
 }
 
 __global__ void __launch_bounds__(S_THREADS, 1)
-gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __restrict__ tiles, int ntiles, int force, int bias_col) {
+gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __restrict__ tiles, int ntiles, int force, int bias_col, int share) {
+  if (share > 1 && blockIdx.z % share != 0) return;   // see gram_tcgen05_kernel
   const Problem& pb = probs[blockIdx.z];
   Ctrl* ctrl = pb.ctrl;
   if (!force && (ctrl->done || !ctrl->need_hess)) return;
@@ -228,7 +233,7 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
   // clear the whole ring once
   for (int e = threadIdx.x; e < SST * S_STAGE_BYTES / 16; e += S_THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0u, 0u, 0u, 0u);
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < SST; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < SST; s++) { mbar_init(&full_bar[s], SPW); mbar_init(&empty_bar[s], 1); }
     mbar_init(acc_bar, 1);
     fence_mbar_init();
   }
@@ -262,46 +267,39 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
       }
       umma_commit(acc_bar);
     }
-  } else if (warp <= SST) {
-    // ===== producers: warp p owns stage p-1 and the K-steps k = p-1, p-1+SST, ...  One K-step = one 32-row group, whose
-    // entries for a 128-column block are one contiguous run of the block-major list: three runs per stage (A block,
-    // two B blocks).  Offsets are fetched two uses ahead and the first 32 entries of each run one use ahead, so the
-    // loads of a use are in flight during the whole previous use.
-    const int st = warp - 1;
+  } else if (warp <= SPW * SST) {
+    // ===== producers: three warps per stage, one per 128-column operand block (A block, first and second B block).
+    // The warps of stage s own the K-steps k = s, s+SST, ...  One K-step = one 32-row group, whose entries for a
+    // 128-column block are one contiguous run of the block-major list.  Offsets are fetched two uses ahead and the
+    // first 64 entries of the run one use ahead, so the loads of a use are in flight during the whole previous use.
+    const int st = (warp - 1) / SPW, strm = (warp - 1) % SPW;
     unsigned char* a_tile = smem + (size_t)st * S_STAGE_BYTES;
-    unsigned char* b_tile = a_tile + S_A_BYTES;
-    unsigned char* const sbase[3] = {a_tile, b_tile, b_tile + 2 * S_BOX_BYTES};
-    const int acol0 = tile.bi * GM, bcol0 = tile.bj * GN;
-    const int nblk = pb.nblk128;
+    unsigned char* const sbase = strm == 0 ? a_tile : a_tile + S_A_BYTES + (strm - 1) * 2 * S_BOX_BYTES;
+    const int blk = strm == 0 ? tile.bi : tile.bj * 2 + (strm - 1);
+    const bool valid = blk < pb.nblk128;
     const long long ngroups = pb.bm_groups;
-    const long long* __restrict__ offs = pb.bm_offs;
+    const long long* __restrict__ my_offs = pb.bm_offs + (size_t)(valid ? blk : 0) * ngroups + (lane & 1);
     const unsigned short* __restrict__ keys = pb.bm_keys;
     const float* __restrict__ bvals = pb.bm_vals;
     const float* __restrict__ sdv = pb.sdvec;
-    // lanes 0..5 fetch {lo, hi} of the three runs
-    const int my_blk = (lane >> 1) == 0 ? tile.bi : tile.bj * 2 + ((lane >> 1) - 1);
-    const bool my_valid = lane < 6 && my_blk < nblk;
-    const long long* my_offs = offs + (size_t)(my_valid ? my_blk : 0) * ngroups + (lane & 1);
     // the bias column (value 1 in every row, llf/LibLinearDataset.java:592-614) is not stored in the CSR rows
-    const bool bias_in_a = bias_col >= acol0 && bias_col < acol0 + GM;
-    const bool bias_in_b = bias_col >= bcol0 && bias_col < bcol0 + GN;
-    const uint32_t bias_off_a = bias_in_a ? sw128_off(lane, bias_col - acol0) : 0u;
-    const uint32_t bias_off_b = bias_in_b ? sw128_off(lane, bias_col - bcol0) : 0u;
+    const bool has_bias_col = valid && bias_col >= blk * 128 && bias_col < blk * 128 + 128;
+    const uint32_t bias_off = has_bias_col ? sw128_off(lane, bias_col - blk * 128) : 0u;
     constexpr uint32_t NOKEY = 0xFFFFFFFFu;
+    const bool fetch = valid && lane < 2;
 
-    long long o_nxt = (my_valid && st < nk) ? my_offs[ks0 + st] : 0;                   // offsets of the use being prefetched
-    long long o_nx2 = (my_valid && st + SST < nk) ? my_offs[ks0 + st + SST] : 0;       // ... and of the one after
-    long long lo[3], hi[3], plo[3] = {0, 0, 0}, phi[3] = {0, 0, 0};
-    uint32_t ckey[3], pkey[3] = {NOKEY, NOKEY, NOKEY};
-    float cval[3], csd;
-    // prefetch use 0
+    long long o_a = (fetch && st < nk) ? my_offs[ks0 + st] : 0;                   // offsets of the use being prefetched
+    long long o_b = (fetch && st + SST < nk) ? my_offs[ks0 + st + SST] : 0;       // ... and of the one after
+    long long lo, hi, plo = 0, phi = 0;
+    uint32_t ckey[2], pkey[2] = {NOKEY, NOKEY};
+    float cval[2], csd;
+    lo = __shfl_sync(0xffffffffu, o_a, 0);
+    hi = __shfl_sync(0xffffffffu, o_a, 1);
 #pragma unroll
-    for (int s = 0; s < 3; s++) {
-      lo[s] = __shfl_sync(0xffffffffu, o_nxt, 2 * s);
-      hi[s] = __shfl_sync(0xffffffffu, o_nxt, 2 * s + 1);
-      const long long e = lo[s] + lane;
-      ckey[s] = e < hi[s] ? (uint32_t)keys[e] : NOKEY;
-      cval[s] = e < hi[s] ? bvals[e] : 0.f;
+    for (int q = 0; q < 2; q++) {
+      const long long e = lo + lane + 32 * q;
+      ckey[q] = e < hi ? (uint32_t)keys[e] : NOKEY;
+      cval[q] = e < hi ? bvals[e] : 0.f;
     }
     {
       const long long r = (ks0 + st) * SK + lane;
@@ -310,18 +308,16 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
     bool prow = false;
     for (int k = st, use = 0; k < nk; k += SST, use++) {
       // ---- issue the loads of the next use
-      long long nlo[3], nhi[3];
-      uint32_t nkey[3];
-      float nval[3], nsd;
-      const long long o_cur_next = o_nx2;
-      o_nx2 = (my_valid && k + 2 * SST < nk) ? my_offs[ks0 + k + 2 * SST] : 0;
+      uint32_t nkey[2];
+      float nval[2], nsd;
+      const long long o_n = o_b;
+      o_b = (fetch && k + 2 * SST < nk) ? my_offs[ks0 + k + 2 * SST] : 0;
+      const long long nlo = __shfl_sync(0xffffffffu, o_n, 0), nhi = __shfl_sync(0xffffffffu, o_n, 1);
 #pragma unroll
-      for (int s = 0; s < 3; s++) {
-        nlo[s] = __shfl_sync(0xffffffffu, o_cur_next, 2 * s);
-        nhi[s] = __shfl_sync(0xffffffffu, o_cur_next, 2 * s + 1);
-        const long long e = nlo[s] + lane;
-        nkey[s] = e < nhi[s] ? (uint32_t)keys[e] : NOKEY;
-        nval[s] = e < nhi[s] ? bvals[e] : 0.f;
+      for (int q = 0; q < 2; q++) {
+        const long long e = nlo + lane + 32 * q;
+        nkey[q] = e < nhi ? (uint32_t)keys[e] : NOKEY;
+        nval[q] = e < nhi ? bvals[e] : 0.f;
       }
       {
         const long long rn = (ks0 + k + SST) * SK + lane;
@@ -331,51 +327,43 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
       if (use > 0) {
         mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
 #pragma unroll
-        for (int s = 0; s < 3; s++) {
-          if (pkey[s] != NOKEY) *reinterpret_cast<unsigned short*>(sbase[s] + pkey[s]) = 0;
-          for (long long e0 = plo[s] + 32; e0 < phi[s]; e0 += 32) {
-            const long long e = e0 + lane;
-            if (e < phi[s]) *reinterpret_cast<unsigned short*>(sbase[s] + keys[e]) = 0;
-          }
+        for (int q = 0; q < 2; q++)
+          if (pkey[q] != NOKEY) *reinterpret_cast<unsigned short*>(sbase + pkey[q]) = 0;
+        for (long long e0 = plo + 64; e0 < phi; e0 += 32) {
+          const long long e = e0 + lane;
+          if (e < phi) *reinterpret_cast<unsigned short*>(sbase + keys[e]) = 0;
         }
-        if (prow && bias_in_a) *reinterpret_cast<unsigned short*>(a_tile + bias_off_a) = 0;
-        if (prow && bias_in_b) *reinterpret_cast<unsigned short*>(b_tile + bias_off_b) = 0;
+        if (prow && has_bias_col) *reinterpret_cast<unsigned short*>(sbase + bias_off) = 0;
       }
       // ---- write this use
-      const long long r = (ks0 + k) * SK + lane;
 #pragma unroll
-      for (int s = 0; s < 3; s++) {
-        {
-          const bool v = ckey[s] != NOKEY;
-          const uint32_t key = v ? ckey[s] : 0u;
-          const float sdk = __shfl_sync(0xffffffffu, csd, (key >> 7) & 31);
-          if (v) *reinterpret_cast<__nv_bfloat16*>(sbase[s] + key) = __float2bfloat16_rn(cval[s] * sdk);
-        }
-        for (long long e0 = lo[s] + 32; e0 < hi[s]; e0 += 32) {
-          const long long e = e0 + lane;
-          const bool v = e < hi[s];
-          const uint32_t key = v ? (uint32_t)keys[e] : 0u;
-          const float val = v ? bvals[e] : 0.f;
-          const float sdk = __shfl_sync(0xffffffffu, csd, (key >> 7) & 31);
-          if (v) *reinterpret_cast<__nv_bfloat16*>(sbase[s] + key) = __float2bfloat16_rn(val * sdk);
-        }
+      for (int q = 0; q < 2; q++) {
+        const bool v = ckey[q] != NOKEY;
+        const uint32_t key = v ? ckey[q] : 0u;
+        const float sdk = __shfl_sync(0xffffffffu, csd, (key >> 7) & 31);
+        if (v) *reinterpret_cast<__nv_bfloat16*>(sbase + key) = __float2bfloat16_rn(cval[q] * sdk);
       }
-      prow = r < n;
-      if (prow && bias_in_a) *reinterpret_cast<__nv_bfloat16*>(a_tile + bias_off_a) = __float2bfloat16_rn(csd);
-      if (prow && bias_in_b) *reinterpret_cast<__nv_bfloat16*>(b_tile + bias_off_b) = __float2bfloat16_rn(csd);
+      for (long long e0 = lo + 64; e0 < hi; e0 += 32) {
+        const long long e = e0 + lane;
+        const bool v = e < hi;
+        const uint32_t key = v ? (uint32_t)keys[e] : 0u;
+        const float val = v ? bvals[e] : 0.f;
+        const float sdk = __shfl_sync(0xffffffffu, csd, (key >> 7) & 31);
+        if (v) *reinterpret_cast<__nv_bfloat16*>(sbase + key) = __float2bfloat16_rn(val * sdk);
+      }
+      prow = (ks0 + k) * SK + lane < n;
+      if (prow && has_bias_col) *reinterpret_cast<__nv_bfloat16*>(sbase + bias_off) = __float2bfloat16_rn(csd);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[st]);
       // ---- rotate
+      plo = lo; phi = hi; lo = nlo; hi = nhi;
 #pragma unroll
-      for (int s = 0; s < 3; s++) {
-        plo[s] = lo[s]; phi[s] = hi[s]; pkey[s] = ckey[s];
-        lo[s] = nlo[s]; hi[s] = nhi[s]; ckey[s] = nkey[s]; cval[s] = nval[s];
-      }
+      for (int q = 0; q < 2; q++) { pkey[q] = ckey[q]; ckey[q] = nkey[q]; cval[q] = nval[q]; }
       csd = nsd;
     }
   } else {
-    // ===== epilogue: warps 9..12 -> TMEM lane quadrant (warp % 4) =====
+    // ===== epilogue: the last four warps -> TMEM lane quadrant (warp % 4) =====
     const int quad = warp & 3;
     float* out = pb.Hpart + (size_t)slice * Dp * Dp;
     const int row = tile.bi * GM + quad * 32 + lane;
@@ -547,7 +535,7 @@ int gram_tile_list(int Dp, short* bi_bj_pairs /*[2*max]*/, int max_tiles) {
 }
 
 cudaError_t gram_launch_tcgen05(const Problem* d_probs, int nprob, const void* d_tmaps, const void* d_tiles, int ntiles,
-                                int nslices, int force, cudaStream_t st, int* launches) {
+                                int nslices, int force, cudaStream_t st, int* launches, int share) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
@@ -555,20 +543,20 @@ cudaError_t gram_launch_tcgen05(const Problem* d_probs, int nprob, const void* d
     configured = true;
   }
   gram_tcgen05_kernel<<<dim3(ntiles, nslices, nprob), G_THREADS, G_SMEM, st>>>(
-      d_probs, reinterpret_cast<const CUtensorMap*>(d_tmaps), reinterpret_cast<const GramTile*>(d_tiles), ntiles, force);
+      d_probs, reinterpret_cast<const CUtensorMap*>(d_tmaps), reinterpret_cast<const GramTile*>(d_tiles), ntiles, force, share);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }
 
 cudaError_t gram_launch_csr_tcgen05(const Problem* d_probs, int nprob, const void* d_tiles, int ntiles, int nslices, int force,
-                                    int bias_col, cudaStream_t st, int* launches) {
+                                    int bias_col, cudaStream_t st, int* launches, int share) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gram_csr_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  gram_csr_tcgen05_kernel<<<dim3(ntiles, nslices, nprob), S_THREADS, S_SMEM, st>>>(d_probs, reinterpret_cast<const GramTile*>(d_tiles), ntiles, force, bias_col);
+  gram_csr_tcgen05_kernel<<<dim3(ntiles, nslices, nprob), S_THREADS, S_SMEM, st>>>(d_probs, reinterpret_cast<const GramTile*>(d_tiles), ntiles, force, bias_col, share);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

@@ -18,8 +18,10 @@ constexpr int NB = 32;   // panel width
 constexpr int TB = 64;   // trailing-update tile
 
 // Hd (lower incl. diagonal) = sum_s Hpart[s] + diag(q); padded rows/cols (>= Dt) = identity.
-__global__ void chol_prep_kernel(const Problem* __restrict__ probs) {
+__global__ void chol_prep_kernel(const Problem* __restrict__ probs, int share) {
   const Problem& pb = probs[blockIdx.z];
+  // share = L > 1: the Gram partials of the group's first problem stand for the whole group (see gram_tcgen05_kernel)
+  const float* __restrict__ hpart = share > 1 ? probs[blockIdx.z - blockIdx.z % share].Hpart : pb.Hpart;
   Ctrl* c = pb.ctrl;
   if (c->done || !c->need_hess) return;
   const int ldh = pb.ldh, Dt = pb.Dt, Dp = pb.Dp, S = pb.gram_slices;
@@ -30,7 +32,7 @@ __global__ void chol_prep_kernel(const Problem* __restrict__ probs) {
   if (i < Dt) {
     double s = 0.0;
     const size_t off = (size_t)i * Dp + j;
-    for (int t = 0; t < S; t++) s += (double)pb.Hpart[(size_t)t * Dp * Dp + off];
+    for (int t = 0; t < S; t++) s += (double)hpart[(size_t)t * Dp * Dp + off];
     if (i == j) s += pb.q[i];
     v = s;
   } else {
@@ -528,11 +530,11 @@ static cudaError_t cholesky_launch_wide(const Problem* d_probs, int nprob, int l
   return dgemm_launch<false, false>(d_probs, nprob, 3, 0, 0, ldh, ldh, 1, st, launches);
 }
 
-cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches) {
+cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches, int share) {
   {
     dim3 blk(32, 8);
     dim3 grd((ldh + 31) / 32, (ldh + 7) / 8, nprob);
-    chol_prep_kernel<<<grd, blk, 0, st>>>(d_probs);
+    chol_prep_kernel<<<grd, blk, 0, st>>>(d_probs, share);
     if (launches) *launches += 1;
   }
   const int nb = ldh / NB;

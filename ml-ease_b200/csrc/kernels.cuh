@@ -7,7 +7,7 @@ namespace mlease {
 // K1 (k1_score_grad.cu)
 bool k1_dense_plan(int ldx, int* R_out, int* S_out, int* G_out, size_t* smem_out, int* ctas_per_sm);
 cudaError_t k1_launch(const Problem* d_probs, int nprob, bool csr, int ldx, int has_bias, int ctas_per_problem,
-                      int force_emit, cudaStream_t stream, int* launches);
+                      int force_emit, cudaStream_t stream, int* launches, int csr_fx = 0);
 
 // Newton state machine (newton.cu)
 cudaError_t newton_begin(const Problem* d_probs, int nprob, double xtol, int max_newton, int hess_policy,
@@ -19,16 +19,16 @@ cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_
 int gram_make_tensor_map(void* out_map_host, const void* xt, long long n, int Dp);
 int gram_tile_list(int Dp, short* bi_bj_pairs, int max_tiles);
 cudaError_t gram_launch_tcgen05(const Problem* d_probs, int nprob, const void* d_tmaps, const void* d_tiles, int ntiles,
-                                int nslices, int force, cudaStream_t st, int* launches);
+                                int nslices, int force, cudaStream_t st, int* launches, int share = 0);
 cudaError_t gram_launch_csr_tcgen05(const Problem* d_probs, int nprob, const void* d_tiles, int ntiles, int nslices, int force,
-                                    int bias_col, cudaStream_t st, int* launches);
+                                    int bias_col, cudaStream_t st, int* launches, int share = 0);
 cudaError_t csr_bm_offsets(long long n, const long long* rowptr, const int* colidx, int nblk, long long ngroups, long long* offs, cudaStream_t st);
 cudaError_t csr_bm_fill(long long n, const long long* rowptr, const int* colidx, const float* vals, int nblk, long long ngroups,
                         const long long* offs, unsigned short* keys, float* bvals, cudaStream_t st);
 cudaError_t gram_launch_simt(const Problem* d_probs, int nprob, int Dp, int force, cudaStream_t st, int* launches);
 
 // K3 (k3_cholesky.cu)
-cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches);
+cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches, int share = 0);
 
 // K4 (k4_consensus.cu)
 cudaError_t admm_reset(const Problem* d_probs, int nprob, int L, double* d_z, int ldv, const double* d_rho_eff,

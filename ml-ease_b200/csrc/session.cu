@@ -64,6 +64,13 @@ __global__ void check_rows_sorted_kernel(long long n, const long long* rowptr, c
     for (long long j = rowptr[i] + 1; j < rowptr[i + 1]; j++)
       if (colidx[j] <= colidx[j - 1]) { atomicOr(bad, 8); break; }
 }
+// max |a[i]| as the bit pattern of a non-negative float (order preserving), NaN ignored
+__global__ void absmax_kernel(long long n, const float* __restrict__ a, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(a[j]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
 __global__ void check_csr_kernel(long long nnz, const int* colidx, float* vals, int Dg, int binary, int* bad) {
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (long long)gridDim.x * blockDim.x) {
     const int c = colidx[j];
@@ -103,6 +110,7 @@ struct PartData {
   float* vals = nullptr;
   long long nnz = 0;
   int csr_unique = 0;
+  float vmax = 0.f, wmax = 1.f;
   long long* bm_offs = nullptr;    // block-major entry list for the CSR Gram (built at upload when rows are sorted & unique)
   unsigned short* bm_keys = nullptr;
   float* bm_vals = nullptr;
@@ -186,7 +194,7 @@ int batch_alloc(Batch& B, int num_sms) {
   long long maxn = 1;
   for (auto& p : B.h) maxn = std::max(maxn, p.n);
   if (B.csr) {
-    const int cps = (size_t)2 * ldx * 4 <= 100 * 1024 ? 2 : 1;   // CTAs per SM the shared-memory gradient allows
+    const int cps = 1;   // 1024-thread CTAs at 64 registers: one per SM
     B.k1_grid = std::max(1, std::min((int)((maxn + 63) / 64), (num_sms * cps) / std::max(1, nprob)));
   } else {
     int R, S, G, cps = 1;
@@ -291,7 +299,7 @@ int batch_alloc(Batch& B, int num_sms) {
 
 // One x-update for every problem of the batch: beta (init), m, q must already be on the device.
 int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int policy, int invalidate, int* h_flag, int* d_flag,
-                  Counters& cnt, Profiler* prof = nullptr) {
+                  Counters& cnt, Profiler* prof = nullptr, int share_first_gram = 0) {
   Profiler nop;
   Profiler& pf = prof ? *prof : nop;
   int launches = 0;
@@ -308,20 +316,25 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
   B.mirror.resize(B.nprob);
   std::vector<Ctrl>& hc = B.mirror;
   int slots = 0;
+  double shared_flops = 0;   // Gram builds that were not run because the group's first problem stood in for them
   while ((flag & 1) && slots < 400) {
     pf.begin(0, st);
-    CK(k1_launch(B.d, B.nprob, B.csr, B.ldx, B.has_bias, B.k1_grid, -1, st, &launches));
+    CK(k1_launch(B.d, B.nprob, B.csr, B.ldx, B.has_bias, B.k1_grid, -1, st, &launches, B.gram_from_csr));
     pf.end(st);
     pf.begin(1, st);
     CK(k1_reduce_decide(B.d, B.nprob, B.Dt, st, &launches));
     pf.end(st);
     if (flag & 2) {
       pf.begin(2, st);
-      if (B.gram_from_csr) CK(gram_launch_csr_tcgen05(B.d, B.nprob, B.d_tiles, B.ntiles, B.gram_slices, 0, B.has_bias ? B.Dt - 1 : -1, st, &launches));
-      else CK(gram_launch_tcgen05(B.d, B.nprob, B.d_tmaps, B.d_tiles, B.ntiles, B.gram_slices, 0, st, &launches));
+      // cold start of a multi-lambda run: the L problems of a partition all sit at beta = 0, their Grams are the same
+      const int share = (slots == 0) ? share_first_gram : 0;
+      if (share > 1)
+        for (int b = 0; b < B.nprob; b++) if (b % share != 0) shared_flops += (double)B.h[b].n * (double)B.Dt * (double)(B.Dt + 1);
+      if (B.gram_from_csr) CK(gram_launch_csr_tcgen05(B.d, B.nprob, B.d_tiles, B.ntiles, B.gram_slices, 0, B.has_bias ? B.Dt - 1 : -1, st, &launches, share));
+      else CK(gram_launch_tcgen05(B.d, B.nprob, B.d_tmaps, B.d_tiles, B.ntiles, B.gram_slices, 0, st, &launches, share));
       pf.end(st);
       pf.begin(3, st);
-      CK(cholesky_launch(B.d, B.nprob, B.ldh, st, &launches));
+      CK(cholesky_launch(B.d, B.nprob, B.ldh, st, &launches, share));
       pf.end(st);
     }
     pf.begin(1, st);
@@ -369,6 +382,7 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
     cnt.gram_flops += (double)c.hess_builds * (double)p.n * (double)B.Dt * (double)(B.Dt + 1);
     cnt.k1_emit_bytes += (double)c.hess_builds * (double)p.n * (double)B.Dp * 2.0;
   }
+  cnt.gram_flops -= shared_flops;
   for (auto& c : hc) {
     cnt.k1_passes += c.evals; cnt.newton_steps += c.newton_steps; cnt.rejected += c.rejects; cnt.gram_builds += c.hess_builds;
     if (c.fail == 3 || !c.done) cnt.not_converged++;
@@ -443,6 +457,7 @@ void fill_problem_data(Problem& p, const PartData& pd) {
   p.rowptr = pd.rowptr; p.colidx = pd.colidx; p.vals = pd.vals; p.nnz_hint = pd.nnz; p.csr_unique = pd.csr_unique;
   p.bm_offs = pd.bm_offs; p.bm_keys = pd.bm_keys; p.bm_vals = pd.bm_vals; p.bm_groups = pd.bm_groups;
   p.nblk128 = pd.nblk128; p.gram_from_csr = pd.bm_offs ? 1 : 0;
+  p.vmax = pd.vmax; p.wmax = pd.wmax;
 }
 
 int finalize(mlease_session* s) {
@@ -621,6 +636,13 @@ static int add_common(mlease_session* s, PartData& pd, const int32_t* response, 
   if (*s->h_flag & 1) return fail(MLEASE_ERR_INVALID, "response (only 1, 0, -1 are allowed)");
   if (*s->h_flag & 2) return fail(MLEASE_ERR_INVALID, "weight cannot < 0");
   pd.y = (signed char*)y; pd.w = (float*)w; pd.o = (float*)o;
+  if (n > 0) {
+    CK(cudaMemsetAsync(s->d_flag, 0, 4, s->stream));
+    absmax_kernel<<<(int)std::min<long long>((n + 255) / 256, 2048), 256, 0, s->stream>>>(n, (const float*)w, (unsigned*)s->d_flag);
+    CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    std::memcpy(&pd.wmax, s->h_flag, 4);
+  }
   return 0;
 }
 
@@ -712,6 +734,13 @@ int mlease_add_partition_csr(mlease_session* s, int32_t pid, int64_t nrows, cons
     CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     if (*s->h_flag) return fail(MLEASE_ERR_INVALID, "feature index out of range");
+    {
+      CK(cudaMemsetAsync(s->d_flag, 0, 4, s->stream));
+      absmax_kernel<<<(int)std::min<long long>((pd.nnz + 255) / 256, 2048), 256, 0, s->stream>>>(pd.nnz, (const float*)vv, (unsigned*)s->d_flag);
+      CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
+      CK(cudaStreamSynchronize(s->stream));
+      std::memcpy(&pd.vmax, s->h_flag, 4);
+    }
     CK(cudaMemsetAsync(s->d_flag, 0, 4, s->stream));
     check_rows_sorted_kernel<<<(int)std::min<long long>((nrows + 255) / 256, 4096), 256, 0, s->stream>>>(nrows, (const long long*)rp, (const int*)ci, s->d_flag);
     CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
@@ -768,7 +797,8 @@ int mlease_admm_local_step(mlease_session* s, double* exchange_dev) {
     if (r != s->rho_fact[l]) invalidate = 1;   // prior precision changed -> stale factors are for another H
     s->rho_fact[l] = r;
   }
-  if (int rc = batch_xupdate(*s->batch, s->stream, s->xtol, s->max_newton, s->cfg.hessian_policy, invalidate, s->h_flag, s->d_flag, s->cnt, &s->prof)) return rc;
+  if (int rc = batch_xupdate(*s->batch, s->stream, s->xtol, s->max_newton, s->cfg.hessian_policy, invalidate, s->h_flag, s->d_flag, s->cnt, &s->prof,
+                             (i == 1 && s->L > 1) ? s->L : 0)) return rc;
   int launches = 0;
   CK(admm_pack(s->batch->d, (int)s->parts.size(), s->L, s->Dt, exchange_dev, s->stream, &launches));
   s->cnt.launches += launches;
@@ -904,7 +934,7 @@ int mlease_objective(mlease_session* s, int32_t pid, const double* w, const doub
   if (int rc = scratch_set(s, w, m, q)) return rc;
   int launches = 0;
   CK(newton_begin(B->d, 1, 1e-8, 1, 1, 1, 0, s->stream, &launches));
-  CK(k1_launch(B->d, 1, B->csr, B->ldx, 1, B->k1_grid, H ? 1 : 0, s->stream, &launches));
+  CK(k1_launch(B->d, 1, B->csr, B->ldx, B->has_bias, B->k1_grid, H ? 1 : 0, s->stream, &launches, B->gram_from_csr));
   CK(k1_reduce_decide(B->d, 1, B->Dt, s->stream, &launches));
   const Problem& p = B->h[0];
   Ctrl c;
@@ -982,7 +1012,7 @@ int mlease_time_kernel(mlease_session* s, int32_t pid, int32_t which, int32_t re
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   // warm-up launch (also produces the scaled copy the Gram needs)
-  CK(k1_launch(B->d, 1, B->csr, B->ldx, 1, B->k1_grid, 1, s->stream, &launches));
+  CK(k1_launch(B->d, 1, B->csr, B->ldx, B->has_bias, B->k1_grid, 1, s->stream, &launches, B->gram_from_csr));
   const int bias_col = B->has_bias ? B->Dt - 1 : -1;
   if (which == 3) {
     if (B->gram_from_csr) CK(gram_launch_csr_tcgen05(B->d, 1, B->d_tiles, B->ntiles, B->gram_slices, 1, bias_col, s->stream, &launches));
@@ -993,7 +1023,7 @@ int mlease_time_kernel(mlease_session* s, int32_t pid, int32_t which, int32_t re
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaEventRecord(e0, s->stream));
   for (int r = 0; r < reps; r++) {
-    if (which == 1) CK(k1_launch(B->d, 1, B->csr, B->ldx, 1, B->k1_grid, emit_scaled ? 1 : 0, s->stream, &launches));
+    if (which == 1) CK(k1_launch(B->d, 1, B->csr, B->ldx, B->has_bias, B->k1_grid, emit_scaled ? 1 : 0, s->stream, &launches, B->gram_from_csr));
     else if (which == 2 && B->gram_from_csr) CK(gram_launch_csr_tcgen05(B->d, 1, B->d_tiles, B->ntiles, B->gram_slices, 1, bias_col, s->stream, &launches));
     else if (which == 2) CK(gram_launch_tcgen05(B->d, 1, B->d_tmaps, B->d_tiles, B->ntiles, B->gram_slices, 1, s->stream, &launches));
     else if (which == 3) CK(cholesky_launch(B->d, 1, B->ldh, s->stream, &launches));

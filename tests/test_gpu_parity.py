@@ -40,6 +40,31 @@ def mb():
     return mlease_b200
 
 
+@pytest.mark.parametrize("n,d,sparse", [(1000, 37, False), (777, 100, False), (300, 1100, False), (500, 2500, False), (1000, 50, True),
+                                        (4000, 3000, True), (50, 20, True)])
+def test_k1_objective_and_gradient(mb, n, d, sparse):
+    """One K1 pass (loss + gradient) against the oracle's fun/grad.  CSR partitions with sorted unique rows take the
+    fixed-point kernel (two 32-bit integer words per gradient entry in shared memory); the pass must also be bitwise
+    reproducible from call to call, whatever order the warps retire in."""
+    X, y, w, o = _mk(n, d, seed=n + d, sparse=sparse)
+    rng = np.random.default_rng(1)
+    wv = rng.normal(0, 0.3, d + 1); pm = rng.normal(0, 0.3, d + 1); pv = rng.uniform(0.2, 2.0, d + 1)
+    with _session(mb, d) as s:
+        if sparse:
+            rp, ci, v = _csr_of(X)
+            s.add_partition_csr(0, rp, ci, v, y, w, o)
+            data = orc.Csr(rp, ci, v, y, w, o, d)
+        else:
+            s.add_partition_dense(0, X, y, w, o)
+            data = orc.Csr.from_dense(X, y, w, o)
+        f, g, _ = s.objective(0, wv, pm, 1.0 / pv)
+        f2, g2, _ = s.objective(0, wv, pm, 1.0 / pv)
+    f_ref, g_ref = orc.objective("grad", data, wv, pm, pv)
+    assert abs(f - f_ref) <= 1e-5 * abs(f_ref), (f, f_ref)
+    assert np.abs(g - g_ref).max() <= 1e-5 * np.abs(g_ref).max(), np.abs(g - g_ref).max() / np.abs(g_ref).max()
+    assert f == f2 and np.array_equal(g, g2)
+
+
 def _bf16_round(a):
     u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
     u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000

@@ -92,6 +92,8 @@ struct Problem {
   double* Ldinv;           // [ldh][32] inverses of the diagonal blocks (lower triangular)
   double* Yinv;            // [ldh][ldh] L^-1 (lower)
   double* Hinv;            // [ldh][ldh] (L L^T)^-1, full symmetric: a Newton direction is one GEMV
+  float* Hinv_f;          // fp32 copy of Hinv for the direction GEMV of wide systems (ldh > 2048; NULL otherwise): H^-1 only
+                          // preconditions (the Gram is bf16), and the GEMV is HBM-bound on D'^2 entries
   int ldh;
   Ctrl* ctrl;
   // ADMM per-problem vectors (float, as the reference's avro files hold them)

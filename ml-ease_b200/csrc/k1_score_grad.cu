@@ -323,20 +323,26 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
 //   hi = rint(c S), lo = rint((c S - hi) 2^k), gradient = (sum hi + sum lo / 2^k) / S,
 // i.e. a resolution of B 2^-(29+k) per contribution (k = 16 at 16k rows per CTA), below fp32 rounding of the
 // contribution itself.  The first 128 entries of a row stay in registers between the margin and the gradient half.
-__global__ void __launch_bounds__(1024, 1) k1_csr_fx_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit, int beta_in_smem) {
+template <bool BSM>   // BSM: beta staged in shared memory (LDS gathers) / read through L1 from global memory
+__global__ void __launch_bounds__(1024, 1) k1_csr_fx_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit) {
   const Problem& pb = probs[blockIdx.y];
   Ctrl* ctrl = pb.ctrl;
   if (ctrl->done) return;
   const bool emit = force_emit >= 0 ? (force_emit != 0) : (ctrl->emit != 0);
   extern __shared__ __align__(16) float csr_sm[];
   const int ldx = pb.ldx, Dt = pb.Dt;
+  // layout: g_hi[ldx + 32] | g_lo[ldx + 32] | beta[ldx]; the 32 extra words are per-lane dummy slots for lanes past
+  // the end of a row (they add 0 there), which keeps the gradient half free of divergent branches
+  const int gs = ldx + 32;
   int* g_hi = reinterpret_cast<int*>(csr_sm);
-  int* g_lo = g_hi + ldx;
-  float* b_s = csr_sm + 2 * (size_t)ldx;
+  int* g_lo = g_hi + gs;
+  float* b_s = csr_sm + 2 * (size_t)gs;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  for (int k = tid; k < ldx; k += blockDim.x) { g_hi[k] = 0; g_lo[k] = 0; if (beta_in_smem) b_s[k] = pb.beta_tf[k]; }
+  for (int k = tid; k < gs; k += blockDim.x) { g_hi[k] = 0; g_lo[k] = 0; }
+  if (BSM)
+    for (int k = tid; k < ldx; k += blockDim.x) b_s[k] = pb.beta_tf[k];
   __syncthreads();
-  const float* __restrict__ bt = beta_in_smem ? b_s : pb.beta_tf;
+  const float* __restrict__ bg = pb.beta_tf;
   const long long n = pb.n;
   const long long per = (n + gridDim.x - 1) / gridDim.x;
   const long long rb = (long long)blockIdx.x * per, re = min(n, rb + per);
@@ -348,34 +354,39 @@ __global__ void __launch_bounds__(1024, 1) k1_csr_fx_kernel(const Problem* __res
   kbits = max(0, min(kbits, 24));
   const float s_hi = ldexpf(1.f, e_hi), s_k = ldexpf(1.f, kbits);
   const long long* __restrict__ rp = pb.rowptr;
-  const int* __restrict__ ci = pb.colidx;
-  const float* __restrict__ vv = pb.vals;
+  const int dummy = ldx + lane;
+  const float bias_b = has_bias ? (BSM ? b_s[Dt - 1] : __ldg(bg + Dt - 1)) : 0.f;
   double loss = 0.0;
   long long i = rb + warp;
-  long long j0 = 0, j1 = 0;
+  long long j0 = 0;
+  int len = 0;
   float yy = 0.f, ww = 0.f, oo = 0.f;
-  if (i < re) { j0 = rp[i]; j1 = rp[i + 1]; yy = (float)pb.y[i]; ww = pb.w[i]; oo = pb.o[i]; }
+  const signed char* __restrict__ yv = pb.y;
+  const float* __restrict__ wv = pb.w;
+  const float* __restrict__ ov = pb.o;
+  if (i < re) { j0 = __ldg(rp + i); len = (int)(__ldg(rp + i + 1) - j0); yy = (float)__ldg(yv + i); ww = __ldg(wv + i); oo = __ldg(ov + i); }
   while (i < re) {
+    const float* __restrict__ vr = pb.vals + j0;
+    const int* __restrict__ cr = pb.colidx + j0;
     float v[4];
     int c[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      const long long j = j0 + lane + 32 * q;
-      const bool ok = j < j1;
-      v[q] = ok ? vv[j] : 0.f;
-      c[q] = ok ? ci[j] : -1;
+      const bool ok = lane + 32 * q < len;
+      v[q] = ok ? __ldg(vr + lane + 32 * q) : 0.f;
+      c[q] = ok ? __ldg(cr + lane + 32 * q) : dummy;
     }
     // the next row's header while this row's entries are in flight
     const long long in = i + nw;
-    long long j0n = 0, j1n = 0;
+    long long j0n = 0;
+    int lenn = 0;
     float yn = 0.f, wn = 0.f, on = 0.f;
-    if (in < re) { j0n = rp[in]; j1n = rp[in + 1]; yn = (float)pb.y[in]; wn = pb.w[in]; on = pb.o[in]; }
+    if (in < re) { j0n = __ldg(rp + in); lenn = (int)(__ldg(rp + in + 1) - j0n); yn = (float)__ldg(yv + in); wn = __ldg(wv + in); on = __ldg(ov + in); }
     float a = 0.f;
 #pragma unroll
-    for (int q = 0; q < 4; q++) a = fmaf(v[q], c[q] >= 0 ? bt[c[q]] : 0.f, a);
-    for (long long j = j0 + 128 + lane; j < j1; j += 32) a = fmaf(vv[j], bt[ci[j]], a);
-    a = warp_sum(a);
-    if (has_bias) a += bt[Dt - 1];
+    for (int q = 0; q < 4; q++) a = fmaf(v[q], BSM ? b_s[min(c[q], ldx - 1)] : __ldg(bg + min(c[q], ldx - 1)), a);   // v = 0 on dummy lanes
+    for (int j = 128 + lane; j < len; j += 32) a = fmaf(__ldg(vr + j), BSM ? b_s[__ldg(cr + j)] : __ldg(bg + __ldg(cr + j)), a);
+    a = warp_sum(a) + bias_b;
     const float t = yy * (a + oo);
     const float e = __expf(-fabsf(t));
     const float inv = __frcp_rn(1.f + e);
@@ -385,15 +396,13 @@ __global__ void __launch_bounds__(1024, 1) k1_csr_fx_kernel(const Problem* __res
     const float rs = -ww * yy * qq * s_hi;     // contribution scale: c S = value * rs
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      if (c[q] >= 0) {
-        const float ts = v[q] * rs, h = rintf(ts);
-        atomicAdd(&g_hi[c[q]], (int)h);
-        atomicAdd(&g_lo[c[q]], __float2int_rn((ts - h) * s_k));
-      }
+      const float ts = v[q] * rs, h = rintf(ts);
+      atomicAdd(&g_hi[c[q]], (int)h);
+      atomicAdd(&g_lo[c[q]], __float2int_rn((ts - h) * s_k));
     }
-    for (long long j = j0 + 128 + lane; j < j1; j += 32) {
-      const float ts = vv[j] * rs, h = rintf(ts);
-      const int cc = ci[j];
+    for (int j = 128 + lane; j < len; j += 32) {
+      const float ts = __ldg(vr + j) * rs, h = rintf(ts);
+      const int cc = __ldg(cr + j);
       atomicAdd(&g_hi[cc], (int)h);
       atomicAdd(&g_lo[cc], __float2int_rn((ts - h) * s_k));
     }
@@ -403,7 +412,7 @@ __global__ void __launch_bounds__(1024, 1) k1_csr_fx_kernel(const Problem* __res
       atomicAdd(&g_lo[Dt - 1], __float2int_rn((rs - h) * s_k));
     }
     if (emit && lane == 0) pb.sdvec[i] = sqrtf(ww * p * qq);   // the Gram kernel assembles the scaled rows itself
-    i = in; j0 = j0n; j1 = j1n; yy = yn; ww = wn; oo = on;
+    i = in; j0 = j0n; len = lenn; yy = yn; ww = wn; oo = on;
   }
   __syncthreads();
   double* gp = pb.gpart + (size_t)blockIdx.x * ldx;
@@ -530,12 +539,15 @@ bool k1_dense_plan(int ldx, int* R_out, int* S_out, int* G_out, size_t* smem_out
 cudaError_t k1_launch(const Problem* d_probs, int nprob, bool csr, int ldx, int has_bias, int ctas_per_problem,
                       int force_emit, cudaStream_t stream, int* launches, int csr_fx) {
   if (csr && csr_fx) {
-    const int beta_in_smem = (size_t)3 * ldx * 4 <= 220 * 1024 ? 1 : 0;
-    const size_t smem = (size_t)(beta_in_smem ? 3 : 2) * ldx * 4;
+    const size_t g_bytes = (size_t)2 * (ldx + 32) * 4;
+    const bool bsm = g_bytes + (size_t)ldx * 4 <= 220 * 1024;
+    const size_t smem = g_bytes + (bsm ? (size_t)ldx * 4 : 0);
     if (smem > 220 * 1024) return cudaErrorInvalidValue;   // > 28k features: needs a column-blocked gradient (not built yet)
-    cudaError_t e = cudaFuncSetAttribute(k1_csr_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = bsm ? cudaFuncSetAttribute(k1_csr_fx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(k1_csr_fx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k1_csr_fx_kernel<<<dim3(ctas_per_problem, nprob), 1024, smem, stream>>>(d_probs, has_bias, force_emit, beta_in_smem);
+    if (bsm) k1_csr_fx_kernel<true><<<dim3(ctas_per_problem, nprob), 1024, smem, stream>>>(d_probs, has_bias, force_emit);
+    else k1_csr_fx_kernel<false><<<dim3(ctas_per_problem, nprob), 1024, smem, stream>>>(d_probs, has_bias, force_emit);
     if (launches) *launches += 1;
     return cudaGetLastError();
   }

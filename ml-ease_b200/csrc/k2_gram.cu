@@ -288,49 +288,46 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
     constexpr uint32_t NOKEY = 0xFFFFFFFFu;
     const bool fetch = valid && lane < 2;
 
-    long long o_a = (fetch && st < nk) ? my_offs[ks0 + st] : 0;                   // offsets of the use being prefetched
-    long long o_b = (fetch && st + SST < nk) ? my_offs[ks0 + st + SST] : 0;       // ... and of the one after
-    long long lo, hi, plo = 0, phi = 0;
-    uint32_t ckey[2], pkey[2] = {NOKEY, NOKEY};
-    float cval[2], csd;
-    lo = __shfl_sync(0xffffffffu, o_a, 0);
-    hi = __shfl_sync(0xffffffffu, o_a, 1);
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const long long e = lo + lane + 32 * q;
-      ckey[q] = e < hi ? (uint32_t)keys[e] : NOKEY;
-      cval[q] = e < hi ? bvals[e] : 0.f;
-    }
-    {
-      const long long r = (ks0 + st) * SK + lane;
-      csd = (st < nk && r < n) ? sdv[r] : 0.f;
-    }
-    bool prow = false;
-    for (int k = st, use = 0; k < nk; k += SST, use++) {
-      // ---- issue the loads of the next use
-      uint32_t nkey[2];
-      float nval[2], nsd;
-      const long long o_n = o_b;
-      o_b = (fetch && k + 2 * SST < nk) ? my_offs[ks0 + k + 2 * SST] : 0;
-      const long long nlo = __shfl_sync(0xffffffffu, o_n, 0), nhi = __shfl_sync(0xffffffffu, o_n, 1);
+    // Pipeline registers: offsets three uses ahead (o_c), entries + sqrt(d) two uses ahead (set 2), one use ahead (set 1),
+    // current (set 0).  A use lasts about SST MMA K-steps (~1 us), less than a DRAM miss under load, hence two in flight.
+    auto ld_offs = [&](int k) -> uint32_t { return (fetch && k < nk) ? (uint32_t)my_offs[ks0 + k] : 0u; };   // the list holds < 2^32 entries (checked at upload)
+    uint32_t lo0, hi0, lo1, hi1, lo2, hi2, plo = 0, phi = 0;
+    uint32_t key0[2], key1[2], key2[2], pkey[2] = {NOKEY, NOKEY};
+    float val0[2], val1[2], val2[2], sd0, sd1, sd2;
+    auto ld_entries = [&](uint32_t lo, uint32_t hi, uint32_t* key, float* val) {
 #pragma unroll
       for (int q = 0; q < 2; q++) {
-        const long long e = nlo + lane + 32 * q;
-        nkey[q] = e < nhi ? (uint32_t)keys[e] : NOKEY;
-        nval[q] = e < nhi ? bvals[e] : 0.f;
+        const uint32_t e = lo + lane + 32 * q;
+        key[q] = e < hi ? (uint32_t)keys[e] : NOKEY;
+        val[q] = e < hi ? bvals[e] : 0.f;
       }
-      {
-        const long long rn = (ks0 + k + SST) * SK + lane;
-        nsd = (k + SST < nk && rn < n) ? sdv[rn] : 0.f;
-      }
+    };
+    auto ld_sd = [&](int k) -> float {
+      const long long r = (ks0 + k) * SK + lane;
+      return (k < nk && r < n) ? sdv[r] : 0.f;
+    };
+    {
+      const uint32_t oa = ld_offs(st), ob = ld_offs(st + SST);
+      lo0 = __shfl_sync(0xffffffffu, oa, 0); hi0 = __shfl_sync(0xffffffffu, oa, 1);
+      lo1 = __shfl_sync(0xffffffffu, ob, 0); hi1 = __shfl_sync(0xffffffffu, ob, 1);
+    }
+    uint32_t o_c = ld_offs(st + 2 * SST);
+    ld_entries(lo0, hi0, key0, val0); sd0 = ld_sd(st);
+    ld_entries(lo1, hi1, key1, val1); sd1 = ld_sd(st + SST);
+    bool prow = false;
+    for (int k = st, use = 0; k < nk; k += SST, use++) {
+      // ---- issue the loads of the use after next
+      lo2 = __shfl_sync(0xffffffffu, o_c, 0); hi2 = __shfl_sync(0xffffffffu, o_c, 1);
+      o_c = ld_offs(k + 3 * SST);
+      ld_entries(lo2, hi2, key2, val2); sd2 = ld_sd(k + 2 * SST);
       // ---- un-write what the previous use of this stage stored (same addresses, zero)
       if (use > 0) {
         mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
 #pragma unroll
         for (int q = 0; q < 2; q++)
           if (pkey[q] != NOKEY) *reinterpret_cast<unsigned short*>(sbase + pkey[q]) = 0;
-        for (long long e0 = plo + 64; e0 < phi; e0 += 32) {
-          const long long e = e0 + lane;
+        for (uint32_t e0 = plo + 64; e0 < phi; e0 += 32) {
+          const uint32_t e = e0 + lane;
           if (e < phi) *reinterpret_cast<unsigned short*>(sbase + keys[e]) = 0;
         }
         if (prow && has_bias_col) *reinterpret_cast<unsigned short*>(sbase + bias_off) = 0;
@@ -338,29 +335,29 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
       // ---- write this use
 #pragma unroll
       for (int q = 0; q < 2; q++) {
-        const bool v = ckey[q] != NOKEY;
-        const uint32_t key = v ? ckey[q] : 0u;
-        const float sdk = __shfl_sync(0xffffffffu, csd, (key >> 7) & 31);
-        if (v) *reinterpret_cast<__nv_bfloat16*>(sbase + key) = __float2bfloat16_rn(cval[q] * sdk);
+        const bool v = key0[q] != NOKEY;
+        const uint32_t key = v ? key0[q] : 0u;
+        const float sdk = __shfl_sync(0xffffffffu, sd0, (key >> 7) & 31);
+        if (v) *reinterpret_cast<__nv_bfloat16*>(sbase + key) = __float2bfloat16_rn(val0[q] * sdk);
       }
-      for (long long e0 = lo + 64; e0 < hi; e0 += 32) {
-        const long long e = e0 + lane;
-        const bool v = e < hi;
+      for (uint32_t e0 = lo0 + 64; e0 < hi0; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        const bool v = e < hi0;
         const uint32_t key = v ? (uint32_t)keys[e] : 0u;
         const float val = v ? bvals[e] : 0.f;
-        const float sdk = __shfl_sync(0xffffffffu, csd, (key >> 7) & 31);
+        const float sdk = __shfl_sync(0xffffffffu, sd0, (key >> 7) & 31);
         if (v) *reinterpret_cast<__nv_bfloat16*>(sbase + key) = __float2bfloat16_rn(val * sdk);
       }
       prow = (ks0 + k) * SK + lane < n;
-      if (prow && has_bias_col) *reinterpret_cast<__nv_bfloat16*>(sbase + bias_off) = __float2bfloat16_rn(csd);
+      if (prow && has_bias_col) *reinterpret_cast<__nv_bfloat16*>(sbase + bias_off) = __float2bfloat16_rn(sd0);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[st]);
       // ---- rotate
-      plo = lo; phi = hi; lo = nlo; hi = nhi;
+      plo = lo0; phi = hi0; lo0 = lo1; hi0 = hi1; lo1 = lo2; hi1 = hi2;
 #pragma unroll
-      for (int q = 0; q < 2; q++) { pkey[q] = ckey[q]; ckey[q] = nkey[q]; cval[q] = nval[q]; }
-      csd = nsd;
+      for (int q = 0; q < 2; q++) { pkey[q] = key0[q]; key0[q] = key1[q]; val0[q] = val1[q]; key1[q] = key2[q]; val1[q] = val2[q]; }
+      sd0 = sd1; sd1 = sd2;
     }
   } else {
     // ===== epilogue: the last four warps -> TMEM lane quadrant (warp % 4) =====

@@ -9,6 +9,7 @@
 // break down when cond(H) approaches 1/eps_fp32; 3.3e8 flop at D'=1001 is latency- not
 // throughput-bound on B200's fp64 pipe.
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(256) hinv_syrk_kernel(const Problem* __restric
 
 
 // ------------------------------------------------------------------------------------------
-// Wide systems (ldh > 2048): the same factorisation / inverse / product, restructured so that almost all flops are
+// Wide systems (ldh > 1000): the same factorisation / inverse / product, restructured so that almost all flops are
 // fp64 tensor-core GEMMs (DMMA m8n8k4) on 128x64 tiles with K chunks of 16 staged through shared memory:
 //   Cholesky : outer panels of WNB columns; inside a panel the NB=32 steps above (panel kernel + K=32 updates limited
 //              to the panel's columns), then one K=WNB trailing update             C -= A A^T      (mode 0)
@@ -475,8 +476,15 @@ __global__ void __launch_bounds__(256, 2) dgemm_kernel(const Problem* __restrict
       } else if (mode == 2) {
         *reinterpret_cast<double2*>(C + (size_t)i * ldh + j) = make_double2(-v0, -v1);
       } else {
-        if (j <= i) { C[(size_t)i * ldh + j] = v0; C[(size_t)j * ldh + i] = v0; }
-        if (j + 1 <= i) { C[(size_t)i * ldh + j + 1] = v1; C[(size_t)(j + 1) * ldh + i] = v1; }
+        float* Cf = pb.Hinv_f;
+        if (j <= i) {
+          C[(size_t)i * ldh + j] = v0; C[(size_t)j * ldh + i] = v0;
+          if (Cf) { Cf[(size_t)i * ldh + j] = (float)v0; Cf[(size_t)j * ldh + i] = (float)v0; }
+        }
+        if (j + 1 <= i) {
+          C[(size_t)i * ldh + j + 1] = v1; C[(size_t)(j + 1) * ldh + i] = v1;
+          if (Cf) { Cf[(size_t)i * ldh + j + 1] = (float)v1; Cf[(size_t)(j + 1) * ldh + i] = (float)v1; }
+        }
       }
     }
   }
@@ -496,6 +504,16 @@ static cudaError_t dgemm_launch(const Problem* d_probs, int nprob, int mode, int
   dgemm_kernel<A_KC, B_KC><<<dim3(tiles, nmerge, nprob), 256, DGEMM_SMEM, st>>>(d_probs, mode, p0, p1);
   if (launches) *launches += 1;
   return cudaGetLastError();
+}
+
+// Systems wider than this take the GEMM-rich path.  MLEASE_WIDE_MIN overrides it (tuning experiments only).
+static int wide_threshold() {
+  static int t = -1;
+  if (t < 0) {
+    const char* e = getenv("MLEASE_WIDE_MIN");
+    t = e ? atoi(e) : 1000;   // measured on B200: D'=1001 (ldh 1024) rebuilds take 4.9 ms (8 problems) / 2.0 ms (1) wide vs 8.1 / 2.75 ms narrow
+  }
+  return t;
 }
 
 static cudaError_t cholesky_launch_wide(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches) {
@@ -530,6 +548,33 @@ static cudaError_t cholesky_launch_wide(const Problem* d_probs, int nprob, int l
   return dgemm_launch<false, false>(d_probs, nprob, 3, 0, 0, ldh, ldh, 1, st, launches);
 }
 
+// Cold start of a multi-lambda run with equal rho: the L problems of a partition have the same H = G + rho I, so only
+// the group's first problem is factorised and inverted; the host then copies its inverse to the others.
+// begin: park the followers (need_hess = 0 makes every factorisation kernel skip them); end: give them the leader's outcome.
+__global__ void chol_share_begin_kernel(const Problem* __restrict__ probs, int nprob, int share) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nprob && b % share != 0) probs[b].ctrl->need_hess = 0;
+}
+__global__ void chol_share_end_kernel(const Problem* __restrict__ probs, int nprob, int share) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nprob || b % share == 0) return;
+  Ctrl* c = probs[b].ctrl;
+  const Ctrl* lead = probs[b - b % share].ctrl;
+  c->need_hess = 1;
+  if (lead->fail == 1) { c->fail = 1; c->done = 1; c->hess_valid = 0; }
+  else { c->hess_valid = 1; c->hess_builds++; c->tot_hess++; c->bfgs_count = 0; }
+}
+cudaError_t cholesky_share_begin(const Problem* d_probs, int nprob, int share, cudaStream_t st, int* launches) {
+  chol_share_begin_kernel<<<(nprob + 127) / 128, 128, 0, st>>>(d_probs, nprob, share);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+cudaError_t cholesky_share_end(const Problem* d_probs, int nprob, int share, cudaStream_t st, int* launches) {
+  chol_share_end_kernel<<<(nprob + 127) / 128, 128, 0, st>>>(d_probs, nprob, share);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
 cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches, int share) {
   {
     dim3 blk(32, 8);
@@ -538,7 +583,7 @@ cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStre
     if (launches) *launches += 1;
   }
   const int nb = ldh / NB;
-  if (ldh > 2048) {
+  if (ldh > wide_threshold()) {
     cudaError_t e = cholesky_launch_wide(d_probs, nprob, ldh, st, launches);
     if (e != cudaSuccess) return e;
   } else {
@@ -554,8 +599,7 @@ cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStre
       }
     }
     // explicit inverse (reads the panel blocks below the diagonal from Lc and the diagonal inverses from Ldinv)
-    if (ldh <= 2048) trinv_kernel<32><<<dim3((ldh + 31) / 32, nprob), 256, 0, st>>>(d_probs, 0);   // more CTAs for small systems
-    else trinv_kernel<64><<<dim3((ldh + 63) / 64, nprob), 256, 0, st>>>(d_probs, 0);
+    trinv_kernel<32><<<dim3((ldh + 31) / 32, nprob), 256, 0, st>>>(d_probs, 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (launches) *launches += 1;

@@ -29,6 +29,8 @@ cudaError_t gram_launch_simt(const Problem* d_probs, int nprob, int Dp, int forc
 
 // K3 (k3_cholesky.cu)
 cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches, int share = 0);
+cudaError_t cholesky_share_begin(const Problem* d_probs, int nprob, int share, cudaStream_t st, int* launches);
+cudaError_t cholesky_share_end(const Problem* d_probs, int nprob, int share, cudaStream_t st, int* launches);
 
 // K4 (k4_consensus.cu)
 cudaError_t admm_reset(const Problem* d_probs, int nprob, int L, double* d_z, int ldv, const double* d_rho_eff,

@@ -246,10 +246,21 @@ __global__ void __launch_bounds__(NT) newton_gemv_kernel(const Problem* __restri
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
   if (r >= pb.Dt) return;
-  const double* Hr = pb.Hinv + (size_t)r * pb.ldh;
   const double* q = pb.g_t;
   double a = 0.0;
-  for (int k = lane; k < pb.Dt; k += 32) a += Hr[k] * q[k];
+  if (pb.Hinv_f) {
+    // wide systems: fp32 copy of the inverse (half the bytes of this HBM-bound product), fp64 accumulation
+    const float* Hr = pb.Hinv_f + (size_t)r * pb.ldh;
+    const int D4 = pb.Dt & ~3;
+    for (int k = lane * 4; k < D4; k += 128) {
+      const float4 h = *reinterpret_cast<const float4*>(Hr + k);
+      a += (double)h.x * q[k] + (double)h.y * q[k + 1] + (double)h.z * q[k + 2] + (double)h.w * q[k + 3];
+    }
+    if (lane < pb.Dt - D4) a += (double)Hr[D4 + lane] * q[D4 + lane];
+  } else {
+    const double* Hr = pb.Hinv + (size_t)r * pb.ldh;
+    for (int k = lane; k < pb.Dt; k += 32) a += Hr[k] * q[k];
+  }
   a = warp_sum(a);
   if (lane == 0) pb.dir[r] = a;   // r = Hinv q (sign applied after the second loop)
 }

@@ -248,6 +248,9 @@ int batch_alloc(Batch& B, int num_sms) {
   if (int rc = dev_alloc(B, (void**)&ldi, (size_t)nprob * B.ldh * 32 * sizeof(double))) return rc;
   if (int rc = dev_alloc(B, (void**)&yi, (size_t)nprob * B.ldh * B.ldh * sizeof(double))) return rc;
   if (int rc = dev_alloc(B, (void**)&hi, (size_t)nprob * B.ldh * B.ldh * sizeof(double))) return rc;
+  float* hif = nullptr;
+  if (B.ldh > 2048)
+    if (int rc = dev_alloc(B, (void**)&hif, (size_t)nprob * B.ldh * B.ldh * sizeof(float))) return rc;
   if (int rc = dev_alloc(B, (void**)&B.d_ctrl, (size_t)nprob * sizeof(Ctrl))) return rc;
   if (int rc = dev_alloc(B, (void**)&B.d, (size_t)nprob * sizeof(Problem))) return rc;
   if (int rc = dev_alloc(B, &B.d_tmaps, (size_t)nprob * sizeof(CUtensorMap))) return rc;
@@ -275,6 +278,7 @@ int batch_alloc(Batch& B, int num_sms) {
     p.Ldinv = ldi + (size_t)b * B.ldh * 32;
     p.Yinv = yi + (size_t)b * B.ldh * B.ldh;
     p.Hinv = hi + (size_t)b * B.ldh * B.ldh;
+    p.Hinv_f = hif ? hif + (size_t)b * B.ldh * B.ldh : nullptr;
     p.ctrl = B.d_ctrl + b;
     if (B.gram_from_csr) {
       void* sv;
@@ -299,7 +303,7 @@ int batch_alloc(Batch& B, int num_sms) {
 
 // One x-update for every problem of the batch: beta (init), m, q must already be on the device.
 int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int policy, int invalidate, int* h_flag, int* d_flag,
-                  Counters& cnt, Profiler* prof = nullptr, int share_first_gram = 0) {
+                  Counters& cnt, Profiler* prof = nullptr, int share_first_gram = 0, int share_first_factor = 0) {
   Profiler nop;
   Profiler& pf = prof ? *prof : nop;
   int launches = 0;
@@ -334,7 +338,19 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
       else CK(gram_launch_tcgen05(B.d, B.nprob, B.d_tmaps, B.d_tiles, B.ntiles, B.gram_slices, 0, st, &launches, share));
       pf.end(st);
       pf.begin(3, st);
+      const bool share_fact = share > 1 && share_first_factor;   // same rho too: same H, one factorisation per group
+      if (share_fact) CK(cholesky_share_begin(B.d, B.nprob, share, st, &launches));
       CK(cholesky_launch(B.d, B.nprob, B.ldh, st, &launches, share));
+      if (share_fact) {
+        CK(cholesky_share_end(B.d, B.nprob, share, st, &launches));
+        const size_t hh = (size_t)B.ldh * B.ldh;
+        for (int b = 0; b < B.nprob; b++) {
+          if (b % share == 0) continue;
+          const Problem& lead = B.h[b - b % share];
+          CK(cudaMemcpyAsync(B.h[b].Hinv, lead.Hinv, hh * sizeof(double), cudaMemcpyDeviceToDevice, st));
+          if (B.h[b].Hinv_f) CK(cudaMemcpyAsync(B.h[b].Hinv_f, lead.Hinv_f, hh * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+      }
       pf.end(st);
     }
     pf.begin(1, st);
@@ -746,7 +762,7 @@ int mlease_add_partition_csr(mlease_session* s, int32_t pid, int64_t nrows, cons
     CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     pd.csr_unique = *s->h_flag ? 0 : 1;
-    if (pd.csr_unique) {
+    if (pd.csr_unique && pd.nnz < (1LL << 32) - 64) {   // the Gram producers index the entry list with 32 bits
       pd.nblk128 = round_up(s->ldx, 128) / 128;
       pd.bm_groups = (nrows + 31) / 32;
       void *bo, *bk, *bv;
@@ -797,8 +813,10 @@ int mlease_admm_local_step(mlease_session* s, double* exchange_dev) {
     if (r != s->rho_fact[l]) invalidate = 1;   // prior precision changed -> stale factors are for another H
     s->rho_fact[l] = r;
   }
+  int same_rho = 1;   // cold start: equal rho across lambdas means equal Hessians (H = G + rho I at beta = 0)
+  for (int l = 1; l < s->L; l++) if (s->rho_fact[l] != s->rho_fact[0]) same_rho = 0;
   if (int rc = batch_xupdate(*s->batch, s->stream, s->xtol, s->max_newton, s->cfg.hessian_policy, invalidate, s->h_flag, s->d_flag, s->cnt, &s->prof,
-                             (i == 1 && s->L > 1) ? s->L : 0)) return rc;
+                             (i == 1 && s->L > 1) ? s->L : 0, same_rho)) return rc;
   int launches = 0;
   CK(admm_pack(s->batch->d, (int)s->parts.size(), s->L, s->Dt, exchange_dev, s->stream, &launches));
   s->cnt.launches += launches;

@@ -112,10 +112,10 @@ def test_gram_tcgen05_vs_oracle_hessian(mb, n, d, sparse):
     assert e_x < 1e-3, ("tcgen05 vs simt", e_x)
 
 
-@pytest.mark.parametrize("n,d,sparse", [(1500, 100, False), (3000, 700, False), (4000, 2303, False), (5000, 2600, True)])
+@pytest.mark.parametrize("n,d,sparse", [(1500, 100, False), (3000, 700, False), (2500, 1100, False), (4000, 2303, False), (5000, 2600, True)])
 def test_inverse_times_hessian_is_identity(mb, n, d, sparse):
-    """The explicit inverse behind every Newton direction, for both factorisation paths: ldh <= 2048 (NB=32 right-looking
-    Cholesky, substitution inverse, SIMT product) and ldh > 2048 (outer panels + DMMA trailing updates, recursive inverse
+    """The explicit inverse behind every Newton direction, for both factorisation paths: ldh <= 1000 (NB=32 right-looking
+    Cholesky, substitution inverse, SIMT product) and ldh > 1000 (outer panels + DMMA trailing updates, recursive inverse
     with DMMA merges, DMMA Y^T Y), including a width that is not a multiple of the leaf / panel size."""
     X, y, w, o = _mk(n, d, seed=7 * n + d, sparse=sparse, density=0.05 if sparse else 0.3)
     rng = np.random.default_rng(5)
@@ -226,6 +226,15 @@ def test_admm_sparse_config3_shape_multi_lambda(mb):
     lambdas = [0.1, 1.0, 10.0]
     ref = orc.admm_run(data, [0, n, 2 * n], lambdas, niters=6, mode="exact", nthreads=8, epsilon=0.0)
     done, z, xs, us, st = _run_gpu_admm(mb, parts, D, lambdas, 6, csr=True, epsilon=0.0)
+    for l in range(3):
+        err = np.abs(z[l] - ref["z_hist"][-1, l]).max() / np.abs(ref["z_hist"][-1, l]).max()
+        assert err < 1e-5, (l, err, st)
+    assert st["not_converged"] == 0
+    # equal rho (the default) lets the cold start share one Gram AND one factorisation per partition across the lambdas;
+    # distinct rho shares only the Gram: both must land on the oracle
+    rhos = [1.0, 3.0, 0.5]
+    ref = orc.admm_run(data, [0, n, 2 * n], lambdas, rhos=rhos, niters=6, mode="exact", nthreads=8, epsilon=0.0)
+    done, z, xs, us, st = _run_gpu_admm(mb, parts, D, lambdas, 6, csr=True, epsilon=0.0, rhos=rhos)
     for l in range(3):
         err = np.abs(z[l] - ref["z_hist"][-1, l]).max() / np.abs(ref["z_hist"][-1, l]).max()
         assert err < 1e-5, (l, err, st)

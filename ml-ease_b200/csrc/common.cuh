@@ -7,7 +7,8 @@
 
 namespace mlease {
 
-constexpr int BFGS_M = 6;   // secant pairs kept on top of the (possibly stale) explicit inverse Hessian
+constexpr int BFGS_M = 16;        // storage for secant pairs kept on top of the (possibly stale) explicit inverse Hessian
+constexpr int BFGS_M_DEFAULT = 6; // pairs actually used (Ctrl::bfgs_m)
 
 // ------------------------------------------------------------------------------------------
 // Per-problem control block, device resident.  A "problem" is one (local partition, lambda)
@@ -28,7 +29,9 @@ struct Ctrl {
   int rejects;       // rejected trial points in this x-update
   int hess_builds;   // Gram+Cholesky rebuilds in this x-update
   int stall;         // consecutive poor contractions
-  int bfgs_count;    // secant pairs stored so far (ring of BFGS_M), reset when the Hessian is rebuilt
+  int bfgs_count;    // secant pairs stored so far (ring of bfgs_m), reset when the Hessian is rebuilt
+  int bfgs_m;        // ring size in use (<= BFGS_M)
+  int k1_chunks;     // number of per-CTA partials the last K1 pass wrote for this problem (gpart / fpart rows)
   int refresh_next;  // rebuild the Hessian at the first point of the NEXT x-update (chord steps contracted slowly)
   double worst_ratio;// largest |g_new|/|g_old| seen over the chord steps of this x-update
   double alpha;      // current step length along dir

@@ -65,6 +65,31 @@ __device__ __forceinline__ float k1_warp_rows_reduce(float (&p)[RT], int lane) {
   return v;
 }
 
+// CTA -> (problem, chunk of the problem's rows).  Static: blockIdx.y is the problem, blockIdx.x the chunk.  Dynamic
+// (nprob_dyn = number of problems, <= 32, one-dimensional grid): the CTAs are dealt round-robin to the problems that are
+// still running, so a slot in which only some problems need a pass still uses every SM.  The chunk count a problem got is
+// published in Ctrl::k1_chunks for the reduction kernels; partial sums are combined in chunk order (deterministic).
+struct K1Map { int prob, chunk, nchunks; };
+__device__ __forceinline__ K1Map k1_map(const Problem* __restrict__ probs, int nprob_dyn) {
+  K1Map m;
+  if (nprob_dyn == 0) { m.prob = blockIdx.y; m.chunk = blockIdx.x; m.nchunks = gridDim.x; return m; }
+  __shared__ int s_act[34];
+  if (threadIdx.x < 32) {
+    const bool a = (int)threadIdx.x < nprob_dyn && probs[threadIdx.x].ctrl->done == 0;
+    const unsigned mask = __ballot_sync(0xffffffffu, a);
+    if (a) s_act[2 + __popc(mask & ((1u << threadIdx.x) - 1u))] = threadIdx.x;
+    if (threadIdx.x == 0) s_act[0] = __popc(mask);
+  }
+  __syncthreads();
+  const int na = s_act[0];
+  if (na == 0) { m.prob = -1; m.chunk = 0; m.nchunks = 1; return m; }
+  const int idx = (int)blockIdx.x % na;
+  m.prob = s_act[2 + idx];
+  m.chunk = (int)blockIdx.x / na;
+  m.nchunks = ((int)gridDim.x - idx + na - 1) / na;
+  return m;
+}
+
 // Thread t owns float4 column group(s) cg = t (+256 g) and RT rows of every tile (rows sl*RT .. sl*RT+RT-1 when
 // several row slices share the 256 threads for narrow matrices).  The tile is read from shared memory ONCE, into
 // registers, and serves both the row dots (phase A) and the column sums / bf16 emit (phase B):
@@ -76,10 +101,13 @@ __device__ __forceinline__ float k1_warp_rows_reduce(float (&p)[RT], int lane) {
 // pd / r / sqrt(d) are double buffered by tile parity, so two barriers per tile are enough.
 template <int G, int RT>
 __global__ void __launch_bounds__(K1_THREADS, (G == 1 ? 2 : 1))
-k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emit) {
-  const Problem& pb = probs[blockIdx.y];
+k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emit, int nprob_dyn) {
+  const K1Map km = k1_map(probs, nprob_dyn);
+  if (km.prob < 0) return;
+  const Problem& pb = probs[km.prob];
   Ctrl* ctrl = pb.ctrl;
   if (ctrl->done) return;
+  if (km.chunk == 0 && threadIdx.x == 0) ctrl->k1_chunks = km.nchunks;
   const bool emit = force_emit >= 0 ? (force_emit != 0) : (ctrl->emit != 0);
 
   const int ldx = pb.ldx;
@@ -104,7 +132,7 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
   double* red_s = reinterpret_cast<double*>(full_bar + 8);
 
   const int ntiles = (int)((n + Rt - 1) / Rt);
-  const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int my_tiles = ntiles > km.chunk ? (ntiles - km.chunk + km.nchunks - 1) / km.nchunks : 0;
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) mbar_init(&full_bar[s], 1);
@@ -122,7 +150,7 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
     bulk_g2s(smem_raw + (size_t)stg * stage_bytes, Xg + row0 * ldx, bytes, bar);
   };
   if (tid == 0) {
-    for (int k = 0; k < S && k < my_tiles; k++) issue((int)blockIdx.x + k * (int)gridDim.x, k);
+    for (int k = 0; k < S && k < my_tiles; k++) issue(km.chunk + k * km.nchunks, k);
   }
 
   // column / row-slice ownership
@@ -146,8 +174,8 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
 
   int st = 0;
   uint32_t par = 0;
-  int tile_no = (int)blockIdx.x;
-  const int tile_step = (int)gridDim.x;
+  int tile_no = km.chunk;
+  const int tile_step = km.nchunks;
   for (int k = 0; k < my_tiles; k++, tile_no += tile_step) {
     const int buf = k & 1;
     const long long row0 = (long long)tile_no * Rt;
@@ -269,7 +297,7 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
 
   // ---- CTA epilogue: reduce row slices, write partials ---------------------------------------------------
   __syncthreads();
-  double* gp = pb.gpart + (size_t)blockIdx.x * ldx;
+  double* gp = pb.gpart + (size_t)km.chunk * ldx;
   if (G == 1 && nsl > 1) {
     double* sc = reinterpret_cast<double*>(smem_raw);  // every bulk copy has completed and been consumed
     if (act) {
@@ -298,7 +326,7 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
   if (tid == 0) {
     double sacc = 0.0;
     for (int wq = 0; wq < K1_WARPS; wq++) sacc += red_s[wq];
-    pb.fpart[blockIdx.x] = sacc;
+    pb.fpart[km.chunk] = sacc;
   }
 }
 
@@ -324,10 +352,13 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
 // i.e. a resolution of B 2^-(29+k) per contribution (k = 16 at 16k rows per CTA), below fp32 rounding of the
 // contribution itself.  The first 128 entries of a row stay in registers between the margin and the gradient half.
 template <bool BSM>   // BSM: beta staged in shared memory (LDS gathers) / read through L1 from global memory
-__global__ void __launch_bounds__(1024, 1) k1_csr_fx_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit) {
-  const Problem& pb = probs[blockIdx.y];
+__global__ void __launch_bounds__(1024, 1) k1_csr_fx_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit, int nprob_dyn) {
+  const K1Map km = k1_map(probs, nprob_dyn);
+  if (km.prob < 0) return;
+  const Problem& pb = probs[km.prob];
   Ctrl* ctrl = pb.ctrl;
   if (ctrl->done) return;
+  if (km.chunk == 0 && threadIdx.x == 0) ctrl->k1_chunks = km.nchunks;
   const bool emit = force_emit >= 0 ? (force_emit != 0) : (ctrl->emit != 0);
   extern __shared__ __align__(16) float csr_sm[];
   const int ldx = pb.ldx, Dt = pb.Dt;
@@ -344,8 +375,8 @@ __global__ void __launch_bounds__(1024, 1) k1_csr_fx_kernel(const Problem* __res
   __syncthreads();
   const float* __restrict__ bg = pb.beta_tf;
   const long long n = pb.n;
-  const long long per = (n + gridDim.x - 1) / gridDim.x;
-  const long long rb = (long long)blockIdx.x * per, re = min(n, rb + per);
+  const long long per = (n + km.nchunks - 1) / km.nchunks;
+  const long long rb = (long long)km.chunk * per, re = min(n, rb + per);
   // fixed-point scales (powers of two: scaling is exact)
   float bound = (float)per * pb.wmax * fmaxf(pb.vmax, has_bias ? 1.f : 0.f);
   if (!(bound > 0.f) || !(bound < 3.0e38f)) bound = 1.f;
@@ -415,7 +446,7 @@ __global__ void __launch_bounds__(1024, 1) k1_csr_fx_kernel(const Problem* __res
     i = in; j0 = j0n; len = lenn; yy = yn; ww = wn; oo = on;
   }
   __syncthreads();
-  double* gp = pb.gpart + (size_t)blockIdx.x * ldx;
+  double* gp = pb.gpart + (size_t)km.chunk * ldx;
   const double inv_hi = (double)ldexpf(1.f, -e_hi), inv_k = (double)ldexpf(1.f, -kbits);
   for (int k = tid; k < ldx; k += blockDim.x) gp[k] = ((double)g_hi[k] + (double)g_lo[k] * inv_k) * inv_hi;
   __shared__ double red[32];
@@ -424,14 +455,17 @@ __global__ void __launch_bounds__(1024, 1) k1_csr_fx_kernel(const Problem* __res
   if (tid == 0) {
     double sacc = 0.0;
     for (int wq = 0; wq < nw; wq++) sacc += red[wq];
-    pb.fpart[blockIdx.x] = sacc;
+    pb.fpart[km.chunk] = sacc;
   }
 }
 
-__global__ void __launch_bounds__(1024) k1_csr_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit, int beta_in_smem) {
-  const Problem& pb = probs[blockIdx.y];
+__global__ void __launch_bounds__(1024) k1_csr_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit, int beta_in_smem, int nprob_dyn) {
+  const K1Map km = k1_map(probs, nprob_dyn);
+  if (km.prob < 0) return;
+  const Problem& pb = probs[km.prob];
   Ctrl* ctrl = pb.ctrl;
   if (ctrl->done) return;
+  if (km.chunk == 0 && threadIdx.x == 0) ctrl->k1_chunks = km.nchunks;
   const bool emit = force_emit >= 0 ? (force_emit != 0) : (ctrl->emit != 0);
   extern __shared__ __align__(16) float csr_sm[];
   const int ldx = pb.ldx, Dt = pb.Dt;
@@ -442,8 +476,8 @@ __global__ void __launch_bounds__(1024) k1_csr_kernel(const Problem* __restrict_
   __syncthreads();
   const float* __restrict__ bt = beta_in_smem ? b_s : pb.beta_tf;
   const long long n = pb.n;
-  const long long per = (n + gridDim.x - 1) / gridDim.x;
-  const long long rb = (long long)blockIdx.x * per, re = min(n, rb + per);
+  const long long per = (n + km.nchunks - 1) / km.nchunks;
+  const long long rb = (long long)km.chunk * per, re = min(n, rb + per);
   const long long* __restrict__ rp = pb.rowptr;
   const int* __restrict__ ci = pb.colidx;
   const float* __restrict__ vv = pb.vals;
@@ -482,7 +516,7 @@ __global__ void __launch_bounds__(1024) k1_csr_kernel(const Problem* __restrict_
     }
   }
   __syncthreads();
-  double* gp = pb.gpart + (size_t)blockIdx.x * ldx;
+  double* gp = pb.gpart + (size_t)km.chunk * ldx;
   for (int k = tid; k < ldx; k += blockDim.x) gp[k] = (double)g_s[k];
   __shared__ double red[32];
   if (lane == 0) red[warp] = loss;
@@ -490,7 +524,7 @@ __global__ void __launch_bounds__(1024) k1_csr_kernel(const Problem* __restrict_
   if (tid == 0) {
     double sacc = 0.0;
     for (int wq = 0; wq < nw; wq++) sacc += red[wq];
-    pb.fpart[blockIdx.x] = sacc;
+    pb.fpart[km.chunk] = sacc;
   }
 }
 
@@ -537,7 +571,9 @@ bool k1_dense_plan(int ldx, int* R_out, int* S_out, int* G_out, size_t* smem_out
 }
 
 cudaError_t k1_launch(const Problem* d_probs, int nprob, bool csr, int ldx, int has_bias, int ctas_per_problem,
-                      int force_emit, cudaStream_t stream, int* launches, int csr_fx) {
+                      int force_emit, cudaStream_t stream, int* launches, int csr_fx, int nprob_dyn) {
+  // dynamic mapping: ctas_per_problem is then the size of the whole one-dimensional grid
+  const dim3 grid_all = nprob_dyn ? dim3(ctas_per_problem, 1) : dim3(ctas_per_problem, nprob);
   if (csr && csr_fx) {
     const size_t g_bytes = (size_t)2 * (ldx + 32) * 4;
     const bool bsm = g_bytes + (size_t)ldx * 4 <= 220 * 1024;
@@ -546,8 +582,8 @@ cudaError_t k1_launch(const Problem* d_probs, int nprob, bool csr, int ldx, int 
     cudaError_t e = bsm ? cudaFuncSetAttribute(k1_csr_fx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                         : cudaFuncSetAttribute(k1_csr_fx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (bsm) k1_csr_fx_kernel<true><<<dim3(ctas_per_problem, nprob), 1024, smem, stream>>>(d_probs, has_bias, force_emit);
-    else k1_csr_fx_kernel<false><<<dim3(ctas_per_problem, nprob), 1024, smem, stream>>>(d_probs, has_bias, force_emit);
+    if (bsm) k1_csr_fx_kernel<true><<<grid_all, 1024, smem, stream>>>(d_probs, has_bias, force_emit, nprob_dyn);
+    else k1_csr_fx_kernel<false><<<grid_all, 1024, smem, stream>>>(d_probs, has_bias, force_emit, nprob_dyn);
     if (launches) *launches += 1;
     return cudaGetLastError();
   }
@@ -557,18 +593,18 @@ cudaError_t k1_launch(const Problem* d_probs, int nprob, bool csr, int ldx, int 
     if (smem > 220 * 1024) return cudaErrorInvalidValue;   // > 56k features: needs a column-blocked gradient (not built yet)
     cudaError_t e = cudaFuncSetAttribute(k1_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k1_csr_kernel<<<dim3(ctas_per_problem, nprob), 1024, smem, stream>>>(d_probs, has_bias, force_emit, beta_in_smem);
+    k1_csr_kernel<<<grid_all, 1024, smem, stream>>>(d_probs, has_bias, force_emit, beta_in_smem, nprob_dyn);
     if (launches) *launches += 1;
     return cudaGetLastError();
   }
   K1Plan p;
   if (!k1_plan(ldx, &p)) return cudaErrorInvalidValue;
-  dim3 grid(ctas_per_problem, nprob);
+  const dim3 grid = grid_all;
   cudaError_t e;
 #define K1_LAUNCH(GG, RR)                                                                                          \
   e = cudaFuncSetAttribute(k1_dense_kernel<GG, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);      \
   if (e != cudaSuccess) return e;                                                                                   \
-  k1_dense_kernel<GG, RR><<<grid, K1_THREADS, p.smem, stream>>>(d_probs, p.S, p.nsl, force_emit);
+  k1_dense_kernel<GG, RR><<<grid, K1_THREADS, p.smem, stream>>>(d_probs, p.S, p.nsl, force_emit, nprob_dyn);
   if (p.G == 1) { K1_LAUNCH(1, 8) } else if (p.G == 2) { K1_LAUNCH(2, 8) } else { K1_LAUNCH(4, 4) }
 #undef K1_LAUNCH
   if (launches) *launches += 1;

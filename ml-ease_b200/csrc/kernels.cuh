@@ -7,11 +7,11 @@ namespace mlease {
 // K1 (k1_score_grad.cu)
 bool k1_dense_plan(int ldx, int* R_out, int* S_out, int* G_out, size_t* smem_out, int* ctas_per_sm);
 cudaError_t k1_launch(const Problem* d_probs, int nprob, bool csr, int ldx, int has_bias, int ctas_per_problem,
-                      int force_emit, cudaStream_t stream, int* launches, int csr_fx = 0);
+                      int force_emit, cudaStream_t stream, int* launches, int csr_fx = 0, int nprob_dyn = 0);
 
 // Newton state machine (newton.cu)
 cudaError_t newton_begin(const Problem* d_probs, int nprob, double xtol, int max_newton, int hess_policy,
-                         int invalidate_hess, int rebuild_is_expensive, cudaStream_t st, int* launches);
+                         int invalidate_hess, int rebuild_is_expensive, cudaStream_t st, int* launches, int bfgs_m = BFGS_M_DEFAULT);
 cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, int Dt, cudaStream_t st, int* launches);
 cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches);
 

@@ -37,7 +37,7 @@ __device__ __forceinline__ double block_max(double v, double* sc) {
 // Start of an x-update: beta = beta_t = init, flags reset.  init/m/q were written by the caller
 // (ADMM consensus kernel or mlease_fit_partition).
 __global__ void newton_begin_kernel(const Problem* __restrict__ probs, double xtol, int max_newton, int hess_policy,
-                                    int invalidate_hess, int rebuild_is_expensive) {
+                                    int invalidate_hess, int rebuild_is_expensive, int bfgs_m) {
   const Problem& pb = probs[blockIdx.x];
   Ctrl* c = pb.ctrl;
   for (int k = threadIdx.x; k < pb.ldx; k += blockDim.x) {
@@ -57,6 +57,7 @@ __global__ void newton_begin_kernel(const Problem* __restrict__ probs, double xt
     c->newton_steps = 0; c->evals = 0; c->rejects = 0; c->hess_builds = 0; c->stall = 0;
     c->alpha = 1.0; c->phi0 = 0.0; c->f_acc = 0.0; c->f_t = 0.0; c->gnorm = 0.0; c->gnorm_prev = 0.0; c->dirnorm = 0.0; c->dirnorm_prev = 0.0;
     c->xtol = xtol; c->max_newton = max_newton; c->hess_policy = hess_policy; c->rebuild_is_expensive = rebuild_is_expensive;
+    if (c->bfgs_m != bfgs_m) { c->bfgs_m = bfgs_m; c->bfgs_count = 0; }
     // Rebuild at the start point when there is no factor, when the policy says always, or when the previous
     // x-update's chord steps contracted slowly: a factor taken at a (nearly) converged point makes every later
     // x-update of the ADMM run a 2-3 pass affair, and costs about as much as 2.5 K1 passes.
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256) k1_partial_reduce_kernel(const Problem* _
   __shared__ double sh[8][33];
   const int c = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + c;
-  const int nct = pb.k1_ctas, ldx = pb.ldx;
+  const int nct = pb.ctrl->k1_chunks, ldx = pb.ldx;
   double s = 0.0;
   if (k < pb.Dt)
     for (int t = grp; t < nct; t += 8) s += pb.gpart[(size_t)t * ldx + k];
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
   __shared__ double sc[NT / 32];
   __shared__ int s_action;  // 1 accept, 0 retry
   __shared__ double s_alpha;
-  const int Dt = pb.Dt, ldx = pb.ldx, nct = pb.k1_ctas;
+  const int Dt = pb.Dt, ldx = pb.ldx, nct = c->k1_chunks;
   const bool have_dir = c->have_dir != 0;
   double prior2 = 0.0, ginf = 0.0, phi = 0.0;
   for (int k = threadIdx.x; k < Dt; k += NT) {
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
     // below runs), so that both loops of the recursion see the same, empty, pair set.
     if (action == 1 && c->need_hess) c->bfgs_count = 0;
     if (action == 1 && have_dir && !c->need_hess && sy > 1e-10 * sqrt(ss * yy2) && sy > 0.0) {   // strictly convex => s.y > 0 up to rounding
-      s_slot = c->bfgs_count % BFGS_M;
+      s_slot = c->bfgs_count % c->bfgs_m;
       pb.bfgs_rho[s_slot] = 1.0 / sy;
       c->bfgs_count++;
     }
@@ -214,12 +215,12 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
   __syncthreads();
   if (c->done || !c->need_solve) return;
   {
-    const int npairs = min(c->bfgs_count, BFGS_M);
+    const int npairs = min(c->bfgs_count, c->bfgs_m);
     double* q = pb.g_t;   // free scratch from here until the next K1 reduce
     for (int k = threadIdx.x; k < Dt; k += NT) q[k] = pb.g_acc[k];
     __syncthreads();
     for (int j = 0; j < npairs; j++) {
-      const int slot = (c->bfgs_count - 1 - j) % BFGS_M;
+      const int slot = (c->bfgs_count - 1 - j) % c->bfgs_m;
       const double* S = pb.bfgs_S + (size_t)slot * ldx;
       const double* Y = pb.bfgs_Y + (size_t)slot * ldx;
       double d = 0.0;
@@ -275,9 +276,9 @@ __global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restr
   const int Dt = pb.Dt, ldx = pb.ldx;
   double* rhs = pb.dir;
   {
-    const int npairs = min(c->bfgs_count, BFGS_M);
+    const int npairs = min(c->bfgs_count, c->bfgs_m);
     for (int j = npairs - 1; j >= 0; j--) {
-      const int slot = (c->bfgs_count - 1 - j) % BFGS_M;
+      const int slot = (c->bfgs_count - 1 - j) % c->bfgs_m;
       const double* S = pb.bfgs_S + (size_t)slot * ldx;
       const double* Y = pb.bfgs_Y + (size_t)slot * ldx;
       double d = 0.0;
@@ -335,8 +336,9 @@ __global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restr
 }
 
 cudaError_t newton_begin(const Problem* d_probs, int nprob, double xtol, int max_newton, int hess_policy,
-                         int invalidate_hess, int rebuild_is_expensive, cudaStream_t st, int* launches) {
-  newton_begin_kernel<<<nprob, 256, 0, st>>>(d_probs, xtol, max_newton, hess_policy, invalidate_hess, rebuild_is_expensive);
+                         int invalidate_hess, int rebuild_is_expensive, cudaStream_t st, int* launches, int bfgs_m) {
+  newton_begin_kernel<<<nprob, 256, 0, st>>>(d_probs, xtol, max_newton, hess_policy, invalidate_hess, rebuild_is_expensive,
+                                             bfgs_m < 1 ? 1 : (bfgs_m > BFGS_M ? BFGS_M : bfgs_m));
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

@@ -125,6 +125,8 @@ struct Batch {
   int has_bias = 1;
   int k1_grid = 1, gram_slices = 1, ntiles = 0;
   int gram_from_csr = 0;          // every problem of the batch assembles its Gram tiles from CSR (no dense bf16 operand)
+  int k1_dyn = 0;                 // > 0: K1 CTAs are dealt to the running problems at run time (value = nprob, <= 32); k1_grid = whole grid
+  int bfgs_m = BFGS_M_DEFAULT;    // secant pairs in use
   int rebuild_is_expensive = 0;   // cost model: Gram + Cholesky + inverse vs one K1 pass (set in batch_alloc)
   std::vector<Problem> h;
   Problem* d = nullptr;
@@ -195,14 +197,18 @@ int batch_alloc(Batch& B, int num_sms) {
   for (auto& p : B.h) maxn = std::max(maxn, p.n);
   if (B.csr) {
     const int cps = 1;   // 1024-thread CTAs at 64 registers: one per SM
-    B.k1_grid = std::max(1, std::min((int)((maxn + 63) / 64), (num_sms * cps) / std::max(1, nprob)));
+    B.k1_dyn = (nprob > 1 && nprob <= 32) ? nprob : 0;
+    if (B.k1_dyn) B.k1_grid = (int)std::max(1LL, std::min((long long)num_sms * cps, (long long)nprob * ((maxn + 63) / 64)));
+    else B.k1_grid = std::max(1, std::min((int)((maxn + 63) / 64), (num_sms * cps) / std::max(1, nprob)));
   } else {
     int R, S, G, cps = 1;
     size_t smem;
     if (!k1_dense_plan(ldx, &R, &S, &G, &smem, &cps))
       return fail(MLEASE_ERR_INVALID, "dense partitions support at most 4095 features (+intercept); use CSR input beyond that");
     const long long row_tiles = (maxn + R - 1) / R;
-    B.k1_grid = (int)std::max(1LL, std::min(row_tiles, (long long)std::max(1, (num_sms * cps) / std::max(1, nprob))));
+    B.k1_dyn = (nprob > 1 && nprob <= 32) ? nprob : 0;
+    if (B.k1_dyn) B.k1_grid = (int)std::max(1LL, std::min((long long)num_sms * cps, (long long)nprob * row_tiles));
+    else B.k1_grid = (int)std::max(1LL, std::min(row_tiles, (long long)std::max(1, (num_sms * cps) / std::max(1, nprob))));
   }
   B.gram_from_csr = B.csr ? 1 : 0;
   for (auto& p : B.h) if (!p.bm_offs) B.gram_from_csr = 0;
@@ -216,6 +222,8 @@ int batch_alloc(Batch& B, int num_sms) {
     // only wide systems qualify: small ones (NaiveTrain's per-key fits, cold-started every time) are launch-bound, not
     // flop-bound, and a mid-update rebuild saves them many lock-step slots
     B.rebuild_is_expensive = (t_rebuild > 8.0 * t_pass && B.Dt > 2048) ? 1 : 0;
+    B.bfgs_m = BFGS_M_DEFAULT;   // measured at 1M x 10k x 1 %: 12 / 16 pairs save 2-4 % of the K1 passes and cost 45-60 % more two-loop time
+    if (const char* e = getenv("MLEASE_BFGS_M")) B.bfgs_m = std::max(1, std::min(BFGS_M, atoi(e)));   // tuning experiments only
   }
   // Gram decomposition
   std::vector<short> tiles(2 * 8192);
@@ -307,7 +315,7 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
   Profiler nop;
   Profiler& pf = prof ? *prof : nop;
   int launches = 0;
-  CK(newton_begin(B.d, B.nprob, xtol, max_newton, policy, invalidate, B.rebuild_is_expensive, st, &launches));
+  CK(newton_begin(B.d, B.nprob, xtol, max_newton, policy, invalidate, B.rebuild_is_expensive, st, &launches, B.bfgs_m));
   // The first slot's flags are known on the host: every problem is running, and a rebuild is due iff the policy says
   // always, the factors were invalidated, or the mirrored control blocks say so (no factor yet / refresh requested).
   const bool small = B.nprob <= 64;   // small batches read the whole control array back each slot (one sync, no poll kernel)
@@ -323,7 +331,7 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
   double shared_flops = 0;   // Gram builds that were not run because the group's first problem stood in for them
   while ((flag & 1) && slots < 400) {
     pf.begin(0, st);
-    CK(k1_launch(B.d, B.nprob, B.csr, B.ldx, B.has_bias, B.k1_grid, -1, st, &launches, B.gram_from_csr));
+    CK(k1_launch(B.d, B.nprob, B.csr, B.ldx, B.has_bias, B.k1_grid, -1, st, &launches, B.gram_from_csr, B.k1_dyn));
     pf.end(st);
     pf.begin(1, st);
     CK(k1_reduce_decide(B.d, B.nprob, B.Dt, st, &launches));

@@ -65,6 +65,41 @@ def test_k1_objective_and_gradient(mb, n, d, sparse):
     assert f == f2 and np.array_equal(g, g2)
 
 
+def test_csr_rows_with_repeated_and_unsorted_columns(mb):
+    """Rows may list a column twice or out of order (TRON's fun/grad/Hv accept that: llf/LogisticRegressionL2.java:115-150;
+    only the reference's hessian() insists on sorted rows, :277).  Such partitions take the general CSR kernels (float
+    gradient accumulation, dense bf16 Gram operand): same objective, gradient, Hessian and fit as the merged rows."""
+    n, d = 1500, 60
+    X, y, w, o = _mk(n, d, seed=91, sparse=True)
+    rng = np.random.default_rng(4)
+    rp, ci, v = [0], [], []
+    for i in range(n):
+        cols = np.nonzero(X[i])[0]
+        vals = X[i, cols].astype(np.float32)
+        if len(cols):   # split the first entry in two, then shuffle the row
+            cols = np.concatenate([cols, cols[:1]]); vals = np.concatenate([vals, vals[:1] * np.float32(0.25)]); vals[0] *= np.float32(0.75)
+            perm = rng.permutation(len(cols)); cols, vals = cols[perm], vals[perm]
+        ci += list(cols); v += list(vals); rp.append(len(ci))
+    rp = np.array(rp, np.int64); ci = np.array(ci, np.int32); v = np.array(v, np.float32)
+    Xm = np.zeros((n, d), np.float32)
+    for i in range(n):
+        np.add.at(Xm[i], ci[rp[i]:rp[i + 1]], v[rp[i]:rp[i + 1]])
+    data = orc.Csr.from_dense(Xm, y, w, o)
+    wv = rng.normal(0, 0.3, d + 1); pm = rng.normal(0, 0.2, d + 1); pv = np.full(d + 1, 0.7)
+    with _session(mb, d) as s:
+        s.add_partition_csr(0, rp, ci, v, y, w, o)
+        f, g, H = s.objective(0, wv, pm, 1.0 / pv, want_hessian=True, tensor=True)
+        _, _, H_simt = s.objective(0, wv, pm, 1.0 / pv, want_hessian=True, tensor=False)   # the dense operand exists on this path
+        x, _ = s.fit_partition(0, np.zeros(d + 1), pm, 1.0 / pv)
+    f_ref, g_ref = orc.objective("grad", data, wv, pm, pv)
+    H_ref = orc.objective("hessian", data, wv, pm, pv)
+    assert abs(f - f_ref) <= 1e-5 * abs(f_ref)
+    assert np.abs(g - g_ref).max() <= 1e-5 * np.abs(g_ref).max()
+    assert np.abs(H - H_ref).max() <= 2e-2 * np.abs(H_ref).max() and np.abs(H - H_simt).max() <= 1e-3 * np.abs(H_ref).max()
+    x_ref, _ = orc.liblinear_train(data, np.zeros(d + 1), pm, pv, 1e-14, 100000)
+    assert np.abs(x - x_ref).max() <= 1e-5 * np.abs(x_ref).max()
+
+
 def _bf16_round(a):
     u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
     u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000

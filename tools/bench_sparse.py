@@ -34,9 +34,36 @@ sess.begin()
 torch.cuda.synchronize()
 print("setup %.2f s, mem %.1f GB" % (time.perf_counter() - t0, torch.cuda.mem_get_info()[0] / 1e9), flush=True)
 sess.profile(2)
+ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+ev0.record()
 for it in range(iters):
     t1 = time.perf_counter()
     md, stop = sess.iterate()
+    if it == 0:
+        ev1.record()
     torch.cuda.synchronize()
-    print("iter %d: %.3f s  maxdiff %.3e  stats %s" % (it + 1, time.perf_counter() - t1, md, {k: v for k, v in sess.stats().items() if k in ("k1_passes", "gram_builds", "newton_steps", "last_iter_slots", "not_converged")}), flush=True)
-print(json.dumps(sess.profile(0)))
+    print("iter %d: %.3f s  maxdiff %.3e  stats %s" % (it + 1, time.perf_counter() - t1, md, {k: v for k, v in sess.stats().items() if k in ("k1_passes", "gram_builds", "newton_steps", "last_iter_slots", "not_converged")}), file=sys.stderr, flush=True)
+ev2.record()
+torch.cuda.synchronize()
+prof = sess.profile(0)
+job_ms, cold_ms = ev0.elapsed_time(ev2), ev0.elapsed_time(ev1)
+peaks = {}
+try:
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+except Exception:
+    pass
+bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1426.5)))
+hbm_peak = float(peaks.get("hbm_gbs", 6575.4))
+gram_tf = prof["gram_flops"] / (prof["ms"]["gram"] * 1e-3) / 1e12 if prof["ms"]["gram"] > 0 else 0.0
+k1_gbs = prof["k1_bytes"] / (prof["ms"]["k1"] * 1e-3) / 1e9 if prof["ms"]["k1"] > 0 else 0.0
+print(json.dumps({
+    "metric": "ADMM iterations/sec", "unit": "ADMM iterations/s", "value": iters / (job_ms * 1e-3), "n_gpus": 1, "steps": iters,
+    "config": {"workload": "BASELINE configs[2] per-GPU share at N=8: %d partition(s) x %d x %d, %d nnz/row, lambdas %s in one run, cold start (z=u=0)"
+               % (P, n, D, nnz, lambdas)},
+    "job_ms": job_ms, "cold_start_iteration_ms": cold_ms, "steady_ms_per_iteration": (job_ms - cold_ms) / max(1, iters - 1),
+    "kernel_ms": prof["ms"], "kernel_launch_counts": prof["launches"],
+    "roofline_gram": {"kernel": "gram_csr_tcgen05_kernel", "bound": "tensor", "achieved": gram_tf, "peak": bf16_peak, "unit": "TFLOP/s",
+                      "frac": gram_tf / bf16_peak, "flops": "n*D'*(D'+1) per build actually run (cold-start builds shared across lambdas)"},
+    "roofline_k1": {"kernel": "k1_csr_fx_kernel", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
+                    "bytes": "(8*nnz + 17*n) per problem-pass; problems of one partition share the rows through L2, so DRAM traffic is ~1/L of this"},
+    "solver": {k: v for k, v in sess.stats().items() if k in ("k1_passes", "gram_builds", "newton_steps", "not_converged")}}))

@@ -11,11 +11,18 @@ import mlease_b200 as mb
 P = int(os.environ.get("P", 1)); n = int(os.environ.get("N", 1_000_000)); D = int(os.environ.get("D", 10_000)); nnz = int(os.environ.get("NNZ", 100))
 lambdas = [float(x) for x in os.environ.get("LAMBDAS", "0.1,1,10").split(",")]
 iters = int(os.environ.get("ITERS", 10))
-dev = "cuda:0"
-g = torch.Generator(device=dev); g.manual_seed(3)
-beta = torch.randn(D, generator=g, device=dev) / nnz ** 0.5
-parts = []
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
+torch.cuda.set_device(local)
+dev = "cuda:%d" % local
+beta = torch.randn(D, generator=torch.Generator(device=dev).manual_seed(3), device=dev) / nnz ** 0.5
+parts = {}
 for p in range(P):
+    if p % world != rank:
+        continue
+    g = torch.Generator(device=dev); g.manual_seed(1000 + p)
     start = torch.randint(0, D, (n, 1), generator=g, device=dev)
     stride = torch.randint(1, D // nnz, (n, 1), generator=g, device=dev)
     cols = (start + stride * torch.arange(nnz, device=dev)[None, :]) % D          # distinct columns per row
@@ -24,15 +31,37 @@ for p in range(P):
     s = (vals * beta[cols]).sum(1) - 1.0
     y = (torch.rand(n, generator=g, device=dev) < torch.sigmoid(s)).to(torch.int32)
     rowptr = torch.arange(n + 1, device=dev, dtype=torch.int64) * nnz
-    parts.append((rowptr, cols.to(torch.int32).reshape(-1).contiguous(), vals.reshape(-1).contiguous(), y))
+    parts[p] = (rowptr, cols.to(torch.int32).reshape(-1).contiguous(), vals.reshape(-1).contiguous(), y)
+    del start, stride, cols, vals, s
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-sess = mb.AdmmSession(P, D, lambdas, epsilon=0.0, stream=torch.cuda.current_stream().cuda_stream)
-for p, (rp, ci, v, y) in enumerate(parts):
+sess = mb.AdmmSession(P, D, lambdas, epsilon=0.0, device=local, stream=torch.cuda.current_stream().cuda_stream)
+for p, (rp, ci, v, y) in parts.items():
     sess.add_partition_csr(p, rp, ci, v, y)
 sess.begin()
 torch.cuda.synchronize()
-print("setup %.2f s, mem %.1f GB" % (time.perf_counter() - t0, torch.cuda.mem_get_info()[0] / 1e9), flush=True)
+print("rank %d: setup %.2f s, free mem %.1f GB" % (rank, time.perf_counter() - t0, torch.cuda.mem_get_info()[0] / 1e9), file=sys.stderr, flush=True)
+if world > 1:
+    from mlease_b200.distributed import run_distributed
+    run_distributed(sess, 2)          # warm-up job (NCCL communicator, kernels)
+    sess.profile(2)
+    ev0, ev2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier(); torch.cuda.synchronize()
+    ev0.record()
+    run_distributed(sess, iters)
+    ev2.record()
+    torch.cuda.synchronize()
+    tms = torch.tensor([ev0.elapsed_time(ev2)], device=dev, dtype=torch.float64)
+    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    prof = sess.profile(0)
+    zsum = float(sum(np.abs(sess.z(l)).sum() for l in range(len(lambdas))))
+    if rank == 0:
+        print(json.dumps({"metric": "ADMM iterations/sec", "unit": "ADMM iterations/s", "value": iters / (tms.item() * 1e-3), "n_gpus": world, "steps": iters,
+                          "config": {"workload": "BASELINE configs[2] shape: %d partitions x %d x %d, %d nnz/row, lambdas %s, partitions p%%N over %d ranks, cold 20-iteration job"
+                                     % (P, n, D, nnz, lambdas, world)},
+                          "job_ms": tms.item(), "kernel_ms_rank0": prof["ms"], "z_checksum": zsum}))
+    dist.destroy_process_group()
+    sys.exit(0)
 sess.profile(2)
 ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 ev0.record()
@@ -66,4 +95,5 @@ print(json.dumps({
                       "frac": gram_tf / bf16_peak, "flops": "n*D'*(D'+1) per build actually run (cold-start builds shared across lambdas)"},
     "roofline_k1": {"kernel": "k1_csr_fx_kernel", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
                     "bytes": "(8*nnz + 17*n) per problem-pass; problems of one partition share the rows through L2, so DRAM traffic is ~1/L of this"},
-    "solver": {k: v for k, v in sess.stats().items() if k in ("k1_passes", "gram_builds", "newton_steps", "not_converged")}}))
+    "solver": {k: v for k, v in sess.stats().items() if k in ("k1_passes", "gram_builds", "newton_steps", "not_converged")},
+    "z_checksum": float(sum(np.abs(sess.z(l)).sum() for l in range(len(lambdas))))}))

@@ -31,6 +31,8 @@ struct Ctrl {
   int stall;         // consecutive poor contractions
   int bfgs_count;    // secant pairs stored so far (ring of bfgs_m), reset when the Hessian is rebuilt
   int bfgs_m;        // ring size in use (<= BFGS_M)
+  int self_scale;    // 1: adapt h0_scale from the secant pairs (set per x-update; wide systems)
+  double h0_scale;   // self-scaling factor applied to the explicit inverse inside the L-BFGS two-loop (wide systems only; 1 after a rebuild)
   int k1_chunks;     // number of per-CTA partials the last K1 pass wrote for this problem (gpart / fpart rows)
   int refresh_next;  // rebuild the Hessian at the first point of the NEXT x-update (chord steps contracted slowly)
   double worst_ratio;// largest |g_new|/|g_old| seen over the chord steps of this x-update

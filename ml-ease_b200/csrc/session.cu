@@ -126,6 +126,7 @@ struct Batch {
   int k1_grid = 1, gram_slices = 1, ntiles = 0;
   int gram_from_csr = 0;          // every problem of the batch assembles its Gram tiles from CSR (no dense bf16 operand)
   int k1_dyn = 0;                 // > 0: K1 CTAs are dealt to the running problems at run time (value = nprob, <= 32); k1_grid = whole grid
+  int self_scale = 0;             // adapt a scalar multiplier of the stale inverse from the secant pairs (wide systems)
   int bfgs_m = BFGS_M_DEFAULT;    // secant pairs in use
   int rebuild_is_expensive = 0;   // cost model: Gram + Cholesky + inverse vs one K1 pass (set in batch_alloc)
   std::vector<Problem> h;
@@ -222,6 +223,8 @@ int batch_alloc(Batch& B, int num_sms) {
     // only wide systems qualify: small ones (NaiveTrain's per-key fits, cold-started every time) are launch-bound, not
     // flop-bound, and a mid-update rebuild saves them many lock-step slots
     B.rebuild_is_expensive = (t_rebuild > 8.0 * t_pass && B.Dt > 2048) ? 1 : 0;
+    B.self_scale = B.rebuild_is_expensive;
+    if (const char* e = getenv("MLEASE_SELF_SCALE")) B.self_scale = atoi(e) ? 1 : 0;   // tuning experiments only
     B.bfgs_m = BFGS_M_DEFAULT;   // measured at 1M x 10k x 1 %: 12 / 16 pairs save 2-4 % of the K1 passes and cost 45-60 % more two-loop time
     if (const char* e = getenv("MLEASE_BFGS_M")) B.bfgs_m = std::max(1, std::min(BFGS_M, atoi(e)));   // tuning experiments only
   }
@@ -315,7 +318,7 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
   Profiler nop;
   Profiler& pf = prof ? *prof : nop;
   int launches = 0;
-  CK(newton_begin(B.d, B.nprob, xtol, max_newton, policy, invalidate, B.rebuild_is_expensive, st, &launches, B.bfgs_m));
+  CK(newton_begin(B.d, B.nprob, xtol, max_newton, policy, invalidate, B.rebuild_is_expensive, st, &launches, B.bfgs_m, B.self_scale));
   // The first slot's flags are known on the host: every problem is running, and a rebuild is due iff the policy says
   // always, the factors were invalidated, or the mirrored control blocks say so (no factor yet / refresh requested).
   const bool small = B.nprob <= 64;   // small batches read the whole control array back each slot (one sync, no poll kernel)
@@ -394,8 +397,8 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
   if (getenv("MLEASE_DEBUG")) {
     fprintf(stderr, "[mlease] x-update: %d problems, %d slots;", B.nprob, slots);
     for (int b = 0; b < B.nprob && b < 4; b++)
-      fprintf(stderr, " p%d{ev %d st %d rej %d hb %d fail %d stall %d |g| %.2e |dir| %.2e}", b, hc[b].evals, hc[b].newton_steps, hc[b].rejects,
-              hc[b].hess_builds, hc[b].fail, hc[b].stall, hc[b].gnorm, hc[b].dirnorm);
+      fprintf(stderr, " p%d{ev %d st %d rej %d hb %d fail %d stall %d |g| %.2e |dir| %.2e h0s %.3f}", b, hc[b].evals, hc[b].newton_steps, hc[b].rejects,
+              hc[b].hess_builds, hc[b].fail, hc[b].stall, hc[b].gnorm, hc[b].dirnorm, hc[b].h0_scale);
     fprintf(stderr, "\n");
   }
   for (int b = 0; b < B.nprob; b++) {

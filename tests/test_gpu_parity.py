@@ -276,6 +276,32 @@ def test_admm_sparse_config3_shape_multi_lambda(mb):
     assert st["not_converged"] == 0
 
 
+def test_admm_wide_systems_keep_the_cold_start_factor(mb):
+    """D' > 2048: the cost model marks a refactorisation as too expensive to repeat mid-run, so every x-update after the
+    first runs on the factor of the cold start (shared across the lambdas), corrected by L-BFGS pairs and the self-scaling
+    of the stale inverse; the wide (DMMA) Cholesky / inverse path is the one in use.  Same gate: oracle-exact z to 1e-5."""
+    P, n, D, nnz = 2, 8000, 2300, 20
+    rng = np.random.default_rng(5)
+    beta = rng.normal(size=D) / np.sqrt(nnz)
+    parts, ci_all, v_all, y_all = [], [], [], []
+    for p in range(P):
+        r = np.random.default_rng(2000 + p)
+        ci = np.stack([np.sort(r.choice(D, nnz, replace=False)) for _ in range(n)]).astype(np.int32)
+        v = r.normal(size=(n, nnz)).astype(np.float32)
+        s = (v * beta[ci]).sum(1) - 0.5
+        y = (r.random(n) < 1 / (1 + np.exp(-s))).astype(np.int32)
+        parts.append((np.arange(n + 1, dtype=np.int64) * nnz, ci.reshape(-1), v.reshape(-1), y))
+        ci_all.append(ci.reshape(-1)); v_all.append(v.reshape(-1)); y_all.append(y)
+    data = orc.Csr(np.arange(P * n + 1, dtype=np.int64) * nnz, np.concatenate(ci_all), np.concatenate(v_all), np.concatenate(y_all), n_features=D)
+    lambdas = [1.0, 10.0]
+    ref = orc.admm_run(data, [0, n, 2 * n], lambdas, niters=5, mode="exact", nthreads=8, epsilon=0.0)
+    done, z, xs, us, st = _run_gpu_admm(mb, parts, D, lambdas, 5, csr=True, epsilon=0.0)
+    for l in range(2):
+        err = np.abs(z[l] - ref["z_hist"][-1, l]).max() / np.abs(ref["z_hist"][-1, l]).max()
+        assert err < 1e-5, (l, err, st)
+    assert st["not_converged"] == 0 and st["gram_builds"] == 4   # one factorisation per (partition, lambda), at the cold start only
+
+
 def test_naive_train_many_keys(mb):
     # BASELINE config 4 shape in small: many independent per-key fits in lock-step batches
     K, n, D = 300, 120, 24

@@ -111,6 +111,7 @@ struct Problem {
   double* bfgs_alpha;      // [BFGS_M] two-loop scratch
   double* x_d;             // x of the last x-update (the ADMM consensus overwrites beta with the next init)
   int lambda_idx;
+  int self_idx;            // index of this problem in its batch (tensor-map slot), valid also in compacted copies
   int part_local;
 };
 

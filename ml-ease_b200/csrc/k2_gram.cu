@@ -72,7 +72,7 @@ gram_tcgen05_kernel(const Problem* __restrict__ probs, const CUtensorMap* __rest
   const Problem& pb = probs[pidx];
   Ctrl* ctrl = pb.ctrl;
   if (!force && (ctrl->done || !ctrl->need_hess)) return;
-  const CUtensorMap* tmap = &tmaps[pidx];
+  const CUtensorMap* tmap = &tmaps[pb.self_idx];   // not blockIdx.z: large batches launch over a compacted copy of the problem array
   const GramTile tile = tiles[blockIdx.x];
   const int slice = blockIdx.y, nslices = gridDim.y;
   const int Dp = pb.Dp;

@@ -86,15 +86,24 @@ __global__ void repack_rows_kernel(float* dst, int ldx, const float* src, long l
     dst[i * ldx + c] = src[i * ld_in + c];
   }
 }
-__global__ void poll2_kernel(const Problem* probs, int nprob, int* flag_out) {
+// End-of-slot poll for large batches (one CTA): flag_out[0] = running | emit << 1; and, for the Gram / Cholesky launches of
+// the NEXT slot, the problems that may rebuild there (running and emit set) are copied, as Problem structs, into `compact`
+// and counted in flag_out[1]: a rebuild slot then launches grids over those only instead of over thousands of finished fits.
+__global__ void poll2_kernel(const Problem* probs, int nprob, int* flag_out, Problem* compact) {
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
   int running = 0, emit = 0;
   for (int b = threadIdx.x; b < nprob; b += blockDim.x) {
     const Ctrl* c = probs[b].ctrl;
-    if (!c->done) { running = 1; if (c->emit) emit = 1; }
+    if (!c->done) {
+      running = 1;
+      if (c->emit) { emit = 1; compact[atomicAdd(&s_cnt, 1)] = probs[b]; }   // order is irrelevant: the problems are independent
+    }
   }
   running = __syncthreads_or(running);
   emit = __syncthreads_or(emit);
-  if (threadIdx.x == 0) *flag_out = running | (emit << 1);
+  if (threadIdx.x == 0) { flag_out[0] = running | (emit << 1); flag_out[1] = s_cnt; }
 }
 
 struct PartData {
@@ -131,6 +140,7 @@ struct Batch {
   int rebuild_is_expensive = 0;   // cost model: Gram + Cholesky + inverse vs one K1 pass (set in batch_alloc)
   std::vector<Problem> h;
   Problem* d = nullptr;
+  Problem* d_compact = nullptr;   // large batches: Problem structs of the problems that may rebuild in the next slot
   Ctrl* d_ctrl = nullptr;
   void* d_tmaps = nullptr;
   void* d_tiles = nullptr;
@@ -264,13 +274,24 @@ int batch_alloc(Batch& B, int num_sms) {
     if (int rc = dev_alloc(B, (void**)&hif, (size_t)nprob * B.ldh * B.ldh * sizeof(float))) return rc;
   if (int rc = dev_alloc(B, (void**)&B.d_ctrl, (size_t)nprob * sizeof(Ctrl))) return rc;
   if (int rc = dev_alloc(B, (void**)&B.d, (size_t)nprob * sizeof(Problem))) return rc;
+  if (nprob > 64)
+    if (int rc = dev_alloc(B, (void**)&B.d_compact, (size_t)nprob * sizeof(Problem))) return rc;
   if (int rc = dev_alloc(B, &B.d_tmaps, (size_t)nprob * sizeof(CUtensorMap))) return rc;
   if (int rc = dev_alloc(B, &B.d_tiles, (size_t)B.ntiles * 2 * sizeof(short))) return rc;
   CK(cudaMemcpy(B.d_tiles, tiles.data(), (size_t)B.ntiles * 2 * sizeof(short), cudaMemcpyHostToDevice));
   std::vector<CUtensorMap> maps(nprob);
+  std::vector<size_t> pool_off(nprob);
+  size_t pool_bytes = 0;
+  for (int b = 0; b < nprob; b++) {
+    pool_off[b] = pool_bytes;
+    const size_t need = B.gram_from_csr ? (size_t)B.h[b].n * sizeof(float) : (B.h[b].Xt ? 0 : (size_t)B.h[b].n * B.Dp * sizeof(__nv_bfloat16));
+    pool_bytes += (need + 255) & ~(size_t)255;
+  }
+  unsigned char* pool = nullptr;
+  if (int rc = dev_alloc(B, (void**)&pool, pool_bytes)) return rc;
   for (int b = 0; b < nprob; b++) {
     Problem& p = B.h[b];
-    p.ldx = ldx; p.Dt = B.Dt; p.Dp = B.Dp; p.ldh = B.ldh;
+    p.ldx = ldx; p.Dt = B.Dt; p.Dp = B.Dp; p.ldh = B.ldh; p.self_idx = b;
     p.k1_ctas = B.k1_grid;
     p.gram_slices = B.gram_slices;
     double* q = dd;
@@ -291,19 +312,15 @@ int batch_alloc(Batch& B, int num_sms) {
     p.Hinv = hi + (size_t)b * B.ldh * B.ldh;
     p.Hinv_f = hif ? hif + (size_t)b * B.ldh * B.ldh : nullptr;
     p.ctrl = B.d_ctrl + b;
+    // Gram operand state, carved out of ONE allocation for the whole batch (NaiveTrain batches hold thousands of problems:
+    // one cudaMalloc / cudaFree each would cost more than the fits)
     if (B.gram_from_csr) {
-      void* sv;
-      if (int rc = dev_alloc(B, &sv, (size_t)p.n * sizeof(float))) return rc;
-      p.sdvec = reinterpret_cast<float*>(sv);
+      p.sdvec = reinterpret_cast<float*>(pool + pool_off[b]);
       p.gram_from_csr = 1;
       std::memset(&maps[b], 0, sizeof(CUtensorMap));
     } else {
       p.gram_from_csr = 0;
-      if (!p.Xt) {
-        void* xt;
-        if (int rc = dev_alloc(B, &xt, (size_t)p.n * B.Dp * sizeof(__nv_bfloat16))) return rc;
-        p.Xt = reinterpret_cast<__nv_bfloat16*>(xt);
-      }
+      if (!p.Xt) p.Xt = reinterpret_cast<__nv_bfloat16*>(pool + pool_off[b]);
       if (gram_make_tensor_map(&maps[b], p.Xt, p.n, B.Dp) != 0) return fail(MLEASE_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     }
   }
@@ -331,6 +348,8 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
   B.mirror.resize(B.nprob);
   std::vector<Ctrl>& hc = B.mirror;
   int slots = 0;
+  const Problem* d_hess = B.d;   // problems the Gram / Cholesky grids run over (large batches: compacted by poll2_kernel)
+  int n_hess = B.nprob;
   double shared_flops = 0;   // Gram builds that were not run because the group's first problem stood in for them
   while ((flag & 1) && slots < 400) {
     pf.begin(0, st);
@@ -339,19 +358,19 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
     pf.begin(1, st);
     CK(k1_reduce_decide(B.d, B.nprob, B.Dt, st, &launches));
     pf.end(st);
-    if (flag & 2) {
+    if ((flag & 2) && n_hess > 0) {
       pf.begin(2, st);
       // cold start of a multi-lambda run: the L problems of a partition all sit at beta = 0, their Grams are the same
       const int share = (slots == 0) ? share_first_gram : 0;
       if (share > 1)
         for (int b = 0; b < B.nprob; b++) if (b % share != 0) shared_flops += (double)B.h[b].n * (double)B.Dt * (double)(B.Dt + 1);
-      if (B.gram_from_csr) CK(gram_launch_csr_tcgen05(B.d, B.nprob, B.d_tiles, B.ntiles, B.gram_slices, 0, B.has_bias ? B.Dt - 1 : -1, st, &launches, share));
-      else CK(gram_launch_tcgen05(B.d, B.nprob, B.d_tmaps, B.d_tiles, B.ntiles, B.gram_slices, 0, st, &launches, share));
+      if (B.gram_from_csr) CK(gram_launch_csr_tcgen05(d_hess, n_hess, B.d_tiles, B.ntiles, B.gram_slices, 0, B.has_bias ? B.Dt - 1 : -1, st, &launches, share));
+      else CK(gram_launch_tcgen05(d_hess, n_hess, B.d_tmaps, B.d_tiles, B.ntiles, B.gram_slices, 0, st, &launches, share));
       pf.end(st);
       pf.begin(3, st);
       const bool share_fact = share > 1 && share_first_factor;   // same rho too: same H, one factorisation per group
       if (share_fact) CK(cholesky_share_begin(B.d, B.nprob, share, st, &launches));
-      CK(cholesky_launch(B.d, B.nprob, B.ldh, st, &launches, share));
+      CK(cholesky_launch(d_hess, n_hess, B.ldh, st, &launches, share));
       if (share_fact) {
         CK(cholesky_share_end(B.d, B.nprob, share, st, &launches));
         const size_t hh = (size_t)B.ldh * B.ldh;
@@ -366,7 +385,7 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
     }
     pf.begin(1, st);
     CK(newton_solve(B.d, B.nprob, B.ldh, st, &launches));
-    if (!small) { poll2_kernel<<<1, 256, 0, st>>>(B.d, B.nprob, d_flag); launches++; }
+    if (!small) { poll2_kernel<<<1, 256, 0, st>>>(B.d, B.nprob, d_flag, B.d_compact); launches++; }
     pf.end(st);
     if (small) {
       CK(cudaMemcpyAsync(hc.data(), B.d_ctrl, (size_t)B.nprob * sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
@@ -374,9 +393,11 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
       flag = 0;
       for (auto& c : hc) if (!c.done) { flag |= 1; if (c.emit) flag |= 2; }
     } else {
-      CK(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(h_flag, d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-      flag = *h_flag;
+      flag = h_flag[0];
+      n_hess = h_flag[1];
+      d_hess = B.d_compact;
     }
     slots++;
     if (getenv("MLEASE_DEBUG") && atoi(getenv("MLEASE_DEBUG")) >= 2) {

@@ -351,8 +351,9 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
 //   hi = rint(c S), lo = rint((c S - hi) 2^k), gradient = (sum hi + sum lo / 2^k) / S,
 // i.e. a resolution of B 2^-(29+k) per contribution (k = 16 at 16k rows per CTA), below fp32 rounding of the
 // contribution itself.  The first 128 entries of a row stay in registers between the margin and the gradient half.
+constexpr int K1_FX_THREADS = 896;   // 28 warps: 72 registers per thread, which holds 7 chunks of a row without spilling
 template <bool BSM>   // BSM: beta staged in shared memory (LDS gathers) / read through L1 from global memory
-__global__ void __launch_bounds__(1024, 1) k1_csr_fx_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit, int nprob_dyn) {
+__global__ void __launch_bounds__(K1_FX_THREADS, 1) k1_csr_fx_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit, int nprob_dyn) {
   const K1Map km = k1_map(probs, nprob_dyn);
   if (km.prob < 0) return;
   const Problem& pb = probs[km.prob];
@@ -385,66 +386,75 @@ __global__ void __launch_bounds__(1024, 1) k1_csr_fx_kernel(const Problem* __res
   kbits = max(0, min(kbits, 24));
   const float s_hi = ldexpf(1.f, e_hi), s_k = ldexpf(1.f, kbits);
   const long long* __restrict__ rp = pb.rowptr;
-  const int dummy = ldx + lane;
-  const float bias_b = has_bias ? (BSM ? b_s[Dt - 1] : __ldg(bg + Dt - 1)) : 0.f;
-  double loss = 0.0;
-  long long i = rb + warp;
-  long long j0 = 0;
-  int len = 0;
-  float yy = 0.f, ww = 0.f, oo = 0.f;
   const signed char* __restrict__ yv = pb.y;
   const float* __restrict__ wv = pb.w;
   const float* __restrict__ ov = pb.o;
+  // Two rows per warp: each half-warp (16 lanes) owns a row, so the per-row work (row header, reduction, sigmoid, loss)
+  // is shared by two rows per instruction and a 100-entry row wastes 12 of 112 lane slots instead of 28 of 128.
+  constexpr int HW = 16, NCH = 7;          // lanes per row, register-resident chunks per row (NCH*HW = 112 entries)
+  const int sub = lane >> 4, sl = lane & 15;
+  const int dummy = ldx + lane;
+  const float bias_b = has_bias ? (BSM ? b_s[Dt - 1] : __ldg(bg + Dt - 1)) : 0.f;
+  double loss = 0.0;
+  const long long rstep = 2LL * nw;
+  long long i = rb + 2 * warp + sub;       // this half-warp's row; the loop runs while either half has one
+  long long j0 = 0;
+  int len = 0;
+  float yy = 0.f, ww = 0.f, oo = 0.f;
   if (i < re) { j0 = __ldg(rp + i); len = (int)(__ldg(rp + i + 1) - j0); yy = (float)__ldg(yv + i); ww = __ldg(wv + i); oo = __ldg(ov + i); }
-  while (i < re) {
+  for (long long ib = rb + 2 * warp; ib < re; ib += rstep) {
+    const bool has_row = i < re;
     const float* __restrict__ vr = pb.vals + j0;
     const int* __restrict__ cr = pb.colidx + j0;
-    float v[4];
-    int c[4];
+    float v[NCH];
+    int c[NCH];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const bool ok = lane + 32 * q < len;
-      v[q] = ok ? __ldg(vr + lane + 32 * q) : 0.f;
-      c[q] = ok ? __ldg(cr + lane + 32 * q) : dummy;
+    for (int q = 0; q < NCH; q++) {
+      const bool ok = sl + HW * q < len;
+      v[q] = ok ? __ldg(vr + sl + HW * q) : 0.f;
+      c[q] = ok ? __ldg(cr + sl + HW * q) : dummy;
     }
     // the next row's header while this row's entries are in flight
-    const long long in = i + nw;
+    const long long in = i + rstep;
     long long j0n = 0;
     int lenn = 0;
     float yn = 0.f, wn = 0.f, on = 0.f;
     if (in < re) { j0n = __ldg(rp + in); lenn = (int)(__ldg(rp + in + 1) - j0n); yn = (float)__ldg(yv + in); wn = __ldg(wv + in); on = __ldg(ov + in); }
     float a = 0.f;
 #pragma unroll
-    for (int q = 0; q < 4; q++) a = fmaf(v[q], BSM ? b_s[min(c[q], ldx - 1)] : __ldg(bg + min(c[q], ldx - 1)), a);   // v = 0 on dummy lanes
-    for (int j = 128 + lane; j < len; j += 32) a = fmaf(__ldg(vr + j), BSM ? b_s[__ldg(cr + j)] : __ldg(bg + __ldg(cr + j)), a);
-    a = warp_sum(a) + bias_b;
+    for (int q = 0; q < NCH; q++) a = fmaf(v[q], BSM ? b_s[min(c[q], ldx - 1)] : __ldg(bg + min(c[q], ldx - 1)), a);   // v = 0 on dummy lanes
+    for (int j = NCH * HW + sl; j < len; j += HW) a = fmaf(__ldg(vr + j), BSM ? b_s[__ldg(cr + j)] : __ldg(bg + __ldg(cr + j)), a);
+#pragma unroll
+    for (int m = HW / 2; m >= 1; m >>= 1) a += __shfl_xor_sync(0xffffffffu, a, m);   // stays inside the half-warp
+    a += bias_b;
     const float t = yy * (a + oo);
     const float e = __expf(-fabsf(t));
     const float inv = __frcp_rn(1.f + e);
     const float p = t >= 0.f ? inv : e * inv;
     const float qq = t >= 0.f ? e * inv : inv;
-    if (lane == 0) loss += (double)(ww * ((t >= 0.f ? 0.f : -t) - __logf(inv)));
-    const float rs = -ww * yy * qq * s_hi;     // contribution scale: c S = value * rs
+    if (sl == 0 && has_row) loss += (double)(ww * ((t >= 0.f ? 0.f : -t) - __logf(inv)));
+    const float rs = has_row ? -ww * yy * qq * s_hi : 0.f;     // contribution scale: c S = value * rs
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < NCH; q++) {
       const float ts = v[q] * rs, h = rintf(ts);
       atomicAdd(&g_hi[c[q]], (int)h);
       atomicAdd(&g_lo[c[q]], __float2int_rn((ts - h) * s_k));
     }
-    for (int j = 128 + lane; j < len; j += 32) {
+    for (int j = NCH * HW + sl; j < len; j += HW) {
       const float ts = __ldg(vr + j) * rs, h = rintf(ts);
       const int cc = __ldg(cr + j);
       atomicAdd(&g_hi[cc], (int)h);
       atomicAdd(&g_lo[cc], __float2int_rn((ts - h) * s_k));
     }
-    if (has_bias && lane == 0) {
+    if (has_bias && sl == 0 && has_row) {
       const float h = rintf(rs);
       atomicAdd(&g_hi[Dt - 1], (int)h);
       atomicAdd(&g_lo[Dt - 1], __float2int_rn((rs - h) * s_k));
     }
-    if (emit && lane == 0) pb.sdvec[i] = sqrtf(ww * p * qq);   // the Gram kernel assembles the scaled rows itself
+    if (emit && sl == 0 && has_row) pb.sdvec[i] = sqrtf(ww * p * qq);   // the Gram kernel assembles the scaled rows itself
     i = in; j0 = j0n; len = lenn; yy = yn; ww = wn; oo = on;
   }
+  loss += __shfl_down_sync(0xffffffffu, loss, 16);   // lane 0 += lane 16
   __syncthreads();
   double* gp = pb.gpart + (size_t)km.chunk * ldx;
   const double inv_hi = (double)ldexpf(1.f, -e_hi), inv_k = (double)ldexpf(1.f, -kbits);
@@ -582,8 +592,8 @@ cudaError_t k1_launch(const Problem* d_probs, int nprob, bool csr, int ldx, int 
     cudaError_t e = bsm ? cudaFuncSetAttribute(k1_csr_fx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                         : cudaFuncSetAttribute(k1_csr_fx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (bsm) k1_csr_fx_kernel<true><<<grid_all, 1024, smem, stream>>>(d_probs, has_bias, force_emit, nprob_dyn);
-    else k1_csr_fx_kernel<false><<<grid_all, 1024, smem, stream>>>(d_probs, has_bias, force_emit, nprob_dyn);
+    if (bsm) k1_csr_fx_kernel<true><<<grid_all, K1_FX_THREADS, smem, stream>>>(d_probs, has_bias, force_emit, nprob_dyn);
+    else k1_csr_fx_kernel<false><<<grid_all, K1_FX_THREADS, smem, stream>>>(d_probs, has_bias, force_emit, nprob_dyn);
     if (launches) *launches += 1;
     return cudaGetLastError();
   }

@@ -75,6 +75,7 @@ struct Problem {
   float vmax, wmax;               // max |stored value| and max record weight of the partition (fixed-point scale of the CSR K1)
   int nblk128;             // number of 128-column blocks (Dp / 128)
   float* sdvec;            // [n] sqrt(d_i) written by K1 when the Gram is assembled straight from CSR (no Xt)
+  float* rvec;             // [n] row residuals r_i, only for CSR partitions wider than one K1 column window (else NULL)
   int gram_from_csr;       // 1: gram_csr_tcgen05_kernel builds the bf16 tiles in shared memory from the sparse rows
   __nv_bfloat16* Xt;       // [n][Dp] bf16 = sqrt(d_i) * x_ij  (Gram operand), zero in [ldx, Dp)
   int Dp;                  // multiple of 128

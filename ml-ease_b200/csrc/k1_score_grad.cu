@@ -351,9 +351,12 @@ k1_dense_kernel(const Problem* __restrict__ probs, int S, int nsl, int force_emi
 //   hi = rint(c S), lo = rint((c S - hi) 2^k), gradient = (sum hi + sum lo / 2^k) / S,
 // i.e. a resolution of B 2^-(29+k) per contribution (k = 16 at 16k rows per CTA), below fp32 rounding of the
 // contribution itself.  The first 128 entries of a row stay in registers between the margin and the gradient half.
-constexpr int K1_FX_THREADS = 896;   // 28 warps: 72 registers per thread, which holds 7 chunks of a row without spilling
-template <bool BSM>   // BSM: beta staged in shared memory (LDS gathers) / read through L1 from global memory
-__global__ void __launch_bounds__(K1_FX_THREADS, 1) k1_csr_fx_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit, int nprob_dyn) {
+constexpr int K1_FX_THREADS = 768;   // 24 warps: 80 registers per thread, which holds 7 chunks of two rows per warp without spilling
+// BSM: beta staged in shared memory (LDS gathers) / read through L1 from global memory.
+// WIN: the accumulators do not fit shared memory for all ldx columns (more than ~28k features): this launch accumulates the
+// columns [0, col_w) only and stores the row residuals r_i in rvec; k1_csr_fx_window_kernel adds the other column windows.
+template <bool BSM, bool WIN>
+__global__ void __launch_bounds__(K1_FX_THREADS, 1) k1_csr_fx_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit, int nprob_dyn, int col_w) {
   const K1Map km = k1_map(probs, nprob_dyn);
   if (km.prob < 0) return;
   const Problem& pb = probs[km.prob];
@@ -363,9 +366,10 @@ __global__ void __launch_bounds__(K1_FX_THREADS, 1) k1_csr_fx_kernel(const Probl
   const bool emit = force_emit >= 0 ? (force_emit != 0) : (ctrl->emit != 0);
   extern __shared__ __align__(16) float csr_sm[];
   const int ldx = pb.ldx, Dt = pb.Dt;
-  // layout: g_hi[ldx + 32] | g_lo[ldx + 32] | beta[ldx]; the 32 extra words are per-lane dummy slots for lanes past
-  // the end of a row (they add 0 there), which keeps the gradient half free of divergent branches
-  const int gs = ldx + 32;
+  // layout: g_hi[W + 32] | g_lo[W + 32] | beta[ldx] (W = ldx unless WIN); the 32 extra words are per-lane dummy slots for
+  // lanes past the end of a row or outside the column window (they add 0 there): no divergent branches in the gradient half
+  const int W = WIN ? col_w : ldx;
+  const int gs = W + 32;
   int* g_hi = reinterpret_cast<int*>(csr_sm);
   int* g_lo = g_hi + gs;
   float* b_s = csr_sm + 2 * (size_t)gs;
@@ -393,15 +397,14 @@ __global__ void __launch_bounds__(K1_FX_THREADS, 1) k1_csr_fx_kernel(const Probl
   // is shared by two rows per instruction and a 100-entry row wastes 12 of 112 lane slots instead of 28 of 128.
   constexpr int HW = 16, NCH = 7;          // lanes per row, register-resident chunks per row (NCH*HW = 112 entries)
   const int sub = lane >> 4, sl = lane & 15;
-  const int dummy = ldx + lane;
+  const int dummy = W + lane;
   const float bias_b = has_bias ? (BSM ? b_s[Dt - 1] : __ldg(bg + Dt - 1)) : 0.f;
   double loss = 0.0;
   const long long rstep = 2LL * nw;
   long long i = rb + 2 * warp + sub;       // this half-warp's row; the loop runs while either half has one
   long long j0 = 0;
   int len = 0;
-  float yy = 0.f, ww = 0.f, oo = 0.f;
-  if (i < re) { j0 = __ldg(rp + i); len = (int)(__ldg(rp + i + 1) - j0); yy = (float)__ldg(yv + i); ww = __ldg(wv + i); oo = __ldg(ov + i); }
+  if (i < re) { j0 = __ldg(rp + i); len = (int)(__ldg(rp + i + 1) - j0); }
   for (long long ib = rb + 2 * warp; ib < re; ib += rstep) {
     const bool has_row = i < re;
     const float* __restrict__ vr = pb.vals + j0;
@@ -414,12 +417,13 @@ __global__ void __launch_bounds__(K1_FX_THREADS, 1) k1_csr_fx_kernel(const Probl
       v[q] = ok ? __ldg(vr + sl + HW * q) : 0.f;
       c[q] = ok ? __ldg(cr + sl + HW * q) : dummy;
     }
-    // the next row's header while this row's entries are in flight
+    // this row's scalars and the next row's extent while the entries are in flight
+    float yy = 0.f, ww = 0.f, oo = 0.f;
+    if (has_row) { yy = (float)__ldg(yv + i); ww = __ldg(wv + i); oo = __ldg(ov + i); }
     const long long in = i + rstep;
     long long j0n = 0;
     int lenn = 0;
-    float yn = 0.f, wn = 0.f, on = 0.f;
-    if (in < re) { j0n = __ldg(rp + in); lenn = (int)(__ldg(rp + in + 1) - j0n); yn = (float)__ldg(yv + in); wn = __ldg(wv + in); on = __ldg(ov + in); }
+    if (in < re) { j0n = __ldg(rp + in); lenn = (int)(__ldg(rp + in + 1) - j0n); }
     float a = 0.f;
 #pragma unroll
     for (int q = 0; q < NCH; q++) a = fmaf(v[q], BSM ? b_s[min(c[q], ldx - 1)] : __ldg(bg + min(c[q], ldx - 1)), a);   // v = 0 on dummy lanes
@@ -437,28 +441,31 @@ __global__ void __launch_bounds__(K1_FX_THREADS, 1) k1_csr_fx_kernel(const Probl
 #pragma unroll
     for (int q = 0; q < NCH; q++) {
       const float ts = v[q] * rs, h = rintf(ts);
-      atomicAdd(&g_hi[c[q]], (int)h);
-      atomicAdd(&g_lo[c[q]], __float2int_rn((ts - h) * s_k));
-    }
-    for (int j = NCH * HW + sl; j < len; j += HW) {
-      const float ts = __ldg(vr + j) * rs, h = rintf(ts);
-      const int cc = __ldg(cr + j);
+      const int cc = (!WIN || c[q] < W) ? c[q] : dummy;
       atomicAdd(&g_hi[cc], (int)h);
       atomicAdd(&g_lo[cc], __float2int_rn((ts - h) * s_k));
     }
-    if (has_bias && sl == 0 && has_row) {
+    for (int j = NCH * HW + sl; j < len; j += HW) {
+      const float ts = __ldg(vr + j) * rs, h = rintf(ts);
+      int cc = __ldg(cr + j);
+      if (WIN && cc >= W) cc = dummy;
+      atomicAdd(&g_hi[cc], (int)h);
+      atomicAdd(&g_lo[cc], __float2int_rn((ts - h) * s_k));
+    }
+    if (has_bias && sl == 0 && has_row && (!WIN || Dt - 1 < W)) {
       const float h = rintf(rs);
       atomicAdd(&g_hi[Dt - 1], (int)h);
       atomicAdd(&g_lo[Dt - 1], __float2int_rn((rs - h) * s_k));
     }
     if (emit && sl == 0 && has_row) pb.sdvec[i] = sqrtf(ww * p * qq);   // the Gram kernel assembles the scaled rows itself
-    i = in; j0 = j0n; len = lenn; yy = yn; ww = wn; oo = on;
+    if (WIN && sl == 0 && has_row) pb.rvec[i] = -ww * yy * qq;           // residual for the other column windows
+    i = in; j0 = j0n; len = lenn;
   }
   loss += __shfl_down_sync(0xffffffffu, loss, 16);   // lane 0 += lane 16
   __syncthreads();
   double* gp = pb.gpart + (size_t)km.chunk * ldx;
   const double inv_hi = (double)ldexpf(1.f, -e_hi), inv_k = (double)ldexpf(1.f, -kbits);
-  for (int k = tid; k < ldx; k += blockDim.x) gp[k] = ((double)g_hi[k] + (double)g_lo[k] * inv_k) * inv_hi;
+  for (int k = tid; k < min(W, ldx); k += blockDim.x) gp[k] = ((double)g_hi[k] + (double)g_lo[k] * inv_k) * inv_hi;
   __shared__ double red[32];
   if (lane == 0) red[warp] = loss;
   __syncthreads();
@@ -467,6 +474,61 @@ __global__ void __launch_bounds__(K1_FX_THREADS, 1) k1_csr_fx_kernel(const Probl
     for (int wq = 0; wq < nw; wq++) sacc += red[wq];
     pb.fpart[km.chunk] = sacc;
   }
+}
+
+// Columns [col_lo, col_lo + col_w) of the gradient for partitions too wide for one shared-memory window: same CTA -> rows
+// mapping and the same fixed-point scales as k1_csr_fx_kernel<.., true>, which ran first in this slot and left r_i in rvec.
+__global__ void __launch_bounds__(K1_FX_THREADS, 1) k1_csr_fx_window_kernel(const Problem* __restrict__ probs, int has_bias, int nprob_dyn,
+                                                                            int col_lo, int col_w) {
+  const K1Map km = k1_map(probs, nprob_dyn);
+  if (km.prob < 0) return;
+  const Problem& pb = probs[km.prob];
+  if (pb.ctrl->done) return;
+  extern __shared__ __align__(16) float csr_sm[];
+  const int ldx = pb.ldx, Dt = pb.Dt;
+  const int gs = col_w + 32;
+  int* g_hi = reinterpret_cast<int*>(csr_sm);
+  int* g_lo = g_hi + gs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int k = tid; k < gs; k += blockDim.x) { g_hi[k] = 0; g_lo[k] = 0; }
+  __syncthreads();
+  const long long n = pb.n;
+  const long long per = (n + km.nchunks - 1) / km.nchunks;
+  const long long rb = (long long)km.chunk * per, re = min(n, rb + per);
+  float bound = (float)per * pb.wmax * fmaxf(pb.vmax, has_bias ? 1.f : 0.f);
+  if (!(bound > 0.f) || !(bound < 3.0e38f)) bound = 1.f;
+  const int e_hi = 29 - (ilogbf(bound) + 1);
+  int kbits = 30 - (64 - __clzll((unsigned long long)max(per, 1LL)));
+  kbits = max(0, min(kbits, 24));
+  const float s_hi = ldexpf(1.f, e_hi), s_k = ldexpf(1.f, kbits);
+  const long long* __restrict__ rp = pb.rowptr;
+  const int sub = lane >> 4, sl = lane & 15;
+  const int dummy = col_w + lane;
+  const int bias_idx = Dt - 1 - col_lo;
+  for (long long i = rb + 2 * warp + sub; i < re; i += 2LL * nw) {
+    const long long j0 = __ldg(rp + i);
+    const int len = (int)(__ldg(rp + i + 1) - j0);
+    const float rs = __ldg(pb.rvec + i) * s_hi;
+    const float* __restrict__ vr = pb.vals + j0;
+    const int* __restrict__ cr = pb.colidx + j0;
+    for (int j = sl; j < len; j += 16) {
+      const float ts = __ldg(vr + j) * rs, h = rintf(ts);
+      const int idx = __ldg(cr + j) - col_lo;
+      const int cc = (unsigned)idx < (unsigned)col_w ? idx : dummy;
+      const bool in = (unsigned)idx < (unsigned)col_w;
+      atomicAdd(&g_hi[cc], in ? (int)h : 0);
+      atomicAdd(&g_lo[cc], in ? __float2int_rn((ts - h) * s_k) : 0);
+    }
+    if (has_bias && sl == 0 && (unsigned)bias_idx < (unsigned)col_w) {
+      const float h = rintf(rs);
+      atomicAdd(&g_hi[bias_idx], (int)h);
+      atomicAdd(&g_lo[bias_idx], __float2int_rn((rs - h) * s_k));
+    }
+  }
+  __syncthreads();
+  double* gp = pb.gpart + (size_t)km.chunk * ldx + col_lo;
+  const double inv_hi = (double)ldexpf(1.f, -e_hi), inv_k = (double)ldexpf(1.f, -kbits);
+  for (int k = tid; k < min(col_w, ldx - col_lo); k += blockDim.x) gp[k] = ((double)g_hi[k] + (double)g_lo[k] * inv_k) * inv_hi;
 }
 
 __global__ void __launch_bounds__(1024) k1_csr_kernel(const Problem* __restrict__ probs, int has_bias, int force_emit, int beta_in_smem, int nprob_dyn) {
@@ -580,21 +642,43 @@ bool k1_dense_plan(int ldx, int* R_out, int* S_out, int* G_out, size_t* smem_out
   return true;
 }
 
+// Column-window width of the CSR K1 when ldx exceeds one shared-memory window (0: everything fits in one launch).
+int k1_csr_window(int ldx) {
+  const size_t cap = 220 * 1024;
+  if ((size_t)2 * (ldx + 32) * 4 <= cap) return 0;
+  return (int)((cap / 8 - 32) & ~(size_t)31);
+}
+
 cudaError_t k1_launch(const Problem* d_probs, int nprob, bool csr, int ldx, int has_bias, int ctas_per_problem,
                       int force_emit, cudaStream_t stream, int* launches, int csr_fx, int nprob_dyn) {
   // dynamic mapping: ctas_per_problem is then the size of the whole one-dimensional grid
   const dim3 grid_all = nprob_dyn ? dim3(ctas_per_problem, 1) : dim3(ctas_per_problem, nprob);
   if (csr && csr_fx) {
+    const size_t cap = 220 * 1024;
     const size_t g_bytes = (size_t)2 * (ldx + 32) * 4;
-    const bool bsm = g_bytes + (size_t)ldx * 4 <= 220 * 1024;
-    const size_t smem = g_bytes + (bsm ? (size_t)ldx * 4 : 0);
-    if (smem > 220 * 1024) return cudaErrorInvalidValue;   // > 28k features: needs a column-blocked gradient (not built yet)
-    cudaError_t e = bsm ? cudaFuncSetAttribute(k1_csr_fx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                        : cudaFuncSetAttribute(k1_csr_fx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    if (bsm) k1_csr_fx_kernel<true><<<grid_all, K1_FX_THREADS, smem, stream>>>(d_probs, has_bias, force_emit, nprob_dyn);
-    else k1_csr_fx_kernel<false><<<grid_all, K1_FX_THREADS, smem, stream>>>(d_probs, has_bias, force_emit, nprob_dyn);
+    cudaError_t e;
+    if (g_bytes <= cap) {
+      const bool bsm = g_bytes + (size_t)ldx * 4 <= cap;
+      const size_t smem = g_bytes + (bsm ? (size_t)ldx * 4 : 0);
+      e = bsm ? cudaFuncSetAttribute(k1_csr_fx_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+              : cudaFuncSetAttribute(k1_csr_fx_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      if (bsm) k1_csr_fx_kernel<true, false><<<grid_all, K1_FX_THREADS, smem, stream>>>(d_probs, has_bias, force_emit, nprob_dyn, ldx);
+      else k1_csr_fx_kernel<false, false><<<grid_all, K1_FX_THREADS, smem, stream>>>(d_probs, has_bias, force_emit, nprob_dyn, ldx);
+      if (launches) *launches += 1;
+      return cudaGetLastError();
+    }
+    // wider than one shared-memory window: the first launch does the margins and columns [0, W), one more launch per window
+    const int W = k1_csr_window(ldx);
+    const size_t smem = (size_t)2 * (W + 32) * 4;
+    if ((e = cudaFuncSetAttribute(k1_csr_fx_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k1_csr_fx_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k1_csr_fx_kernel<false, true><<<grid_all, K1_FX_THREADS, smem, stream>>>(d_probs, has_bias, force_emit, nprob_dyn, W);
     if (launches) *launches += 1;
+    for (int lo = W; lo < ldx; lo += W) {
+      k1_csr_fx_window_kernel<<<grid_all, K1_FX_THREADS, smem, stream>>>(d_probs, has_bias, nprob_dyn, lo, W);
+      if (launches) *launches += 1;
+    }
     return cudaGetLastError();
   }
   if (csr) {

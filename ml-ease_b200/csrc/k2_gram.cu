@@ -536,11 +536,16 @@ int gram_tile_list(int Dp, short* bi_bj_pairs /*[2*max]*/, int max_tiles) {
 
 cudaError_t gram_launch_tcgen05(const Problem* d_probs, int nprob, const void* d_tmaps, const void* d_tiles, int ntiles,
                                 int nslices, int force, cudaStream_t st, int* launches, int share) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
+  {
+    // the attribute is per device: set it once for every device this process launches on
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+      if (e != cudaSuccess) return e;
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
   }
   gram_tcgen05_kernel<<<dim3(ntiles, nslices, nprob), G_THREADS, G_SMEM, st>>>(
       d_probs, reinterpret_cast<const CUtensorMap*>(d_tmaps), reinterpret_cast<const GramTile*>(d_tiles), ntiles, force, share);
@@ -550,11 +555,16 @@ cudaError_t gram_launch_tcgen05(const Problem* d_probs, int nprob, const void* d
 
 cudaError_t gram_launch_csr_tcgen05(const Problem* d_probs, int nprob, const void* d_tiles, int ntiles, int nslices, int force,
                                     int bias_col, cudaStream_t st, int* launches, int share) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gram_csr_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
+  {
+    // the attribute is per device: set it once for every device this process launches on
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(gram_csr_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_SMEM);
+      if (e != cudaSuccess) return e;
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
   }
   gram_csr_tcgen05_kernel<<<dim3(ntiles, nslices, nprob), S_THREADS, S_SMEM, st>>>(d_probs, reinterpret_cast<const GramTile*>(d_tiles), ntiles, force, bias_col, share);
   if (launches) *launches += 1;

@@ -493,11 +493,16 @@ __global__ void __launch_bounds__(256, 2) dgemm_kernel(const Problem* __restrict
 template <bool A_KC, bool B_KC>
 static cudaError_t dgemm_launch(const Problem* d_probs, int nprob, int mode, int p0, int p1, int M, int N, int nmerge, cudaStream_t st,
                                 int* launches) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dgemm_kernel<A_KC, B_KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DGEMM_SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
+  {
+    // the attribute is per device: set it once for every device this process launches on
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(dgemm_kernel<A_KC, B_KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DGEMM_SMEM);
+      if (e != cudaSuccess) return e;
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
   }
   const int tiles = ((M + DM - 1) / DM) * ((N + DN - 1) / DN);
   if (tiles <= 0 || nmerge <= 0) return cudaSuccess;

@@ -6,6 +6,7 @@ namespace mlease {
 
 // K1 (k1_score_grad.cu)
 bool k1_dense_plan(int ldx, int* R_out, int* S_out, int* G_out, size_t* smem_out, int* ctas_per_sm);
+int k1_csr_window(int ldx);
 cudaError_t k1_launch(const Problem* d_probs, int nprob, bool csr, int ldx, int has_bias, int ctas_per_problem,
                       int force_emit, cudaStream_t stream, int* launches, int csr_fx = 0, int nprob_dyn = 0);
 

@@ -239,8 +239,9 @@ int batch_alloc(Batch& B, int num_sms) {
     if (const char* e = getenv("MLEASE_BFGS_M")) B.bfgs_m = std::max(1, std::min(BFGS_M, atoi(e)));   // tuning experiments only
   }
   // Gram decomposition
-  std::vector<short> tiles(2 * 8192);
-  B.ntiles = gram_tile_list(B.Dp, tiles.data(), 8192);
+  constexpr int MAX_TILES = 1 << 18;   // lower 128x256 tiles of Dp up to ~90k
+  std::vector<short> tiles(2 * (size_t)MAX_TILES);
+  B.ntiles = gram_tile_list(B.Dp, tiles.data(), MAX_TILES);
   if (B.ntiles <= 0) return fail(MLEASE_ERR_INVALID, "Gram tile list overflow");
   {
     const long long ksteps = (maxn + 63) / 64;
@@ -284,7 +285,8 @@ int batch_alloc(Batch& B, int num_sms) {
   size_t pool_bytes = 0;
   for (int b = 0; b < nprob; b++) {
     pool_off[b] = pool_bytes;
-    const size_t need = B.gram_from_csr ? (size_t)B.h[b].n * sizeof(float) : (B.h[b].Xt ? 0 : (size_t)B.h[b].n * B.Dp * sizeof(__nv_bfloat16));
+    const bool windows = B.gram_from_csr && k1_csr_window(ldx) > 0;   // then a second [n] vector (row residuals) follows sdvec
+    const size_t need = B.gram_from_csr ? (size_t)B.h[b].n * sizeof(float) * (windows ? 2 : 1) : (B.h[b].Xt ? 0 : (size_t)B.h[b].n * B.Dp * sizeof(__nv_bfloat16));
     pool_bytes += (need + 255) & ~(size_t)255;
   }
   unsigned char* pool = nullptr;
@@ -316,6 +318,7 @@ int batch_alloc(Batch& B, int num_sms) {
     // one cudaMalloc / cudaFree each would cost more than the fits)
     if (B.gram_from_csr) {
       p.sdvec = reinterpret_cast<float*>(pool + pool_off[b]);
+      p.rvec = k1_csr_window(ldx) > 0 ? p.sdvec + p.n : nullptr;
       p.gram_from_csr = 1;
       std::memset(&maps[b], 0, sizeof(CUtensorMap));
     } else {

@@ -100,6 +100,42 @@ def test_csr_rows_with_repeated_and_unsorted_columns(mb):
     assert np.abs(x - x_ref).max() <= 1e-5 * np.abs(x_ref).max()
 
 
+def test_csr_feature_space_wider_than_one_gradient_window(mb):
+    """30 001 columns: the per-CTA fixed-point gradient (8 bytes per column) no longer fits shared memory in one piece, so
+    K1 runs one launch for the margins + the first 28 128 columns and one more per further column window; the Gram tile
+    list, the DMMA factorisation and the fp32 inverse copy are exercised at ldh = 30 016 as well."""
+    n, D, nnz = 3000, 30000, 8
+    r = np.random.default_rng(12)
+    ci = np.stack([np.sort(r.choice(D, nnz, replace=False)) for _ in range(n)]).astype(np.int32)
+    ci[:, -1] = D - 1 - (np.arange(n) % 5)            # make sure the last window and the columns next to the intercept are hit
+    ci.sort(axis=1)
+    for i in range(n):                                 # keep rows strictly increasing after the overwrite
+        while len(np.unique(ci[i])) < nnz:
+            ci[i] = np.sort(r.choice(D, nnz, replace=False))
+    v = r.normal(size=(n, nnz)).astype(np.float32)
+    beta = r.normal(size=D) / np.sqrt(nnz)
+    y = (r.random(n) < 1 / (1 + np.exp(-((v * beta[ci]).sum(1) - 0.3)))).astype(np.int32)
+    w = r.uniform(0.5, 2.0, n).astype(np.float32); o = r.normal(0, 0.1, n).astype(np.float32)
+    rp = np.arange(n + 1, dtype=np.int64) * nnz
+    data = orc.Csr(rp, ci.reshape(-1), v.reshape(-1), y, w, o, D)
+    wv = r.normal(0, 0.3, D + 1); pm = r.normal(0, 0.3, D + 1); pv = r.uniform(0.5, 2.0, D + 1)
+    # columns that never occur in the partition are not part of the reference's local problem (llf/LibLinear.java:491-493;
+    # their coefficient is the prior mean, :374-383): evaluate at a point that agrees with that, so that fun/grad compare
+    absent = np.ones(D + 1, bool); absent[ci.reshape(-1)] = False; absent[D] = False
+    wv[absent] = pm[absent]
+    with _session(mb, D) as s:
+        s.add_partition_csr(0, rp, ci.reshape(-1), v.reshape(-1), y, w, o)
+        f, g, _ = s.objective(0, wv, pm, 1.0 / pv)
+        f2, g2, _ = s.objective(0, wv, pm, 1.0 / pv)
+        x, steps = s.fit_partition(0, np.zeros(D + 1), pm, 1.0 / pv)
+    f_ref, g_ref = orc.objective("grad", data, wv, pm, pv)
+    assert abs(f - f_ref) <= 1e-5 * abs(f_ref), (f, f_ref)
+    assert np.abs(g - g_ref).max() <= 1e-5 * np.abs(g_ref).max(), np.abs(g - g_ref).max() / np.abs(g_ref).max()
+    assert f == f2 and np.array_equal(g, g2)
+    x_ref, _ = orc.liblinear_train(data, np.zeros(D + 1), pm, pv, 1e-14, 100000)
+    assert np.abs(x - x_ref).max() <= 1e-5 * np.abs(x_ref).max(), (np.abs(x - x_ref).max() / np.abs(x_ref).max(), steps)
+
+
 def _bf16_round(a):
     u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
     u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -1189,6 +1190,16 @@ int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(MLEASE_ERR_CUDA, "this build targets sm_100a (B200) only");
   const int Dt = Dg + 1, ldx = round_up(Dt, 4);
+  // MLEASE_DEBUG: wall-clock of the host-side phases (allocation, ingest, solve, read-back)
+  const bool dbg = getenv("MLEASE_DEBUG") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!dbg) return;
+    cudaStreamSynchronize((cudaStream_t)stream);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[mlease] naive_train %-12s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   std::vector<long long> krs(K + 1);
   CK(cudaMemcpy(krs.data(), key_rowstart, (size_t)(K + 1) * 8, cudaMemcpyDefault));
   const long long ntot = krs[K];
@@ -1201,8 +1212,18 @@ int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg
   if (int rc = t.get(&dflag, 16)) return rc;
   CK(cudaMallocHost((void**)&hflag, 64));
   struct HF { int* p; ~HF() { cudaFreeHost(p); } } hf{hflag};
-  CK(cudaMemcpy2DAsync(dX, (size_t)ldx * 4, X, (size_t)ldx_in * 4, (size_t)Dg * 4, (size_t)ntot, cudaMemcpyDefault, st));
+  lap("alloc");
+  {
+    // rows are re-pitched from ldx_in to ldx floats: a kernel for device input (the copy engine moves 1 KB rows slowly),
+    // a pitched copy for host input
+    cudaPointerAttributes pa;
+    const bool on_device = cudaPointerGetAttributes(&pa, X) == cudaSuccess && (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    if (on_device) repack_rows_kernel<<<4096, 256, 0, st>>>(dX, ldx, X, ldx_in, ntot, Dg);
+    else CK(cudaMemcpy2DAsync(dX, (size_t)ldx * 4, X, (size_t)ldx_in * 4, (size_t)Dg * 4, (size_t)ntot, cudaMemcpyDefault, st));
+  }
   fill_bias_pad_kernel<<<1024, 256, 0, st>>>(dX, ntot, ldx, Dg, has_intercept ? 1 : 0);
+  lap("ingest X");
   {
     const int* d_r; const float *d_wi, *d_oi;
     if (int rc = to_device(t, (const int*)response, (size_t)ntot, &d_r, st)) return rc;
@@ -1215,6 +1236,7 @@ int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg
     if (*hflag & 1) return fail(MLEASE_ERR_INVALID, "response (only 1, 0, -1 are allowed)");
     if (*hflag & 2) return fail(MLEASE_ERR_INVALID, "weight cannot < 0");
   }
+  lap("labels");
   // prior (jobs/RegressionNaiveTrain.java:333-343,395)
   std::vector<double> q(ldx, 1.0), m(ldx, 0.0), zero(ldx, 0.0);
   std::vector<float> lm;
@@ -1263,6 +1285,7 @@ int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg
       p.y = dy + krs[k]; p.w = dw + krs[k]; p.o = dofs + krs[k];
     }
     if (int rc = batch_alloc(B, prop.multiProcessorCount)) return rc;
+    lap("batch_alloc");
     {
       double *dm, *dq, *dout;
       if (int rc = t.get(&dm, (size_t)ldx)) return rc;
@@ -1272,6 +1295,7 @@ int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg
       CK(cudaMemcpyAsync(dq, q.data(), ldx * 8, cudaMemcpyHostToDevice, st));
       naive_init_kernel<<<B.nprob, 128, 0, st>>>(B.d, dm, dq);   // init = 0 (null initParam), prior mean / precision
       if (int rc = batch_xupdate(B, st, 2e-7, 100, 0, 1, hflag, dflag, cnt)) return rc;
+      lap("solve");
       gather_beta_kernel<<<B.nprob, 128, 0, st>>>(B.d, Dt, dout);
       std::vector<double> xs((size_t)B.nprob * Dt);
       CK(cudaMemcpyAsync(xs.data(), dout, xs.size() * 8, cudaMemcpyDeviceToHost, st));
@@ -1280,6 +1304,7 @@ int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg
         std::memcpy(out_model + (size_t)todo[pos + b] * Dt, xs.data() + (size_t)b * Dt, Dt * 8);
         if (!has_intercept) out_model[(size_t)todo[pos + b] * Dt + Dg] = 0.0;
       }
+      lap("read-back");
     }
     pos = end;
   }

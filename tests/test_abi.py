@@ -60,3 +60,18 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert not bad.search(txt), os.path.join(dp, f)
+
+
+def test_tools_and_bench_scripts_parse():
+    """The GPU-side scripts cannot run here, but they must at least be valid Python and bench.py must keep its CLI contract."""
+    import ast
+    import glob
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in glob.glob(os.path.join(root, "tools", "*.py")) + [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]:
+        ast.parse(open(path).read(), filename=path)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0
+    for flag in ("--gpus", "--steps", "--warmup", "--impl"):
+        assert flag in out.stdout

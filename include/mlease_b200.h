@@ -96,6 +96,11 @@ int mlease_add_partition_csr(mlease_session* s, int32_t partition_id, int64_t nr
  * all-reduce (sum, double, in place on `buf` which is DEVICE memory, ordered on `stream`). */
 typedef int (*mlease_allreduce_fn)(void* ctx, double* buf, size_t count, void* stream);
 int mlease_admm_begin(mlease_session* s);
+/* initialize.boost.rate > 0 (jobs/RegressionAdmmTrain.java:236-266, 313-316): the run starts from z0 ([num_lambdas][num_features+1]
+ * doubles on the host, intercept last: the mean of per-partition RegressionNaiveTrain fits, which the caller obtains with
+ * mlease_fit_partition) instead of z = {}, u is empty, and the reducers use rho * boost_rate from iteration 1 on -- for the
+ * whole run unless rho_adapt_coefficient > 0, because the reference's driver never resets the conf value otherwise (:316, :323-327). */
+int mlease_admm_begin_initialized(mlease_session* s, const double* z0, float boost_rate);
 int mlease_admm_local_step(mlease_session* s, double* exchange_dev);
 int mlease_admm_consensus(mlease_session* s, const double* exchange_sum_dev, double* maxdiff, int32_t* stop);
 int mlease_admm_run(mlease_session* s, int32_t num_iters, mlease_allreduce_fn allreduce, void* ctx, int32_t* iters_done);

@@ -29,6 +29,18 @@ __global__ void admm_reset_kernel(const Problem* __restrict__ probs, int L, doub
   if (threadIdx.x == 0) pb.ctrl->hess_valid = 0;
 }
 
+// Start from a given z (initialize.boost.rate): the reducers read z as float from the init-value file
+// (jobs/RegressionAdmmTrain.java:330-331, models/LinearModel.java:716); u is the empty map, so priorMean = z - u = float(z).
+__global__ void admm_init_kernel(const Problem* __restrict__ probs, const double* __restrict__ z, int ldv) {
+  const Problem& pb = probs[blockIdx.x];
+  const int l = pb.lambda_idx;
+  for (int k = threadIdx.x; k < pb.Dt; k += blockDim.x) {
+    const double zf = (double)(float)z[(size_t)l * ldv + k];
+    pb.m[k] = zf;
+    pb.beta[k] = zf;   // init = z (:692-693)
+  }
+}
+
 __global__ void admm_pack_kernel(const Problem* __restrict__ probs, int nparts, int L, int Dt, double* __restrict__ exch) {
   const int l = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,6 +99,11 @@ __global__ void __launch_bounds__(256) admm_consensus_kernel(const Problem* __re
 cudaError_t admm_reset(const Problem* d_probs, int nprob, int L, double* d_z, int ldv, const double* d_rho_eff, cudaStream_t st,
                        int* launches) {
   admm_reset_kernel<<<nprob, 256, 0, st>>>(d_probs, L, d_z, ldv, d_rho_eff);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+cudaError_t admm_init(const Problem* d_probs, int nprob, const double* d_z, int ldv, cudaStream_t st, int* launches) {
+  admm_init_kernel<<<nprob, 256, 0, st>>>(d_probs, d_z, ldv);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

@@ -36,6 +36,7 @@ cudaError_t cholesky_share_end(const Problem* d_probs, int nprob, int share, cud
 // K4 (k4_consensus.cu)
 cudaError_t admm_reset(const Problem* d_probs, int nprob, int L, double* d_z, int ldv, const double* d_rho_eff,
                        cudaStream_t st, int* launches);
+cudaError_t admm_init(const Problem* d_probs, int nprob, const double* d_z, int ldv, cudaStream_t st, int* launches);
 cudaError_t admm_pack(const Problem* d_probs, int nlocal_parts, int L, int Dt, double* d_exchange, cudaStream_t st,
                       int* launches);
 cudaError_t admm_consensus(const Problem* d_probs, int nlocal_parts, int L, int Dt, int ldv, int P, const double* d_exchange_sum,

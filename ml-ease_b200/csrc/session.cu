@@ -475,6 +475,7 @@ struct mlease_session {
   double mindiff = 99999999;
   double last_maxdiff = 0;
   bool begun = false;
+  float boost_rate = 0.f;    // initialize.boost.rate of the current run (0: cold start from z = {})
   Counters cnt;
   Profiler prof;
   double xtol = 1e-8;
@@ -568,10 +569,9 @@ double rho_eff_for_iter(mlease_session* s, int l, int iter) {
   // reducer: rho = lambdaRho[lambda] (float -> double), times rho.adapt.rate if != 1 (jobs/RegressionAdmmTrain.java:652-658);
   // rate = (float) exp(-(i-1)*coef) for i > 1 (:323-327)
   double r = (double)s->rhos[l];
-  if (iter > 1 && s->cfg.rho_adapt_coefficient > 0) {
-    const float rate = (float)std::exp(-(iter - 1) * s->cfg.rho_adapt_coefficient);
-    if (rate != 1.0f) r = r * (double)rate;
-  }
+  float rate = s->boost_rate > 0.f ? s->boost_rate : 1.0f;   // the conf value persists once set at iteration 1 (:313-316)
+  if (iter > 1 && s->cfg.rho_adapt_coefficient > 0) rate = (float)std::exp(-(iter - 1) * s->cfg.rho_adapt_coefficient);
+  if (rate != 1.0f) r = r * (double)rate;
   return r;
 }
 
@@ -818,20 +818,37 @@ int mlease_add_partition_csr(mlease_session* s, int32_t pid, int64_t nrows, cons
   return 0;
 }
 
-int mlease_admm_begin(mlease_session* s) {
+static int admm_begin_impl(mlease_session* s, const double* z0, float boost_rate) {
   if (!s) return fail(MLEASE_ERR_INVALID, "null session");
   CK(cudaSetDevice(s->cfg.device));
   if (int rc = finalize(s)) return rc;
+  s->boost_rate = z0 ? boost_rate : 0.f;
   s->iter = 0; s->liblinear_eps = 0.01f; s->mindiff = 99999999; s->last_maxdiff = 0;
   for (int l = 0; l < s->L; l++) s->h_small[l] = rho_eff_for_iter(s, l, 1);
   CK(cudaMemcpyAsync(s->d_rho, s->h_small, s->L * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   int launches = 0;
   CK(admm_reset(s->batch->d, s->batch->nprob, s->L, s->d_z, s->ldx, s->d_rho, s->stream, &launches));
+  if (z0) {
+    std::vector<double> zh((size_t)s->L * s->ldx, 0.0);
+    for (int l = 0; l < s->L; l++) std::memcpy(&zh[(size_t)l * s->ldx], z0 + (size_t)l * s->Dt, (size_t)s->Dt * sizeof(double));
+    CK(cudaMemcpyAsync(s->d_z, zh.data(), zh.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CK(admm_init(s->batch->d, s->batch->nprob, s->d_z, s->ldx, s->stream, &launches));
+    CK(cudaStreamSynchronize(s->stream));   // zh is a stack-lifetime buffer
+  }
   CK(cudaStreamSynchronize(s->stream));
   s->cnt.launches += launches;
   s->rho_fact.assign(s->L, -1.0);
   s->begun = true;
   return 0;
+}
+
+int mlease_admm_begin(mlease_session* s) { return admm_begin_impl(s, nullptr, 0.f); }
+
+int mlease_admm_begin_initialized(mlease_session* s, const double* z0, float boost_rate) {
+  if (!z0) return fail(MLEASE_ERR_INVALID, "null z0");
+  if (!(boost_rate > 0.f)) return fail(MLEASE_ERR_INVALID, "initialize.boost.rate must be > 0 to start from a model");
+  if (s && s->cfg.regularizer != 2) return fail(MLEASE_ERR_INVALID, "mean-model initialization is an L2 feature (jobs/RegressionAdmmTrain.java:236)");
+  return admm_begin_impl(s, z0, boost_rate);
 }
 
 int mlease_admm_local_step(mlease_session* s, double* exchange_dev) {
@@ -852,7 +869,7 @@ int mlease_admm_local_step(mlease_session* s, double* exchange_dev) {
   int same_rho = 1;   // cold start: equal rho across lambdas means equal Hessians (H = G + rho I at beta = 0)
   for (int l = 1; l < s->L; l++) if (s->rho_fact[l] != s->rho_fact[0]) same_rho = 0;
   if (int rc = batch_xupdate(*s->batch, s->stream, s->xtol, s->max_newton, s->cfg.hessian_policy, invalidate, s->h_flag, s->d_flag, s->cnt, &s->prof,
-                             (i == 1 && s->L > 1) ? s->L : 0, same_rho)) return rc;
+                             (i == 1 && s->L > 1 && s->boost_rate == 0.f) ? s->L : 0, same_rho)) return rc;   // sharing needs beta = 0 for every lambda
   int launches = 0;
   CK(admm_pack(s->batch->d, (int)s->parts.size(), s->L, s->Dt, exchange_dev, s->stream, &launches));
   s->cnt.launches += launches;

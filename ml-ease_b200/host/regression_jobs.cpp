@@ -407,7 +407,7 @@ void run_admm_train(const JobConfig& c) {
     for (auto& t : c.get_list("rho")) rhos.push_back(std::stof(t));
     if ((int)rhos.size() != L) io_error("The number of rho's should be exactly the same as the number of lambda's. OR: don't claim rho!");
   } else for (float l : lambdas) rhos.push_back(l <= 100 ? 1.0f : 10.0f);
-  if (c.get_float("initialize.boost.rate", 0) > 0) io_error("initialize.boost.rate > 0 is not on the accelerated path yet (SURVEY 8f-2)");
+  const float boost_rate = c.get_float("initialize.boost.rate", 0);
   if (!c.get("lambda.map", "").empty()) io_error("lambda.map files are not wired into the host job yet (the C ABI accepts a per-feature lambda_map)");
 
   Dictionary dict;
@@ -473,7 +473,30 @@ void run_admm_train(const JobConfig& c) {
     (void)as_float;
     return m;
   };
-  ck(mlease_admm_begin(S.s));
+  const bool initialized = boost_rate > 0 && reg == 2;   // jobs/RegressionAdmmTrain.java:236
+  if (initialized) {
+    // Mean-model initialization: one RegressionNaiveTrain fit per (lambda, partition) -- prior variance 1/lambda, intercept
+    // variance 100000 unless penalize.intercept, prior mean 0, start 0 (jobs/RegressionNaiveTrain.java:333-343,395) -- kept
+    // under <out>/initialModel like the reference (:239-260), then averaged as float models (cons/MeanLinearModelConsumer.java:44-70).
+    std::vector<double> z0((size_t)L * Dt, 0.0);
+    std::vector<std::pair<std::string, std::vector<float>>> init_models;
+    for (int l = 0; l < L; l++) {
+      std::vector<double> q(Dt, (double)lambdas[l]), zero(Dt, 0.0);
+      if (!cfg.penalize_intercept) q[D] = 1.0 / 100000.0;
+      for (int p = 0; p < nblocks; p++) {
+        std::vector<double> x(Dt, 0.0);
+        int32_t steps = 0;
+        ck(mlease_fit_partition(S.s, p, x.data(), zero.data(), q.data(), &steps));
+        std::vector<float> xf(Dt);
+        for (int k = 0; k < Dt; k++) { xf[k] = (float)x[k]; z0[(size_t)l * Dt + k] = 1.0 * z0[(size_t)l * Dt + k] + (1.0 / nblocks) * (double)xf[k]; }
+        init_models.emplace_back(java_float_to_string(lambdas[l]) + "#" + std::to_string(p), xf);
+      }
+    }
+    write_linear_models(out + "/initialModel/part-r-00000.avro", dict, init_models);
+    ck(mlease_admm_begin_initialized(S.s, z0.data(), boost_rate));
+  } else {
+    ck(mlease_admm_begin(S.s));
+  }
   int i;
   for (i = 1; i <= niter; i++) {
     const std::string it = out + "/iter-" + std::to_string(i);
@@ -486,7 +509,7 @@ void run_admm_train(const JobConfig& c) {
           us.emplace_back(java_float_to_string(lambdas[l]) + "#" + std::to_string(p), u);
         }
       write_linear_models(it + "/u/part-r-00000.avro", dict, us);
-      if (i > 1) write_linear_models(it + "/init-value/part-r-00000.avro", dict, models_z(true));
+      if (i > 1 || initialized) write_linear_models(it + "/init-value/part-r-00000.avro", dict, models_z(true));
       else {   // z = {lambda -> new LinearModel()} (:184): one record per lambda holding only the zero intercept
         Dictionary none; std::vector<std::pair<std::string, std::vector<float>>> z0;
         for (int l = 0; l < L; l++) z0.emplace_back(java_float_to_string(lambdas[l]), std::vector<float>(1, 0.f));

@@ -55,6 +55,7 @@ def lib():
             "mlease_add_partition_dense": [vp, i32, i64, vp, i64, vp, vp, vp],
             "mlease_add_partition_csr": [vp, i32, i64, vp, vp, vp, vp, vp, vp],
             "mlease_admm_begin": [vp],
+            "mlease_admm_begin_initialized": [vp, vp, C.c_float],
             "mlease_admm_local_step": [vp, vp],
             "mlease_admm_consensus": [vp, vp, C.POINTER(f64), C.POINTER(i32)],
             "mlease_admm_run": [vp, i32, vp, vp, C.POINTER(i32)],
@@ -82,7 +83,7 @@ def lib():
 
 
 EXPORTED = ["mlease_last_error", "mlease_abi_version", "mlease_session_create", "mlease_session_destroy",
-            "mlease_add_partition_dense", "mlease_add_partition_csr", "mlease_admm_begin", "mlease_admm_local_step",
+            "mlease_add_partition_dense", "mlease_add_partition_csr", "mlease_admm_begin", "mlease_admm_begin_initialized", "mlease_admm_local_step",
             "mlease_admm_consensus", "mlease_admm_run", "mlease_admm_iterate", "mlease_get_z", "mlease_get_final_model", "mlease_get_x", "mlease_get_u",
             "mlease_get_uplusx", "mlease_get_stats", "mlease_objective", "mlease_fit_partition", "mlease_naive_train_dense",
             "mlease_score", "mlease_test_loglik", "mlease_time_kernel", "mlease_profile"]

@@ -91,8 +91,30 @@ class AdmmSession:
         check(lib().mlease_add_partition_csr(self._h, int(partition_id), len(r), ptr(rp), ptr(ci), ptr(v), ptr(r), ptr(w), ptr(o)))
 
     # ---- ADMM ----
-    def begin(self):
-        check(lib().mlease_admm_begin(self._h))
+    def begin(self, z0=None, boost_rate=0.0):
+        """Cold start (z = {}), or -- initialize.boost.rate > 0 -- from z0 [L][D+1] with the reducers' rho scaled by boost_rate
+        (jobs/RegressionAdmmTrain.java:236-266, 313-316)."""
+        if z0 is None:
+            check(lib().mlease_admm_begin(self._h))
+        else:
+            z = np.ascontiguousarray(z0, np.float64).reshape(self.L, self.Dt)
+            check(lib().mlease_admm_begin_initialized(self._h, ptr(z), C.c_float(boost_rate)))
+
+    def mean_naive_model(self, partition_ids, penalize_intercept=False):
+        """z0 of initialize.boost.rate for a single-process job: per (partition, lambda) the RegressionNaiveTrain fit (prior
+        variance 1/lambda, intercept variance 100000 unless penalised, prior mean 0, start 0: jobs/RegressionNaiveTrain.java:333-343,395),
+        written as float and averaged by MeanLinearModelConsumer (cons/MeanLinearModelConsumer.java:44-70).  Multi-process jobs
+        sum the per-rank partial means with one all-reduce of this array."""
+        z0 = np.zeros((self.L, self.Dt), np.float64)
+        nb = float(self.num_blocks)
+        for li, lam in enumerate(self.lambdas):
+            q = np.full(self.Dt, float(lam), np.float64)
+            if not penalize_intercept:
+                q[-1] = 1.0 / 100000.0
+            for pid in partition_ids:
+                x, _ = self.fit_partition(pid, np.zeros(self.Dt), np.zeros(self.Dt), q)
+                z0[li] = 1.0 * z0[li] + (1.0 / nb) * x.astype(np.float32).astype(np.float64)
+        return z0
 
     def local_step(self, exchange_dev_ptr):
         check(lib().mlease_admm_local_step(self._h, ptr(exchange_dev_ptr)))

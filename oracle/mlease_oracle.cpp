@@ -541,7 +541,8 @@ int orc_admm_run(int P, int Dg, const int64_t* part_rowstart, const int64_t* row
                  const float* lambdas, const float* rhos, int niters, double epsilon, int mode, int penalize_intercept,
                  int aggressive_decay, float rho_adapt_coefficient, int binary_feature, int nthreads, double* z_hist,
                  double* diff_hist, float* eps_hist, double* x_last, float* u_last, float* uplusx_last,
-                 int* iters_done, int64_t* passes_out, int64_t* tron_outer_out, int64_t* tron_cg_out) {
+                 int* iters_done, int64_t* passes_out, int64_t* tron_outer_out, int64_t* tron_cg_out,
+                 float initialize_boost_rate, float init_liblinear_epsilon) {
   const int Dt = Dg + 1;
   for (int a = 0; a < L; a++)
     for (int b = a + 1; b < L; b++)
@@ -575,8 +576,33 @@ int orc_admm_run(int P, int Dg, const int64_t* part_rowstart, const int64_t* row
   std::mutex stat_mu;
   int i;
   int done = 0;
+  // initialize.boost.rate > 0 (:236-266): z starts at the mean of per-partition RegressionNaiveTrain fits (prior variance
+  // 1/lambda, intercept variance 100000 unless penalize.intercept, prior mean 0, init 0, liblinear.epsilon 0.01 unless the
+  // job sets one: jobs/RegressionNaiveTrain.java:333-343,395), averaged by MeanLinearModelConsumer over the float models.
+  if (initialize_boost_rate > 0) {
+    std::vector<vecd> xi(P * L, vecd(Dt, 0.0));
+    parallel_for(P * L, nthreads, [&](int t) {
+      int p = t / L, l = t % L;
+      const Dataset& d = ds[p];
+      int n = d.n;
+      vecd param(n, 0.0), pm(n, 0.0), pv(n, 1.0 / (double)lambdas[l]);
+      for (int k = 0; k < n; k++)
+        if (d.local2global[k] == Dg && !penalize_intercept) pv[k] = 100000.0;
+      double eps = mode == 0 ? java_float_via_string_to_double(init_liblinear_epsilon) : 1e-14;
+      TronStats st; int64_t ps = 0;
+      liblinear_train(d, param, pm, pv, eps, mode == 0 ? 10000 : 100000, &st, &ps, mode != 0);
+      for (int k = 0; k < n; k++) xi[t][d.local2global[k]] = param[k];
+      std::lock_guard<std::mutex> lk(stat_mu);
+      passes += ps; touter += st.outer; tcg += st.cg_total;
+    });
+    for (int l = 0; l < L; l++)
+      for (int p = 0; p < P; p++)
+        for (int k = 0; k < Dt; k++) z[l][k] = 1.0 * z[l][k] + (1.0 / P) * (double)(float)xi[p * L + l][k];
+    z_has_keys = true;
+  }
+  float rhoAdaptRate = 1.0f;                                 // conf value: it persists from one iteration to the next (:316, :326)
   for (i = 1; i <= niters; i++) {
-    float rhoAdaptRate = 1.0f;                               // :621 default
+    if (i == 1 && initialize_boost_rate > 0) rhoAdaptRate = initialize_boost_rate;   // :313-316
     // u = float(uplusx) - z, written as float (:736-765, models/LinearModel.java:716)
     if (i == 1) {
       for (auto& uu : u) std::fill(uu.begin(), uu.end(), 0.f);   // empty map (:312)

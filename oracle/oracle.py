@@ -105,7 +105,8 @@ def liblinear_train(data: Csr, init, prior_mean, prior_var, epsilon, max_iter=10
 
 
 def admm_run(data: Csr, part_rowstart, lambdas, rhos=None, niters=10, epsilon=1e-4, mode="exact", penalize_intercept=False,
-             aggressive_decay=False, rho_adapt_coefficient=0.0, binary_feature=False, nthreads=1):
+             aggressive_decay=False, rho_adapt_coefficient=0.0, binary_feature=False, nthreads=1, initialize_boost_rate=0.0,
+             init_liblinear_epsilon=0.01):
     """RegressionAdmmTrain.run restated (jobs/RegressionAdmmTrain.java:130-522). Returns dict."""
     prs = np.ascontiguousarray(part_rowstart, np.int64)
     P = len(prs) - 1
@@ -126,7 +127,8 @@ def admm_run(data: Csr, part_rowstart, lambdas, rhos=None, niters=10, epsilon=1e
                             C.c_double(epsilon), 0 if mode == "faithful" else 1, int(penalize_intercept), int(aggressive_decay),
                             C.c_float(rho_adapt_coefficient), int(binary_feature), int(nthreads), _p(z_hist, C.c_double),
                             _p(diff_hist, C.c_double), _p(eps_hist, C.c_float), _p(x_last, C.c_double), _p(u_last, C.c_float),
-                            _p(uplusx_last, C.c_float), C.byref(done), C.byref(passes), C.byref(touter), C.byref(tcg)))
+                            _p(uplusx_last, C.c_float), C.byref(done), C.byref(passes), C.byref(touter), C.byref(tcg),
+                            C.c_float(initialize_boost_rate), C.c_float(init_liblinear_epsilon)))
     n = done.value
     return dict(z_hist=z_hist[:n], diff_hist=diff_hist[:n], eps_hist=eps_hist[:n], x_last=x_last, u_last=u_last,
                 uplusx_last=uplusx_last, iters_done=n, passes=passes.value, tron_outer=touter.value, tron_cg=tcg.value,

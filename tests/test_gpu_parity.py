@@ -338,6 +338,33 @@ def test_admm_wide_systems_keep_the_cold_start_factor(mb):
     assert st["not_converged"] == 0 and st["gram_builds"] == 4   # one factorisation per (partition, lambda), at the cold start only
 
 
+def test_admm_initialize_boost_rate(mb, fixture_data, frozen):
+    """initialize.boost.rate (jobs/RegressionAdmmTrain.java:236-266, 313-316): start from the mean NaiveTrain model, reducers on
+    rho * boost for the whole run (or for iteration 1 only when rho.adapt.coefficient > 0)."""
+    d = fixture_data
+    prs = frozen["part_rowstart"]
+    parts = []
+    for p in range(len(prs) - 1):
+        r0, r1 = prs[p], prs[p + 1]
+        rp = d.rowptr[r0:r1 + 1] - d.rowptr[r0]
+        sl = slice(d.rowptr[r0], d.rowptr[r1])
+        parts.append((rp, d.colidx[sl], d.val[sl], d.response[r0:r1], d.weight[r0:r1], d.offset[r0:r1]))
+    lambdas = [1.0, 10.0]
+    for coef in (0.0, 0.05):
+        ref = orc.admm_run(d, prs, lambdas, niters=6, mode="exact", nthreads=8, epsilon=0.0, initialize_boost_rate=2.5, rho_adapt_coefficient=coef)
+        with mb.AdmmSession(len(parts), d.n_features, lambdas, epsilon=0.0, rho_adapt_coefficient=coef) as s:
+            for p, part in enumerate(parts):
+                s.add_partition_csr(p, *part)
+            z0 = s.mean_naive_model(range(len(parts)))
+            s.begin(z0, 2.5)
+            for it in range(6):
+                s.iterate()
+                for l in range(2):
+                    zr = ref["z_hist"][it, l]
+                    assert np.abs(s.z(l) - zr).max() / np.abs(zr).max() < 1e-5, (coef, it, l)
+            assert s.stats()["not_converged"] == 0
+
+
 def test_naive_train_many_keys(mb):
     # BASELINE config 4 shape in small: many independent per-key fits in lock-step batches
     K, n, D = 300, 120, 24

@@ -214,3 +214,31 @@ def test_naive_train_matches_sklearn():
     assert sk3.all() and not m3.any()
     m4, _, _ = orc.naive_train(data2, krs, 2.0, has_intercept=False, mode="exact")
     assert np.all(m4[:, -1] == 0)
+
+
+def test_initialize_boost_rate_restated():
+    """initialize.boost.rate > 0 (jobs/RegressionAdmmTrain.java:236-266, 313-316): z starts at the mean of per-partition
+    NaiveTrain fits and the reducers use rho * boost -- from iteration 1 ON, because the driver never resets the conf value
+    unless rho.adapt.coefficient > 0.  The z-update keeps the un-boosted rho (:381), so the fixed point is the pooled fit
+    with lambda * boost: checked against scikit-learn."""
+    from sklearn.linear_model import LogisticRegression
+    data, X = synth(n=900, d=10, seed=21)
+    data = orc.Csr.from_dense(X, data.response, data.weight)          # sklearn has no offsets
+    prs = [0, 300, 600, 900]
+    lam, boost = 2.0, 3.0
+    base = orc.admm_run(data, prs, [lam], niters=3, mode="exact", epsilon=0)
+    run = orc.admm_run(data, prs, [lam], niters=400, mode="exact", epsilon=0, initialize_boost_rate=boost)
+    # (1) the first reducers start from, and are pulled towards, the mean NaiveTrain model: iteration 1 differs from the cold run
+    naive, _, _ = orc.naive_train(data, prs, lam, mode="exact")
+    z0 = sum((1.0 / 3) * naive[k].astype(np.float32).astype(np.float64) for k in range(3))
+    assert np.abs(run["z_hist"][0, 0] - base["z_hist"][0, 0]).max() > 1e-3
+    assert np.abs(run["z_hist"][0, 0] - z0).max() < np.abs(base["z_hist"][0, 0] - z0).max()
+    # (2) fixed point = pooled fit with lambda * boost (x-update uses rho*boost, z-update weight uses rho)
+    clf = LogisticRegression(C=1 / (lam * boost), solver="newton-cholesky", tol=1e-12, max_iter=500)
+    clf.fit(X.astype(np.float64), data.response, sample_weight=data.weight.astype(np.float64))
+    ref = np.concatenate([clf.coef_.ravel(), clf.intercept_])
+    assert np.abs(run["z_hist"][-1, 0] - ref).max() / np.abs(ref).max() < 1e-5
+    # (3) with rho.adapt.coefficient > 0 the boost only lasts one iteration and the fixed point is the un-boosted one again
+    run2 = orc.admm_run(data, prs, [lam], niters=3, mode="exact", epsilon=0, initialize_boost_rate=boost, rho_adapt_coefficient=1e-9)
+    np.testing.assert_array_equal(run2["z_hist"][0], run["z_hist"][0])
+    assert np.abs(run2["z_hist"][1] - run["z_hist"][1]).max() > 1e-6

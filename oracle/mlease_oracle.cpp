@@ -15,8 +15,8 @@
 //   models/= com/linkedin/mlease/models/
 //   utils/ = com/linkedin/mlease/utils/
 //
-// PARITY PINNING: the reference ships no golden vectors and cannot be built here (no JVM,
-// see DESIGN.md).  This oracle is pinned by (1) finite differences of fun/grad/Hv/hessian,
+// PARITY PINNING -- "parity unpinned" by the reference: it ships no golden vectors, known-answer tests or expected outputs,
+// and cannot be built or run here (no JVM).  This oracle is pinned by (1) finite differences of fun/grad/Hv/hessian,
 // (2) scikit-learn's independent solver at the ADMM fixed point on the reference's only
 // fixture (examples/sample-data.avro, decoded into tests/golden/), and (3) frozen outputs
 // in tests/golden/.  It is therefore "pinned by independent implementation", not by

@@ -98,8 +98,9 @@ typedef int (*mlease_allreduce_fn)(void* ctx, double* buf, size_t count, void* s
 int mlease_admm_begin(mlease_session* s);
 /* initialize.boost.rate > 0 (jobs/RegressionAdmmTrain.java:236-266, 313-316): the run starts from z0 ([num_lambdas][num_features+1]
  * doubles on the host, intercept last: the mean of per-partition RegressionNaiveTrain fits, which the caller obtains with
- * mlease_fit_partition) instead of z = {}, u is empty, and the reducers use rho * boost_rate from iteration 1 on -- for the
- * whole run unless rho_adapt_coefficient > 0, because the reference's driver never resets the conf value otherwise (:316, :323-327). */
+ * mlease_fit_partition) instead of z = {}, u is empty, and the reducers of ITERATION 1 use rho * boost_rate: the driver builds a
+ * new JobConf every iteration (:286-291), so rho.adapt.rate is back at the reducers' default 1.0f (:621) from iteration 2 on
+ * (or follows rho_adapt_coefficient, :323-327).  The factors built with the boosted rho are invalidated at iteration 2. */
 int mlease_admm_begin_initialized(mlease_session* s, const double* z0, float boost_rate);
 int mlease_admm_local_step(mlease_session* s, double* exchange_dev);
 int mlease_admm_consensus(mlease_session* s, const double* exchange_sum_dev, double* maxdiff, int32_t* stop);

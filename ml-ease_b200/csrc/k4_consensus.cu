@@ -3,7 +3,7 @@
 //   admm_pack      (before the all-reduce)  per local problem: x_f = float(x), uplusx_f = float(u + x)
 //                  (jobs/RegressionAdmmTrain.java:706-711, models/LinearModel.java:703,716) and the local
 //                  exchange vector  S_local[l][k] = sum_p float(x_p)[k] + u_p[k]  in double.
-//   admm_consensus (after the all-reduce)   z = wz * S / P   (:362-404; wz = P rho/(lambda+P rho) computed on
+//   admm_consensus (after the all-reduce)   z = wz * S / P   (L2, :362-404; L1: thresholded mean, :406-451; wz = P rho/(lambda+P rho) computed on
 //                  the host in the reference's float arithmetic :381, 1 for the unpenalised intercept :392-403,
 //                  per-feature lambda.map weights :382-386), |z - z_prev|_inf (:456-472), and the NEXT
 //                  iteration's reducer inputs: u = float(uplusx - z) (computeU :736-765), z as float (:330-331),
@@ -62,13 +62,26 @@ __global__ void admm_pack_kernel(const Problem* __restrict__ probs, int nparts, 
 __global__ void __launch_bounds__(256) admm_consensus_kernel(const Problem* __restrict__ probs, int nparts, int L, int Dt, int ldv,
                                                              int P, const double* __restrict__ exch, double* __restrict__ z,
                                                              const double* __restrict__ wz, const double* __restrict__ rho_next,
-                                                             double* __restrict__ diff) {
+                                                             double* __restrict__ diff, const double* __restrict__ l1_thr) {
   const int l = blockIdx.x;
   __shared__ double sc[8];
   double dmax = 0.0;
   const double invP = 1.0 / (double)P;
+  // regularizer = 1 (l1_thr != NULL): z = xbar + ubar, then the reference's "iterative thresholding" of the coefficients
+  // (jobs/RegressionAdmmTrain.java:406-437): val > t -> val - t, val < -t -> val + t, values inside [-t, t] stay as they are
+  // (the reference does not zero them); the intercept (not in getCoefficients()) is the plain mean (:438-449).
+  const double thr = l1_thr ? l1_thr[l] : 0.0;
   for (int k = threadIdx.x; k < Dt; k += 256) {
-    const double zn = wz[(size_t)l * ldv + k] * (exch[(size_t)l * Dt + k] * invP);
+    double zn;
+    if (l1_thr) {
+      zn = exch[(size_t)l * Dt + k] * invP;
+      if (k < Dt - 1) {
+        if (zn > thr) zn -= thr;
+        else if (zn < -thr) zn += thr;
+      }
+    } else {
+      zn = wz[(size_t)l * ldv + k] * (exch[(size_t)l * Dt + k] * invP);
+    }
     const double zo = z[(size_t)l * ldv + k];
     dmax = fmax(dmax, fabs(zo - zn));
     z[(size_t)l * ldv + k] = zn;
@@ -114,8 +127,8 @@ cudaError_t admm_pack(const Problem* d_probs, int nlocal_parts, int L, int Dt, d
 }
 cudaError_t admm_consensus(const Problem* d_probs, int nlocal_parts, int L, int Dt, int ldv, int P, const double* d_exchange_sum,
                            double* d_z, const double* d_wz, const double* d_rho_eff_next, double* d_diff, cudaStream_t st,
-                           int* launches) {
-  admm_consensus_kernel<<<L, 256, 0, st>>>(d_probs, nlocal_parts, L, Dt, ldv, P, d_exchange_sum, d_z, d_wz, d_rho_eff_next, d_diff);
+                           int* launches, const double* d_l1_thr) {
+  admm_consensus_kernel<<<L, 256, 0, st>>>(d_probs, nlocal_parts, L, Dt, ldv, P, d_exchange_sum, d_z, d_wz, d_rho_eff_next, d_diff, d_l1_thr);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

@@ -41,7 +41,7 @@ cudaError_t admm_pack(const Problem* d_probs, int nlocal_parts, int L, int Dt, d
                       int* launches);
 cudaError_t admm_consensus(const Problem* d_probs, int nlocal_parts, int L, int Dt, int ldv, int P, const double* d_exchange_sum,
                            double* d_z, const double* d_wz, const double* d_rho_eff_next, double* d_diff, cudaStream_t st,
-                           int* launches);
+                           int* launches, const double* d_l1_thr = nullptr);
 
 // K5 (k5_score.cu)
 cudaError_t score_launch(int Dg, long long nrows, const long long* rowptr, const int* colidx, const float* vals, long long ldx,

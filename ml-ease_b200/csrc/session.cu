@@ -465,6 +465,7 @@ struct mlease_session {
   double* d_wz = nullptr;
   double* d_rho = nullptr;   // [L] rho_eff of the coming iteration
   double* d_diff = nullptr;
+  double* d_l1thr = nullptr; // [L] soft-threshold of the L1 z-update (regularizer = 1), else NULL
   double* d_exch = nullptr;  // [L][Dt] for mlease_admm_run
   int* d_flag = nullptr;
   int* h_flag = nullptr;     // pinned
@@ -550,6 +551,14 @@ int finalize(mlease_session* s) {
     wz[l * ldv + s->Dg] = s->cfg.penalize_intercept ? weight : 1.0;
   }
   CK(cudaMemcpy(s->d_wz, wz.data(), wz.size() * sizeof(double), cudaMemcpyHostToDevice));
+  if (s->cfg.regularizer == 1) {
+    // weight = l / (r * nblocks + 0.0) (jobs/RegressionAdmmTrain.java:409): float product, double division.  The weightmap
+    // built from lambda.map (:411-415) is never used by the thresholding loop, so lambda_map has no effect under L1.
+    std::vector<double> thr(s->L);
+    for (int l = 0; l < s->L; l++) thr[l] = (double)s->lambdas[l] / ((double)(s->rhos[l] * (float)s->P) + 0.0);
+    if (int rc = sess_alloc(s, (void**)&s->d_l1thr, s->L * sizeof(double))) return rc;
+    CK(cudaMemcpy(s->d_l1thr, thr.data(), thr.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 
@@ -569,7 +578,9 @@ double rho_eff_for_iter(mlease_session* s, int l, int iter) {
   // reducer: rho = lambdaRho[lambda] (float -> double), times rho.adapt.rate if != 1 (jobs/RegressionAdmmTrain.java:652-658);
   // rate = (float) exp(-(i-1)*coef) for i > 1 (:323-327)
   double r = (double)s->rhos[l];
-  float rate = s->boost_rate > 0.f ? s->boost_rate : 1.0f;   // the conf value persists once set at iteration 1 (:313-316)
+  // rho.adapt.rate is a key of the per-iteration JobConf, which the driver re-creates every iteration (:286-291 ->
+  // com/linkedin/mapred/AbstractAvroJob.java:101-115): the boost is seen by the reducers of iteration 1 only (:313-316)
+  float rate = (iter == 1 && s->boost_rate > 0.f) ? s->boost_rate : 1.0f;
   if (iter > 1 && s->cfg.rho_adapt_coefficient > 0) rate = (float)std::exp(-(iter - 1) * s->cfg.rho_adapt_coefficient);
   if (rate != 1.0f) r = r * (double)rate;
   return r;
@@ -619,8 +630,7 @@ int mlease_abi_version(void) { return 1; }
 
 int mlease_session_create(const mlease_admm_config* cfg, mlease_session** out) {
   if (!cfg || !out) return fail(MLEASE_ERR_INVALID, "null argument");
-  if (cfg->regularizer == 1) return fail(MLEASE_ERR_INVALID, "regularizer=1 (L1) is outside the accelerated path (SURVEY 8f-4)");
-  if (cfg->regularizer != 2) return fail(MLEASE_ERR_INVALID, "Only L1 and L2 regularization supported!");
+  if (cfg->regularizer != 1 && cfg->regularizer != 2) return fail(MLEASE_ERR_INVALID, "Only L1 and L2 regularization supported!");
   if (cfg->num_blocks <= 0 || cfg->num_features <= 0 || cfg->num_lambdas <= 0 || !cfg->lambdas)
     return fail(MLEASE_ERR_INVALID, "num.blocks, num_features and lambda must be set");
   int ndev = 0;
@@ -868,8 +878,16 @@ int mlease_admm_local_step(mlease_session* s, double* exchange_dev) {
   }
   int same_rho = 1;   // cold start: equal rho across lambdas means equal Hessians (H = G + rho I at beta = 0)
   for (int l = 1; l < s->L; l++) if (s->rho_fact[l] != s->rho_fact[0]) same_rho = 0;
+  const int nc_before = s->cnt.not_converged;
   if (int rc = batch_xupdate(*s->batch, s->stream, s->xtol, s->max_newton, s->cfg.hessian_policy, invalidate, s->h_flag, s->d_flag, s->cnt, &s->prof,
                              (i == 1 && s->L > 1 && s->boost_rate == 0.f) ? s->L : 0, same_rho)) return rc;   // sharing needs beta = 0 for every lambda
+  // An x-update that ran out of Newton steps (or slots) is a failed fit: the reducer wraps any fit exception as
+  // IOException("Model fitting error!") and the job dies (jobs/RegressionAdmmTrain.java:713-716); an unconverged x_p must not
+  // be averaged into z silently.
+  if (s->cnt.not_converged > nc_before)
+    return fail(MLEASE_ERR_NUMERIC, "Model fitting error! (" + std::to_string(s->cnt.not_converged - nc_before) +
+                                        " x-update(s) of iteration " + std::to_string(i) + " did not converge within max_newton = " +
+                                        std::to_string(s->max_newton) + " steps)");
   int launches = 0;
   CK(admm_pack(s->batch->d, (int)s->parts.size(), s->L, s->Dt, exchange_dev, s->stream, &launches));
   s->cnt.launches += launches;
@@ -883,7 +901,7 @@ int mlease_admm_consensus(mlease_session* s, const double* exchange_sum_dev, dou
   for (int l = 0; l < s->L; l++) s->h_small[l] = rho_eff_for_iter(s, l, s->iter + 1);
   CK(cudaMemcpyAsync(s->d_rho, s->h_small, s->L * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   int launches = 0;
-  CK(admm_consensus(s->batch->d, (int)s->parts.size(), s->L, s->Dt, s->ldx, s->P, exchange_sum_dev, s->d_z, s->d_wz, s->d_rho, s->d_diff, s->stream, &launches));
+  CK(admm_consensus(s->batch->d, (int)s->parts.size(), s->L, s->Dt, s->ldx, s->P, exchange_sum_dev, s->d_z, s->d_wz, s->d_rho, s->d_diff, s->stream, &launches, s->d_l1thr));
   s->cnt.launches += launches;
   double* hd = s->h_small + s->L;
   CK(cudaMemcpyAsync(hd, s->d_diff, s->L * sizeof(double), cudaMemcpyDeviceToHost, s->stream));

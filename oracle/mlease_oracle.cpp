@@ -542,7 +542,13 @@ int orc_admm_run(int P, int Dg, const int64_t* part_rowstart, const int64_t* row
                  int aggressive_decay, float rho_adapt_coefficient, int binary_feature, int nthreads, double* z_hist,
                  double* diff_hist, float* eps_hist, double* x_last, float* u_last, float* uplusx_last,
                  int* iters_done, int64_t* passes_out, int64_t* tron_outer_out, int64_t* tron_cg_out,
-                 float initialize_boost_rate, float init_liblinear_epsilon) {
+                 float initialize_boost_rate, float init_liblinear_epsilon, int regularizer, const float* lambda_map) {
+  // regularizer: 2 = L2 z-update (:377-404), 1 = L1 "iterative thresholding" z-update (:406-451); anything else is the
+  // driver's IOException (:144-147).  lambda_map: [Dg] or NULL, entries > 0 = the features listed in the lambda.map file
+  // (ReadLambdaMapConsumer, cons/ReadLambdaMapConsumer.java:33-52; :186-196).  It only enters the L2 z-update weights
+  // (:382-386) and the NaiveTrain fits of the initialize.boost.rate start (:248); the L1 branch builds a weightmap
+  // (:411-415) but never uses it.
+  if (regularizer != 1 && regularizer != 2) { g_err = "Only L1 and L2 regularization supported!"; return 1; }
   const int Dt = Dg + 1;
   for (int a = 0; a < L; a++)
     for (int b = a + 1; b < L; b++)
@@ -579,15 +585,18 @@ int orc_admm_run(int P, int Dg, const int64_t* part_rowstart, const int64_t* row
   // initialize.boost.rate > 0 (:236-266): z starts at the mean of per-partition RegressionNaiveTrain fits (prior variance
   // 1/lambda, intercept variance 100000 unless penalize.intercept, prior mean 0, init 0, liblinear.epsilon 0.01 unless the
   // job sets one: jobs/RegressionNaiveTrain.java:333-343,395), averaged by MeanLinearModelConsumer over the float models.
-  if (initialize_boost_rate > 0) {
+  if (initialize_boost_rate > 0 && regularizer == 2) {       // `initializeBoostRate > 0 && reg==2` (:236)
     std::vector<vecd> xi(P * L, vecd(Dt, 0.0));
     parallel_for(P * L, nthreads, [&](int t) {
       int p = t / L, l = t % L;
       const Dataset& d = ds[p];
       int n = d.n;
       vecd param(n, 0.0), pm(n, 0.0), pv(n, 1.0 / (double)lambdas[l]);
-      for (int k = 0; k < n; k++)
-        if (d.local2global[k] == Dg && !penalize_intercept) pv[k] = 100000.0;
+      for (int k = 0; k < n; k++) {
+        const int g = d.local2global[k];
+        if (g == Dg) { if (!penalize_intercept) pv[k] = 100000.0; }
+        else if (lambda_map && lambda_map[g] > 0) pv[k] = 1.0 / (double)lambda_map[g];   // propsIni.put(LAMBDA_MAP, ...) (:248)
+      }
       double eps = mode == 0 ? java_float_via_string_to_double(init_liblinear_epsilon) : 1e-14;
       TronStats st; int64_t ps = 0;
       liblinear_train(d, param, pm, pv, eps, mode == 0 ? 10000 : 100000, &st, &ps, mode != 0);
@@ -600,9 +609,12 @@ int orc_admm_run(int P, int Dg, const int64_t* part_rowstart, const int64_t* row
         for (int k = 0; k < Dt; k++) z[l][k] = 1.0 * z[l][k] + (1.0 / P) * (double)(float)xi[p * L + l][k];
     z_has_keys = true;
   }
-  float rhoAdaptRate = 1.0f;                                 // conf value: it persists from one iteration to the next (:316, :326)
   for (i = 1; i <= niters; i++) {
-    if (i == 1 && initialize_boost_rate > 0) rhoAdaptRate = initialize_boost_rate;   // :313-316
+    // rho.adapt.rate lives in the per-iteration JobConf: `conf = createJobConf(...)` (:286-291) builds a NEW JobConf every
+    // iteration (com/linkedin/mapred/AbstractAvroJob.java:101-115), so the reducers' default 1.0f (:621) is back unless this
+    // iteration sets it: the boost reaches the reducers of iteration 1 only (:313-316), rho.adapt.coefficient those of i > 1 (:323-327).
+    float rhoAdaptRate = 1.0f;
+    if (i == 1 && initialize_boost_rate > 0 && regularizer == 2) rhoAdaptRate = initialize_boost_rate;   // :313-316
     // u = float(uplusx) - z, written as float (:736-765, models/LinearModel.java:716)
     if (i == 1) {
       for (auto& uu : u) std::fill(uu.begin(), uu.end(), 0.f);   // empty map (:312)
@@ -657,18 +669,39 @@ int orc_admm_run(int P, int Dg, const int64_t* part_rowstart, const int64_t* row
         }
       bool ubar_empty = (i == 1);                                                 // u file is empty at i==1
       float lf = lambdas[l], rf = rho[l];
-      double weight = (double)((float)(P * rf) / (lf + (float)(P * rf)));          // :381 -- float arithmetic
       vecd lastz = z[l];
       vecd& zz = z[l];
-      for (int k = 0; k < Dg; k++) {
-        double vv = 0 + weight * xbar[k];                                          // :387 (z cleared :373)
-        if (!ubar_empty) vv = 1.0 * vv + weight * ubar[k];                        // :388-391
-        zz[k] = vv;
+      if (regularizer == 2) {
+        double weight = (double)((float)(P * rf) / (lf + (float)(P * rf)));        // :381 -- float arithmetic
+        for (int k = 0; k < Dg; k++) {
+          double wk = weight;
+          // weightmap.put(k, nblocks * r / (lambdaMap.get(k) + nblocks * r + 0.0)) (:384): float sum, then double division
+          if (lambda_map && lambda_map[k] > 0) wk = (double)(float)(P * rf) / ((double)(lambda_map[k] + (float)(P * rf)) + 0.0);
+          double vv = 0 + wk * xbar[k];                                            // :387 (z cleared :373)
+          if (!ubar_empty) vv = 1.0 * vv + wk * ubar[k];                          // :388-391
+          zz[k] = vv;
+        }
+        double ic = 1.0 * 0.0 + weight * xbar[Dg];
+        if (!ubar_empty) ic = 1.0 * ic + weight * ubar[Dg];
+        if (!penalize_intercept) ic = ubar_empty ? xbar[Dg] : xbar[Dg] + ubar[Dg];  // :392-403
+        zz[Dg] = ic;
+      } else {
+        // L1 (:406-451): z = xbar (+ ubar), then "iterative thresholding" of the coefficients (the intercept is not in
+        // getCoefficients()): val > t -> val - t, val < -t -> val + t, and -- as written in the reference -- values inside
+        // [-t, t] are LEFT UNCHANGED (no zeroing).  t = l / (r * nblocks + 0.0): float product, double division (:409).
+        const double thr = (double)lf / ((double)(rf * (float)P) + 0.0);
+        for (int k = 0; k < Dg; k++) {
+          double vv = 1.0 * 0.0 + 1.0 * xbar[k];
+          if (!ubar_empty) vv = 1.0 * vv + 1.0 * ubar[k];
+          if (vv > thr) vv = vv - thr;
+          else if (vv < -thr) vv = vv + thr;
+          zz[k] = vv;
+        }
+        double ic = 1.0 * 0.0 + 1.0 * xbar[Dg];
+        if (!ubar_empty) ic = 1.0 * ic + 1.0 * ubar[Dg];
+        if (!penalize_intercept) ic = ubar_empty ? xbar[Dg] : xbar[Dg] + ubar[Dg];  // :438-449 (the same value either way)
+        zz[Dg] = ic;
       }
-      double ic = 1.0 * 0.0 + weight * xbar[Dg];
-      if (!ubar_empty) ic = 1.0 * ic + weight * ubar[Dg];
-      if (!penalize_intercept) ic = ubar_empty ? xbar[Dg] : xbar[Dg] + ubar[Dg];   // :392-403
-      zz[Dg] = ic;
       double diff = 0;
       for (int k = 0; k < Dt; k++) diff = std::max(diff, std::fabs(1 * lastz[k] + (-1) * zz[k]));  // :463-464
       if (diff_hist) diff_hist[(size_t)(i - 1) * L + l] = diff;

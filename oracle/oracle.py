@@ -106,7 +106,7 @@ def liblinear_train(data: Csr, init, prior_mean, prior_var, epsilon, max_iter=10
 
 def admm_run(data: Csr, part_rowstart, lambdas, rhos=None, niters=10, epsilon=1e-4, mode="exact", penalize_intercept=False,
              aggressive_decay=False, rho_adapt_coefficient=0.0, binary_feature=False, nthreads=1, initialize_boost_rate=0.0,
-             init_liblinear_epsilon=0.01):
+             init_liblinear_epsilon=0.01, regularizer=2, lambda_map=None):
     """RegressionAdmmTrain.run restated (jobs/RegressionAdmmTrain.java:130-522). Returns dict."""
     prs = np.ascontiguousarray(part_rowstart, np.int64)
     P = len(prs) - 1
@@ -121,6 +121,7 @@ def admm_run(data: Csr, part_rowstart, lambdas, rhos=None, niters=10, epsilon=1e
     u_last = np.zeros((P, L, Dt), np.float32)
     uplusx_last = np.zeros((P, L, Dt), np.float32)
     done, passes, touter, tcg = C.c_int(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    lmap = None if lambda_map is None else np.ascontiguousarray(lambda_map, np.float32)
     _chk(lib().orc_admm_run(P, data.n_features, _p(prs, C.c_int64), _p(data.rowptr, C.c_int64), _p(data.colidx, C.c_int32),
                             _p(data.val, C.c_float), _p(data.response, C.c_int32), _p(data.weight, C.c_float),
                             _p(data.offset, C.c_float), L, _p(lam, C.c_float), _p(rh, C.c_float), int(niters),
@@ -128,7 +129,8 @@ def admm_run(data: Csr, part_rowstart, lambdas, rhos=None, niters=10, epsilon=1e
                             C.c_float(rho_adapt_coefficient), int(binary_feature), int(nthreads), _p(z_hist, C.c_double),
                             _p(diff_hist, C.c_double), _p(eps_hist, C.c_float), _p(x_last, C.c_double), _p(u_last, C.c_float),
                             _p(uplusx_last, C.c_float), C.byref(done), C.byref(passes), C.byref(touter), C.byref(tcg),
-                            C.c_float(initialize_boost_rate), C.c_float(init_liblinear_epsilon)))
+                            C.c_float(initialize_boost_rate), C.c_float(init_liblinear_epsilon), int(regularizer),
+                            _p(lmap, C.c_float)))
     n = done.value
     return dict(z_hist=z_hist[:n], diff_hist=diff_hist[:n], eps_hist=eps_hist[:n], x_last=x_last, u_last=u_last,
                 uplusx_last=uplusx_last, iters_done=n, passes=passes.value, tron_outer=touter.value, tron_cg=tcg.value,

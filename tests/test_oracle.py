@@ -218,27 +218,39 @@ def test_naive_train_matches_sklearn():
 
 def test_initialize_boost_rate_restated():
     """initialize.boost.rate > 0 (jobs/RegressionAdmmTrain.java:236-266, 313-316): z starts at the mean of per-partition
-    NaiveTrain fits and the reducers use rho * boost -- from iteration 1 ON, because the driver never resets the conf value
-    unless rho.adapt.coefficient > 0.  The z-update keeps the un-boosted rho (:381), so the fixed point is the pooled fit
-    with lambda * boost: checked against scikit-learn."""
+    NaiveTrain fits and the reducers of ITERATION 1 use rho * boost.  The driver builds a new JobConf every iteration
+    (`conf = createJobConf(...)`, :286-291 -> com/linkedin/mapred/AbstractAvroJob.java:101-115), so rho.adapt.rate falls back to
+    the reducers' default 1.0f (:621) from iteration 2 on: the fixed point is the UN-boosted pooled fit (scikit-learn)."""
     from sklearn.linear_model import LogisticRegression
     data, X = synth(n=900, d=10, seed=21)
     data = orc.Csr.from_dense(X, data.response, data.weight)          # sklearn has no offsets
     prs = [0, 300, 600, 900]
     lam, boost = 2.0, 3.0
-    base = orc.admm_run(data, prs, [lam], niters=3, mode="exact", epsilon=0)
-    run = orc.admm_run(data, prs, [lam], niters=400, mode="exact", epsilon=0, initialize_boost_rate=boost)
+    rho = 20.0                                                        # curvature-matched: ADMM contracts fast
+    base = orc.admm_run(data, prs, [lam], [rho], niters=3, mode="exact", epsilon=0)
+    run = orc.admm_run(data, prs, [lam], [rho], niters=400, mode="exact", epsilon=0, initialize_boost_rate=boost)
     # (1) the first reducers start from, and are pulled towards, the mean NaiveTrain model: iteration 1 differs from the cold run
     naive, _, _ = orc.naive_train(data, prs, lam, mode="exact")
     z0 = sum((1.0 / 3) * naive[k].astype(np.float32).astype(np.float64) for k in range(3))
     assert np.abs(run["z_hist"][0, 0] - base["z_hist"][0, 0]).max() > 1e-3
     assert np.abs(run["z_hist"][0, 0] - z0).max() < np.abs(base["z_hist"][0, 0] - z0).max()
-    # (2) fixed point = pooled fit with lambda * boost (x-update uses rho*boost, z-update weight uses rho)
-    clf = LogisticRegression(C=1 / (lam * boost), solver="newton-cholesky", tol=1e-12, max_iter=500)
+    # (2) iteration 1 is one ADMM step from z0 with the reducers on rho * boost: x_p = argmin loss_p + (rho boost / 2)|x - z0|^2,
+    #     z_1 = w * mean(float(x_p)) with the UN-boosted rho in w (:381), intercept = plain mean (:392-403)
+    xs = []
+    for k in range(3):
+        sub = orc.Csr.from_dense(X[prs[k]:prs[k + 1]], data.response[prs[k]:prs[k + 1]], data.weight[prs[k]:prs[k + 1]])
+        z0f = z0.astype(np.float32).astype(np.float64)
+        xk, _ = orc.liblinear_train(sub, z0f, z0f, np.full(11, 1.0 / (rho * boost)), 1e-14, max_iter=100000)
+        xs.append(xk.astype(np.float32).astype(np.float64))
+    xbar = sum(xs) / 3.0
+    wgt = float(np.float32(3 * rho) / (np.float32(lam) + np.float32(3 * rho)))
+    z1 = np.concatenate([wgt * xbar[:-1], xbar[-1:]])
+    assert np.abs(run["z_hist"][0, 0] - z1).max() < 2e-6
+    # (3) fixed point = the un-boosted pooled fit: the boost is gone from iteration 2 on
+    clf = LogisticRegression(C=1 / lam, solver="newton-cholesky", tol=1e-12, max_iter=500)
     clf.fit(X.astype(np.float64), data.response, sample_weight=data.weight.astype(np.float64))
     ref = np.concatenate([clf.coef_.ravel(), clf.intercept_])
     assert np.abs(run["z_hist"][-1, 0] - ref).max() / np.abs(ref).max() < 1e-5
-    # (3) with rho.adapt.coefficient > 0 the boost only lasts one iteration and the fixed point is the un-boosted one again
-    run2 = orc.admm_run(data, prs, [lam], niters=3, mode="exact", epsilon=0, initialize_boost_rate=boost, rho_adapt_coefficient=1e-9)
-    np.testing.assert_array_equal(run2["z_hist"][0], run["z_hist"][0])
-    assert np.abs(run2["z_hist"][1] - run["z_hist"][1]).max() > 1e-6
+    # (4) a tiny rho.adapt.coefficient (rate = float(exp(-(i-1) c)) == 1.0f) must therefore change nothing
+    run2 = orc.admm_run(data, prs, [lam], [rho], niters=3, mode="exact", epsilon=0, initialize_boost_rate=boost, rho_adapt_coefficient=1e-9)
+    np.testing.assert_array_equal(run2["z_hist"], run["z_hist"][:3])

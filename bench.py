@@ -229,13 +229,13 @@ def cpu_arm(args, wl, steps):
     single-threaded solve per (partition, lambda) like one Hadoop reducer each (reducers = nblocks x #lambda,
     jobs/RegressionAdmmTrain.java:355), min(P*L, cores) of them in parallel.  It times x-update + z/u update only (no Hadoop job
     launch, shuffle or per-iteration avro re-ingest: this flatters the reference).  Bounded sample: `rows` rows of every
-    partition; iterations/s are extrapolated linearly in rows to the full partition size, and the same job on a quarter of the
-    rows is timed as well so that the linearity of the extrapolation is evidenced in the line itself."""
+    partition; iterations/s are extrapolated linearly in rows to the full partition size (same pass count, per-pass cost linear
+    in nnz), and the same job on a quarter of the rows is timed as well so that the per-pass linearity is evidenced in the line."""
     from oracle import oracle as orc
     cores = os.cpu_count() or 1
     P, L = wl["P"], len(wl["lambdas"])
     threads = min(P * L, cores)
-    rows = args.cpu_rows or (100_000 if wl["nnz"] is not None else 10_000)
+    rows = args.cpu_rows or (250_000 if wl["nnz"] is not None else 10_000)
     rows = min(rows, wl["n"])
     iters = args.cpu_iters or (min(steps, 5) if wl["nnz"] is not None else min(steps, 20))
     data, prs = _cpu_data(wl, rows)
@@ -258,7 +258,10 @@ def cpu_arm(args, wl, steps):
                        % (P, rows, 100 * scale, wl["n"], wl["D"], "" if wl["nnz"] is None else " at %d nnz/row" % wl["nnz"], L, P * L, threads,
                           its, dt, r["passes"], cores),
                 linearity={"rows": [q, rows], "seconds": [dt4, dt], "passes": [int(r4["passes"]), int(r["passes"])],
-                           "time_ratio_measured": dt / dt4, "rows_ratio": rows / float(q)},
+                           "time_ratio_measured": dt / dt4, "rows_ratio": rows / float(q),
+                           # the cost of ONE sparse pass is what is linear in the rows; how many passes TRON needs depends on the
+                           # conditioning (fewer rows per feature -> more CG steps), so the two samples are compared per pass
+                           "seconds_per_pass_per_row": [dt4 / max(int(r4["passes"]), 1) / q, dt / max(int(r["passes"]), 1) / rows]},
                 seconds=dt, iters=its, passes=int(r["passes"]))
 
 
@@ -297,7 +300,7 @@ def run_admm_workload(cx, wl, K, W, want_e2e):
     import torch
     import torch.distributed as dist
     import mlease_b200 as mb
-    from mlease_b200.distributed import CudaAdmmBackend, admm_loop, shard_partitions
+    from mlease_b200.distributed import shard_partitions
 
     args, world, rank, dev, local_rank = cx.args, cx.world, cx.rank, cx.dev, cx.local_rank
     P, n, D, nnz, lambdas = wl["P"], wl["n"], wl["D"], wl["nnz"], wl["lambdas"]
@@ -307,16 +310,17 @@ def run_admm_workload(cx, wl, K, W, want_e2e):
     beta = true_beta(wl)
     stream = torch.cuda.current_stream().cuda_stream
 
-    def allreduce(buf):
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     def make_session():
-        return mb.AdmmSession(P, D, lambdas, device=local_rank, stream=stream, epsilon=0.0, hessian_policy=args.hessian_policy)
+        # the whole loop runs in C (mlease_admm_run); with N > 1 the per-iteration exchange is the library's own ncclAllReduce
+        s = mb.AdmmSession(P, D, lambdas, device=local_rank, stream=stream, epsilon=0.0, hessian_policy=args.hessian_policy)
+        if cx.comm is not None:
+            s.set_comm(cx.comm)
+        return s
 
     # ---------------- device-resident leg ("value") ----------------
     t_gen = time.perf_counter()
@@ -338,10 +342,8 @@ def run_admm_workload(cx, wl, K, W, want_e2e):
         torch.cuda.empty_cache()
     torch.cuda.synchronize()
     log("rank %d %s: data + upload %.1f s, free HBM %.1f GB" % (rank, wl["name"], time.perf_counter() - t_gen, torch.cuda.mem_get_info()[0] / 1e9))
-    be = CudaAdmmBackend(sess)
-    ar = allreduce if world > 1 else None
     if W > 0:
-        admm_loop(be, W, ar)                                    # warm-up: a throw-away job of W iterations
+        sess.run(W)                                             # warm-up: a throw-away job of W iterations
     barrier()
     sess.profile(2)
     st0 = sess.stats()
@@ -349,7 +351,7 @@ def run_admm_workload(cx, wl, K, W, want_e2e):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    done, hist = admm_loop(be, K, ar)
+    done = sess.run(K)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -367,7 +369,8 @@ def run_admm_workload(cx, wl, K, W, want_e2e):
     if world > 1:
         dist.all_reduce(usum, op=dist.ReduceOp.SUM)
     launches = st1["kernel_launches"] - st0["kernel_launches"]
-    sess.close(); del be, sess
+    last_maxdiff = st1["last_maxdiff"]
+    sess.close(); del sess
     torch.cuda.empty_cache()
 
     # ---------------- end-to-end leg (host buffers, public API) ----------------
@@ -381,8 +384,7 @@ def run_admm_workload(cx, wl, K, W, want_e2e):
             hp = host_parts[p]
             (s2.add_partition_csr if sparse else s2.add_partition_dense)(p, *hp)   # pinned host -> device inside the timed region
             h2d += sum(t.numel() * t.element_size() for t in hp)
-        be2 = CudaAdmmBackend(s2)
-        done2, _ = admm_loop(be2, K, ar)
+        done2 = s2.run(K)
         models = [s2.final_model(l) for l in range(L)]          # device -> host read of the job's result
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -394,7 +396,7 @@ def run_admm_workload(cx, wl, K, W, want_e2e):
                "d2h_bytes_per_step": (sum(m.nbytes for m in models) + 8 * done2) * world / done2, "seconds": float(tdt.item()),
                "note": "upload once (the reference re-ingests every iteration), K iterations, model read-back"}
         s2.close()
-        del be2, s2, host_parts
+        del s2, host_parts
         torch.cuda.empty_cache()
 
     if rank != 0:
@@ -432,9 +434,8 @@ def run_admm_workload(cx, wl, K, W, want_e2e):
            "kernel_ms": prof["ms"], "kernel_launch_counts": prof["launches"],
            "solver": {"k1_passes": st1["k1_passes"] - st0["k1_passes"], "gram_builds": st1["gram_builds"] - st0["gram_builds"],
                       "newton_steps": st1["newton_steps"] - st0["newton_steps"], "rejected": st1["rejected_steps"] - st0["rejected_steps"],
-                      "not_converged": st1["not_converged"], "last_maxdiff": hist[-1] if hist else None},
-           "checks": {"sum_over_partitions_of_u_intercept": [float(v) for v in usum.tolist()],
-                      "maxdiff_first_last": [hist[0], hist[-1]] if hist else None},
+                      "not_converged": st1["not_converged"], "last_maxdiff": last_maxdiff},
+           "checks": {"sum_over_partitions_of_u_intercept": [float(v) for v in usum.tolist()], "last_maxdiff": last_maxdiff},
            "z_checksum": float(np.abs(z_final).sum())}
     if e2e:
         out["e2e"] = e2e
@@ -534,7 +535,7 @@ def main():
            "nnz_per_row": wl["nnz"], "lambdas": wl["lambdas"], "num_iters": K,
            "timed_region": "cold-start job of K iterations (z=u=0), Gram + Cholesky of every partition included",
            "l2": "inputs_larger_than_L2 (>= 0.8 GB per partition)",
-           "parallelism": "partitions p%%N over %d rank(s), one NCCL all-reduce of [L][D'] fp64 per iteration" % world}
+           "parallelism": "partitions p%%N over %d rank(s); the loop runs in C (mlease_admm_run) with one ncclAllReduce of [L][D']+1 fp64 per iteration inside the library" % world}
     base = {"metric": "ADMM iterations/sec", "unit": "ADMM iterations/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
             "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32 data / f64 reductions / bf16 Gram operands",
             "data": "synthetic", "config": cfg}
@@ -561,10 +562,13 @@ def main():
     torch.cuda.set_device(local_rank)
     cx = Ctx()
     cx.args, cx.world, cx.rank, cx.local_rank, cx.dev = args, world, rank, local_rank, "cuda:%d" % local_rank
+    cx.comm = None
     if world > 1:
         # keep stdout to the single JSON line: NCCL's version banner / debug lines go to a file
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device(cx.dev))
+        from mlease_b200.distributed import make_comm
+        cx.comm = make_comm(local_rank)      # the library's own NCCL communicator; torch.distributed ships its id and times the ranks
 
     out = dict(base)
     if wl["name"] == "cfg5":

@@ -28,6 +28,8 @@ extern "C" {
 #endif
 
 typedef struct mlease_session mlease_session;
+typedef struct mlease_comm mlease_comm;     /* one NCCL communicator rank (multi-GPU jobs) */
+typedef struct mlease_world mlease_world;   /* N sessions on N GPUs of this process */
 
 #define MLEASE_OK 0
 #define MLEASE_ERR_INVALID 1   /* bad argument / config (reference: IOException in the job) */
@@ -39,12 +41,12 @@ const char* mlease_last_error(void);
 int mlease_abi_version(void);
 
 /* ---------------------------------------------------------------------------------------
- * Session = one RegressionAdmmTrain job on one GPU (one process per GPU; partitions are
- * sharded over processes, the caller owns the inter-process all-reduce).
+ * Session = one RegressionAdmmTrain job on one GPU (partitions are sharded over sessions; the
+ * all-reduce between them is the library's, see "Multi-GPU" below, or a caller-supplied callback).
  * Config keys mirrored (jobs/RegressionAdmmTrain.java:78-122,138-185):
  *   num.blocks, lambda (list, Float.parseFloat), rho (list or NULL -> 1 if lambda<=100 else 10),
- *   regularizer (must be 2 here; 1 = L1 is out of scope, anything else -> "Only L1 and L2
- *   regularization supported!"), penalize.intercept, epsilon, rho.adapt.coefficient,
+ *   regularizer (2 = L2 z-update :377-404, 1 = L1 thresholded z-update :406-451, anything else -> "Only L1 and L2
+ *   regularization supported!" :144-147), penalize.intercept, epsilon, rho.adapt.coefficient,
  *   aggressive.liblinear.epsilon.decay (pure control: only moves the stop rule :493-496).
  * ------------------------------------------------------------------------------------- */
 typedef struct {
@@ -55,7 +57,7 @@ typedef struct {
   const float* lambdas;        /* [L] host */
   const float* rhos;           /* [L] host or NULL */
   const float* lambda_map;     /* [num_features] host or NULL; >0 entries override lambda per feature (:382-386) */
-  int32_t regularizer;         /* 2 */
+  int32_t regularizer;         /* 1 or 2 */
   int32_t penalize_intercept;  /* default 0 */
   int32_t aggressive_decay;    /* default 0 */
   int32_t binary_feature;      /* binary.feature: ignore values, use 1 (regression/liblinearfunc/LibLinearBinaryDataset.java) */
@@ -105,9 +107,46 @@ int mlease_admm_begin_initialized(mlease_session* s, const double* z0, float boo
 int mlease_admm_local_step(mlease_session* s, double* exchange_dev);
 int mlease_admm_consensus(mlease_session* s, const double* exchange_sum_dev, double* maxdiff, int32_t* stop);
 int mlease_admm_run(mlease_session* s, int32_t num_iters, mlease_allreduce_fn allreduce, void* ctx, int32_t* iters_done);
-/* One iteration of a single-process job (all num_blocks partitions resident): local_step + consensus on the session's own
- * exchange buffer.  Lets a host job write the reference's iter-<i>/ files between iterations. */
+/* One iteration with the exchange inside the library: local_step, all-reduce over the attached communicator (none for a
+ * single-process job holding all num_blocks partitions), consensus.  Lets a host job write the reference's iter-<i>/ files
+ * between iterations.  A failed fit on any rank returns MLEASE_ERR_NUMERIC on every rank ("Model fitting error!", :713-716). */
 int mlease_admm_iterate(mlease_session* s, double* maxdiff, int32_t* stop);
+
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU: the path shards exactly where ADMM does -- partitions are independent in the x-update and meet in ONE
+ * all-reduce (sum, fp64, [L][num_features+1] (+1 failure counter)) per iteration, the mean the reference's driver takes over
+ * the reducer outputs (:362-364, cons/MeanLinearModelConsumer.java:44-70).  NCCL is loaded at run time (libnccl.so.2).
+ *  (a) one process per GPU: rank 0 calls mlease_comm_unique_id and ships the 128 bytes to the other ranks by any means;
+ *      every rank creates its communicator, attaches it to its session (which holds the partitions p with p % nranks == rank)
+ *      and calls mlease_admm_run(s, iters, NULL, NULL, &done): the whole RegressionAdmmTrain loop runs in C.
+ *  (b) one process, several GPUs (a single-JVM driver, the C++ job layer): mlease_world_* below -- same calls as a session,
+ *      partitions routed to GPU  partition_id % ndev, one worker thread per GPU, ncclCommInitAll inside.
+ * ------------------------------------------------------------------------------------- */
+#define MLEASE_COMM_ID_BYTES 128
+int mlease_comm_unique_id(void* id128);
+int mlease_comm_create(const void* id128, int32_t rank, int32_t nranks, int32_t device, mlease_comm** out);
+int mlease_comm_destroy(mlease_comm* c);
+int mlease_comm_info(const mlease_comm* c, int32_t* rank, int32_t* nranks, int32_t* nccl_version);
+int mlease_session_set_comm(mlease_session* s, mlease_comm* comm);   /* not owned; NULL detaches */
+
+int mlease_world_create(const mlease_admm_config* cfg /* .device/.stream ignored */, const int32_t* devices /* NULL = 0..ndev-1 */,
+                        int32_t ndev, mlease_world** out);
+int mlease_world_destroy(mlease_world* w);
+int mlease_world_num_devices(const mlease_world* w);
+int mlease_world_add_partition_dense(mlease_world* w, int32_t partition_id, int64_t nrows, const float* X, int64_t ldx,
+                                     const int32_t* response, const float* weight, const float* offset);
+int mlease_world_add_partition_csr(mlease_world* w, int32_t partition_id, int64_t nrows, const int64_t* rowptr, const int32_t* colidx,
+                                   const float* vals, const int32_t* response, const float* weight, const float* offset);
+int mlease_world_begin(mlease_world* w);
+int mlease_world_begin_initialized(mlease_world* w, const double* z0, float boost_rate);
+int mlease_world_iterate(mlease_world* w, double* maxdiff, int32_t* stop);
+int mlease_world_run(mlease_world* w, int32_t num_iters, int32_t* iters_done);
+int mlease_world_get_z(mlease_world* w, int32_t lambda_idx, double* out);
+int mlease_world_get_final_model(mlease_world* w, int32_t lambda_idx, float* out);
+int mlease_world_get_x(mlease_world* w, int32_t partition_id, int32_t lambda_idx, double* out);
+int mlease_world_get_u(mlease_world* w, int32_t partition_id, int32_t lambda_idx, float* out);
+int mlease_world_get_uplusx(mlease_world* w, int32_t partition_id, int32_t lambda_idx, float* out);
+int mlease_world_fit_partition(mlease_world* w, int32_t partition_id, double* x, const double* m, const double* q, int32_t* newton_steps);
 
 /* State readback (host buffers).  z: driver-side double z (:365-404); final model = float(z)
  * (models/LinearModel.java:697-720 toAvro).  After consensus of iteration i: x = the double x_p of iteration i
@@ -131,6 +170,7 @@ typedef struct {
   float liblinear_epsilon;  /* schedule variable (:279,338-346), control only */
 } mlease_stats;
 int mlease_get_stats(mlease_session* s, mlease_stats* out);
+int mlease_world_get_stats(mlease_world* w, mlease_stats* out);   /* counters summed over the devices */
 /* Per-kernel device timing for roofline reporting (CUDA events on the session stream around every launch of
  * the Newton slot; categories: 0 = K1 fused pass, 1 = small kernels (reduce/decide, solve, poll), 2 = Gram (tcgen05),
  * 3 = Cholesky).  enable: 1 on, 0 off, 2 on + reset accumulators, -1 read only.  Outputs (any may be NULL) are the
@@ -155,12 +195,37 @@ int mlease_objective(mlease_session* s, int32_t partition_id, const double* w, c
 int mlease_fit_partition(mlease_session* s, int32_t partition_id, double* x, const double* m, const double* q,
                          int32_t* newton_steps);
 
+/* Posterior variance of the model w of one resident partition under prior precision q (= 1/priorVar), the
+ * computePosteriorVar / computeFullPostVar tail of LibLinear.train (regression/liblinearfunc/LibLinear.java:315-334) that
+ * ItemModelTrain reports as "posteriorVar" (jobs/ItemModelTrain.java:257-266):
+ *   full = 0: var[k] = 1 / (q[k] + sum_i weight_i p_i (1-p_i) x_ik^2)         (hessianDiagonal, LogisticRegressionL2.java:304-327)
+ *   full = 1: var = diag(H^-1), H = LogisticRegressionL2.hessian (:258-297) accumulated in fp64 (NOT the bf16 tensor-core
+ *             Gram, which only preconditions), Cholesky + explicit inverse in fp64; cov (may be NULL) receives H^-1,
+ *             [Dt x Dt] row-major.  Needs rows with strictly increasing column ids, as the reference's hessian() does (:277).
+ * var has num_features+1 entries, intercept last; a feature absent from the partition gets its prior variance 1/q[k]
+ * (the reference lists only the features present in the dataset). */
+int mlease_posterior_variance(mlease_session* s, int32_t partition_id, const double* w, const double* q, int32_t full,
+                              double* var, double* cov);
+
 /* ---------------------------------------------------------------------------------------
- * RegressionNaiveTrain (jobs/RegressionNaiveTrain.java:302-415): K independent fits, key k owns rows
- * [key_rowstart[k], key_rowstart[k+1]) of a dense row-major matrix (host-or-device).  priorVar = 1/lambda,
- * intercept variance 100000 unless penalize_intercept (:333-343), per-feature lambda_map, prior.mean,
- * has.intercept, data.size.threshold (skipped keys -> skipped[k]=1, model 0).  out_model [K][D+1] double.
+ * RegressionNaiveTrain (jobs/RegressionNaiveTrain.java:302-415): num_keys x num_lambdas independent fits ("lambda#key"
+ * reducers, :228-241).  Key k owns rows [key_rowstart[k], key_rowstart[k+1]) of ONE matrix, uploaded once for all lambdas:
+ *   CSR   (rowptr != NULL): rowptr [nrows+1] int64, colidx (global ids), vals -- the reference's per-key sparse datasets
+ *         (:360-398).  A feature that no row of a key lists is not in that key's dataset, hence not in its model
+ *         (regression/liblinearfunc/LibLinear.java:343-350): its output coefficient is 0, whatever prior.mean is.
+ *         binary_feature: every listed feature counts as 1 (LibLinearBinaryDataset).
+ *   dense (rowptr == NULL): vals = X row-major [nrows x num_features], leading dimension ldx; every feature is present.
+ * priorVar = 1/lambda, 1/lambda_map[k] for listed features (lambda_map [num_features] or NULL, entries > 0), intercept variance
+ * 100000 unless penalize_intercept (:333-343), prior.mean, has.intercept, data.size.threshold (skipped keys -> skipped[k]=1,
+ * model 0, :379-382).  out_model [num_lambdas][num_keys][num_features+1] double, intercept last.  All pointers host-or-device
+ * except out_model / skipped (host).  A fit that does not converge -> MLEASE_ERR_NUMERIC ("Model fitting error!", :400-412).
  * ------------------------------------------------------------------------------------- */
+int mlease_naive_train(int32_t device, void* stream, int32_t num_keys, int32_t num_features, const int64_t* key_rowstart,
+                       const int64_t* rowptr, const int32_t* colidx, const float* vals, int64_t ldx, const int32_t* response,
+                       const float* weight, const float* offset, int32_t num_lambdas, const float* lambdas, const float* lambda_map,
+                       float prior_mean, int32_t penalize_intercept, int32_t has_intercept, int32_t data_size_threshold,
+                       int32_t binary_feature, double* out_model, int32_t* skipped);
+/* single-lambda dense form of the above (kept from ABI version 1) */
 int mlease_naive_train_dense(int32_t device, void* stream, int32_t num_keys, int32_t num_features,
                              const int64_t* key_rowstart, const float* X, int64_t ldx, const int32_t* response,
                              const float* weight, const float* offset, float lambda, const float* lambda_map,

@@ -580,8 +580,9 @@ cudaError_t cholesky_share_end(const Problem* d_probs, int nprob, int share, cud
   return cudaGetLastError();
 }
 
-cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches, int share) {
-  {
+// skip_prep: Lc already holds H (lower triangle + diag(q) + identity padding), e.g. the exact fp64 Hessian of k6_postvar.cu
+cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches, int share, int skip_prep) {
+  if (!skip_prep) {
     dim3 blk(32, 8);
     dim3 grd((ldh + 31) / 32, (ldh + 7) / 8, nprob);
     chol_prep_kernel<<<grd, blk, 0, st>>>(d_probs, share);

@@ -29,7 +29,7 @@ cudaError_t csr_bm_fill(long long n, const long long* rowptr, const int* colidx,
 cudaError_t gram_launch_simt(const Problem* d_probs, int nprob, int Dp, int force, cudaStream_t st, int* launches);
 
 // K3 (k3_cholesky.cu)
-cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches, int share = 0);
+cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches, int share = 0, int skip_prep = 0);
 cudaError_t cholesky_share_begin(const Problem* d_probs, int nprob, int share, cudaStream_t st, int* launches);
 cudaError_t cholesky_share_end(const Problem* d_probs, int nprob, int share, cudaStream_t st, int* launches);
 
@@ -42,6 +42,12 @@ cudaError_t admm_pack(const Problem* d_probs, int nlocal_parts, int L, int Dt, d
 cudaError_t admm_consensus(const Problem* d_probs, int nlocal_parts, int L, int Dt, int ldv, int P, const double* d_exchange_sum,
                            double* d_z, const double* d_wz, const double* d_rho_eff_next, double* d_diff, cudaStream_t st,
                            int* launches, const double* d_l1_thr = nullptr);
+
+// posterior variance (k6_postvar.cu): exact fp64 Hessian diagonal / full Hessian into Lc
+cudaError_t postvar_rowweights(const Problem* d_prob, const double* d_w, int has_bias, double* d_dvec, cudaStream_t st, int* launches);
+cudaError_t postvar_diag(const Problem* d_prob, const double* d_dvec, int has_bias, double* d_H, cudaStream_t st, int* launches);
+cudaError_t postvar_hessian(const Problem* d_prob, bool csr, int ldh, const double* d_dvec, const double* d_q, int has_bias, cudaStream_t st,
+                            int* launches);
 
 // K5 (k5_score.cu)
 cudaError_t score_launch(int Dg, long long nrows, const long long* rowptr, const int* colidx, const float* vals, long long ldx,

@@ -25,6 +25,11 @@ int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+}  // namespace
+// comm.cu reports through the same thread-local error string
+extern "C" int mlease_internal_set_error(int code, const char* msg) { return fail(code, msg ? msg : ""); }
+extern "C" int mlease_internal_allreduce(mlease_comm* c, double* buf, size_t count, void* stream);
+namespace {
 #define CK(call)                                                                                                  \
   do {                                                                                                            \
     cudaError_t e__ = (call);                                                                                     \
@@ -466,7 +471,8 @@ struct mlease_session {
   double* d_rho = nullptr;   // [L] rho_eff of the coming iteration
   double* d_diff = nullptr;
   double* d_l1thr = nullptr; // [L] soft-threshold of the L1 z-update (regularizer = 1), else NULL
-  double* d_exch = nullptr;  // [L][Dt] for mlease_admm_run
+  double* d_exch = nullptr;  // [L][Dt] (+1: failed-fit count of this rank) for mlease_admm_run / mlease_admm_iterate
+  mlease_comm* comm = nullptr;   // NCCL communicator of a multi-GPU job (not owned), or NULL
   int* d_flag = nullptr;
   int* h_flag = nullptr;     // pinned
   double* h_small = nullptr; // pinned, >= 4*L doubles
@@ -536,7 +542,7 @@ int finalize(mlease_session* s) {
   if (int rc = sess_alloc(s, (void**)&s->d_wz, s->L * ldv * sizeof(double))) return rc;
   if (int rc = sess_alloc(s, (void**)&s->d_rho, s->L * sizeof(double))) return rc;
   if (int rc = sess_alloc(s, (void**)&s->d_diff, s->L * sizeof(double))) return rc;
-  if (int rc = sess_alloc(s, (void**)&s->d_exch, (size_t)s->L * s->Dt * sizeof(double))) return rc;
+  if (int rc = sess_alloc(s, (void**)&s->d_exch, ((size_t)s->L * s->Dt + 1) * sizeof(double))) return rc;
   // z-update weights (jobs/RegressionAdmmTrain.java:381-386,392-403), in the reference's mixed float/double arithmetic
   std::vector<double> wz(s->L * ldv, 0.0);
   for (int l = 0; l < s->L; l++) {
@@ -616,9 +622,22 @@ __global__ void naive_init_kernel(const Problem* probs, const double* m, const d
   const Problem& pb = probs[blockIdx.x];
   for (int k = threadIdx.x; k < pb.ldx; k += blockDim.x) { pb.beta[k] = 0.0; pb.m[k] = m[k]; pb.q[k] = q[k]; }
 }
-__global__ void gather_beta_kernel(const Problem* probs, int Dt, double* out) {
+__global__ void gather_beta_kernel(const Problem* probs, int Dt, double* out, const unsigned char* mask) {
   const Problem& pb = probs[blockIdx.x];
-  for (int k = threadIdx.x; k < Dt; k += blockDim.x) out[(size_t)blockIdx.x * Dt + k] = pb.beta[k];
+  for (int k = threadIdx.x; k < Dt; k += blockDim.x)
+    out[(size_t)blockIdx.x * Dt + k] = (!mask || mask[(size_t)blockIdx.x * Dt + k]) ? pb.beta[k] : 0.0;
+}
+// mask[b][c] = 1 for every feature listed in some row of problem b (+ the intercept)
+__global__ void naive_present_kernel(const Problem* probs, int Dt, int has_bias, unsigned char* mask) {
+  const Problem& pb = probs[blockIdx.x];
+  unsigned char* mk = mask + (size_t)blockIdx.x * Dt;
+  const long long j0 = pb.rowptr[0], j1 = pb.rowptr[pb.n];
+  for (long long j = j0 + threadIdx.x; j < j1; j += blockDim.x) mk[pb.colidx[j]] = 1;
+  if (threadIdx.x == 0 && has_bias) mk[Dt - 1] = 1;
+}
+__global__ void gather_i64_kernel(const long long* src, const long long* idx, int n, long long* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
 }
 }  // namespace
 
@@ -915,21 +934,54 @@ int mlease_admm_consensus(mlease_session* s, const double* exchange_sum_dev, dou
   return 0;
 }
 
+int mlease_session_set_comm(mlease_session* s, mlease_comm* comm) {
+  if (!s) return fail(MLEASE_ERR_INVALID, "null session");
+  s->comm = comm;
+  return 0;
+}
+
+// One iteration with the exchange inside: local x-updates, all-reduce (NCCL communicator, caller's callback, or nothing for
+// a single-process job), z/u update.  A rank whose fit failed still enters the collective -- with its failure counted in the
+// extra last element of the buffer -- so that every rank leaves with the same error instead of the others hanging in NCCL
+// (the reference: one failed reducer fails the whole iteration job, jobs/RegressionAdmmTrain.java:713-716).
+static int admm_iterate_impl(mlease_session* s, mlease_allreduce_fn allreduce, void* ctx, double* maxdiff, int32_t* stop) {
+  const size_t cnt = (size_t)s->L * s->Dt;
+  int rc_local = mlease_admm_local_step(s, s->d_exch);
+  std::string local_msg;
+  if (rc_local == MLEASE_ERR_NUMERIC) local_msg = g_err;
+  else if (rc_local) return rc_local;                      // CUDA / state errors are not recoverable: no collective
+  const bool multi = s->comm != nullptr || allreduce != nullptr;
+  if (multi) {
+    const double flag = rc_local ? 1.0 : 0.0;
+    CK(cudaMemcpyAsync(s->d_exch + cnt, &flag, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (s->comm) { if (int rc = mlease_internal_allreduce(s->comm, s->d_exch, cnt + 1, (void*)s->stream)) return rc; }
+    else if (allreduce(ctx, s->d_exch, cnt + 1, (void*)s->stream) != 0) return fail(MLEASE_ERR_CUDA, "all-reduce callback failed");
+    double failed = 0;
+    CK(cudaMemcpyAsync(&failed, s->d_exch + cnt, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    if (rc_local) return fail(rc_local, local_msg);
+    if (failed > 0) return fail(MLEASE_ERR_NUMERIC, "Model fitting error! (the x-update failed on " + std::to_string((int)failed) + " other rank(s))");
+  } else if (rc_local) {
+    return fail(rc_local, local_msg);
+  }
+  return mlease_admm_consensus(s, s->d_exch, maxdiff, stop);
+}
+
+static int check_partitions_present(mlease_session* s, bool multi) {
+  if (!multi && (int)s->parts.size() != s->P)
+    return fail(MLEASE_ERR_STATE, "Some models failed! (" + std::to_string(s->parts.size()) + " of " + std::to_string(s->P) +
+                                      " partitions present and neither a communicator nor an all-reduce was given)");
+  return 0;
+}
+
 int mlease_admm_run(mlease_session* s, int32_t num_iters, mlease_allreduce_fn allreduce, void* ctx, int32_t* iters_done) {
   if (!s) return fail(MLEASE_ERR_INVALID, "null session");
-  if (!allreduce && (int)s->parts.size() != s->P && s->batch == nullptr)
-    ;  // checked below once finalized
   if (int rc = mlease_admm_begin(s)) return rc;
-  if (!allreduce && (int)s->parts.size() != s->P)
-    return fail(MLEASE_ERR_STATE, "Some models failed! (" + std::to_string(s->parts.size()) + " of " + std::to_string(s->P) + " partitions present and no all-reduce given)");
+  if (int rc = check_partitions_present(s, s->comm != nullptr || allreduce != nullptr)) return rc;
   int done = 0;
   for (int i = 1; i <= num_iters; i++) {
-    if (int rc = mlease_admm_local_step(s, s->d_exch)) return rc;
-    if (allreduce) {
-      if (allreduce(ctx, s->d_exch, (size_t)s->L * s->Dt, (void*)s->stream) != 0) return fail(MLEASE_ERR_CUDA, "all-reduce callback failed");
-    }
     double md; int32_t stop;
-    if (int rc = mlease_admm_consensus(s, s->d_exch, &md, &stop)) return rc;
+    if (int rc = admm_iterate_impl(s, allreduce, ctx, &md, &stop)) return rc;
     done = i;
     if (stop) break;
   }
@@ -940,10 +992,8 @@ int mlease_admm_run(mlease_session* s, int32_t num_iters, mlease_allreduce_fn al
 int mlease_admm_iterate(mlease_session* s, double* maxdiff, int32_t* stop) {
   if (!s) return fail(MLEASE_ERR_INVALID, "null session");
   if (!s->begun) return fail(MLEASE_ERR_STATE, "mlease_admm_begin was not called");
-  if ((int)s->parts.size() != s->P)
-    return fail(MLEASE_ERR_STATE, "Some models failed! (" + std::to_string(s->parts.size()) + " of " + std::to_string(s->P) + " partitions present)");
-  if (int rc = mlease_admm_local_step(s, s->d_exch)) return rc;
-  return mlease_admm_consensus(s, s->d_exch, maxdiff, stop);
+  if (int rc = check_partitions_present(s, s->comm != nullptr)) return rc;
+  return admm_iterate_impl(s, nullptr, nullptr, maxdiff, stop);
 }
 
 int mlease_get_z(mlease_session* s, int32_t l, double* out) {
@@ -1087,6 +1137,56 @@ int mlease_fit_partition(mlease_session* s, int32_t pid, double* x, const double
   return 0;
 }
 
+int mlease_posterior_variance(mlease_session* s, int32_t pid, const double* w, const double* q, int32_t full, double* var, double* cov) {
+  if (!s || !w || !q || !var) return fail(MLEASE_ERR_INVALID, "null argument");
+  if (cov && !full) return fail(MLEASE_ERR_INVALID, "the covariance matrix is only available with full = 1 (computeFullPostVar)");
+  CK(cudaSetDevice(s->cfg.device));
+  const int pi = find_part(s, pid);
+  if (pi < 0) return fail(MLEASE_ERR_INVALID, "partition not resident in this session");
+  if (int rc = ensure_scratch(s, pi)) return rc;
+  Batch* B = s->scratch;
+  const Problem& p = B->h[0];
+  if (full && B->csr && !s->parts[pi].csr_unique)
+    return fail(MLEASE_ERR_INVALID, "the full Hessian needs rows with strictly increasing column ids (llf/LogisticRegressionL2.java:277)");
+  std::vector<double> zero(s->Dt, 0.0);
+  if (int rc = scratch_set(s, w, zero.data(), q)) return rc;          // beta = w, q = prior precision (1 on the padding)
+  TmpDev t;
+  double* dvec;
+  if (int rc = t.get(&dvec, (size_t)p.n)) return rc;
+  int launches = 0;
+  CK(postvar_rowweights(B->d, p.beta, 1, dvec, s->stream, &launches));
+  if (!full) {
+    // H[k] = 1/priorVar[k] + sum_i weight_i p_i (1-p_i) x_ik^2, postVar = 1/H (llf/LibLinear.java:330-333)
+    CK(cudaMemcpyAsync(p.g_t, p.q, (size_t)s->ldx * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    CK(postvar_diag(B->d, dvec, 1, p.g_t, s->stream, &launches));
+    CK(cudaMemcpyAsync(var, p.g_t, (size_t)s->Dt * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    for (int k = 0; k < s->Dt; k++) var[k] = 1.0 / var[k];
+    s->cnt.launches += launches;
+    return 0;
+  }
+  // exact fp64 Hessian -> K3's factorisation and explicit inverse (llf/LibLinear.java:318-326)
+  CK(postvar_hessian(B->d, B->csr, B->ldh, dvec, p.q, 1, s->stream, &launches));
+  Ctrl c; std::memset(&c, 0, sizeof(c)); c.need_hess = 1;
+  CK(cudaMemcpyAsync(B->d_ctrl, &c, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
+  CK(cholesky_launch(B->d, 1, B->ldh, s->stream, &launches, 0, 1));
+  std::vector<double> hi((size_t)B->ldh * B->ldh);
+  CK(cudaMemcpyAsync(hi.data(), p.Hinv, hi.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(&c, B->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  s->cnt.launches += launches;
+  if (c.fail) return fail(MLEASE_ERR_NUMERIC, "Model fitting error! (Hessian not positive definite)");
+  for (int i = 0; i < s->Dt; i++) {
+    var[i] = hi[(size_t)i * B->ldh + i];
+    if (cov) for (int j = 0; j < s->Dt; j++) cov[(size_t)i * s->Dt + j] = hi[(size_t)i * B->ldh + j];
+  }
+  // the stale-factor bookkeeping of the scratch problem no longer matches its Lc/Hinv: force a rebuild on its next use
+  Ctrl c2; std::memset(&c2, 0, sizeof(c2));
+  CK(cudaMemcpy(B->d_ctrl, &c2, sizeof(Ctrl), cudaMemcpyHostToDevice));
+  B->mirror.clear();
+  return 0;
+}
+
 int mlease_time_kernel(mlease_session* s, int32_t pid, int32_t which, int32_t reps, int32_t emit_scaled, float* avg_ms) {
   if (!s || !avg_ms || reps <= 0) return fail(MLEASE_ERR_INVALID, "bad argument");
   CK(cudaSetDevice(s->cfg.device));
@@ -1212,13 +1312,19 @@ int mlease_test_loglik(int32_t device, void* stream, int64_t nrows, const int32_
 }
 
 // ------------------------------------------------------------------------------------------
-// RegressionNaiveTrain: K independent fits, processed in lockstep chunks.
+// RegressionNaiveTrain: K independent fits per lambda, processed in lockstep chunks.  The rows are uploaded ONCE and serve
+// every lambda (the reference fans each record out once per lambda through the shuffle, jobs/RegressionNaiveTrain.java:228-241).
 // ------------------------------------------------------------------------------------------
-int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg, const int64_t* key_rowstart, const float* X, int64_t ldx_in,
-                             const int32_t* response, const float* weight, const float* offset, float lambda, const float* lambda_map,
-                             float prior_mean, int32_t penalize_intercept, int32_t has_intercept, int32_t data_size_threshold,
-                             double* out_model, int32_t* skipped) {
-  if (K <= 0 || Dg <= 0 || !key_rowstart || !X || !response || !out_model) return fail(MLEASE_ERR_INVALID, "bad argument");
+int mlease_naive_train(int32_t device, void* stream, int32_t K, int32_t Dg, const int64_t* key_rowstart, const int64_t* rowptr,
+                       const int32_t* colidx, const float* vals, int64_t ldx_in, const int32_t* response, const float* weight,
+                       const float* offset, int32_t L, const float* lambdas, const float* lambda_map, float prior_mean,
+                       int32_t penalize_intercept, int32_t has_intercept, int32_t data_size_threshold, int32_t binary_feature,
+                       double* out_model, int32_t* skipped) {
+  if (K <= 0 || Dg <= 0 || L <= 0 || !lambdas || !key_rowstart || !vals || !response || !out_model) return fail(MLEASE_ERR_INVALID, "bad argument");
+  const bool csr = rowptr != nullptr;
+  if (csr && !colidx) return fail(MLEASE_ERR_INVALID, "null colidx");
+  if (!csr && binary_feature) return fail(MLEASE_ERR_INVALID, "binary.feature needs CSR input (every listed feature counts as 1)");
+  if (!csr && ldx_in < Dg) return fail(MLEASE_ERR_INVALID, "ldx < num_features");
   if (int rc = need_device(device)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   cudaDeviceProp prop;
@@ -1238,9 +1344,12 @@ int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg
   std::vector<long long> krs(K + 1);
   CK(cudaMemcpy(krs.data(), key_rowstart, (size_t)(K + 1) * 8, cudaMemcpyDefault));
   const long long ntot = krs[K];
+  for (int k = 0; k < K; k++) if (krs[k + 1] < krs[k]) return fail(MLEASE_ERR_INVALID, "key_rowstart must be non-decreasing");
   TmpDev t;
-  float* dX; signed char* dy; float *dw, *dofs; int* dflag; int* hflag;
-  if (int rc = t.get(&dX, (size_t)ntot * ldx)) return rc;
+  float* dX = nullptr; signed char* dy; float *dw, *dofs; int* dflag; int* hflag;
+  const long long* d_rp = nullptr; const int* d_ci = nullptr; float* d_v = nullptr;
+  std::vector<long long> key_nnz0(K + 1, 0);   // CSR: rowptr at the key boundaries
+  int csr_unique = 0;
   if (int rc = t.get(&dy, (size_t)ntot)) return rc;
   if (int rc = t.get(&dw, (size_t)ntot)) return rc;
   if (int rc = t.get(&dofs, (size_t)ntot)) return rc;
@@ -1248,16 +1357,44 @@ int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg
   CK(cudaMallocHost((void**)&hflag, 64));
   struct HF { int* p; ~HF() { cudaFreeHost(p); } } hf{hflag};
   lap("alloc");
-  {
+  if (!csr) {
+    if (int rc = t.get(&dX, (size_t)ntot * ldx)) return rc;
     // rows are re-pitched from ldx_in to ldx floats: a kernel for device input (the copy engine moves 1 KB rows slowly),
     // a pitched copy for host input
     cudaPointerAttributes pa;
-    const bool on_device = cudaPointerGetAttributes(&pa, X) == cudaSuccess && (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged);
+    const bool on_device = cudaPointerGetAttributes(&pa, vals) == cudaSuccess && (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged);
     cudaGetLastError();
-    if (on_device) repack_rows_kernel<<<4096, 256, 0, st>>>(dX, ldx, X, ldx_in, ntot, Dg);
-    else CK(cudaMemcpy2DAsync(dX, (size_t)ldx * 4, X, (size_t)ldx_in * 4, (size_t)Dg * 4, (size_t)ntot, cudaMemcpyDefault, st));
+    if (on_device) repack_rows_kernel<<<4096, 256, 0, st>>>(dX, ldx, vals, ldx_in, ntot, Dg);
+    else CK(cudaMemcpy2DAsync(dX, (size_t)ldx * 4, vals, (size_t)ldx_in * 4, (size_t)Dg * 4, (size_t)ntot, cudaMemcpyDefault, st));
+    fill_bias_pad_kernel<<<1024, 256, 0, st>>>(dX, ntot, ldx, Dg, has_intercept ? 1 : 0);
+  } else {
+    if (int rc = to_device(t, (const long long*)rowptr, (size_t)ntot + 1, &d_rp, st)) return rc;
+    long long nnz = 0, first = 0;
+    CK(cudaMemcpyAsync(&nnz, d_rp + ntot, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&first, d_rp, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (first != 0) return fail(MLEASE_ERR_INVALID, "rowptr[0] must be 0");
+    if (int rc = to_device(t, colidx, (size_t)nnz, &d_ci, st)) return rc;
+    // values are copied even when they already live on the device: binary.feature rewrites them
+    if (int rc = t.get(&d_v, (size_t)std::max<long long>(nnz, 1))) return rc;
+    CK(cudaMemcpyAsync(d_v, vals, (size_t)nnz * 4, cudaMemcpyDefault, st));
+    CK(cudaMemsetAsync(dflag, 0, 8, st));
+    if (nnz > 0) {
+      check_csr_kernel<<<(int)std::min<long long>((nnz + 255) / 256, 4096), 256, 0, st>>>(nnz, d_ci, d_v, Dg, binary_feature, dflag);
+      check_rows_sorted_kernel<<<(int)std::min<long long>((ntot + 255) / 256, 4096), 256, 0, st>>>(ntot, d_rp, d_ci, dflag + 1);
+    }
+    CK(cudaMemcpyAsync(hflag, dflag, 8, cudaMemcpyDeviceToHost, st));
+    // rowptr at the key boundaries (nnz per key for the cost model and the byte accounting)
+    long long* d_kn; long long* d_krs;
+    if (int rc = t.get(&d_kn, (size_t)K + 1)) return rc;
+    if (int rc = t.get(&d_krs, (size_t)K + 1)) return rc;
+    CK(cudaMemcpyAsync(d_krs, krs.data(), (size_t)(K + 1) * 8, cudaMemcpyHostToDevice, st));
+    gather_i64_kernel<<<(K + 256) / 256, 256, 0, st>>>(d_rp, d_krs, K + 1, d_kn);
+    CK(cudaMemcpyAsync(key_nnz0.data(), d_kn, (size_t)(K + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hflag[0]) return fail(MLEASE_ERR_INVALID, "feature index out of range");
+    csr_unique = hflag[1] ? 0 : 1;
   }
-  fill_bias_pad_kernel<<<1024, 256, 0, st>>>(dX, ntot, ldx, Dg, has_intercept ? 1 : 0);
   lap("ingest X");
   {
     const int* d_r; const float *d_wi, *d_oi;
@@ -1272,25 +1409,16 @@ int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg
     if (*hflag & 2) return fail(MLEASE_ERR_INVALID, "weight cannot < 0");
   }
   lap("labels");
-  // prior (jobs/RegressionNaiveTrain.java:333-343,395)
-  std::vector<double> q(ldx, 1.0), m(ldx, 0.0), zero(ldx, 0.0);
   std::vector<float> lm;
   if (lambda_map) { lm.resize(Dg); CK(cudaMemcpy(lm.data(), lambda_map, (size_t)Dg * 4, cudaMemcpyDefault)); }
-  for (int k = 0; k < Dg; k++) {
-    q[k] = (!lm.empty() && lm[k] > 0.f) ? 1.0 / (1.0 / (double)lm[k]) : 1.0 / (1.0 / (double)lambda);
-    m[k] = (double)prior_mean;
-  }
-  // intercept: variance 100000 unless penalised (then the default 1/lambda); without intercept the bias column is 0
-  q[Dg] = has_intercept ? (penalize_intercept ? 1.0 / (1.0 / (double)lambda) : 1.0 / 100000.0) : 1.0;
-  m[Dg] = has_intercept ? (double)prior_mean : 0.0;
-  for (int k = 0; k < K; k++) {
-    for (int j = 0; j < Dt; j++) out_model[(size_t)k * Dt + j] = 0.0;
-    if (skipped) skipped[k] = 0;
-  }
+  std::vector<float> lams(L);
+  CK(cudaMemcpy(lams.data(), lambdas, (size_t)L * 4, cudaMemcpyDefault));
+  for (size_t e = 0; e < (size_t)L * K * Dt; e++) out_model[e] = 0.0;
   std::vector<int> todo;
   for (int k = 0; k < K; k++) {
     const long long nk = krs[k + 1] - krs[k];
-    if (nk < data_size_threshold || nk <= 0) { if (skipped) skipped[k] = 1; }
+    if (skipped) skipped[k] = 0;
+    if (nk < data_size_threshold || nk <= 0) { if (skipped) skipped[k] = 1; }   // "data size < threshold": no model (:379-382)
     else todo.push_back(k);
   }
   // chunk size bounded by memory: Xt (n*Dp*2) + Hpart + Lc per problem
@@ -1310,34 +1438,61 @@ int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg
       end++;
     }
     Batch B;
-    B.nprob = (int)(end - pos); B.Dt = Dt; B.ldx = ldx; B.csr = false; B.has_bias = has_intercept ? 1 : 0;
+    B.nprob = (int)(end - pos); B.Dt = Dt; B.ldx = ldx; B.csr = csr; B.has_bias = has_intercept ? 1 : 0;
     B.h.resize(B.nprob);
     for (int b = 0; b < B.nprob; b++) {
       const int k = todo[pos + b];
       Problem& p = B.h[b];
       std::memset(&p, 0, sizeof(Problem));
-      p.X = dX + (size_t)krs[k] * ldx; p.n = krs[k + 1] - krs[k];
+      p.n = krs[k + 1] - krs[k];
       p.y = dy + krs[k]; p.w = dw + krs[k]; p.o = dofs + krs[k];
+      if (csr) {
+        // a key = a row range of the one CSR: the row pointers keep their absolute offsets into colidx / vals
+        p.rowptr = d_rp + krs[k]; p.colidx = d_ci; p.vals = d_v; p.nnz_hint = key_nnz0[k + 1] - key_nnz0[k]; p.csr_unique = csr_unique;
+      } else {
+        p.X = dX + (size_t)krs[k] * ldx;
+      }
     }
     if (int rc = batch_alloc(B, prop.multiProcessorCount)) return rc;
     lap("batch_alloc");
-    {
-      double *dm, *dq, *dout;
-      if (int rc = t.get(&dm, (size_t)ldx)) return rc;
-      if (int rc = t.get(&dq, (size_t)ldx)) return rc;
-      if (int rc = t.get(&dout, (size_t)B.nprob * Dt)) return rc;
+    double *dm, *dq, *dout; unsigned char* dmask = nullptr;
+    if (int rc = t.get(&dm, (size_t)ldx)) return rc;
+    if (int rc = t.get(&dq, (size_t)ldx)) return rc;
+    if (int rc = t.get(&dout, (size_t)B.nprob * Dt)) return rc;
+    if (csr) {
+      // features absent from a key's rows are not part of its dataset, hence not of its model (llf/LibLinear.java:343-350;
+      // no priorMean map is passed by NaiveTrain, so :374-383 adds nothing): mask them out of the dense result
+      if (int rc = t.get(&dmask, (size_t)B.nprob * Dt)) return rc;
+      CK(cudaMemsetAsync(dmask, 0, (size_t)B.nprob * Dt, st));
+      naive_present_kernel<<<B.nprob, 256, 0, st>>>(B.d, Dt, has_intercept ? 1 : 0, dmask);
+    }
+    std::vector<double> xs((size_t)B.nprob * Dt);
+    for (int l = 0; l < L; l++) {
+      // prior (jobs/RegressionNaiveTrain.java:333-343,395): variance 1/lambdaMap[k] for listed features, 1/lambda otherwise,
+      // 100000 for the intercept unless penalised; mean prior.mean; the fit starts at 0 (null initParam)
+      const float lambda = lams[l];
+      std::vector<double> q(ldx, 1.0), m(ldx, 0.0);
+      for (int k = 0; k < Dg; k++) {
+        q[k] = (!lm.empty() && lm[k] > 0.f) ? 1.0 / (1.0 / (double)lm[k]) : 1.0 / (1.0 / (double)lambda);
+        m[k] = (double)prior_mean;
+      }
+      // without an intercept the bias column is 0 and its coefficient stays at 0
+      q[Dg] = has_intercept ? (penalize_intercept ? 1.0 / (1.0 / (double)lambda) : 1.0 / 100000.0) : 1.0;
+      m[Dg] = has_intercept ? (double)prior_mean : 0.0;
       CK(cudaMemcpyAsync(dm, m.data(), ldx * 8, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(dq, q.data(), ldx * 8, cudaMemcpyHostToDevice, st));
-      naive_init_kernel<<<B.nprob, 128, 0, st>>>(B.d, dm, dq);   // init = 0 (null initParam), prior mean / precision
+      CK(cudaStreamSynchronize(st));   // q / m are reused by the next lambda
+      naive_init_kernel<<<B.nprob, 128, 0, st>>>(B.d, dm, dq);
+      B.mirror.clear();                // the factors of the previous lambda belong to another prior
       if (int rc = batch_xupdate(B, st, 2e-7, 100, 0, 1, hflag, dflag, cnt)) return rc;
       lap("solve");
-      gather_beta_kernel<<<B.nprob, 128, 0, st>>>(B.d, Dt, dout);
-      std::vector<double> xs((size_t)B.nprob * Dt);
+      gather_beta_kernel<<<B.nprob, 128, 0, st>>>(B.d, Dt, dout, dmask);
       CK(cudaMemcpyAsync(xs.data(), dout, xs.size() * 8, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       for (int b = 0; b < B.nprob; b++) {
-        std::memcpy(out_model + (size_t)todo[pos + b] * Dt, xs.data() + (size_t)b * Dt, Dt * 8);
-        if (!has_intercept) out_model[(size_t)todo[pos + b] * Dt + Dg] = 0.0;
+        double* dst = out_model + ((size_t)l * K + todo[pos + b]) * Dt;
+        std::memcpy(dst, xs.data() + (size_t)b * Dt, Dt * 8);
+        if (!has_intercept) dst[Dg] = 0.0;
       }
       lap("read-back");
     }
@@ -1345,6 +1500,14 @@ int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg
   }
   if (cnt.not_converged) return fail(MLEASE_ERR_NUMERIC, "Model fitting error! (" + std::to_string(cnt.not_converged) + " fits did not converge)");
   return 0;
+}
+
+int mlease_naive_train_dense(int32_t device, void* stream, int32_t K, int32_t Dg, const int64_t* key_rowstart, const float* X, int64_t ldx_in,
+                             const int32_t* response, const float* weight, const float* offset, float lambda, const float* lambda_map,
+                             float prior_mean, int32_t penalize_intercept, int32_t has_intercept, int32_t data_size_threshold,
+                             double* out_model, int32_t* skipped) {
+  return mlease_naive_train(device, stream, K, Dg, key_rowstart, nullptr, nullptr, X, ldx_in, response, weight, offset, 1, &lambda, lambda_map,
+                            prior_mean, penalize_intercept, has_intercept, data_size_threshold, 0, out_model, skipped);
 }
 
 }  // extern "C"

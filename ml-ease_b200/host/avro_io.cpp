@@ -196,6 +196,7 @@ int64_t rd_long(const std::string& b, size_t& p) {
   while (true) {
     if (p >= b.size()) throw std::runtime_error("avro: truncated varint");
     uint8_t c = (uint8_t)b[p++];
+    if (sh > 63) throw std::runtime_error("avro: varint longer than 10 bytes");
     acc |= (uint64_t)(c & 0x7F) << sh;
     if (!(c & 0x80)) break;
     sh += 7;
@@ -207,16 +208,20 @@ void wr_long(std::string& o, int64_t v) {
   while (z & ~0x7FULL) { o.push_back((char)((z & 0x7F) | 0x80)); z >>= 7; }
   o.push_back((char)z);
 }
+// every read of file content is bounds-checked: a truncated or corrupt data file is an error, never an out-of-bounds read
+inline void need(const std::string& b, size_t p, int64_t n) {
+  if (n < 0 || (uint64_t)n > b.size() || p > b.size() - (size_t)n) throw std::runtime_error("avro: truncated or corrupt block (value runs past the end of the data)");
+}
 void decode(const std::string& b, size_t& p, const Schema& s, Value& v) {
   v.type = s.type; v.items.clear(); v.s.clear();
   switch (s.type) {
     case Schema::Null: break;
-    case Schema::Boolean: v.i = b[p++] != 0; break;
+    case Schema::Boolean: need(b, p, 1); v.i = b[p++] != 0; break;
     case Schema::Int: case Schema::Long: v.i = rd_long(b, p); break;
-    case Schema::Float: { float f; memcpy(&f, &b[p], 4); p += 4; v.d = f; break; }
-    case Schema::Double: { double d; memcpy(&d, &b[p], 8); p += 8; v.d = d; break; }
-    case Schema::String: case Schema::Bytes: { int64_t n = rd_long(b, p); v.s.assign(b, p, (size_t)n); p += (size_t)n; break; }
-    case Schema::Fixed: v.s.assign(b, p, (size_t)s.fixed_size); p += s.fixed_size; break;
+    case Schema::Float: { need(b, p, 4); float f; memcpy(&f, &b[p], 4); p += 4; v.d = f; break; }
+    case Schema::Double: { need(b, p, 8); double d; memcpy(&d, &b[p], 8); p += 8; v.d = d; break; }
+    case Schema::String: case Schema::Bytes: { int64_t n = rd_long(b, p); need(b, p, n); v.s.assign(b, p, (size_t)n); p += (size_t)n; break; }
+    case Schema::Fixed: need(b, p, s.fixed_size); v.s.assign(b, p, (size_t)s.fixed_size); p += s.fixed_size; break;
     case Schema::Enum: v.i = rd_long(b, p); break;
     case Schema::Union: { int64_t br = rd_long(b, p); if (br < 0 || br >= (int64_t)s.branches.size()) throw std::runtime_error("avro: bad union branch"); decode(b, p, *s.branches[br], v); break; }
     case Schema::Record: v.items.resize(s.fields.size()); for (size_t k = 0; k < s.fields.size(); k++) decode(b, p, *s.fields[k].second, v.items[k]); v.type = Schema::Record; break;
@@ -234,7 +239,13 @@ void decode(const std::string& b, size_t& p, const Schema& s, Value& v) {
         int64_t n = rd_long(b, p);
         if (n == 0) break;
         if (n < 0) { n = -n; rd_long(b, p); }
-        for (int64_t k = 0; k < n; k++) { int64_t l = rd_long(b, p); std::string key(b, p, (size_t)l); p += (size_t)l; v.items.emplace_back(); decode(b, p, *s.items, v.items.back()); v.items.back().s = key; }
+        for (int64_t k = 0; k < n; k++) {
+          int64_t l = rd_long(b, p);
+          need(b, p, l);
+          std::string key(b, p, (size_t)l); p += (size_t)l;
+          v.items.emplace_back(); decode(b, p, *s.items, v.items.back());
+          v.items.back().map_key = key;   // kept apart from the value (a string value has its own .s)
+        }
       }
       v.type = Schema::Map;
       break;
@@ -274,7 +285,7 @@ void encode(std::string& o, const Schema& s, const Value& v) {
       wr_long(o, 0);
       break;
     case Schema::Map:
-      if (!v.items.empty()) { wr_long(o, (int64_t)v.items.size()); for (auto& e : v.items) { wr_long(o, (int64_t)e.s.size()); o += e.s; encode(o, *s.items, e); } }
+      if (!v.items.empty()) { wr_long(o, (int64_t)v.items.size()); for (auto& e : v.items) { wr_long(o, (int64_t)e.map_key.size()); o += e.map_key; encode(o, *s.items, e); } }
       wr_long(o, 0);
       break;
   }
@@ -322,21 +333,25 @@ AvroReader::AvroReader(const std::string& path) {
     if (n == 0) break;
     if (n < 0) { n = -n; rd_long(data_, pos_); }
     for (int64_t k = 0; k < n; k++) {
-      int64_t kl = rd_long(data_, pos_); std::string key(data_, pos_, (size_t)kl); pos_ += (size_t)kl;
-      int64_t vl = rd_long(data_, pos_); std::string val(data_, pos_, (size_t)vl); pos_ += (size_t)vl;
+      int64_t kl = rd_long(data_, pos_); need(data_, pos_, kl); std::string key(data_, pos_, (size_t)kl); pos_ += (size_t)kl;
+      int64_t vl = rd_long(data_, pos_); need(data_, pos_, vl); std::string val(data_, pos_, (size_t)vl); pos_ += (size_t)vl;
       if (key == "avro.schema") schema_json_ = val;
       if (key == "avro.codec") codec_ = val;
     }
   }
   if (codec_ != "null" && codec_ != "deflate") throw std::runtime_error("avro: unsupported codec " + codec_);
   schema_ = schema_parse(schema_json_);
+  need(data_, pos_, 16);
   sync_.assign(data_, pos_, 16); pos_ += 16;
 }
 bool AvroReader::load_block() {
   if (pos_ >= data_.size()) return false;
   remaining_ = rd_long(data_, pos_);
   int64_t bytes = rd_long(data_, pos_);
+  if (remaining_ < 0) throw std::runtime_error("avro: negative record count in block header");
+  need(data_, pos_, bytes);
   std::string raw(data_, pos_, (size_t)bytes); pos_ += (size_t)bytes;
+  need(data_, pos_, 16);
   if (data_.compare(pos_, 16, sync_)) throw std::runtime_error("avro: sync marker mismatch");
   pos_ += 16;
   block_ = codec_ == "deflate" ? inflate_raw(raw) : raw;

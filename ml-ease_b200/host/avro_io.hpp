@@ -53,7 +53,8 @@ struct Value {
   int64_t i = 0;       // boolean / int / long / enum index
   double d = 0;        // float / double
   std::string s;       // string / bytes / fixed
-  std::vector<Value> items;   // array elements, record fields (by index), map values (s = key in each item)
+  std::string map_key; // key of this value when it is an entry of a map
+  std::vector<Value> items;   // array elements, record fields (by index), map values (map_key = key of each item)
   bool is_null() const { return type == Schema::Null; }
   static Value null() { return Value(); }
   static Value of_int(int64_t v) { Value x; x.type = Schema::Int; x.i = v; return x; }

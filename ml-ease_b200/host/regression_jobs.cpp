@@ -4,7 +4,7 @@
 //
 //   Regression            jobs/Regression.java:37-80         Prepare -> AdmmTrain -> Test -> TestLoglik
 //   RegressionPrepare     jobs/RegressionPrepare.java:58-191
-//   RegressionAdmmTrain   jobs/RegressionAdmmTrain.java:130-522 (L2 branch)
+//   RegressionAdmmTrain   jobs/RegressionAdmmTrain.java:130-522 (L2 and L1 z-updates, lambda.map, initialize.boost.rate; gpu.devices = several GPUs)
 //   RegressionTest        jobs/RegressionTest.java:65-170
 //   RegressionTestLoglik  jobs/RegressionTestLoglik.java:57-201
 //   RegressionNaiveTrain  jobs/RegressionNaiveTrain.java:99-415 (+ jobs/PartitionIdAssigner.java:41-101)
@@ -118,6 +118,46 @@ std::string java_float_to_string(float f) {
     } else out = "0." + std::string(-ex - 1, '0') + digits;
   } else out = digits.substr(0, 1) + "." + (digits.size() > 1 ? digits.substr(1) : "0") + "E" + std::to_string(ex);
   return neg ? "-" + out : out;
+}
+// Double.toString: same shortest-repr rule as Float.toString on the double's own digits
+std::string java_double_to_string(double f) {
+  if (std::isnan(f)) return "NaN";
+  if (std::isinf(f)) return f > 0 ? "Infinity" : "-Infinity";
+  if (f == 0) return std::signbit(f) ? "-0.0" : "0.0";
+  char buf[64];
+  auto res = std::to_chars(buf, buf + sizeof(buf), f, std::chars_format::scientific);
+  std::string s(buf, res.ptr);
+  bool neg = s[0] == '-';
+  if (neg) s = s.substr(1);
+  size_t e = s.find('e');
+  std::string digits;
+  for (char c : s.substr(0, e)) if (c != '.') digits.push_back(c);
+  int ex = std::atoi(s.c_str() + e + 1);
+  std::string out;
+  if (ex >= -3 && ex < 7) {
+    if (ex >= 0) {
+      std::string ip = digits.substr(0, std::min<size_t>(digits.size(), ex + 1));
+      while ((int)ip.size() < ex + 1) ip.push_back('0');
+      out = ip + "." + (digits.size() > (size_t)ex + 1 ? digits.substr(ex + 1) : "0");
+    } else out = "0." + std::string(-ex - 1, '0') + digits;
+  } else out = digits.substr(0, 1) + "." + (digits.size() > 1 ? digits.substr(1) : "0") + "E" + std::to_string(ex);
+  return neg ? "-" + out : out;
+}
+// Integer.parseInt: optional sign, decimal digits only, the whole string, 32-bit range; anything else is a NumberFormatException
+int java_parse_int(const std::string& s) {
+  size_t i = 0;
+  bool neg = false;
+  if (!s.empty() && (s[0] == '-' || s[0] == '+')) { neg = s[0] == '-'; i = 1; }
+  if (i >= s.size()) io_error("For input string: \"" + s + "\"");
+  long long v = 0;
+  for (; i < s.size(); i++) {
+    if (s[i] < '0' || s[i] > '9') io_error("For input string: \"" + s + "\"");
+    v = v * 10 + (s[i] - '0');
+    if (v > 2147483648LL) io_error("For input string: \"" + s + "\"");
+  }
+  if (neg) v = -v;
+  if (v > 2147483647LL) io_error("For input string: \"" + s + "\"");
+  return (int)v;
 }
 int32_t java_string_hash(const std::string& s) { uint32_t h = 0; for (unsigned char c : s) h = 31u * h + c; return (int32_t)h; }
 
@@ -273,6 +313,42 @@ struct Session {
   mlease_session* s = nullptr;
   ~Session() { if (s) mlease_session_destroy(s); }
 };
+// N GPUs of this process behind the session calls (include/mlease_b200.h "Multi-GPU" (b)); N = 1 is a plain session
+struct World {
+  mlease_world* w = nullptr;
+  ~World() { if (w) mlease_world_destroy(w); }
+};
+// gpu.devices = 0,1,2,...  (falls back to the single gpu.device, default 0).  Not a reference key: the reference's
+// parallelism is Hadoop's (one reducer per (partition, lambda), jobs/RegressionAdmmTrain.java:355).
+std::vector<int32_t> gpu_devices(const JobConfig& c) {
+  std::vector<int32_t> d;
+  if (c.has("gpu.devices")) for (auto& t : c.get_list("gpu.devices")) d.push_back(std::stoi(t));
+  if (d.empty()) d.push_back(c.get_int("gpu.device", 0));
+  return d;
+}
+
+// lambda.map file (ReadLambdaMapConsumer, regression/consumers/ReadLambdaMapConsumer.java:33-52; jobs/RegressionAdmmTrain.java:186-196,
+// jobs/RegressionNaiveTrain.java:318-332): records {name, term, value}; key = name or name\u0001term; value cast to float.
+// Returned as a dense [D] vector over the job's feature dictionary, 0 = not listed (features outside the dictionary cannot
+// occur in any model of this job and are dropped).
+std::vector<float> read_lambda_map(const std::string& path, const Dictionary& dict) {
+  std::vector<float> lm(dict.names.size(), 0.f);
+  for (auto& f : list_avro_files(path)) {
+    AvroReader rd(f);
+    const Schema& s = rec_schema(rd.schema());
+    Value rec;
+    while (rd.next(rec)) {
+      const Value* nm = field(rec, s, "name"); const Value* vl = field(rec, s, "value");
+      if (!nm || !vl) continue;                                   // `record.get("name") != null && record.get("value") != null` (:36)
+      const Value* tm = field(rec, s, "term");
+      const float lam = (float)num_of(*vl);
+      if (!(lam > 0.f)) io_error("lambda.map: lambda of feature " + nm->s + " must be > 0 (it becomes the prior variance 1/lambda)");
+      int k = dict.find(feature_key(nm->s, tm ? tm->s : ""));
+      if (k >= 0) lm[k] = lam;
+    }
+  }
+  return lm;
+}
 
 std::vector<float> parse_lambdas(const JobConfig& c) {
   std::vector<float> l;
@@ -350,7 +426,11 @@ void run_prepare(const JobConfig& c) {
       if (!mapkey.empty()) {
         const Value* k = field(rec, s, mapkey);
         if (!k) io_error("map.key is wrongly specified! No such key exists in some lines of the data!");
-        key = k->type == Schema::String ? k->s : (k->type == Schema::Float || k->type == Schema::Double) ? std::to_string(k->d) : std::to_string(k->i);
+        // data.get(map.key).toString() (:107): Float / Double print as Java does ("1.0", not "1.000000"), Boolean as true / false
+        key = k->type == Schema::String ? k->s
+              : k->type == Schema::Float ? java_float_to_string((float)k->d)
+              : k->type == Schema::Double ? java_double_to_string(k->d)
+              : k->type == Schema::Boolean ? (k->i ? "true" : "false") : std::to_string(k->i);
       } else {
         key = std::to_string((int)std::floor(rng.next() * nblocks));
       }
@@ -369,14 +449,21 @@ void run_prepare(const JobConfig& c) {
       }
       double weight = 1.0;
       if (auto wv = field(rec, s, "weight")) weight = num_of(*wv);
-      if (auto rv = field(rec, s, "response")) { if (num_of(*rv) == 1) weight = weight / reps; }   // tests field `response` (:159)
+      {
+        // Util.getIntAvro(data, "response") (:159, utils/Util.java:55-63): the field must exist and be an Integer, even when the
+        // response itself was taken from click / label
+        const Value* rv = field(rec, s, "response");
+        if (!rv) io_error("response is null");
+        if (rv->type != Schema::Int) io_error("response=" + std::string(rv->type == Schema::Boolean ? (rv->i ? "true" : "false") : "?") + " is not an integer");
+        if (rv->i == 1) weight = weight / reps;
+      }
       double offset = 0.0;
       if (auto ov = field(rec, s, "offset")) offset = num_of(*ov);
       Value o; o.type = Schema::Record; o.items.resize(5);
       o.items[1] = Value::of_int(response); o.items[2] = feats;
       o.items[3] = Value::of_float((float)weight); o.items[4] = Value::of_float((float)offset);
       if (mapkey.empty() && response == 1) {
-        int pid = std::stoi(key);
+        int pid = java_parse_int(key);
         for (int i = 0; i < reps; i++) {
           if (pid >= nblocks) pid -= nblocks;
           o.items[0] = Value::of_string(std::to_string(pid));
@@ -408,7 +495,6 @@ void run_admm_train(const JobConfig& c) {
     if ((int)rhos.size() != L) io_error("The number of rho's should be exactly the same as the number of lambda's. OR: don't claim rho!");
   } else for (float l : lambdas) rhos.push_back(l <= 100 ? 1.0f : 10.0f);
   const float boost_rate = c.get_float("initialize.boost.rate", 0);
-  if (!c.get("lambda.map", "").empty()) io_error("lambda.map files are not wired into the host job yet (the C ABI accepts a per-feature lambda_map)");
 
   Dictionary dict;
   Rows rows;
@@ -418,30 +504,36 @@ void run_admm_train(const JobConfig& c) {
   // group rows by partition id (AdmmMapper: Integer.parseInt(key), :558; AdmmPartitioner range check :585-588)
   std::vector<std::vector<size_t>> by_part(nblocks);
   for (size_t i = 0; i < rows.n(); i++) {
-    int p;
-    try { p = std::stoi(rows.key[i]); } catch (...) { io_error("For input string: \"" + rows.key[i] + "\" (partition key must be an int)"); }
+    const int p = java_parse_int(rows.key[i]);   // Integer.parseInt(key) (AdmmMapper, :558)
     if (p < 0 || p >= nblocks) io_error("Map key is wrong! key has to be in the range of [0,numPartitions-1].");
     by_part[p].push_back(i);
   }
   for (int p = 0; p < nblocks; p++) if (by_part[p].empty()) io_error("Some models failed!");   // an empty reducer emits no model (utils/LinearModelUtils.java:77-83)
 
+  std::vector<float> lambda_map;
+  if (!c.get("lambda.map", "").empty()) lambda_map = read_lambda_map(c.get("lambda.map"), dict);
+  fprintf(stderr, "[RegressionAdmmTrain] Lambda Map has size = %d\n", (int)std::count_if(lambda_map.begin(), lambda_map.end(), [](float v) { return v > 0; }));
+
+  std::vector<int32_t> devs = gpu_devices(c);
+  if ((int)devs.size() > nblocks) devs.resize(nblocks);           // a GPU without a partition has nothing to reduce
   mlease_admm_config cfg; std::memset(&cfg, 0, sizeof(cfg));
-  cfg.device = c.get_int("gpu.device", 0); cfg.num_blocks = nblocks; cfg.num_features = D; cfg.num_lambdas = L;
+  cfg.device = devs[0]; cfg.num_blocks = nblocks; cfg.num_features = D; cfg.num_lambdas = L;
   cfg.lambdas = lambdas.data(); cfg.rhos = rhos.data(); cfg.regularizer = reg;
+  cfg.lambda_map = lambda_map.empty() ? nullptr : lambda_map.data();
   cfg.penalize_intercept = c.get_bool("penalize.intercept", false);
   cfg.aggressive_decay = c.get_bool("aggressive.liblinear.epsilon.decay", false);
   cfg.binary_feature = ignore_value;
   cfg.epsilon = c.get_double("epsilon", 0.0001);
   cfg.rho_adapt_coefficient = c.get_float("rho.adapt.coefficient", 0);
-  Session S;
-  ck(mlease_session_create(&cfg, &S.s));
+  World S;
+  ck(mlease_world_create(&cfg, devs.data(), (int32_t)devs.size(), &S.w));
   for (int p = 0; p < nblocks; p++) {
     std::vector<int64_t> rp{0}; std::vector<int32_t> ci; std::vector<float> vv, ww, oo; std::vector<int32_t> rr;
     for (size_t i : by_part[p]) {
       for (int64_t j = rows.rowptr[i]; j < rows.rowptr[i + 1]; j++) { ci.push_back(rows.colidx[j]); vv.push_back(rows.vals[j]); }
       rp.push_back((int64_t)ci.size()); rr.push_back(rows.response[i]); ww.push_back(rows.weight[i]); oo.push_back(rows.offset[i]);
     }
-    ck(mlease_add_partition_csr(S.s, p, (int64_t)rr.size(), rp.data(), ci.data(), vv.data(), rr.data(), ww.data(), oo.data()));
+    ck(mlease_world_add_partition_csr(S.w, p, (int64_t)rr.size(), rp.data(), ci.data(), vv.data(), rr.data(), ww.data(), oo.data()));
   }
 
   // lambda-rho map (:200-201, :721-734)
@@ -466,7 +558,7 @@ void run_admm_train(const JobConfig& c) {
   auto models_z = [&](bool as_float) {
     std::vector<std::pair<std::string, std::vector<float>>> m;
     for (int l = 0; l < L; l++) {
-      std::vector<double> z(Dt); ck(mlease_get_z(S.s, l, z.data()));
+      std::vector<double> z(Dt); ck(mlease_world_get_z(S.w, l, z.data()));
       std::vector<float> zf(Dt); for (int k = 0; k < Dt; k++) zf[k] = (float)z[k];
       m.emplace_back(java_float_to_string(lambdas[l]), zf);
     }
@@ -482,20 +574,21 @@ void run_admm_train(const JobConfig& c) {
     std::vector<std::pair<std::string, std::vector<float>>> init_models;
     for (int l = 0; l < L; l++) {
       std::vector<double> q(Dt, (double)lambdas[l]), zero(Dt, 0.0);
+      for (int k = 0; k < D; k++) if (!lambda_map.empty() && lambda_map[k] > 0) q[k] = (double)lambda_map[k];   // propsIni.put(LAMBDA_MAP, ...) (:248)
       if (!cfg.penalize_intercept) q[D] = 1.0 / 100000.0;
       for (int p = 0; p < nblocks; p++) {
         std::vector<double> x(Dt, 0.0);
         int32_t steps = 0;
-        ck(mlease_fit_partition(S.s, p, x.data(), zero.data(), q.data(), &steps));
+        ck(mlease_world_fit_partition(S.w, p, x.data(), zero.data(), q.data(), &steps));
         std::vector<float> xf(Dt);
         for (int k = 0; k < Dt; k++) { xf[k] = (float)x[k]; z0[(size_t)l * Dt + k] = 1.0 * z0[(size_t)l * Dt + k] + (1.0 / nblocks) * (double)xf[k]; }
         init_models.emplace_back(java_float_to_string(lambdas[l]) + "#" + std::to_string(p), xf);
       }
     }
     write_linear_models(out + "/initialModel/part-r-00000.avro", dict, init_models);
-    ck(mlease_admm_begin_initialized(S.s, z0.data(), boost_rate));
+    ck(mlease_world_begin_initialized(S.w, z0.data(), boost_rate));
   } else {
-    ck(mlease_admm_begin(S.s));
+    ck(mlease_world_begin(S.w));
   }
   int i;
   for (i = 1; i <= niter; i++) {
@@ -505,7 +598,7 @@ void run_admm_train(const JobConfig& c) {
       std::vector<std::pair<std::string, std::vector<float>>> us;
       if (i > 1)
         for (int p = 0; p < nblocks; p++) for (int l = 0; l < L; l++) {
-          std::vector<float> u(Dt); ck(mlease_get_u(S.s, p, l, u.data()));
+          std::vector<float> u(Dt); ck(mlease_world_get_u(S.w, p, l, u.data()));
           us.emplace_back(java_float_to_string(lambdas[l]) + "#" + std::to_string(p), u);
         }
       write_linear_models(it + "/u/part-r-00000.avro", dict, us);
@@ -517,13 +610,13 @@ void run_admm_train(const JobConfig& c) {
       }
     }
     double maxdiff = 0; int32_t stop = 0;
-    ck(mlease_admm_iterate(S.s, &maxdiff, &stop));
+    ck(mlease_world_iterate(S.w, &maxdiff, &stop));
     // reducer outputs (:706-711)
     {
       AvroWriter w(it + "/model/part-r-00000.avro", schema_train_output());
       for (int p = 0; p < nblocks; p++) for (int l = 0; l < L; l++) {
         std::vector<double> x(Dt); std::vector<float> xf(Dt), ux(Dt);
-        ck(mlease_get_x(S.s, p, l, x.data())); ck(mlease_get_uplusx(S.s, p, l, ux.data()));
+        ck(mlease_world_get_x(S.w, p, l, x.data())); ck(mlease_world_get_uplusx(S.w, p, l, ux.data()));
         for (int k = 0; k < Dt; k++) xf[k] = (float)x[k];
         Value r; r.type = Schema::Record; r.items.resize(3);
         r.items[0] = Value::of_string(java_float_to_string(lambdas[l]) + "#" + std::to_string(p));
@@ -537,7 +630,7 @@ void run_admm_train(const JobConfig& c) {
     if (test_per_iter) {   // updateLogLikBestModel (:812-845)
       AvroWriter w(out + "/sample-test-loglik/iteration-" + std::to_string(i) + ".avro", SCHEMA_SAMPLE_LOGLIK);
       for (int l = 0; l < L; l++) {
-        std::vector<double> z(Dt); ck(mlease_get_z(S.s, l, z.data()));
+        std::vector<double> z(Dt); ck(mlease_world_get_z(S.w, l, z.data()));
         double ll = sample_test_loglik(test, dict, test2model, z);
         Value r; r.type = Schema::Record; r.items = {Value::of_string(java_float_to_string(lambdas[l])), Value::of_int(i), Value::of_float((float)ll)};
         w.append(r);
@@ -647,13 +740,14 @@ void run_naive_train(const JobConfig& c) {
   const bool mean = c.get_bool("compute.model.mean", true);
   const int nblocks = mean ? c.get_int("num.blocks") : -1;
   const bool ignore_value = c.get_bool("binary.feature", false);
-  if (ignore_value) io_error("binary.feature needs CSR input; the dense NaiveTrain path does not support it");
-  if (!c.get("lambda.map", "").empty()) io_error("lambda.map files are not wired into the host job yet");
   std::set<float> lambda_set; for (auto& t : c.get_list("lambda")) lambda_set.insert(std::stof(t));
   std::vector<float> lambdas(lambda_set.begin(), lambda_set.end());
+  const int L = (int)lambdas.size();
   Dictionary dict; Rows rows;
-  read_prepared(c.get("input.paths", out + "/tmp-data"), dict, rows, false);
+  read_prepared(c.get("input.paths", out + "/tmp-data"), dict, rows, ignore_value);
   const int D = (int)dict.names.size(), Dt = D + 1;
+  std::vector<float> lambda_map;
+  if (!c.get("lambda.map", "").empty()) lambda_map = read_lambda_map(c.get("lambda.map"), dict);
   std::map<std::string, std::vector<size_t>> by_key;
   for (size_t i = 0; i < rows.n(); i++) by_key[rows.key[i]].push_back(i);
   if (heavy) {
@@ -662,31 +756,35 @@ void run_naive_train(const JobConfig& c) {
     for (auto& kv : assign_partition_ids(ks, lambdas)) { Value r; r.type = Schema::Record; r.items = {Value::of_string(kv.first), Value::of_int(kv.second)}; w.append(r); }
     w.close();
   }
-  // dense gather (features absent from a row are 0; a feature absent from a key is an all-zero column -> coefficient = prior mean)
+  // per-key sparse datasets (jobs/RegressionNaiveTrain.java:360-378): the rows of one key are contiguous in ONE CSR, uploaded
+  // once for all lambdas; a feature no row of the key lists is not part of that key's model
   const int K = (int)by_key.size();
-  std::vector<int64_t> krs{0}; std::vector<std::string> knames;
-  std::vector<float> X((size_t)rows.n() * D, 0.f), ww, oo; std::vector<int32_t> rr;
-  size_t r = 0;
+  std::vector<int64_t> krs{0}, rp{0}; std::vector<std::string> knames;
+  std::vector<int32_t> ci, rr; std::vector<float> vv, ww, oo;
   for (auto& kv : by_key) {
     knames.push_back(kv.first);
     for (size_t i : kv.second) {
-      for (int64_t j = rows.rowptr[i]; j < rows.rowptr[i + 1]; j++) X[r * D + rows.colidx[j]] += rows.vals[j];
-      rr.push_back(rows.response[i]); ww.push_back(rows.weight[i]); oo.push_back(rows.offset[i]); r++;
+      std::vector<std::pair<int32_t, float>> ent;
+      for (int64_t j = rows.rowptr[i]; j < rows.rowptr[i + 1]; j++) ent.emplace_back(rows.colidx[j], rows.vals[j]);
+      std::sort(ent.begin(), ent.end(), [](auto& a, auto& b) { return a.first < b.first; });   // rows sorted by index (llf/LibLinearDataset.java:481-482)
+      for (auto& e : ent) { ci.push_back(e.first); vv.push_back(e.second); }
+      rp.push_back((int64_t)ci.size());
+      rr.push_back(rows.response[i]); ww.push_back(rows.weight[i]); oo.push_back(rows.offset[i]);
     }
-    krs.push_back((int64_t)r);
+    krs.push_back((int64_t)rr.size());
   }
   std::vector<std::pair<std::string, std::vector<float>>> models;
   std::map<std::string, std::pair<int, std::vector<double>>> sums;
-  for (float lam : lambdas) {
-    std::vector<double> m((size_t)K * Dt); std::vector<int32_t> skipped(K);
-    ck(mlease_naive_train_dense(c.get_int("gpu.device", 0), nullptr, K, D, krs.data(), X.data(), D, rr.data(), ww.data(), oo.data(), lam, nullptr,
-                                c.get_float("prior.mean", 0.0f), c.get_bool("penalize.intercept", false), c.get_bool("has.intercept", true),
-                                c.get_int("data.size.threshold", 0), m.data(), skipped.data()));
-    const std::string ls = java_float_to_string(lam);
+  std::vector<double> m((size_t)L * K * Dt); std::vector<int32_t> skipped(K);
+  ck(mlease_naive_train(gpu_devices(c)[0], nullptr, K, D, krs.data(), rp.data(), ci.data(), vv.data(), 0, rr.data(), ww.data(), oo.data(), L, lambdas.data(),
+                        lambda_map.empty() ? nullptr : lambda_map.data(), c.get_float("prior.mean", 0.0f), c.get_bool("penalize.intercept", false),
+                        c.get_bool("has.intercept", true), c.get_int("data.size.threshold", 0), ignore_value ? 1 : 0, m.data(), skipped.data()));
+  for (int l = 0; l < L; l++) {
+    const std::string ls = java_float_to_string(lambdas[l]);
     auto& acc = sums[ls]; acc.second.assign(Dt, 0.0);
     for (int k = 0; k < K; k++) {
       if (skipped[k]) continue;
-      std::vector<float> mf(Dt); for (int j = 0; j < Dt; j++) mf[j] = (float)m[(size_t)k * Dt + j];
+      std::vector<float> mf(Dt); for (int j = 0; j < Dt; j++) mf[j] = (float)m[((size_t)l * K + k) * Dt + j];
       models.emplace_back(ls + "#" + knames[k], mf);
       acc.first++;
       if (mean) for (int j = 0; j < Dt; j++) acc.second[j] = 1.0 * acc.second[j] + (1.0 / nblocks) * (double)mf[j];   // cons/MeanLinearModelConsumer.java:59-63

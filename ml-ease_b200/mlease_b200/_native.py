@@ -73,6 +73,29 @@ def lib():
             "mlease_test_loglik": [i32, vp, i64, vp, vp, vp, i64, C.POINTER(f32), C.POINTER(f64)],
             "mlease_time_kernel": [vp, i32, i32, i32, i32, C.POINTER(f32)],
             "mlease_profile": [vp, i32, vp, vp, C.POINTER(f64), C.POINTER(f64), C.POINTER(f64)],
+            "mlease_posterior_variance": [vp, i32, vp, vp, i32, vp, vp],
+            "mlease_naive_train": [i32, vp, i32, i32, vp, vp, vp, vp, i64, vp, vp, vp, i32, vp, vp, f32, i32, i32, i32, i32, vp, vp],
+            "mlease_comm_unique_id": [vp],
+            "mlease_comm_create": [vp, i32, i32, i32, C.POINTER(vp)],
+            "mlease_comm_destroy": [vp],
+            "mlease_comm_info": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
+            "mlease_session_set_comm": [vp, vp],
+            "mlease_world_create": [C.POINTER(AdmmConfigC), vp, i32, C.POINTER(vp)],
+            "mlease_world_destroy": [vp],
+            "mlease_world_num_devices": [vp],
+            "mlease_world_add_partition_dense": [vp, i32, i64, vp, i64, vp, vp, vp],
+            "mlease_world_add_partition_csr": [vp, i32, i64, vp, vp, vp, vp, vp, vp],
+            "mlease_world_begin": [vp],
+            "mlease_world_begin_initialized": [vp, vp, C.c_float],
+            "mlease_world_iterate": [vp, C.POINTER(f64), C.POINTER(i32)],
+            "mlease_world_run": [vp, i32, C.POINTER(i32)],
+            "mlease_world_get_z": [vp, i32, vp],
+            "mlease_world_get_final_model": [vp, i32, vp],
+            "mlease_world_get_x": [vp, i32, i32, vp],
+            "mlease_world_get_u": [vp, i32, i32, vp],
+            "mlease_world_get_uplusx": [vp, i32, i32, vp],
+            "mlease_world_fit_partition": [vp, i32, vp, vp, vp, C.POINTER(i32)],
+            "mlease_world_get_stats": [vp, C.POINTER(StatsC)],
         }
         for name, args in sig.items():
             fn = getattr(_lib, name)
@@ -86,7 +109,12 @@ EXPORTED = ["mlease_last_error", "mlease_abi_version", "mlease_session_create", 
             "mlease_add_partition_dense", "mlease_add_partition_csr", "mlease_admm_begin", "mlease_admm_begin_initialized", "mlease_admm_local_step",
             "mlease_admm_consensus", "mlease_admm_run", "mlease_admm_iterate", "mlease_get_z", "mlease_get_final_model", "mlease_get_x", "mlease_get_u",
             "mlease_get_uplusx", "mlease_get_stats", "mlease_objective", "mlease_fit_partition", "mlease_naive_train_dense",
-            "mlease_score", "mlease_test_loglik", "mlease_time_kernel", "mlease_profile"]
+            "mlease_score", "mlease_test_loglik", "mlease_time_kernel", "mlease_profile",
+            "mlease_posterior_variance", "mlease_naive_train", "mlease_comm_unique_id", "mlease_comm_create", "mlease_comm_destroy", "mlease_comm_info", "mlease_session_set_comm",
+            "mlease_world_create", "mlease_world_destroy", "mlease_world_num_devices", "mlease_world_add_partition_dense",
+            "mlease_world_add_partition_csr", "mlease_world_begin", "mlease_world_begin_initialized", "mlease_world_iterate",
+            "mlease_world_run", "mlease_world_get_z", "mlease_world_get_final_model", "mlease_world_get_x", "mlease_world_get_u",
+            "mlease_world_get_uplusx", "mlease_world_fit_partition", "mlease_world_get_stats"]
 
 
 def check(rc):

@@ -1,4 +1,9 @@
-"""One process per GPU: partition sharding and the per-iteration all-reduce (torch.distributed is plumbing only).
+"""One process per GPU: partition sharding and the per-iteration all-reduce.
+
+Product path (`make_comm` + `AdmmSession.set_comm` + `session.run`): the all-reduce is the library's own NCCL call inside the
+C loop (csrc/comm.cu); torch.distributed only ships the 128-byte NCCL id between the processes.  `admm_loop` below is the
+same control flow written out in Python over an abstract backend -- it is what the gloo CPU tests drive (and a fallback
+driver for callers that want to own the collective through the `mlease_allreduce_fn` callback).
 
 The path shards exactly where ADMM does: partitions are independent in the x-update (AdmmReducer.reduce,
 jobs/RegressionAdmmTrain.java:642-718) and meet in ONE exchange per iteration, the mean of x+u the driver
@@ -56,10 +61,30 @@ class CudaAdmmBackend:
         return self.session.consensus(exchange.data_ptr())
 
 
-def run_distributed(session, num_iters, group=None):
-    """Multi-process ADMM: all ranks call this with their own session (local partitions already added)."""
+def make_comm(device, group=None):
+    """The library's NCCL communicator for this rank of an initialised torch.distributed job (None for a single process):
+    rank 0 draws the id, torch.distributed broadcasts the 128 bytes, every rank joins with its own GPU."""
     import torch.distributed as dist
-    be = CudaAdmmBackend(session)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        return admm_loop(be, num_iters, lambda buf: dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group))
-    return admm_loop(be, num_iters, None)
+    from .admm import Comm
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return Comm(box[0], rank, world, device)
+
+
+def run_distributed(session, num_iters, group=None, comm=None):
+    """Multi-process ADMM: all ranks call this with their own session (local partitions already added).  The loop runs in C
+    (mlease_admm_run) with one ncclAllReduce per iteration on the session's stream.  Returns (iters_done, [last maxdiff])."""
+    own = comm is None
+    if own:
+        comm = make_comm(session.device, group)
+    session.set_comm(comm)
+    try:
+        done = session.run(num_iters)
+        return done, [session.stats()["last_maxdiff"]]
+    finally:
+        session.set_comm(None)
+        if own and comm is not None:
+            comm.close()

@@ -595,3 +595,145 @@ def test_errors_follow_reference_conventions(mb):
         s.add_partition_dense(0, X, y)
         with pytest.raises(mb.MleaseError, match="Some models failed"):
             s.run(2)
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_posterior_variance_diag_and_full(mb, sparse):
+    """ItemModelTrain's "posteriorVar" (jobs/ItemModelTrain.java:257-266): LibLinear.train's computePosteriorVar tail
+    (llf/LibLinear.java:315-334).  Diagonal mode = 1 / hessianDiagonal (llf/LogisticRegressionL2.java:304-327); full mode =
+    diag of the inverse of hessian() (:258-297).  The GPU accumulates the Hessian in fp64 from the fp32 data, so the
+    tolerance is 1e-9 / 1e-8 relative, not the bf16 Gram's."""
+    n, d = 2500, 45
+    X, y, w, o = _mk(n, d, seed=17, sparse=sparse, density=0.25)
+    rng = np.random.default_rng(2)
+    pm = rng.normal(0, 0.2, d + 1); pv = rng.uniform(0.3, 3.0, d + 1)
+    with _session(mb, d) as s:
+        if sparse:
+            rp, ci, v = _csr_of(X)
+            s.add_partition_csr(0, rp, ci, v, y, w, o)
+            data = orc.Csr(rp, ci, v, y, w, o, d)
+        else:
+            s.add_partition_dense(0, X, y, w, o)
+            data = orc.Csr.from_dense(X, y, w, o)
+        x, _ = s.fit_partition(0, np.zeros(d + 1), pm, 1.0 / pv)
+        var_d = s.posterior_variance(0, x, 1.0 / pv)
+        var_f, cov = s.posterior_variance(0, x, 1.0 / pv, full=True, want_cov=True)
+        x2, _ = s.fit_partition(0, np.zeros(d + 1), pm, 1.0 / pv)        # the scratch factor was overwritten: the next fit rebuilds
+    hd = orc.objective("hessian_diag", data, x, pm, pv)
+    assert np.abs(var_d - 1.0 / hd).max() <= 1e-9 * np.abs(1.0 / hd).max()
+    H = orc.objective("hessian", data, x, pm, pv)
+    ref = np.linalg.inv(H)
+    assert np.abs(cov - ref).max() <= 1e-8 * np.abs(ref).max()
+    assert np.array_equal(var_f, np.diag(cov)) and np.abs(cov - cov.T).max() == 0.0
+    assert np.all(var_f >= var_d * (1 - 1e-12))                           # diag(H^-1) >= 1 / diag(H) for SPD H
+    assert np.abs(x2 - x).max() <= 1e-9 * np.abs(x).max()
+    with _session(mb, d) as s:
+        s.add_partition_dense(0, X, y, w, o)
+        with pytest.raises(mb.MleaseError, match="full = 1"):
+            import ctypes as C
+            from mlease_b200._native import check, lib, ptr
+            cov = np.zeros((d + 1, d + 1)); var = np.zeros(d + 1)
+            check(lib().mlease_posterior_variance(s._h, 0, ptr(x), ptr(1.0 / pv), 0, ptr(var), ptr(cov)))
+
+
+def test_naive_train_csr_multi_lambda_lambda_map_and_absent_features(mb):
+    """RegressionNaiveTrain on per-key SPARSE datasets (jobs/RegressionNaiveTrain.java:360-398): one CSR upload, keys = row ranges,
+    all lambdas in one call.  A feature no row of a key lists is not in that key's model (coefficient 0 even with prior.mean != 0);
+    lambda.map gives listed features their own prior variance; binary.feature counts every listed feature as 1."""
+    K, n, D, nnz = 6, 400, 80, 9
+    r = np.random.default_rng(8)
+    beta = r.normal(size=D) / np.sqrt(nnz)
+    ci = np.stack([np.sort(r.choice(D - 10 * (i // n % 2), nnz, replace=False)) for i in range(K * n)]).astype(np.int32)   # odd keys never see the last 10 features
+    v = r.normal(size=(K * n, nnz)).astype(np.float32)
+    y = (r.random(K * n) < 1 / (1 + np.exp(-((v * beta[ci]).sum(1) - 0.4)))).astype(np.int32)
+    w = r.uniform(0.5, 2.0, K * n).astype(np.float32); o = r.normal(0, 0.1, K * n).astype(np.float32)
+    rp = np.arange(K * n + 1, dtype=np.int64) * nnz
+    krs = np.arange(K + 1) * n
+    data = orc.Csr(rp, ci.reshape(-1), v.reshape(-1), y, w, o, D)
+    lm = np.zeros(D, np.float32); lm[[1, 5, 40]] = [0.02, 9.0, 2.0]
+    lambdas = [0.5, 4.0]
+    got, skipped = mb.naive_train(v.reshape(-1), krs, y, lambdas, rowptr=rp, colidx=ci.reshape(-1), num_features=D, weight=w, offset=o,
+                                  lambda_map=lm, prior_mean=0.3)
+    assert got.shape == (2, K, D + 1) and not skipped.any()
+    for li, lam in enumerate(lambdas):
+        ref, _, _ = orc.naive_train(data, krs, lam, lambda_map=lm, prior_mean=0.3, mode="exact", nthreads=6)
+        assert np.abs(got[li] - ref).max() / np.abs(ref).max() < 1e-5, li
+        assert np.all(got[li][1::2, D - 10:D] == 0.0) and np.all(ref[1::2, D - 10:D] == 0.0)     # absent features: not in the model
+    # binary.feature == the same call on explicit ones; has.intercept = false; data.size.threshold
+    gb, _ = mb.naive_train(v.reshape(-1), krs, y, [1.0], rowptr=rp, colidx=ci.reshape(-1), num_features=D, weight=w, offset=o, binary_feature=True)
+    ones = orc.Csr(rp, ci.reshape(-1), np.ones(K * n * nnz, np.float32), y, w, o, D)
+    rb, _, _ = orc.naive_train(ones, krs, 1.0, mode="exact", nthreads=6)
+    assert np.abs(gb[0] - rb).max() / np.abs(rb).max() < 1e-5
+    gn, sk = mb.naive_train(v.reshape(-1), krs, y, [1.0], rowptr=rp, colidx=ci.reshape(-1), num_features=D, has_intercept=False, data_size_threshold=401)
+    assert sk.all() and not gn.any()
+    gn, sk = mb.naive_train(v.reshape(-1), krs, y, [1.0], rowptr=rp, colidx=ci.reshape(-1), num_features=D, weight=w, has_intercept=False, penalize_intercept=True)
+    rn, _, _ = orc.naive_train(orc.Csr(rp, ci.reshape(-1), v.reshape(-1), y, w, None, D), krs, 1.0, has_intercept=False, penalize_intercept=True, mode="exact", nthreads=6)
+    assert np.abs(gn[0] - rn).max() / np.abs(rn).max() < 1e-5 and np.all(gn[0][:, -1] == 0)
+    # the dense entry point is the same code on dense rows
+    Xd = np.zeros((K * n, D), np.float32)
+    np.put_along_axis(Xd, ci.astype(np.int64), v, axis=1)
+    gd, _ = mb.naive_train(Xd, krs, y, lambdas, weight=w, offset=o)
+    g1, _ = mb.naive_train_dense(Xd, krs, y, lambdas[1], weight=w, offset=o)
+    assert np.array_equal(gd[1], g1)
+    rd, _, _ = orc.naive_train(orc.Csr.from_dense(Xd, y, w, o), krs, lambdas[1], mode="exact", nthreads=6)
+    assert np.abs(g1 - rd).max() / np.abs(rd).max() < 1e-5
+
+
+def test_world_of_one_gpu_is_a_session(mb, fixture_data, frozen):
+    """mlease_world with a single device = the session calls (no NCCL involved): same z, x, u as the frozen oracle run."""
+    d = fixture_data
+    prs = frozen["part_rowstart"]
+    with mb.World([0], len(prs) - 1, d.n_features, [1.0, 10.0, 100.0], epsilon=0.0) as w:
+        for p in range(len(prs) - 1):
+            r0, r1 = prs[p], prs[p + 1]
+            sl = slice(d.rowptr[r0], d.rowptr[r1])
+            w.add_partition_csr(p, d.rowptr[r0:r1 + 1] - d.rowptr[r0], d.colidx[sl], d.val[sl], d.response[r0:r1], d.weight[r0:r1], d.offset[r0:r1])
+        assert w.run(20) == 20
+        for l in range(3):
+            ref = frozen["exact_z_hist"][19, l]
+            assert np.abs(w.z(l) - ref).max() / np.abs(ref).max() < 1e-5
+        xs = np.stack([[w.x(p, l) for l in range(3)] for p in range(len(prs) - 1)])
+        assert np.abs(xs - frozen["exact_x_last"]).max() / np.abs(frozen["exact_x_last"]).max() < 1e-5
+        assert w.stats()["not_converged"] == 0
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
+def test_two_gpus_world_and_process_per_gpu_match_the_oracle(mb, fixture_data, frozen, tmp_path):
+    """N = 2, both ways the boundary offers it: (b) one process, mlease_world over GPUs 0 and 1; (a) one process per GPU with the
+    library's NCCL communicator (tests/dist_worker.py under torch.distributed.run).  Same z as the oracle's exact run."""
+    import subprocess
+    import sys
+    d = fixture_data
+    prs = frozen["part_rowstart"]
+    with mb.World([0, 1], len(prs) - 1, d.n_features, [1.0, 10.0, 100.0], epsilon=0.0) as w:
+        for p in range(len(prs) - 1):
+            r0, r1 = prs[p], prs[p + 1]
+            sl = slice(d.rowptr[r0], d.rowptr[r1])
+            w.add_partition_csr(p, d.rowptr[r0:r1 + 1] - d.rowptr[r0], d.colidx[sl], d.val[sl], d.response[r0:r1], d.weight[r0:r1], d.offset[r0:r1])
+        w.begin()
+        for it in range(20):
+            md, stop = w.iterate()
+        zw = np.stack([w.z(l) for l in range(3)])
+        us = np.stack([w.u(p, 0) for p in range(len(prs) - 1)])
+    for l in range(3):
+        ref = frozen["exact_z_hist"][19, l]
+        assert np.abs(zw[l] - ref).max() / np.abs(ref).max() < 1e-5
+    assert abs(us[:, -1].astype(np.float64).sum()) < 1e-5
+    out = str(tmp_path / "z.npy")
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29531", __import__("os").path.join(root, "tests", "dist_worker.py"), out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    zp = np.load(out)
+    for l in range(3):
+        ref = frozen["exact_z_hist"][19, l]
+        assert np.abs(zp[l] - ref).max() / np.abs(ref).max() < 1e-5
+    assert np.abs(zp - zw).max() <= 1e-6 * np.abs(zw).max()

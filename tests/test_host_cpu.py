@@ -138,3 +138,46 @@ def test_job_config_errors(host, tmp_path):
     assert rc != 0 and "unknown job class" in err
     rc, err = _run(host, "RegressionAdmmTrain", str(tmp_path / "missing.job"))
     assert rc != 0 and "cannot open" in err
+
+
+def test_corrupt_and_truncated_avro_files_are_errors_not_overruns(host, tmp_path):
+    """Every read of file content is bounds-checked: a truncated or corrupted container is an error message."""
+    npz = np.load(os.path.join(GOLDEN, "sample_data.npz"))
+    src = str(tmp_path / "in.avro")
+    au.write_avro(src, au.PIG_SCHEMA, au.fixture_records(npz)[:60], block=20)
+    raw = open(src, "rb").read()
+    n, nb = C.c_int64(0), C.c_int64(0)
+    for name, blob in (("trunc_mid", raw[:len(raw) // 2]), ("trunc_tail", raw[:-5]), ("trunc_head", raw[:40]),
+                       ("bad_len", raw[:-400] + b"\xff\xff\xff\xff\xff\xff\xff\xff\xff\xff\x7f" + raw[-389:])):
+        bad = str(tmp_path / (name + ".avro"))
+        open(bad, "wb").write(blob)
+        rc = host.mlease_avro_copy(bad.encode(), str(tmp_path / "o.avro").encode(), b"null", C.byref(n), C.byref(nb))
+        assert rc != 0, name
+        assert "avro" in host.mlease_job_last_error().decode(), name
+
+
+def test_prepare_key_strings_and_strict_partition_keys_follow_java(host, tmp_path):
+    """map.key values print as Java's toString ("1.0" for a float/double 1, not "1.000000"); the `response` field itself must
+    exist as an int (Util.getIntAvro, jobs/RegressionPrepare.java:159); AdmmTrain's partition keys go through Integer.parseInt
+    (:558): "1.9" or "3abc" are NumberFormatExceptions, not partition 1 / 3."""
+    schema = {"type": "record", "name": "r", "fields": [
+        {"name": "features", "type": {"type": "array", "items": {"type": "record", "name": "f", "fields": [
+            {"name": "name", "type": "string"}, {"name": "term", "type": "string"}, {"name": "value", "type": "float"}]}}},
+        {"name": "response", "type": ["null", "int"]}, {"name": "fkey", "type": "double"}, {"name": "gkey", "type": "float"}]}
+    recs = [{"features": [{"name": "a", "term": "", "value": 1.0}], "response": i % 2, "fkey": float(i % 3), "gkey": 0.5 + i % 2} for i in range(12)]
+    au.write_avro(str(tmp_path / "in" / "p.avro"), schema, recs)
+    for mk, expect in (("fkey", ["0.0", "1.0", "2.0"]), ("gkey", ["0.5", "1.5"])):
+        cfg = _write_cfg(str(tmp_path / (mk + ".job")), input_paths=str(tmp_path / "in"), output_path=str(tmp_path / ("out_" + mk)), map_key=mk, num_blocks=3)
+        rc, err = _run(host, "RegressionPrepare", cfg)
+        assert rc == 0, err
+        assert sorted({r["key"] for r in au.read_dir(str(tmp_path / ("out_" + mk)))}) == expect
+    recs2 = [dict(r, response=None) for r in recs]
+    au.write_avro(str(tmp_path / "in2" / "p.avro"), schema, recs2)
+    cfg = _write_cfg(str(tmp_path / "nr.job"), input_paths=str(tmp_path / "in2"), output_path=str(tmp_path / "out_nr"), map_key="fkey", num_blocks=3)
+    rc, err = _run(host, "RegressionPrepare", cfg)
+    assert rc != 0 and ("response" in err)
+    # AdmmTrain on prepared data whose keys are "0.0", "1.0", "2.0": rejected before any GPU work
+    cfg = _write_cfg(str(tmp_path / "t.job"), input_paths=str(tmp_path / "out_fkey"), output_base_path=str(tmp_path / "o"), num_blocks=3, regularizer=2)
+    open(cfg, "a").write("lambda=1\n")
+    rc, err = _run(host, "RegressionAdmmTrain", cfg)
+    assert rc != 0 and 'For input string: "' in err

@@ -168,6 +168,10 @@ typedef struct {
   int32_t last_iter_slots;  /* evaluation slots used by the last local_step */
   double last_maxdiff;
   float liblinear_epsilon;  /* schedule variable (:279,338-346), control only */
+  int32_t k1_fused;         /* 1: the fused multi-lambda CSR K1 (csrc/k1_csr_fused.cu) serves this session's ADMM problems */
+  double k1_shared_bytes;   /* CSR sessions: K1 bytes when the lambdas of a partition count as ONE read of its rows
+                               (8*nnz + 9*n per partition pass + 8*n per lambda served); k1_bytes of mlease_profile counts every
+                               (partition, lambda) pass separately, as SURVEY 8d defines the unit */
 } mlease_stats;
 int mlease_get_stats(mlease_session* s, mlease_stats* out);
 int mlease_world_get_stats(mlease_world* w, mlease_stats* out);   /* counters summed over the devices */

@@ -284,6 +284,7 @@ int mlease_world_get_stats(mlease_world* w, mlease_stats* out) {
     if (int rc = mlease_get_stats(w->sess[d], &s)) return rc;
     out->k1_passes += s.k1_passes; out->gram_builds += s.gram_builds; out->newton_steps += s.newton_steps;
     out->rejected_steps += s.rejected_steps; out->kernel_launches += s.kernel_launches; out->not_converged += s.not_converged;
+    out->k1_shared_bytes += s.k1_shared_bytes; out->k1_fused = s.k1_fused;
     if (d == 0) { out->last_iter_slots = s.last_iter_slots; out->last_maxdiff = s.last_maxdiff; out->liblinear_epsilon = s.liblinear_epsilon; }
   }
   return 0;

@@ -74,6 +74,15 @@ struct Problem {
   long long bm_groups;            // number of 32-row groups
   float vmax, wmax;               // max |stored value| and max record weight of the partition (fixed-point scale of the CSR K1)
   int nblk128;             // number of 128-column blocks (Dp / 128)
+  // fused multi-lambda CSR K1 (k1_csr_fused.cu): the partition's rows cut into sg_S segments of sg_rows rows; per segment the
+  // stored values regrouped by column: 32 columns (lanes) per group, groups of columns of similar length, entries [k][lane]
+  int sg_S, sg_rows, sg_ngrp;
+  const int* sg_perm;               // [sg_S][sg_ngrp*32] column id of each lane slot, -1 = unused slot
+  const int* sg_depth;              // [sg_S][sg_ngrp] entries per lane of the group
+  const long long* sg_goff;         // [sg_S][sg_ngrp] first 32-lane row of the group in sg_row16 / sg_val
+  const unsigned short* sg_row16;   // [..][32] row inside the segment
+  const float* sg_val;              // [..][32] value (0 in padding slots)
+  float* gpart_f;                   // [sg_S][ldx] per-segment partial gradients when the fused K1 runs (else NULL; gpart is used)
   float* sdvec;            // [n] sqrt(d_i) written by K1 when the Gram is assembled straight from CSR (no Xt)
   float* rvec;             // [n] row residuals r_i, only for CSR partitions wider than one K1 column window (else NULL)
   int gram_from_csr;       // 1: gram_csr_tcgen05_kernel builds the bf16 tiles in shared memory from the sparse rows

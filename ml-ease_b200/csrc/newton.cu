@@ -80,8 +80,10 @@ __global__ void __launch_bounds__(256) k1_partial_reduce_kernel(const Problem* _
   const int k = blockIdx.x * 32 + c;
   const int nct = pb.ctrl->k1_chunks, ldx = pb.ldx;
   double s = 0.0;
-  if (k < pb.Dt)
-    for (int t = grp; t < nct; t += 8) s += pb.gpart[(size_t)t * ldx + k];
+  if (k < pb.Dt) {
+    if (pb.gpart_f) { for (int t = grp; t < nct; t += 8) s += (double)pb.gpart_f[(size_t)t * ldx + k]; }   // fused CSR K1: fp32 per-segment partials
+    else { for (int t = grp; t < nct; t += 8) s += pb.gpart[(size_t)t * ldx + k]; }
+  }
   sh[grp][c] = s;
   __syncthreads();
   if (grp == 0 && k < pb.Dt) {

@@ -131,6 +131,10 @@ struct PartData {
   float* bm_vals = nullptr;
   long long bm_groups = 0;
   int nblk128 = 0;
+  // segment lists of the fused multi-lambda CSR K1 (k1_csr_fused.cu), built at upload for rows with unique sorted columns
+  int sg_S = 0, sg_rows = 0, sg_ngrp = 0;
+  int* sg_perm = nullptr; int* sg_depth = nullptr; long long* sg_goff = nullptr; unsigned short* sg_row16 = nullptr; float* sg_val = nullptr;
+  long long sg_total = 0;   // 32-lane rows stored (padding included)
 };
 
 // A batch of problems with identical shape that advance in lockstep through the Newton slots.
@@ -140,6 +144,10 @@ struct Batch {
   int has_bias = 1;
   int k1_grid = 1, gram_slices = 1, ntiles = 0;
   int gram_from_csr = 0;          // every problem of the batch assembles its Gram tiles from CSR (no dense bf16 operand)
+  int group_L = 1;                // problems b = g * group_L + l share the data of partition g (the lambdas of one partition)
+  int k1_fused = 0;               // the fused multi-lambda CSR K1 runs (segment lists present): one launch, grid (sg_S, nprob / group_L)
+  int k1f_LP = 1;                 // lambdas padded to 1 / 2 / 4 in the interleaved shared-memory vectors
+  size_t k1f_smem = 0;
   int k1_dyn = 0;                 // > 0: K1 CTAs are dealt to the running problems at run time (value = nprob, <= 32); k1_grid = whole grid
   int self_scale = 0;             // adapt a scalar multiplier of the stale inverse from the secant pairs (wide systems)
   int bfgs_m = BFGS_M_DEFAULT;    // secant pairs in use
@@ -163,6 +171,8 @@ struct Counters {
   double k1_bytes = 0;     // algorithmic bytes of all K1 passes: dense n*(4*ldx+9), CSR 8*nnz+8*n+9*n
   double k1_emit_bytes = 0;// extra bytes written by passes that emitted the scaled bf16 copy (n*Dp*2)
   double gram_flops = 0;   // algorithmic flops of all Gram builds: n*Dt*(Dt+1) (lower triangle, 2 flop/MAC)
+  double k1_shared_bytes = 0;  // CSR: bytes of the K1 passes when the lambdas of a partition are counted as ONE read of its rows:
+                               // per (partition, slot) with A active lambdas 8*nnz + 9*n + 8*n*A (rows once, r/d out per lambda)
 };
 
 // Optional per-kernel device timing (CUDA events on the launching stream) for bench.py's roofline.
@@ -229,6 +239,18 @@ int batch_alloc(Batch& B, int num_sms) {
   }
   B.gram_from_csr = B.csr ? 1 : 0;
   for (auto& p : B.h) if (!p.bm_offs) B.gram_from_csr = 0;
+  // fused multi-lambda CSR K1: every problem has segment lists, the groups are whole, and the shared-memory vectors fit
+  B.k1_fused = 0;
+  if (B.csr && B.gram_from_csr && B.group_L >= 1 && B.group_L <= 4 && nprob % B.group_L == 0 && !getenv("MLEASE_NO_FUSED_K1")) {
+    bool ok = true;
+    for (auto& p : B.h) if (!p.sg_perm || p.sg_S != B.h[0].sg_S || p.sg_rows != B.h[0].sg_rows) ok = false;
+    if (ok) {
+      B.k1f_LP = B.group_L <= 1 ? 1 : (B.group_L == 2 ? 2 : 4);
+      B.k1f_smem = (size_t)ldx * 4 * B.k1f_LP + (size_t)B.h[0].sg_rows * 4 * B.k1f_LP;
+      if (B.k1f_smem <= 224 * 1024) { B.k1_fused = 1; B.k1_dyn = 0; B.k1_grid = B.h[0].sg_S; }
+    }
+  }
+  const int gpart_rows = B.k1_fused ? 1 : B.k1_grid;   // the fused kernel keeps its partials in gpart_f (fp32)
   // Cost model for the rebuild policy (seconds, order of magnitude): one K1 pass streams the partition at ~5 TB/s; a rebuild
   // is n*Dt^2 bf16 flop at ~1 PFLOP/s (tcgen05 Gram, lower triangle) plus ~Dt^3 fp64 flop at ~5 TFLOP/s (Cholesky + inverse).
   {
@@ -265,11 +287,14 @@ int batch_alloc(Batch& B, int num_sms) {
     while (best > 1 && (double)best * B.Dp * B.Dp * 4.0 * nprob > 1024.0 * 1024 * 1024) best--;
     B.gram_slices = best;
   }
-  const size_t nd = (size_t)nprob * ((8 + 2 * BFGS_M) * (size_t)ldx + 2 * BFGS_M + (size_t)B.k1_grid * ldx + (size_t)B.k1_grid + 8);
+  const size_t nd = (size_t)nprob * ((8 + 2 * BFGS_M) * (size_t)ldx + 2 * BFGS_M + (size_t)gpart_rows * ldx + (size_t)B.k1_grid + 8);
   const size_t nf = (size_t)nprob * 4 * ldx;
   double* dd; float* ff; float* hp; double* lc; double* ld; double* ldi; double* yi; double* hi;
   if (int rc = dev_alloc(B, (void**)&dd, nd * sizeof(double))) return rc;
   if (int rc = dev_alloc(B, (void**)&ff, nf * sizeof(float))) return rc;
+  float* gpf = nullptr;
+  if (B.k1_fused)
+    if (int rc = dev_alloc(B, (void**)&gpf, (size_t)nprob * B.k1_grid * ldx * sizeof(float))) return rc;
   if (int rc = dev_alloc(B, (void**)&hp, (size_t)nprob * B.gram_slices * B.Dp * B.Dp * sizeof(float))) return rc;
   if (int rc = dev_alloc(B, (void**)&lc, (size_t)nprob * B.ldh * B.ldh * sizeof(double))) return rc;
   if (int rc = dev_alloc(B, (void**)&ld, (size_t)nprob * B.ldh * 32 * sizeof(double))) return rc;
@@ -306,7 +331,8 @@ int batch_alloc(Batch& B, int num_sms) {
     p.beta = q; q += ldx; p.beta_t = q; q += ldx; p.m = q; q += ldx; p.q = q; q += ldx;
     p.g_t = q; q += ldx; p.g_acc = q; q += ldx; p.dir = q; q += ldx; p.x_d = q; q += ldx;
     p.bfgs_S = q; q += (size_t)BFGS_M * ldx; p.bfgs_Y = q; q += (size_t)BFGS_M * ldx; p.bfgs_rho = q; q += BFGS_M; p.bfgs_alpha = q; q += BFGS_M;
-    p.gpart = q; q += (size_t)p.k1_ctas * ldx;
+    p.gpart = q; q += (size_t)gpart_rows * ldx;
+    p.gpart_f = gpf ? gpf + (size_t)b * B.k1_grid * ldx : nullptr;
     p.fpart = q; q += B.k1_grid + 8;
     dd = q;
     float* f = ff;
@@ -338,6 +364,13 @@ int batch_alloc(Batch& B, int num_sms) {
   return 0;
 }
 
+// K1 of a slot: the fused multi-lambda CSR kernel when the batch has segment lists, the per-problem kernels otherwise
+cudaError_t batch_k1(Batch& B, int force_emit, cudaStream_t st, int* launches) {
+  if (B.k1_fused)
+    return k1f_launch(B.d, B.nprob / B.group_L, B.group_L, B.h[0].sg_S, B.k1f_LP, B.k1f_smem, B.has_bias, force_emit, st, launches);
+  return k1_launch(B.d, B.nprob, B.csr, B.ldx, B.has_bias, B.k1_grid, force_emit, st, launches, B.gram_from_csr, B.k1_dyn);
+}
+
 // One x-update for every problem of the batch: beta (init), m, q must already be on the device.
 int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int policy, int invalidate, int* h_flag, int* d_flag,
                   Counters& cnt, Profiler* prof = nullptr, int share_first_gram = 0, int share_first_factor = 0) {
@@ -362,7 +395,7 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
   double shared_flops = 0;   // Gram builds that were not run because the group's first problem stood in for them
   while ((flag & 1) && slots < 400) {
     pf.begin(0, st);
-    CK(k1_launch(B.d, B.nprob, B.csr, B.ldx, B.has_bias, B.k1_grid, -1, st, &launches, B.gram_from_csr, B.k1_dyn));
+    CK(batch_k1(B, -1, st, &launches));
     pf.end(st);
     pf.begin(1, st);
     CK(k1_reduce_decide(B.d, B.nprob, B.Dt, st, &launches));
@@ -440,6 +473,17 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
     cnt.k1_emit_bytes += (double)c.hess_builds * (double)p.n * (double)B.Dp * 2.0;
   }
   cnt.gram_flops -= shared_flops;
+  if (B.csr) {
+    // the problems of a group advance in lock step from the first slot and drop out as they converge: slot t serves the
+    // problems with evals > t, so a group's passes = max evals, and the lambdas served in total = sum of evals
+    const int gl = std::max(1, B.group_L);
+    for (int g0 = 0; g0 + gl <= B.nprob; g0 += gl) {
+      int mx = 0; long long sum = 0;
+      for (int l = 0; l < gl; l++) { mx = std::max(mx, hc[g0 + l].evals); sum += hc[g0 + l].evals; }
+      const Problem& p = B.h[g0];
+      cnt.k1_shared_bytes += (double)mx * (8.0 * (double)p.nnz_hint + 9.0 * (double)p.n) + (double)sum * 8.0 * (double)p.n;
+    }
+  }
   for (auto& c : hc) {
     cnt.k1_passes += c.evals; cnt.newton_steps += c.newton_steps; cnt.rejected += c.rejects; cnt.gram_builds += c.hess_builds;
     if (c.fail == 3 || !c.done) cnt.not_converged++;
@@ -518,6 +562,8 @@ void fill_problem_data(Problem& p, const PartData& pd) {
   p.bm_offs = pd.bm_offs; p.bm_keys = pd.bm_keys; p.bm_vals = pd.bm_vals; p.bm_groups = pd.bm_groups;
   p.nblk128 = pd.nblk128; p.gram_from_csr = pd.bm_offs ? 1 : 0;
   p.vmax = pd.vmax; p.wmax = pd.wmax;
+  p.sg_S = pd.sg_S; p.sg_rows = pd.sg_rows; p.sg_ngrp = pd.sg_ngrp; p.sg_perm = pd.sg_perm; p.sg_depth = pd.sg_depth; p.sg_goff = pd.sg_goff;
+  p.sg_row16 = pd.sg_row16; p.sg_val = pd.sg_val;
 }
 
 int finalize(mlease_session* s) {
@@ -529,6 +575,7 @@ int finalize(mlease_session* s) {
   s->batch = B;
   B->nprob = (int)s->parts.size() * s->L;
   B->Dt = s->Dt; B->ldx = s->ldx; B->csr = s->any_csr; B->has_bias = 1;
+  B->group_L = s->L;
   B->h.resize(B->nprob);
   for (size_t pi = 0; pi < s->parts.size(); pi++)
     for (int l = 0; l < s->L; l++) {
@@ -645,7 +692,7 @@ __global__ void gather_i64_kernel(const long long* src, const long long* idx, in
 extern "C" {
 
 const char* mlease_last_error(void) { return g_err.c_str(); }
-int mlease_abi_version(void) { return 1; }
+int mlease_abi_version(void) { return 2; }
 
 int mlease_session_create(const mlease_admm_config* cfg, mlease_session** out) {
   if (!cfg || !out) return fail(MLEASE_ERR_INVALID, "null argument");
@@ -838,6 +885,15 @@ int mlease_add_partition_csr(mlease_session* s, int32_t pid, int64_t nrows, cons
       CK(csr_bm_fill(nrows, (const long long*)rp, (const int*)ci, (const float*)vv, pd.nblk128, pd.bm_groups, (const long long*)bo,
                      (unsigned short*)bk, (float*)bv, s->stream));
       pd.bm_offs = (long long*)bo; pd.bm_keys = (unsigned short*)bk; pd.bm_vals = (float*)bv;
+      // segment lists of the fused multi-lambda K1
+      int S = 0, rows = 0, LP = 0; size_t smem = 0;
+      if (!getenv("MLEASE_NO_FUSED_K1") && k1f_plan(nrows, s->ldx, s->L, s->num_sms, &S, &rows, &LP, &smem)) {
+        CK(k1f_build(nrows, s->Dg, pd.nnz, (const long long*)rp, (const int*)ci, (const float*)vv, S, rows, &pd.sg_ngrp, &pd.sg_perm, &pd.sg_depth,
+                     &pd.sg_goff, &pd.sg_row16, &pd.sg_val, &pd.sg_total, s->stream));
+        pd.sg_S = S; pd.sg_rows = rows;
+        s->owned.push_back(pd.sg_perm); s->owned.push_back(pd.sg_depth); s->owned.push_back(pd.sg_goff);
+        s->owned.push_back(pd.sg_row16); s->owned.push_back(pd.sg_val);
+      }
     }
   }
   pd.rowptr = (long long*)rp; pd.colidx = (int*)ci; pd.vals = (float*)vv;
@@ -1043,6 +1099,8 @@ int mlease_get_stats(mlease_session* s, mlease_stats* out) {
   out->k1_passes = s->cnt.k1_passes; out->gram_builds = s->cnt.gram_builds; out->newton_steps = s->cnt.newton_steps;
   out->rejected_steps = s->cnt.rejected; out->kernel_launches = s->cnt.launches; out->not_converged = s->cnt.not_converged;
   out->last_iter_slots = s->cnt.last_slots; out->last_maxdiff = s->last_maxdiff; out->liblinear_epsilon = s->liblinear_eps;
+  out->k1_shared_bytes = s->cnt.k1_shared_bytes;
+  out->k1_fused = (s->batch && s->batch->k1_fused) ? 1 : 0;
   return 0;
 }
 
@@ -1073,7 +1131,7 @@ int mlease_objective(mlease_session* s, int32_t pid, const double* w, const doub
   if (int rc = scratch_set(s, w, m, q)) return rc;
   int launches = 0;
   CK(newton_begin(B->d, 1, 1e-8, 1, 1, 1, 0, s->stream, &launches));
-  CK(k1_launch(B->d, 1, B->csr, B->ldx, B->has_bias, B->k1_grid, H ? 1 : 0, s->stream, &launches, B->gram_from_csr));
+  CK(batch_k1(*B, H ? 1 : 0, s->stream, &launches));
   CK(k1_reduce_decide(B->d, 1, B->Dt, s->stream, &launches));
   const Problem& p = B->h[0];
   Ctrl c;
@@ -1201,7 +1259,7 @@ int mlease_time_kernel(mlease_session* s, int32_t pid, int32_t which, int32_t re
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   // warm-up launch (also produces the scaled copy the Gram needs)
-  CK(k1_launch(B->d, 1, B->csr, B->ldx, B->has_bias, B->k1_grid, 1, s->stream, &launches, B->gram_from_csr));
+  CK(batch_k1(*B, 1, s->stream, &launches));
   const int bias_col = B->has_bias ? B->Dt - 1 : -1;
   if (which == 3) {
     if (B->gram_from_csr) CK(gram_launch_csr_tcgen05(B->d, 1, B->d_tiles, B->ntiles, B->gram_slices, 1, bias_col, s->stream, &launches));
@@ -1212,7 +1270,7 @@ int mlease_time_kernel(mlease_session* s, int32_t pid, int32_t which, int32_t re
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaEventRecord(e0, s->stream));
   for (int r = 0; r < reps; r++) {
-    if (which == 1) CK(k1_launch(B->d, 1, B->csr, B->ldx, B->has_bias, B->k1_grid, emit_scaled ? 1 : 0, s->stream, &launches, B->gram_from_csr));
+    if (which == 1) CK(batch_k1(*B, emit_scaled ? 1 : 0, s->stream, &launches));
     else if (which == 2 && B->gram_from_csr) CK(gram_launch_csr_tcgen05(B->d, 1, B->d_tiles, B->ntiles, B->gram_slices, 1, bias_col, s->stream, &launches));
     else if (which == 2) CK(gram_launch_tcgen05(B->d, 1, B->d_tmaps, B->d_tiles, B->ntiles, B->gram_slices, 1, s->stream, &launches));
     else if (which == 3) CK(cholesky_launch(B->d, 1, B->ldh, s->stream, &launches));

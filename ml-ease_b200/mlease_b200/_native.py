@@ -32,7 +32,7 @@ class AdmmConfigC(C.Structure):
 class StatsC(C.Structure):
     _fields_ = [("k1_passes", C.c_int64), ("gram_builds", C.c_int64), ("newton_steps", C.c_int64), ("rejected_steps", C.c_int64),
                 ("kernel_launches", C.c_int64), ("not_converged", C.c_int32), ("last_iter_slots", C.c_int32),
-                ("last_maxdiff", C.c_double), ("liblinear_epsilon", C.c_float)]
+                ("last_maxdiff", C.c_double), ("liblinear_epsilon", C.c_float), ("k1_fused", C.c_int32), ("k1_shared_bytes", C.c_double)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported():
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, missing
     assert sorted(EXPORTED) == declared, (sorted(set(declared) ^ set(EXPORTED)))
-    assert mlease_b200.lib().mlease_abi_version() == 1
+    assert mlease_b200.lib().mlease_abi_version() == 2
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")

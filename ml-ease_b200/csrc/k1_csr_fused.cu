@@ -79,16 +79,17 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_csr_fused_kernel(const Prob
   const float* __restrict__ wv = p0.w;
   const float* __restrict__ ov = p0.o;
   const int sub = lane >> 4, sl = lane & 15;
-  V bias_b;
-  {
-    float* bb = reinterpret_cast<float*>(&bias_b);
-    const float* bs = reinterpret_cast<const float*>(beta_s);
-#pragma unroll
-    for (int l = 0; l < LP; l++) bb[l] = has_bias ? bs[(size_t)(Dt - 1) * LP + l] : 0.f;
-  }
-  float loss[LP], rsum[LP];
-#pragma unroll
-  for (int l = 0; l < LP; l++) { loss[l] = 0.f; rsum[l] = 0.f; }
+  // After the half-warp reduction below, the 16 lanes of a row hold the LP margins distributed: lane sl owns lambda
+  // lam_of = bits (3,2) of sl for LP = 4 (bit 3 for LP = 2), and the lanes with (sl & 3) == 0 do that lambda's sigmoid / loss /
+  // residual -- the L sigmoids of a row run in parallel lanes instead of one lane doing them one after the other.
+  const int lam_of = LP == 4 ? (sl >> 2) : (LP == 2 ? (sl >> 3) : 0);
+  const bool lam_lane = (LP == 4 ? (sl & 3) == 0 : (LP == 2 ? (sl & 7) == 0 : sl == 0));
+  const bool lam_on = lam_lane && lam_of < L && ((act >> lam_of) & 1);
+  const bool lam_emit = lam_on && ((emit >> lam_of) & 1);
+  const float bias_l = has_bias ? reinterpret_cast<const float*>(beta_s)[(size_t)(Dt - 1) * LP + lam_of] : 0.f;
+  float* __restrict__ sd_l = lam_emit ? probs[b0 + lam_of].sdvec : nullptr;
+  float* r_sf = reinterpret_cast<float*>(r_s);
+  float loss = 0.f, rsum = 0.f;
   const long long rstep = 2LL * nw;
   long long i = rb + 2 * warp + sub;
   long long j0 = 0;
@@ -127,41 +128,49 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_csr_fused_kernel(const Prob
 #pragma unroll
       for (int l = 0; l < LP; l++) a[l] = fmaf(vj, vget(bb, l), a[l]);
     }
+    // transposed half-warp reduction: LP values x 16 lanes -> one value per lane (5 shuffles for LP = 4 instead of 16)
+    float av;
+    if constexpr (LP == 4) {
+      const bool up = (sl & 8) != 0;
+      const float k0 = (up ? a[2] : a[0]) + __shfl_xor_sync(0xffffffffu, up ? a[0] : a[2], 8);
+      const float k1 = (up ? a[3] : a[1]) + __shfl_xor_sync(0xffffffffu, up ? a[1] : a[3], 8);
+      const bool up2 = (sl & 4) != 0;
+      av = (up2 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, up2 ? k0 : k1, 4);
+      av += __shfl_xor_sync(0xffffffffu, av, 2);
+      av += __shfl_xor_sync(0xffffffffu, av, 1);
+    } else if constexpr (LP == 2) {
+      const bool up = (sl & 8) != 0;
+      av = (up ? a[LP - 1] : a[0]) + __shfl_xor_sync(0xffffffffu, up ? a[0] : a[LP - 1], 8);
+      av += __shfl_xor_sync(0xffffffffu, av, 4);
+      av += __shfl_xor_sync(0xffffffffu, av, 2);
+      av += __shfl_xor_sync(0xffffffffu, av, 1);
+    } else {
+      av = a[0];
 #pragma unroll
-    for (int l = 0; l < LP; l++) {
-#pragma unroll
-      for (int m = K1F_HW / 2; m >= 1; m >>= 1) a[l] += __shfl_xor_sync(0xffffffffu, a[l], m);   // stays inside the half-warp
+      for (int m = K1F_HW / 2; m >= 1; m >>= 1) av += __shfl_xor_sync(0xffffffffu, av, m);
     }
-    if (sl == 0 && has_row) {
-      V rr;
-      float* rrp = reinterpret_cast<float*>(&rr);
-#pragma unroll
-      for (int l = 0; l < LP; l++) {
-        const float t = yy * (a[l] + vget(bias_b, l) + oo);
-        const float e = __expf(-fabsf(t));
-        const float inv = __frcp_rn(1.f + e);
-        const float p = t >= 0.f ? inv : e * inv;
-        const float qq = t >= 0.f ? e * inv : inv;
-        const bool on = l < L && ((act >> l) & 1);
-        const float r = on ? -ww * yy * qq : 0.f;
-        rrp[l] = r;
-        if (on) {
-          loss[l] += ww * ((t >= 0.f ? 0.f : -t) - __logf(inv));
-          rsum[l] += r;
-          if ((emit >> l) & 1) probs[b0 + l].sdvec[i] = sqrtf(ww * p * qq);   // the Gram kernel assembles the scaled rows itself
-        }
+    if (lam_lane && has_row) {
+      const float t = yy * (av + bias_l + oo);
+      const float e = __expf(-fabsf(t));
+      const float inv = __frcp_rn(1.f + e);
+      const float p = t >= 0.f ? inv : e * inv;
+      const float qq = t >= 0.f ? e * inv : inv;
+      const float r = lam_on ? -ww * yy * qq : 0.f;
+      r_sf[(size_t)(i - rb) * LP + lam_of] = r;
+      if (lam_on) {
+        loss += ww * ((t >= 0.f ? 0.f : -t) - __logf(inv));
+        rsum += r;
+        if (lam_emit) sd_l[i] = sqrtf(ww * p * qq);   // the Gram kernel assembles the scaled rows itself
       }
-      r_s[i - rb] = rr;
     }
     i = in; j0 = j0n; len = lenn;
   }
-  // loss / bias-gradient partials of this segment: warp shuffle, then one fp64 sum per lambda in warp order
+  // loss / bias-gradient partials of this segment: the two rows of a warp, then one fp64 sum per lambda in warp order
   __shared__ float red[2][LP][K1F_THREADS / 32];
-#pragma unroll
-  for (int l = 0; l < LP; l++) {
-    float a = loss[l] + __shfl_down_sync(0xffffffffu, loss[l], 16);   // the two sl == 0 lanes of the warp
-    float b = rsum[l] + __shfl_down_sync(0xffffffffu, rsum[l], 16);
-    if (lane == 0) { red[0][l][warp] = a; red[1][l][warp] = b; }
+  {
+    const float la = loss + __shfl_down_sync(0xffffffffu, loss, 16);
+    const float lb = rsum + __shfl_down_sync(0xffffffffu, rsum, 16);
+    if (lam_lane && sub == 0) { red[0][lam_of][warp] = la; red[1][lam_of][warp] = lb; }
   }
   __syncthreads();   // r_s complete, red complete
   if (tid < LP && tid < L && ((act >> tid) & 1)) {
@@ -181,29 +190,40 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_csr_fused_kernel(const Prob
   for (int g = warp; g < ngrp; g += nw) {
     const int col = __ldg(perm + g * 32 + lane);
     const int dep = __ldg(depth + g);
-    const size_t base = (size_t)__ldg(goff + g) * 32 + lane;
+    const unsigned short* __restrict__ pr = r16 + (size_t)__ldg(goff + g) * 32 + lane;
+    const float* __restrict__ pv = sv + (size_t)__ldg(goff + g) * 32 + lane;
     float acc[LP];
 #pragma unroll
     for (int l = 0; l < LP; l++) acc[l] = 0.f;
     int k = 0;
-    for (; k + 4 <= dep; k += 4) {
-      unsigned short rw[4];
-      float vv[4];
+    constexpr int UB = 8;   // 16 independent loads in flight per lane: phase B is pure latency otherwise
+    for (; k + UB <= dep; k += UB) {
+      unsigned short rw[UB];
+      float vv[UB];
 #pragma unroll
-      for (int u = 0; u < 4; u++) { rw[u] = __ldg(r16 + base + (size_t)(k + u) * 32); vv[u] = __ldg(sv + base + (size_t)(k + u) * 32); }
+      for (int u = 0; u < UB; u++) { rw[u] = __ldg(pr + (k + u) * 32); vv[u] = __ldg(pv + (k + u) * 32); }
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < UB; u++) {
         const V rr = r_s[rw[u]];
 #pragma unroll
         for (int l = 0; l < LP; l++) acc[l] = fmaf(vv[u], vget(rr, l), acc[l]);
       }
     }
-    for (; k < dep; k++) {
-      const unsigned short rw = __ldg(r16 + base + (size_t)k * 32);
-      const float vv = __ldg(sv + base + (size_t)k * 32);
-      const V rr = r_s[rw];
+    if (k < dep) {   // tail: predicated loads (padding value 0 * r_s[0])
+      unsigned short rw[UB];
+      float vv[UB];
 #pragma unroll
-      for (int l = 0; l < LP; l++) acc[l] = fmaf(vv, vget(rr, l), acc[l]);
+      for (int u = 0; u < UB; u++) {
+        const bool ok = k + u < dep;
+        rw[u] = ok ? __ldg(pr + (k + u) * 32) : (unsigned short)0;
+        vv[u] = ok ? __ldg(pv + (k + u) * 32) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < UB; u++) {
+        const V rr = r_s[rw[u]];
+#pragma unroll
+        for (int l = 0; l < LP; l++) acc[l] = fmaf(vv[u], vget(rr, l), acc[l]);
+      }
     }
     if (col >= 0) {
 #pragma unroll

@@ -97,7 +97,10 @@ __global__ void __launch_bounds__(256) k1_partial_reduce_kernel(const Problem* _
 // Prior term, objective, then the accept/shrink decision and (fused) the first L-BFGS loop of the next direction.
 //   g_t = sum_cta gpart + q*(beta_t - m)           (llf/LogisticRegressionL2.java:223-224)
 //   f_t = sum_cta fpart + 1/2 sum q (beta_t-m)^2   (:181-190)
-__global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __restrict__ probs) {
+// spec != 0: the host enqueued this slot before it knew the outcome of the previous one (slot pipelining), hence WITHOUT the
+// Gram / Cholesky launches a rebuild needs: a rebuild that is due is deferred (emit stays set, the step is a chord step on
+// the factor at hand; the host sees emit in the next flag word and runs a regular rebuild slot).
+__global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __restrict__ probs, int spec) {
   const Problem& pb = probs[blockIdx.x];
   Ctrl* c = pb.ctrl;
   if (c->done) return;
@@ -168,7 +171,8 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
       } else {
         c->need_solve = 1;
         // a rebuild happens only if K1 wrote the scaled copy at THIS point (emit was set before the pass)
-        c->need_hess = c->emit ? 1 : 0;
+        const int deferred = (spec && c->emit) ? 1 : 0;
+        c->need_hess = (c->emit && !spec) ? 1 : 0;
         // policy for the NEXT accepted point: refresh when the chord step contracted poorly
         if (c->hess_policy == 1) {
           c->emit = 1;
@@ -176,6 +180,7 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
           const bool poor = !c->rebuild_is_expensive && have_dir && c->gnorm_prev > 0.0 && ginf > 0.25 * c->gnorm_prev;
           c->emit = (poor && !c->need_hess) ? 1 : 0;
           if (!c->need_hess && !c->hess_valid) { c->emit = 1; }
+          if (deferred) c->emit = 1;
         }
       }
     } else {
@@ -360,9 +365,9 @@ cudaError_t newton_begin(const Problem* d_probs, int nprob, double xtol, int max
   if (launches) *launches += 1;
   return cudaGetLastError();
 }
-cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, int Dt, cudaStream_t st, int* launches) {
+cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, int Dt, cudaStream_t st, int* launches, int spec) {
   k1_partial_reduce_kernel<<<dim3((Dt + 31) / 32, nprob), 256, 0, st>>>(d_probs);
-  k1_reduce_decide_kernel<<<nprob, NT, 0, st>>>(d_probs);
+  k1_reduce_decide_kernel<<<nprob, NT, 0, st>>>(d_probs, spec);
   if (launches) *launches += 2;
   return cudaGetLastError();
 }

@@ -159,9 +159,12 @@ struct Batch {
   void* d_tmaps = nullptr;
   void* d_tiles = nullptr;
   std::vector<Ctrl> mirror;   // host copy of the control blocks as of the last read-back
+  Ctrl* h_ctrl[2] = {nullptr, nullptr};   // pinned read-back buffers of the slot pipeline (small batches)
+  cudaEvent_t slot_ev[2] = {nullptr, nullptr};
   std::vector<void*> owned;
   ~Batch() {
     for (void* p : owned) cudaFree(p);
+    for (int i = 0; i < 2; i++) { if (h_ctrl[i]) cudaFreeHost(h_ctrl[i]); if (slot_ev[i]) cudaEventDestroy(slot_ev[i]); }
   }
 };
 
@@ -393,17 +396,18 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
   const Problem* d_hess = B.d;   // problems the Gram / Cholesky grids run over (large batches: compacted by poll2_kernel)
   int n_hess = B.nprob;
   double shared_flops = 0;   // Gram builds that were not run because the group's first problem stood in for them
-  while ((flag & 1) && slots < 400) {
+  // One slot's launches.  with_hess: the Gram / Cholesky launches of a rebuild are included; spec: see k1_reduce_decide_kernel.
+  auto enqueue_slot = [&](int slot_idx, bool with_hess, bool spec) -> int {
     pf.begin(0, st);
     CK(batch_k1(B, -1, st, &launches));
     pf.end(st);
     pf.begin(1, st);
-    CK(k1_reduce_decide(B.d, B.nprob, B.Dt, st, &launches));
+    CK(k1_reduce_decide(B.d, B.nprob, B.Dt, st, &launches, spec ? 1 : 0));
     pf.end(st);
-    if ((flag & 2) && n_hess > 0) {
+    if (with_hess && n_hess > 0) {
       pf.begin(2, st);
       // cold start of a multi-lambda run: the L problems of a partition all sit at beta = 0, their Grams are the same
-      const int share = (slots == 0) ? share_first_gram : 0;
+      const int share = (slot_idx == 0) ? share_first_gram : 0;
       if (share > 1)
         for (int b = 0; b < B.nprob; b++) if (b % share != 0) shared_flops += (double)B.h[b].n * (double)B.Dt * (double)(B.Dt + 1);
       if (B.gram_from_csr) CK(gram_launch_csr_tcgen05(d_hess, n_hess, B.d_tiles, B.ntiles, B.gram_slices, 0, B.has_bias ? B.Dt - 1 : -1, st, &launches, share));
@@ -429,25 +433,70 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
     CK(newton_solve(B.d, B.nprob, B.ldh, st, &launches));
     if (!small) { poll2_kernel<<<1, 256, 0, st>>>(B.d, B.nprob, d_flag, B.d_compact); launches++; }
     pf.end(st);
-    if (small) {
-      CK(cudaMemcpyAsync(hc.data(), B.d_ctrl, (size_t)B.nprob * sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      flag = 0;
-      for (auto& c : hc) if (!c.done) { flag |= 1; if (c.emit) flag |= 2; }
-    } else {
-      CK(cudaMemcpyAsync(h_flag, d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      flag = h_flag[0];
-      n_hess = h_flag[1];
-      d_hess = B.d_compact;
+    return 0;
+  };
+  if (small) {
+    // Slot pipeline: the host runs ONE slot ahead of what it knows.  While slot s executes, slot s+1 is already enqueued in
+    // speculative form (no rebuild launches; a rebuild that turns out to be due is deferred by the decide kernel and shows
+    // up as `emit` in the flags, after which a regular rebuild slot follows).  The read-back of the control blocks goes to
+    // pinned double buffers and is awaited per slot (event), so the GPU never idles on the host between slots; a finished
+    // x-update leaves at most one slot of early-exit kernels behind.
+    for (int i = 0; i < 2; i++) {
+      if (!B.h_ctrl[i]) CK(cudaMallocHost((void**)&B.h_ctrl[i], (size_t)B.nprob * sizeof(Ctrl)));
+      if (!B.slot_ev[i]) CK(cudaEventCreateWithFlags(&B.slot_ev[i], cudaEventDisableTiming));
     }
+    const bool may_spec = policy == 0 && !getenv("MLEASE_NO_SLOT_PIPELINE");
+    auto flags_of = [&](const Ctrl* c, bool* all_valid) {
+      int f = 0; bool v = true;
+      for (int b = 0; b < B.nprob; b++) if (!c[b].done) { f |= 1; if (c[b].emit) f |= 2; if (!c[b].hess_valid) v = false; }
+      *all_valid = v;
+      return f;
+    };
+    auto finish_slot = [&](int idx) -> int {
+      CK(cudaMemcpyAsync(B.h_ctrl[idx & 1], B.d_ctrl, (size_t)B.nprob * sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+      CK(cudaEventRecord(B.slot_ev[idx & 1], st));
+      return 0;
+    };
+    // what is known before slot 0: every problem runs; a rebuild is due iff emit0; factors are valid iff the mirror says so
+    bool known_valid = !(flag & 2);
+    if (int rc = enqueue_slot(0, (flag & 2) != 0, false)) return rc;
+    if (int rc = finish_slot(0)) return rc;
+    int s_cur = 0;          // newest slot in flight whose outcome is not known yet
+    bool next_in_flight = false;
+    int known_flag = flag;  // flags as of the newest COMPLETED slot (before slot 0: the host-side prediction)
+    while (true) {
+      // speculate slot s_cur + 1 on what is known (the state BEFORE slot s_cur): no rebuild pending, every factor valid
+      const bool spec_next = may_spec && known_valid && !(known_flag & 2) && s_cur + 1 < 400;
+      if (spec_next) {
+        if (int rc = enqueue_slot(s_cur + 1, false, true)) return rc;
+        if (int rc = finish_slot(s_cur + 1)) return rc;
+        next_in_flight = true;
+      }
+      CK(cudaEventSynchronize(B.slot_ev[s_cur & 1]));
+      std::memcpy(hc.data(), B.h_ctrl[s_cur & 1], (size_t)B.nprob * sizeof(Ctrl));
+      slots = s_cur + 1;
+      known_flag = flags_of(hc.data(), &known_valid);
+      if (getenv("MLEASE_DEBUG") && atoi(getenv("MLEASE_DEBUG")) >= 2) {
+        const Ctrl& c0 = hc[0];
+        fprintf(stderr, "[mlease]   slot %d p0: done %d steps %d hb %d emit %d f %.10e |g| %.3e |dir| %.3e phi0 %.3e alpha %.2f wr %.3f\n", slots, c0.done,
+                c0.newton_steps, c0.hess_builds, c0.emit, c0.f_acc, c0.gnorm, c0.dirnorm, c0.phi0, c0.alpha, c0.worst_ratio);
+      }
+      if (!(known_flag & 1) || slots >= 400) break;          // finished (a speculative slot in flight is a no-op)
+      if (next_in_flight) { s_cur++; next_in_flight = false; continue; }
+      if (int rc = enqueue_slot(s_cur + 1, (known_flag & 2) != 0, false)) return rc;
+      if (int rc = finish_slot(s_cur + 1)) return rc;
+      s_cur++;
+    }
+    flag = known_flag;
+  }
+  while (!small && (flag & 1) && slots < 400) {
+    if (int rc = enqueue_slot(slots, (flag & 2) != 0, false)) return rc;
+    CK(cudaMemcpyAsync(h_flag, d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    flag = h_flag[0];
+    n_hess = h_flag[1];
+    d_hess = B.d_compact;
     slots++;
-    if (getenv("MLEASE_DEBUG") && atoi(getenv("MLEASE_DEBUG")) >= 2) {
-      Ctrl c0;
-      cudaMemcpy(&c0, B.d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[mlease]   slot %d p0: done %d steps %d hb %d emit %d f %.10e |g| %.3e |dir| %.3e phi0 %.3e alpha %.2f wr %.3f\n", slots, c0.done,
-              c0.newton_steps, c0.hess_builds, c0.emit, c0.f_acc, c0.gnorm, c0.dirnorm, c0.phi0, c0.alpha, c0.worst_ratio);
-    }
   }
   if (!small) {
     CK(cudaMemcpyAsync(hc.data(), B.d_ctrl, (size_t)B.nprob * sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
@@ -456,6 +505,7 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
   cnt.launches += launches;
   cnt.last_slots = slots;
   int bad_spd = 0, bad_ls = 0;
+  if (pf.on) CK(cudaStreamSynchronize(st));   // a trailing speculative slot may still be running: its events must have completed
   pf.resolve();
   if (getenv("MLEASE_DEBUG")) {
     fprintf(stderr, "[mlease] x-update: %d problems, %d slots;", B.nprob, slots);

@@ -135,67 +135,12 @@ def test_csr_rows_with_repeated_and_unsorted_columns(mb):
 
 
 @pytest.mark.parametrize("fused", [False, True])
-@pytest.mark.parametrize("n,d", [(1000, 50), (4000, 3000)])
-def test_k1_per_problem_csr_kernels_without_segment_lists(mb, no_fused_k1, n, d):
-    """The pre-fusion CSR K1 (two-word fixed-point accumulation with native integer shared-memory atomics) stays the path for
-    partitions without segment lists (more than 4 lambdas, feature spaces too wide for the builder): same parity gate."""
-    X, y, w, o = _mk(n, d, seed=n + d, sparse=True)
-    rng = np.random.default_rng(1)
-    wv = rng.normal(0, 0.3, d + 1); pm = rng.normal(0, 0.3, d + 1); pv = rng.uniform(0.2, 2.0, d + 1)
-    rp, ci, v = _csr_of(X)
-    with _session(mb, d) as s:
-        s.add_partition_csr(0, rp, ci, v, y, w, o)
-        f, g, _ = s.objective(0, wv, pm, 1.0 / pv)
-        f2, g2, _ = s.objective(0, wv, pm, 1.0 / pv)
-        x, _ = s.fit_partition(0, np.zeros(d + 1), pm, 1.0 / pv)
-    data = orc.Csr(rp, ci, v, y, w, o, d)
-    f_ref, g_ref = orc.objective("grad", data, wv, pm, pv)
-    assert abs(f - f_ref) <= 1e-5 * abs(f_ref) and np.abs(g - g_ref).max() <= 1e-5 * np.abs(g_ref).max()
-    assert f == f2 and np.array_equal(g, g2)
-    x_ref, _ = orc.liblinear_train(data, np.zeros(d + 1), pm, pv, 1e-14, 100000)
-    assert np.abs(x - x_ref).max() <= 1e-5 * np.abs(x_ref).max()
-
-
-def test_csr_rows_with_repeated_and_unsorted_columns(mb):
-    """Rows may list a column twice or out of order (TRON's fun/grad/Hv accept that: llf/LogisticRegressionL2.java:115-150;
-    only the reference's hessian() insists on sorted rows, :277).  Such partitions take the general CSR kernels (float
-    gradient accumulation, dense bf16 Gram operand): same objective, gradient, Hessian and fit as the merged rows."""
-    n, d = 1500, 60
-    X, y, w, o = _mk(n, d, seed=91, sparse=True)
-    rng = np.random.default_rng(4)
-    rp, ci, v = [0], [], []
-    for i in range(n):
-        cols = np.nonzero(X[i])[0]
-        vals = X[i, cols].astype(np.float32)
-        if len(cols):   # split the first entry in two, then shuffle the row
-            cols = np.concatenate([cols, cols[:1]]); vals = np.concatenate([vals, vals[:1] * np.float32(0.25)]); vals[0] *= np.float32(0.75)
-            perm = rng.permutation(len(cols)); cols, vals = cols[perm], vals[perm]
-        ci += list(cols); v += list(vals); rp.append(len(ci))
-    rp = np.array(rp, np.int64); ci = np.array(ci, np.int32); v = np.array(v, np.float32)
-    Xm = np.zeros((n, d), np.float32)
-    for i in range(n):
-        np.add.at(Xm[i], ci[rp[i]:rp[i + 1]], v[rp[i]:rp[i + 1]])
-    data = orc.Csr.from_dense(Xm, y, w, o)
-    wv = rng.normal(0, 0.3, d + 1); pm = rng.normal(0, 0.2, d + 1); pv = np.full(d + 1, 0.7)
-    with _session(mb, d) as s:
-        s.add_partition_csr(0, rp, ci, v, y, w, o)
-        f, g, H = s.objective(0, wv, pm, 1.0 / pv, want_hessian=True, tensor=True)
-        _, _, H_simt = s.objective(0, wv, pm, 1.0 / pv, want_hessian=True, tensor=False)   # the dense operand exists on this path
-        x, _ = s.fit_partition(0, np.zeros(d + 1), pm, 1.0 / pv)
-    f_ref, g_ref = orc.objective("grad", data, wv, pm, pv)
-    H_ref = orc.objective("hessian", data, wv, pm, pv)
-    assert abs(f - f_ref) <= 1e-5 * abs(f_ref)
-    assert np.abs(g - g_ref).max() <= 1e-5 * np.abs(g_ref).max()
-    assert np.abs(H - H_ref).max() <= 2e-2 * np.abs(H_ref).max() and np.abs(H - H_simt).max() <= 1e-3 * np.abs(H_ref).max()
-    x_ref, _ = orc.liblinear_train(data, np.zeros(d + 1), pm, pv, 1e-14, 100000)
-    assert np.abs(x - x_ref).max() <= 1e-5 * np.abs(x_ref).max()
-
-
-@pytest.mark.parametrize("fused", [False, True])
 def test_csr_feature_space_wider_than_one_gradient_window(mb, monkeypatch, fused):
     """30 001 columns: the per-CTA fixed-point gradient (8 bytes per column) no longer fits shared memory in one piece, so
     K1 runs one launch for the margins + the first 28 128 columns and one more per further column window; the Gram tile
     list, the DMMA factorisation and the fp32 inverse copy are exercised at ldh = 30 016 as well."""
+    if not fused:
+        monkeypatch.setenv("MLEASE_NO_FUSED_K1", "1")   # the column-window kernels; with segment lists the fused kernel takes 30k columns in one launch
     n, D, nnz = 3000, 30000, 8
     r = np.random.default_rng(12)
     ci = np.stack([np.sort(r.choice(D, nnz, replace=False)) for _ in range(n)]).astype(np.int32)
@@ -224,29 +169,6 @@ def test_csr_feature_space_wider_than_one_gradient_window(mb, monkeypatch, fused
     assert abs(f - f_ref) <= 1e-5 * abs(f_ref), (f, f_ref)
     assert np.abs(g - g_ref).max() <= 1e-5 * np.abs(g_ref).max(), np.abs(g - g_ref).max() / np.abs(g_ref).max()
     assert f == f2 and np.array_equal(g, g2)
-    if sparse:
-        assert f == f0 and np.array_equal(g, g0)
-
-
-@pytest.mark.parametrize("n,d", [(1000, 50), (4000, 3000)])
-def test_k1_per_problem_csr_kernels_without_segment_lists(mb, no_fused_k1, n, d):
-    """The pre-fusion CSR K1 (two-word fixed-point accumulation with native integer shared-memory atomics) stays the path for
-    partitions without segment lists (more than 4 lambdas, feature spaces too wide for the builder): same parity gate."""
-    X, y, w, o = _mk(n, d, seed=n + d, sparse=True)
-    rng = np.random.default_rng(1)
-    wv = rng.normal(0, 0.3, d + 1); pm = rng.normal(0, 0.3, d + 1); pv = rng.uniform(0.2, 2.0, d + 1)
-    rp, ci, v = _csr_of(X)
-    with _session(mb, d) as s:
-        s.add_partition_csr(0, rp, ci, v, y, w, o)
-        f, g, _ = s.objective(0, wv, pm, 1.0 / pv)
-        f2, g2, _ = s.objective(0, wv, pm, 1.0 / pv)
-        x, _ = s.fit_partition(0, np.zeros(d + 1), pm, 1.0 / pv)
-    data = orc.Csr(rp, ci, v, y, w, o, d)
-    f_ref, g_ref = orc.objective("grad", data, wv, pm, pv)
-    assert abs(f - f_ref) <= 1e-5 * abs(f_ref) and np.abs(g - g_ref).max() <= 1e-5 * np.abs(g_ref).max()
-    assert f == f2 and np.array_equal(g, g2)
-    x_ref, _ = orc.liblinear_train(data, np.zeros(d + 1), pm, pv, 1e-14, 100000)
-    assert np.abs(x - x_ref).max() <= 1e-5 * np.abs(x_ref).max()
     x_ref, _ = orc.liblinear_train(data, np.zeros(D + 1), pm, pv, 1e-14, 100000)
     assert np.abs(x - x_ref).max() <= 1e-5 * np.abs(x_ref).max(), (np.abs(x - x_ref).max() / np.abs(x_ref).max(), steps)
 

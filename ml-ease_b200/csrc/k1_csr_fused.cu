@@ -284,22 +284,52 @@ __global__ void k1f_rowid_kernel(long long n, int sg_rows, const long long* __re
     for (long long j = rowptr[i] + lane; j < rowptr[i + 1]; j += 32) ent_row[j] = r;
   }
 }
-// pass 2: one warp per segment walks the segment's stored values IN ORDER (they are contiguous in the CSR arrays, row after
-// row), 32 at a time, so every column's entries end up in row order: a fixed summation order for phase B.  Lanes of one step
-// that hit the same column (possible when a step spans two short rows) are ranked by lane = by row.
+// pass 2a: column histogram of every chunk of a segment's stored values (K1F_CHUNKS chunks per segment, consecutive in the CSR)
+constexpr int K1F_CHUNKS = 8;
+__device__ __forceinline__ void k1f_chunk_range(long long j0, long long j1, int chunk, long long* a, long long* b) {
+  const long long per = (((j1 - j0) + K1F_CHUNKS - 1) / K1F_CHUNKS + 31) / 32 * 32;
+  *a = min(j1, j0 + (long long)chunk * per);
+  *b = min(j1, *a + per);
+}
+__global__ void __launch_bounds__(256) k1f_hist_kernel(long long n, int sg_rows, int Dg, const long long* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                      unsigned short* __restrict__ hist) {
+  extern __shared__ int k1f_hist_sm[];
+  const int seg = blockIdx.x, chunk = blockIdx.y;
+  for (int c = threadIdx.x; c < Dg; c += blockDim.x) k1f_hist_sm[c] = 0;
+  __syncthreads();
+  const long long rb = (long long)seg * sg_rows, re = min(n, rb + sg_rows);
+  if (rb < re) {
+    long long a, b;
+    k1f_chunk_range(rowptr[rb], rowptr[re], chunk, &a, &b);
+    for (long long j = a + threadIdx.x; j < b; j += blockDim.x) atomicAdd(&k1f_hist_sm[colidx[j]], 1);
+  }
+  __syncthreads();
+  unsigned short* out = hist + ((size_t)seg * K1F_CHUNKS + chunk) * Dg;
+  for (int c = threadIdx.x; c < Dg; c += blockDim.x) out[c] = (unsigned short)k1f_hist_sm[c];
+}
+// pass 2b: one warp per (segment, chunk) walks the chunk's stored values IN ORDER (they are contiguous in the CSR arrays, row
+// after row), 32 at a time; its per-column counters start at the number of entries the earlier chunks hold, so every column's
+// entries end up in row order: a fixed summation order for phase B.  Lanes of one step that hit the same column (possible when
+// a step spans two short rows) are ranked by lane = by row.
 __global__ void __launch_bounds__(32) k1f_fill_kernel(long long n, int sg_rows, int Dg, int ngrp, const long long* __restrict__ rowptr,
                                                      const int* __restrict__ colidx, const float* __restrict__ vals,
                                                      const unsigned short* __restrict__ ent_row, const int* __restrict__ inv,
-                                                     const long long* __restrict__ goff, unsigned short* __restrict__ row16, float* __restrict__ sval) {
+                                                     const long long* __restrict__ goff, const unsigned short* __restrict__ hist,
+                                                     unsigned short* __restrict__ row16, float* __restrict__ sval) {
   extern __shared__ unsigned short k1f_fill_sm[];
-  const int seg = blockIdx.x, lane = threadIdx.x;
-  for (int c = lane; c < Dg; c += 32) k1f_fill_sm[c] = 0;
+  const int seg = blockIdx.x, chunk = blockIdx.y, lane = threadIdx.x;
+  for (int c = lane; c < Dg; c += 32) {
+    int s0 = 0;
+    for (int q = 0; q < chunk; q++) s0 += hist[((size_t)seg * K1F_CHUNKS + q) * Dg + c];
+    k1f_fill_sm[c] = (unsigned short)s0;
+  }
   __syncwarp();
   const long long rb = (long long)seg * sg_rows, re = min(n, rb + sg_rows);
   if (rb >= re) return;
   const int* __restrict__ iv = inv + (size_t)seg * Dg;
   const long long* __restrict__ go = goff + (size_t)seg * ngrp;
-  const long long j0 = rowptr[rb], j1 = rowptr[re];
+  long long j0, j1;
+  k1f_chunk_range(rowptr[rb], rowptr[re], chunk, &j0, &j1);
 #pragma unroll 4
   for (long long jb = j0; jb < j1; jb += 32) {
     const long long j = jb + lane;
@@ -353,11 +383,12 @@ cudaError_t k1f_build(long long n, int Dg, long long nnz, const long long* rowpt
   long long *goff = nullptr, *d64 = nullptr;
   unsigned short* row16 = nullptr;
   unsigned short* ent_row = nullptr;
+  unsigned short* hist = nullptr;
   float* sval = nullptr;
   void* tmp = nullptr;
   const size_t sd = (size_t)S * Dg;
   auto cleanup = [&](bool all) {
-    cudaFree(cnt); cudaFree(cnt_s); cudaFree(ids); cudaFree(ids_s); cudaFree(offs); cudaFree(inv); cudaFree(d64); cudaFree(tmp); cudaFree(ent_row);
+    cudaFree(cnt); cudaFree(cnt_s); cudaFree(ids); cudaFree(ids_s); cudaFree(offs); cudaFree(inv); cudaFree(d64); cudaFree(tmp); cudaFree(ent_row); cudaFree(hist);
     if (all) { cudaFree(perm); cudaFree(depth); cudaFree(goff); cudaFree(row16); cudaFree(sval); }
   };
 #define K1F_CK(x) do { e = (x); if (e != cudaSuccess) { cleanup(true); return e; } } while (0)
@@ -388,8 +419,11 @@ cudaError_t k1f_build(long long n, int Dg, long long nnz, const long long* rowpt
   K1F_CK(cudaMemsetAsync(sval, 0, (size_t)total * 32 * 4, st));
   K1F_CK(cudaMalloc(&ent_row, std::max<size_t>((size_t)nnz * 2, 16)));
   k1f_rowid_kernel<<<2368, 256, 0, st>>>(n, sg_rows, rowptr, ent_row);
+  K1F_CK(cudaMalloc(&hist, sd * K1F_CHUNKS * 2));
+  K1F_CK(cudaFuncSetAttribute(k1f_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dg * 4));
+  k1f_hist_kernel<<<dim3(S, K1F_CHUNKS), 256, (size_t)Dg * 4, st>>>(n, sg_rows, Dg, rowptr, colidx, hist);
   K1F_CK(cudaFuncSetAttribute(k1f_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dg * 2));
-  k1f_fill_kernel<<<S, 32, (size_t)Dg * 2, st>>>(n, sg_rows, Dg, ngrp, rowptr, colidx, vals, ent_row, inv, goff, row16, sval);
+  k1f_fill_kernel<<<dim3(S, K1F_CHUNKS), 32, (size_t)Dg * 2, st>>>(n, sg_rows, Dg, ngrp, rowptr, colidx, vals, ent_row, inv, goff, hist, row16, sval);
   K1F_CK(cudaGetLastError());
   K1F_CK(cudaStreamSynchronize(st));
 #undef K1F_CK

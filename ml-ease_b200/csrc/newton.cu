@@ -55,7 +55,7 @@ __global__ void newton_begin_kernel(const Problem* __restrict__ probs, double xt
     if (invalidate_hess) c->hess_valid = 0;
     if (!(c->h0_scale > 0.0)) c->h0_scale = 1.0;
     c->done = 0; c->have_dir = 0; c->need_solve = 0; c->need_hess = 0; c->fail = 0;
-    c->newton_steps = 0; c->evals = 0; c->rejects = 0; c->hess_builds = 0; c->stall = 0;
+    c->newton_steps = 0; c->evals = 0; c->rejects = 0; c->hess_builds = 0; c->stall = 0; c->build_step = 0;
     c->alpha = 1.0; c->phi0 = 0.0; c->f_acc = 0.0; c->f_t = 0.0; c->gnorm = 0.0; c->gnorm_prev = 0.0; c->dirnorm = 0.0; c->dirnorm_prev = 0.0;
     c->xtol = xtol; c->max_newton = max_newton; c->hess_policy = hess_policy; c->rebuild_is_expensive = rebuild_is_expensive;
     if (c->bfgs_m != bfgs_m) { c->bfgs_m = bfgs_m; c->bfgs_count = 0; }
@@ -177,7 +177,12 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
         if (c->hess_policy == 1) {
           c->emit = 1;
         } else {
-          const bool poor = !c->rebuild_is_expensive && have_dir && c->gnorm_prev > 0.0 && ginf > 0.25 * c->gnorm_prev;
+          // Wide systems (a rebuild costs more than ~8 passes) lean on the secant pairs instead of refactorising -- but not for
+          // ever: a dozen steps on the same factor that still contract by less than 2x mean the factor was taken too far
+          // away (a cold fit whose IRLS weights moved a lot), and one rebuild here is cheaper than the steps it saves.
+          const bool stuck = c->rebuild_is_expensive && have_dir && c->gnorm_prev > 0.0 && ginf > 0.5 * c->gnorm_prev &&
+                             c->newton_steps - c->build_step >= 12;
+          const bool poor = stuck || (!c->rebuild_is_expensive && have_dir && c->gnorm_prev > 0.0 && ginf > 0.25 * c->gnorm_prev);
           c->emit = (poor && !c->need_hess) ? 1 : 0;
           if (!c->need_hess && !c->hess_valid) { c->emit = 1; }
           if (deferred) c->emit = 1;

@@ -18,6 +18,7 @@
 // A fp32 SIMT kernel computing the same partials from the same bf16 operand is kept ONLY as a
 // debug cross-check reachable through mlease_objective(tensor=0); the product path never uses it.
 #include <cuda.h>
+#include <cuda_fp8.h>
 
 #include <algorithm>
 #include <cub/device/device_scan.cuh>
@@ -196,17 +197,24 @@ gram_tcgen05_kernel(const Problem* __restrict__ probs, const CUtensorMap* __rest
 // ------------------------------------------------------------------------------------------
 constexpr int SK = 32;                       // data rows (K) per stage
 constexpr int SST = 8;                       // ring stages
-constexpr int S_A_BYTES = SK * GM * 2;       // 8 KB  : 2 boxes of [32 k][64 cols]
-constexpr int S_B_BYTES = SK * GN * 2;       // 16 KB : 4 boxes
+constexpr int S_A_BYTES = SK * GM;           // 4 KB : one [32 k][128 cols] e4m3 block
+constexpr int S_B_BYTES = SK * GN;           // 8 KB : two blocks
 constexpr int S_STAGE_BYTES = S_A_BYTES + S_B_BYTES;
-constexpr int S_BOX_BYTES = SK * 128;        // 4 KB
+constexpr int S_BOX_BYTES = SK * 128;        // 4 KB = one 128-column MN group of 32 K-rows
 constexpr int SPW = 3;                       // producer warps per stage: one per 128-column operand block
 constexpr int S_THREADS = (1 + SPW * SST + 4) * 32;   // MMA warp, producers, 4 epilogue warps
 constexpr size_t S_SMEM = (size_t)SST * S_STAGE_BYTES + 1024 + 256;
 
-__device__ __forceinline__ uint32_t sw128_off(int k, int col) {   // byte offset of element (row k, column col) inside an operand tile
-  const int box = col >> 6, cc = col & 63;
-  return (uint32_t)(box * S_BOX_BYTES + k * 128 + ((((cc >> 3) ^ (k & 7)) << 4) | ((cc & 7) << 1)));
+// byte offset of element (K-row k, column col < 128) inside one [32 k][128 cols] operand block of 1-byte elements: the canonical
+// MN-major SWIZZLE_128B layout has 128 B (= 128 e4m3 elements along MN) per K-row, 8 K-rows per 1024-B swizzle atom, and the
+// 16-byte chunk index XOR-ed with the row inside the atom
+__device__ __forceinline__ uint32_t sw128_off(int k, int col) {
+  return (uint32_t)(k * 128 + ((((col >> 4) ^ (k & 7)) << 4) | (col & 15)));
+}
+// Instruction descriptor for kind::f8f6f4: c_format F32 (1) @4, a/b_format E4M3 (0) @7/@10, a_major/b_major = MN (1) @15/@16
+// (valid for the 8-bit formats, cute/arch/mma_sm100_desc.hpp), N>>3 @17, M>>4 @24.
+__device__ __forceinline__ uint32_t umma_idesc_e4m3_mn(int M, int N) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __global__ void __launch_bounds__(S_THREADS, 1)
@@ -253,19 +261,18 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
   if (warp == 0) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      const uint32_t idesc = umma_idesc_bf16_mn(GM, GN);
+      // one tcgen05.mma.kind::f8f6f4 per stage: K = 32 = the stage's 32-row group (4 swizzle atoms, SBO = 1024 B apart);
+      // the B tile's second 128-column group sits LBO = 4 KB after the first
+      const uint32_t idesc = umma_idesc_e4m3_mn(GM, GN);
       for (int k = 0; k < nk; k++) {
         const int st = k % SST;
         mbar_wait(&full_bar[st], (uint32_t)((k / SST) & 1));
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + (size_t)st * S_STAGE_BYTES);
         const uint32_t b_addr = a_addr + S_A_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < SK / UK; kk++) {
-          const uint64_t da = umma_desc_mn_sw128(a_addr + kk * (UK * 128), S_BOX_BYTES, 1024);
-          const uint64_t db = umma_desc_mn_sw128(b_addr + kk * (UK * 128), S_BOX_BYTES, 1024);
-          umma_f16(tmem_base, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
-        }
+        const uint64_t da = umma_desc_mn_sw128(a_addr, S_BOX_BYTES, 1024);
+        const uint64_t db = umma_desc_mn_sw128(b_addr, S_BOX_BYTES, 1024);
+        umma_f8(tmem_base, da, db, idesc, k != 0 ? 1u : 0u);
         umma_commit(&empty_bar[st]);
       }
       umma_commit(acc_bar);
@@ -277,7 +284,7 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
     // first 64 entries of the run one use ahead, so the loads of a use are in flight during the whole previous use.
     const int st = (warp - 1) / SPW, strm = (warp - 1) % SPW;
     unsigned char* a_tile = smem + (size_t)st * S_STAGE_BYTES;
-    unsigned char* const sbase = strm == 0 ? a_tile : a_tile + S_A_BYTES + (strm - 1) * 2 * S_BOX_BYTES;
+    unsigned char* const sbase = strm == 0 ? a_tile : a_tile + S_A_BYTES + (strm - 1) * S_BOX_BYTES;
     const int blk = strm == 0 ? tile.bi : tile.bj * 2 + (strm - 1);
     const bool valid = blk < pb.nblk128;
     const long long ngroups = pb.bm_groups;
@@ -305,10 +312,12 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
         val[q] = e < hi ? bvals[e] : 0.f;
       }
     };
+    const float gscale = pb.gram_scale;   // power of two: keeps sqrt(d) x in e4m3's normal range; undone exactly by chol_prep
     auto ld_sd = [&](int k) -> float {
       const long long r = (ks0 + k) * SK + lane;
-      return (k < nk && r < n) ? sdv[r] : 0.f;
+      return (k < nk && r < n) ? sdv[r] * gscale : 0.f;
     };
+    auto to_e4m3 = [](float x) -> unsigned char { return (unsigned char)__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3); };
     {
       const uint32_t oa = ld_offs(st), ob = ld_offs(st + SST);
       lo0 = __shfl_sync(0xffffffffu, oa, 0); hi0 = __shfl_sync(0xffffffffu, oa, 1);
@@ -328,12 +337,12 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
         mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
 #pragma unroll
         for (int q = 0; q < 2; q++)
-          if (pkey[q] != NOKEY) *reinterpret_cast<unsigned short*>(sbase + pkey[q]) = 0;
+          if (pkey[q] != NOKEY) sbase[pkey[q]] = 0;
         for (uint32_t e0 = plo + 64; e0 < phi; e0 += 32) {
           const uint32_t e = e0 + lane;
-          if (e < phi) *reinterpret_cast<unsigned short*>(sbase + keys[e]) = 0;
+          if (e < phi) sbase[keys[e]] = 0;
         }
-        if (prow && has_bias_col) *reinterpret_cast<unsigned short*>(sbase + bias_off) = 0;
+        if (prow && has_bias_col) sbase[bias_off] = 0;
       }
       // ---- write this use
 #pragma unroll
@@ -341,7 +350,7 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
         const bool v = key0[q] != NOKEY;
         const uint32_t key = v ? key0[q] : 0u;
         const float sdk = __shfl_sync(0xffffffffu, sd0, (key >> 7) & 31);
-        if (v) *reinterpret_cast<__nv_bfloat16*>(sbase + key) = __float2bfloat16_rn(val0[q] * sdk);
+        if (v) sbase[key] = to_e4m3(val0[q] * sdk);
       }
       for (uint32_t e0 = lo0 + 64; e0 < hi0; e0 += 32) {
         const uint32_t e = e0 + lane;
@@ -349,10 +358,10 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
         const uint32_t key = v ? (uint32_t)keys[e] : 0u;
         const float val = v ? bvals[e] : 0.f;
         const float sdk = __shfl_sync(0xffffffffu, sd0, (key >> 7) & 31);
-        if (v) *reinterpret_cast<__nv_bfloat16*>(sbase + key) = __float2bfloat16_rn(val * sdk);
+        if (v) sbase[key] = to_e4m3(val * sdk);
       }
       prow = (ks0 + k) * SK + lane < n;
-      if (prow && has_bias_col) *reinterpret_cast<__nv_bfloat16*>(sbase + bias_off) = __float2bfloat16_rn(sd0);
+      if (prow && has_bias_col) sbase[bias_off] = to_e4m3(sd0);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[st]);

@@ -34,6 +34,7 @@ __global__ void chol_prep_kernel(const Problem* __restrict__ probs, int share) {
     double s = 0.0;
     const size_t off = (size_t)i * Dp + j;
     for (int t = 0; t < S; t++) s += (double)hpart[(size_t)t * Dp * Dp + off];
+    s *= (double)pb.gram_unscale;   // e4m3 operands of the CSR Gram carry a power-of-two scale
     if (i == j) s += pb.q[i];
     v = s;
   } else {

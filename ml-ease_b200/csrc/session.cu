@@ -358,6 +358,7 @@ int batch_alloc(Batch& B, int num_sms) {
       std::memset(&maps[b], 0, sizeof(CUtensorMap));
     } else {
       p.gram_from_csr = 0;
+      p.gram_scale = 1.f; p.gram_unscale = 1.f;   // bf16 dense-operand Gram: no operand scale
       if (!p.Xt) p.Xt = reinterpret_cast<__nv_bfloat16*>(pool + pool_off[b]);
       if (gram_make_tensor_map(&maps[b], p.Xt, p.n, B.Dp) != 0) return fail(MLEASE_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     }
@@ -614,6 +615,16 @@ void fill_problem_data(Problem& p, const PartData& pd) {
   p.vmax = pd.vmax; p.wmax = pd.wmax;
   p.sg_S = pd.sg_S; p.sg_rows = pd.sg_rows; p.sg_ngrp = pd.sg_ngrp; p.sg_perm = pd.sg_perm; p.sg_depth = pd.sg_depth; p.sg_goff = pd.sg_goff;
   p.sg_row16 = pd.sg_row16; p.sg_val = pd.sg_val;
+  p.gram_scale = 1.f; p.gram_unscale = 1.f;
+  if (pd.bm_offs) {
+    // e4m3 operands of the CSR Gram: |sqrt(d) x| <= 0.5 sqrt(wmax) max(|x|max, 1); scale the largest to ~224 (e4m3 max 448)
+    const float amax = 0.5f * std::sqrt(std::max(pd.wmax, 1e-30f)) * std::max(pd.vmax, 1.f);
+    int e = 0;
+    std::frexp(224.f / amax, &e);
+    e = std::max(-60, std::min(60, e - 1));
+    p.gram_scale = std::ldexp(1.f, e);
+    p.gram_unscale = std::ldexp(1.f, -2 * e);
+  }
 }
 
 int finalize(mlease_session* s) {
@@ -1218,6 +1229,7 @@ int mlease_objective(mlease_session* s, int32_t pid, const double* w, const doub
       for (int j = 0; j <= i; j++) {
         double a = 0;
         for (int t = 0; t < B->gram_slices; t++) a += (double)hp[t * per + (size_t)i * B->Dp + j];
+        if (B->gram_from_csr) a *= (double)p.gram_unscale;
         if (i == j) a += q[i];
         H[(size_t)i * Dt + j] = a;
         H[(size_t)j * Dt + i] = a;

@@ -110,8 +110,10 @@ struct Problem {
   double* Ldinv;           // [ldh][32] inverses of the diagonal blocks (lower triangular)
   double* Yinv;            // [ldh][ldh] L^-1 (lower)
   double* Hinv;            // [ldh][ldh] (L L^T)^-1, full symmetric: a Newton direction is one GEMV
-  float* Hinv_f;          // fp32 copy of Hinv for the direction GEMV of wide systems (ldh > 2048; NULL otherwise): H^-1 only
-                          // preconditions (the Gram is bf16), and the GEMV is HBM-bound on D'^2 entries
+  float* Hinv_f;          // wide systems (ldh > 2048; NULL otherwise): fp32 operand of the direction product.  It holds Y = L^-1 in
+                          // symmetric storage M[i][j] = Y[max(i,j)][min(i,j)] (k3_cholesky.cu ysym_kernel): H^-1 q = Y^T (Y q) is two
+                          // row-wise triangular GEMVs over it, HBM-bound on D'^2 fp32 entries in total
+  double* tvec;           // [ldx] scratch of that product (t = Y q)
   int ldh;
   Ctrl* ctrl;
   // ADMM per-problem vectors (float, as the reference's avro files hold them)

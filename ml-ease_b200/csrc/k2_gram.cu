@@ -196,13 +196,14 @@ gram_tcgen05_kernel(const Problem* __restrict__ probs, const CUtensorMap* __rest
 // the dense kernel's; the producers wait on the empty barriers 2/3 of the time).
 // ------------------------------------------------------------------------------------------
 constexpr int SK = 32;                       // data rows (K) per stage
-constexpr int SST = 8;                       // ring stages
+constexpr int SST = 16;                      // ring stages (12 KB each)
+constexpr int NTRIO = 8;                     // producer trios; trio t fills the K-steps k = t (mod 8), i.e. stages t and t + 8 in turn
 constexpr int S_A_BYTES = SK * GM;           // 4 KB : one [32 k][128 cols] e4m3 block
 constexpr int S_B_BYTES = SK * GN;           // 8 KB : two blocks
 constexpr int S_STAGE_BYTES = S_A_BYTES + S_B_BYTES;
 constexpr int S_BOX_BYTES = SK * 128;        // 4 KB = one 128-column MN group of 32 K-rows
 constexpr int SPW = 3;                       // producer warps per stage: one per 128-column operand block
-constexpr int S_THREADS = (1 + SPW * SST + 4) * 32;   // MMA warp, producers, 4 epilogue warps
+constexpr int S_THREADS = (1 + SPW * NTRIO + 4) * 32;   // MMA warp, producers, 4 epilogue warps
 constexpr size_t S_SMEM = (size_t)SST * S_STAGE_BYTES + 1024 + 256;
 
 // byte offset of element (K-row k, column col < 128) inside one [32 k][128 cols] operand block of 1-byte elements: the canonical
@@ -277,14 +278,16 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
       }
       umma_commit(acc_bar);
     }
-  } else if (warp <= SPW * SST) {
+  } else if (warp <= SPW * NTRIO) {
     // ===== producers: three warps per stage, one per 128-column operand block (A block, first and second B block).
     // The warps of stage s own the K-steps k = s, s+SST, ...  One K-step = one 32-row group, whose entries for a
     // 128-column block are one contiguous run of the block-major list.  Offsets are fetched two uses ahead and the
     // first 64 entries of the run one use ahead, so the loads of a use are in flight during the whole previous use.
-    const int st = (warp - 1) / SPW, strm = (warp - 1) % SPW;
-    unsigned char* a_tile = smem + (size_t)st * S_STAGE_BYTES;
-    unsigned char* const sbase = strm == 0 ? a_tile : a_tile + S_A_BYTES + (strm - 1) * S_BOX_BYTES;
+    // Trio t = (warp - 1) / SPW owns the K-steps k = t, t + NTRIO, ...; K-step k lives in ring stage k % SST, so a trio
+    // alternates between the stages t and t + NTRIO: twice as many stages in flight as trios, because the refill round trip
+    // (empty barrier -> clear -> fill -> fence -> full barrier) is several MMA periods long at the e4m3 rate.
+    const int trio = (warp - 1) / SPW, strm = (warp - 1) % SPW;
+    const size_t strm_off = strm == 0 ? 0 : (size_t)S_A_BYTES + (size_t)(strm - 1) * S_BOX_BYTES;
     const int blk = strm == 0 ? tile.bi : tile.bj * 2 + (strm - 1);
     const bool valid = blk < pb.nblk128;
     const long long ngroups = pb.bm_groups;
@@ -299,10 +302,10 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
     const bool fetch = valid && lane < 2;
 
     // Pipeline registers: offsets three uses ahead (o_c), entries + sqrt(d) two uses ahead (set 2), one use ahead (set 1),
-    // current (set 0).  A use lasts about SST MMA K-steps (~1 us), less than a DRAM miss under load, hence two in flight.
+    // current (set 0); what the last TWO uses stored (p1 = previous use = the other stage, p2 = the use before = this stage).
     auto ld_offs = [&](int k) -> uint32_t { return (fetch && k < nk) ? (uint32_t)my_offs[ks0 + k] : 0u; };   // the list holds < 2^32 entries (checked at upload)
-    uint32_t lo0, hi0, lo1, hi1, lo2, hi2, plo = 0, phi = 0;
-    uint32_t key0[2], key1[2], key2[2], pkey[2] = {NOKEY, NOKEY};
+    uint32_t lo0, hi0, lo1, hi1, lo2, hi2, p1lo = 0, p1hi = 0, p2lo = 0, p2hi = 0;
+    uint32_t key0[2], key1[2], key2[2], p1key[2] = {NOKEY, NOKEY}, p2key[2] = {NOKEY, NOKEY};
     float val0[2], val1[2], val2[2], sd0, sd1, sd2;
     auto ld_entries = [&](uint32_t lo, uint32_t hi, uint32_t* key, float* val) {
 #pragma unroll
@@ -319,30 +322,33 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
     };
     auto to_e4m3 = [](float x) -> unsigned char { return (unsigned char)__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3); };
     {
-      const uint32_t oa = ld_offs(st), ob = ld_offs(st + SST);
+      const uint32_t oa = ld_offs(trio), ob = ld_offs(trio + NTRIO);
       lo0 = __shfl_sync(0xffffffffu, oa, 0); hi0 = __shfl_sync(0xffffffffu, oa, 1);
       lo1 = __shfl_sync(0xffffffffu, ob, 0); hi1 = __shfl_sync(0xffffffffu, ob, 1);
     }
-    uint32_t o_c = ld_offs(st + 2 * SST);
-    ld_entries(lo0, hi0, key0, val0); sd0 = ld_sd(st);
-    ld_entries(lo1, hi1, key1, val1); sd1 = ld_sd(st + SST);
-    bool prow = false;
-    for (int k = st, use = 0; k < nk; k += SST, use++) {
+    uint32_t o_c = ld_offs(trio + 2 * NTRIO);
+    ld_entries(lo0, hi0, key0, val0); sd0 = ld_sd(trio);
+    ld_entries(lo1, hi1, key1, val1); sd1 = ld_sd(trio + NTRIO);
+    bool p1row = false, p2row = false;
+    for (int k = trio, use = 0; k < nk; k += NTRIO, use++) {
+      const int st = k % SST;
+      unsigned char* const sbase = smem + (size_t)st * S_STAGE_BYTES + strm_off;
       // ---- issue the loads of the use after next
       lo2 = __shfl_sync(0xffffffffu, o_c, 0); hi2 = __shfl_sync(0xffffffffu, o_c, 1);
-      o_c = ld_offs(k + 3 * SST);
-      ld_entries(lo2, hi2, key2, val2); sd2 = ld_sd(k + 2 * SST);
-      // ---- un-write what the previous use of this stage stored (same addresses, zero)
-      if (use > 0) {
-        mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
+      o_c = ld_offs(k + 3 * NTRIO);
+      ld_entries(lo2, hi2, key2, val2); sd2 = ld_sd(k + 2 * NTRIO);
+      // ---- un-write what the previous use of THIS STAGE (two uses ago) stored (same addresses, zero)
+      const int fill = k / SST;   // how many times this stage has been filled before
+      if (fill > 0) {
+        mbar_wait(&empty_bar[st], (uint32_t)((fill - 1) & 1));
 #pragma unroll
         for (int q = 0; q < 2; q++)
-          if (pkey[q] != NOKEY) sbase[pkey[q]] = 0;
-        for (uint32_t e0 = plo + 64; e0 < phi; e0 += 32) {
+          if (p2key[q] != NOKEY) sbase[p2key[q]] = 0;
+        for (uint32_t e0 = p2lo + 64; e0 < p2hi; e0 += 32) {
           const uint32_t e = e0 + lane;
-          if (e < phi) sbase[keys[e]] = 0;
+          if (e < p2hi) sbase[keys[e]] = 0;
         }
-        if (prow && has_bias_col) sbase[bias_off] = 0;
+        if (p2row && has_bias_col) sbase[bias_off] = 0;
       }
       // ---- write this use
 #pragma unroll
@@ -360,15 +366,16 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
         const float sdk = __shfl_sync(0xffffffffu, sd0, (key >> 7) & 31);
         if (v) sbase[key] = to_e4m3(val * sdk);
       }
-      prow = (ks0 + k) * SK + lane < n;
-      if (prow && has_bias_col) sbase[bias_off] = to_e4m3(sd0);
+      const bool row_now = (ks0 + k) * SK + lane < n;
+      if (row_now && has_bias_col) sbase[bias_off] = to_e4m3(sd0);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[st]);
       // ---- rotate
-      plo = lo0; phi = hi0; lo0 = lo1; hi0 = hi1; lo1 = lo2; hi1 = hi2;
+      p2lo = p1lo; p2hi = p1hi; p2row = p1row; p1lo = lo0; p1hi = hi0; p1row = row_now;
+      lo0 = lo1; hi0 = hi1; lo1 = lo2; hi1 = hi2;
 #pragma unroll
-      for (int q = 0; q < 2; q++) { pkey[q] = key0[q]; key0[q] = key1[q]; val0[q] = val1[q]; key1[q] = key2[q]; val1[q] = val2[q]; }
+      for (int q = 0; q < 2; q++) { p2key[q] = p1key[q]; p1key[q] = key0[q]; key0[q] = key1[q]; val0[q] = val1[q]; key1[q] = key2[q]; val1[q] = val2[q]; }
       sd0 = sd1; sd1 = sd2;
     }
   } else {

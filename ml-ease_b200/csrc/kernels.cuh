@@ -36,7 +36,9 @@ cudaError_t csr_bm_fill(long long n, const long long* rowptr, const int* colidx,
 cudaError_t gram_launch_simt(const Problem* d_probs, int nprob, int Dp, int force, cudaStream_t st, int* launches);
 
 // K3 (k3_cholesky.cu)
-cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches, int share = 0, int skip_prep = 0);
+cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches, int share = 0, int skip_prep = 0,
+                            int want_hinv = 0);
+bool cholesky_factored_direction(int ldh);   // wide systems: Hinv_f holds Y = L^-1 in symmetric storage, the direction is Y^T (Y q)
 cudaError_t cholesky_share_begin(const Problem* d_probs, int nprob, int share, cudaStream_t st, int* launches);
 cudaError_t cholesky_share_end(const Problem* d_probs, int nprob, int share, cudaStream_t st, int* launches);
 

@@ -272,21 +272,37 @@ __global__ void __launch_bounds__(NT) newton_gemv_kernel(const Problem* __restri
   if (r >= pb.Dt) return;
   const double* q = pb.g_t;
   double a = 0.0;
-  if (pb.Hinv_f) {
-    // wide systems: fp32 copy of the inverse (half the bytes of this HBM-bound product), fp64 accumulation
-    const float* Hr = pb.Hinv_f + (size_t)r * pb.ldh;
-    const int D4 = pb.Dt & ~3;
-    for (int k = lane * 4; k < D4; k += 128) {
-      const float4 h = *reinterpret_cast<const float4*>(Hr + k);
-      a += (double)h.x * q[k] + (double)h.y * q[k + 1] + (double)h.z * q[k + 2] + (double)h.w * q[k + 3];
-    }
-    if (lane < pb.Dt - D4) a += (double)Hr[D4 + lane] * q[D4 + lane];
-  } else {
-    const double* Hr = pb.Hinv + (size_t)r * pb.ldh;
-    for (int k = lane; k < pb.Dt; k += 32) a += Hr[k] * q[k];
-  }
+  const double* Hr = pb.Hinv + (size_t)r * pb.ldh;
+  for (int k = lane; k < pb.Dt; k += 32) a += Hr[k] * q[k];
   a = warp_sum(a);
   if (lane == 0) pb.dir[r] = a;   // r = Hinv q (sign applied after the second loop)
+}
+
+// Wide systems: r = Y^T (Y q) on the symmetric fp32 storage of Y = L^-1 (Hinv_f, see ysym_kernel).  phase 0: t = Y q (row r of
+// the lower part, columns 0..r); phase 1: dir = Y^T t (row c of the upper part incl. the diagonal, columns c..Dt-1).
+// fp32 operand, fp64 accumulation; each phase reads half of the matrix.
+__global__ void __launch_bounds__(NT) newton_gemv_tri_kernel(const Problem* __restrict__ probs, int phase) {
+  const Problem& pb = probs[blockIdx.y];
+  Ctrl* c = pb.ctrl;
+  if (c->done || !c->need_solve) return;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  if (r >= pb.Dt) return;
+  const float* __restrict__ Mr = pb.Hinv_f + (size_t)r * pb.ldh;
+  const double* __restrict__ x = phase == 0 ? pb.g_t : pb.tvec;
+  const int k0 = phase == 0 ? 0 : (r & ~3), k1 = phase == 0 ? r + 1 : pb.Dt;
+  double a = 0.0;
+  for (int k = k0 + lane * 4; k < k1; k += 128) {
+    const float4 h = *reinterpret_cast<const float4*>(Mr + k);   // rows are ldh (multiple of 32) floats long: reading past k1 stays inside the row
+    const float hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int kk = k + e;
+      if (kk < k1 && (phase == 0 || kk >= r)) a += (double)hv[e] * x[kk];
+    }
+  }
+  a = warp_sum(a);
+  if (lane == 0) (phase == 0 ? pb.tvec : pb.dir)[r] = a;
 }
 
 // Direction bookkeeping: norms, termination test, next trial point.  One CTA per problem.
@@ -377,7 +393,14 @@ cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, int Dt, cudaStre
   return cudaGetLastError();
 }
 cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches) {
-  newton_gemv_kernel<<<dim3((ldh + NT / 32 - 1) / (NT / 32), nprob), NT, 0, st>>>(d_probs);
+  const dim3 grid((ldh + NT / 32 - 1) / (NT / 32), nprob);
+  if (cholesky_factored_direction(ldh)) {
+    newton_gemv_tri_kernel<<<grid, NT, 0, st>>>(d_probs, 0);
+    newton_gemv_tri_kernel<<<grid, NT, 0, st>>>(d_probs, 1);
+    if (launches) *launches += 1;
+  } else {
+    newton_gemv_kernel<<<grid, NT, 0, st>>>(d_probs);
+  }
   newton_solve_kernel<<<nprob, NT, 0, st>>>(d_probs);
   if (launches) *launches += 2;
   return cudaGetLastError();

@@ -290,7 +290,7 @@ int batch_alloc(Batch& B, int num_sms) {
     while (best > 1 && (double)best * B.Dp * B.Dp * 4.0 * nprob > 1024.0 * 1024 * 1024) best--;
     B.gram_slices = best;
   }
-  const size_t nd = (size_t)nprob * ((8 + 2 * BFGS_M) * (size_t)ldx + 2 * BFGS_M + (size_t)gpart_rows * ldx + (size_t)B.k1_grid + 8);
+  const size_t nd = (size_t)nprob * ((9 + 2 * BFGS_M) * (size_t)ldx + 2 * BFGS_M + (size_t)gpart_rows * ldx + (size_t)B.k1_grid + 8);
   const size_t nf = (size_t)nprob * 4 * ldx;
   double* dd; float* ff; float* hp; double* lc; double* ld; double* ldi; double* yi; double* hi;
   if (int rc = dev_alloc(B, (void**)&dd, nd * sizeof(double))) return rc;
@@ -332,7 +332,7 @@ int batch_alloc(Batch& B, int num_sms) {
     p.gram_slices = B.gram_slices;
     double* q = dd;
     p.beta = q; q += ldx; p.beta_t = q; q += ldx; p.m = q; q += ldx; p.q = q; q += ldx;
-    p.g_t = q; q += ldx; p.g_acc = q; q += ldx; p.dir = q; q += ldx; p.x_d = q; q += ldx;
+    p.g_t = q; q += ldx; p.g_acc = q; q += ldx; p.dir = q; q += ldx; p.x_d = q; q += ldx; p.tvec = q; q += ldx;
     p.bfgs_S = q; q += (size_t)BFGS_M * ldx; p.bfgs_Y = q; q += (size_t)BFGS_M * ldx; p.bfgs_rho = q; q += BFGS_M; p.bfgs_alpha = q; q += BFGS_M;
     p.gpart = q; q += (size_t)gpart_rows * ldx;
     p.gpart_f = gpf ? gpf + (size_t)b * B.k1_grid * ldx : nullptr;
@@ -424,7 +424,8 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
         for (int b = 0; b < B.nprob; b++) {
           if (b % share == 0) continue;
           const Problem& lead = B.h[b - b % share];
-          CK(cudaMemcpyAsync(B.h[b].Hinv, lead.Hinv, hh * sizeof(double), cudaMemcpyDeviceToDevice, st));
+          // wide systems work on the factored form Y = L^-1 (fp32, Hinv_f): that is all a follower needs
+          if (!cholesky_factored_direction(B.ldh)) CK(cudaMemcpyAsync(B.h[b].Hinv, lead.Hinv, hh * sizeof(double), cudaMemcpyDeviceToDevice, st));
           if (B.h[b].Hinv_f) CK(cudaMemcpyAsync(B.h[b].Hinv_f, lead.Hinv_f, hh * sizeof(float), cudaMemcpyDeviceToDevice, st));
         }
       }
@@ -1209,7 +1210,7 @@ int mlease_objective(mlease_session* s, int32_t pid, const double* w, const doub
       // the inverse the Newton direction uses: split-K Gram partials + diag(q) -> fp64 Cholesky -> explicit inverse
       Ctrl c2; std::memset(&c2, 0, sizeof(c2)); c2.need_hess = 1;
       CK(cudaMemcpyAsync(B->d_ctrl, &c2, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
-      CK(cholesky_launch(B->d, 1, B->ldh, s->stream, &launches));
+      CK(cholesky_launch(B->d, 1, B->ldh, s->stream, &launches, 0, 0, 1));
       std::vector<double> hi((size_t)B->ldh * B->ldh);
       CK(cudaMemcpyAsync(hi.data(), p.Hinv, hi.size() * 8, cudaMemcpyDeviceToHost, s->stream));
       CK(cudaMemcpyAsync(&c2, B->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
@@ -1289,7 +1290,7 @@ int mlease_posterior_variance(mlease_session* s, int32_t pid, const double* w, c
   CK(postvar_hessian(B->d, B->csr, B->ldh, dvec, p.q, 1, s->stream, &launches));
   Ctrl c; std::memset(&c, 0, sizeof(c)); c.need_hess = 1;
   CK(cudaMemcpyAsync(B->d_ctrl, &c, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
-  CK(cholesky_launch(B->d, 1, B->ldh, s->stream, &launches, 0, 1));
+  CK(cholesky_launch(B->d, 1, B->ldh, s->stream, &launches, 0, 1, 1));
   std::vector<double> hi((size_t)B->ldh * B->ldh);
   CK(cudaMemcpyAsync(hi.data(), p.Hinv, hi.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaMemcpyAsync(&c, B->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));

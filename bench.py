@@ -384,16 +384,22 @@ def run_admm_workload(cx, wl, K, W, want_e2e):
             hp = host_parts[p]
             (s2.add_partition_csr if sparse else s2.add_partition_dense)(p, *hp)   # pinned host -> device inside the timed region
             h2d += sum(t.numel() * t.element_size() for t in hp)
+        torch.cuda.synchronize()
+        t_up = time.perf_counter()
+        s2.begin()                                              # solver-state allocation (D'^2 buffers) happens here
+        torch.cuda.synchronize()
+        t_alloc = time.perf_counter()
         done2 = s2.run(K)
         models = [s2.final_model(l) for l in range(L)]          # device -> host read of the job's result
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        phases = {"upload_and_layout_s": t_up - t0, "solver_state_alloc_s": t_alloc - t_up, "iterations_and_readback_s": t0 + dt - t_alloc}
         tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
         th = torch.tensor([float(h2d)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tdt, op=dist.ReduceOp.MAX); dist.all_reduce(th, op=dist.ReduceOp.SUM)
         e2e = {"value": done2 / float(tdt.item()), "unit": "ADMM iterations/s", "h2d_bytes_per_step": float(th.item()) / done2,
-               "d2h_bytes_per_step": (sum(m.nbytes for m in models) + 8 * done2) * world / done2, "seconds": float(tdt.item()),
+               "d2h_bytes_per_step": (sum(m.nbytes for m in models) + 8 * done2) * world / done2, "seconds": float(tdt.item()), "phases_rank0": phases,
                "note": "upload once (the reference re-ingests every iteration), K iterations, model read-back"}
         s2.close()
         del s2, host_parts

@@ -275,13 +275,23 @@ __global__ void k1f_groups_kernel(int S, int Dg, int ngrp, const int* __restrict
     }
   }
 }
-// pass 1 (parallel): the row id inside its segment, per stored value
-__global__ void k1f_rowid_kernel(long long n, int sg_rows, const long long* __restrict__ rowptr, unsigned short* __restrict__ ent_row) {
+// pass 1 (parallel): per stored value, the row id inside its segment and the position of its column's lane slot:
+// (first 32-lane row of the column's group) * 32 + lane.  The value's final place is that + 32 * (its rank in the column).
+__global__ void k1f_rowid_kernel(long long n, int sg_rows, int Dg, int ngrp, const long long* __restrict__ rowptr, const int* __restrict__ colidx,
+                                 const int* __restrict__ inv, const long long* __restrict__ goff, unsigned short* __restrict__ ent_row,
+                                 unsigned* __restrict__ ent_base) {
   const int lane = threadIdx.x & 31;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nw) {
-    const unsigned short r = (unsigned short)(i % sg_rows);
-    for (long long j = rowptr[i] + lane; j < rowptr[i + 1]; j += 32) ent_row[j] = r;
+    const int seg = (int)(i / sg_rows);
+    const unsigned short r = (unsigned short)(i - (long long)seg * sg_rows);
+    const int* __restrict__ iv = inv + (size_t)seg * Dg;
+    const long long* __restrict__ go = goff + (size_t)seg * ngrp;
+    for (long long j = rowptr[i] + lane; j < rowptr[i + 1]; j += 32) {
+      const int slot = iv[colidx[j]];
+      ent_row[j] = r;
+      ent_base[j] = (unsigned)(go[slot >> 5] * 32 + (slot & 31));
+    }
   }
 }
 // pass 2a: column histogram of every chunk of a segment's stored values (K1F_CHUNKS chunks per segment, consecutive in the CSR)
@@ -311,11 +321,11 @@ __global__ void __launch_bounds__(256) k1f_hist_kernel(long long n, int sg_rows,
 // after row), 32 at a time; its per-column counters start at the number of entries the earlier chunks hold, so every column's
 // entries end up in row order: a fixed summation order for phase B.  Lanes of one step that hit the same column (possible when
 // a step spans two short rows) are ranked by lane = by row.
-__global__ void __launch_bounds__(32) k1f_fill_kernel(long long n, int sg_rows, int Dg, int ngrp, const long long* __restrict__ rowptr,
+__global__ void __launch_bounds__(32) k1f_fill_kernel(long long n, int sg_rows, int Dg, const long long* __restrict__ rowptr,
                                                      const int* __restrict__ colidx, const float* __restrict__ vals,
-                                                     const unsigned short* __restrict__ ent_row, const int* __restrict__ inv,
-                                                     const long long* __restrict__ goff, const unsigned short* __restrict__ hist,
-                                                     unsigned short* __restrict__ row16, float* __restrict__ sval) {
+                                                     const unsigned short* __restrict__ ent_row, const unsigned* __restrict__ ent_base,
+                                                     const unsigned short* __restrict__ hist, unsigned short* __restrict__ row16,
+                                                     float* __restrict__ sval) {
   extern __shared__ unsigned short k1f_fill_sm[];
   const int seg = blockIdx.x, chunk = blockIdx.y, lane = threadIdx.x;
   for (int c = lane; c < Dg; c += 32) {
@@ -326,19 +336,23 @@ __global__ void __launch_bounds__(32) k1f_fill_kernel(long long n, int sg_rows, 
   __syncwarp();
   const long long rb = (long long)seg * sg_rows, re = min(n, rb + sg_rows);
   if (rb >= re) return;
-  const int* __restrict__ iv = inv + (size_t)seg * Dg;
-  const long long* __restrict__ go = goff + (size_t)seg * ngrp;
   long long j0, j1;
   k1f_chunk_range(rowptr[rb], rowptr[re], chunk, &j0, &j1);
-#pragma unroll 4
-  for (long long jb = j0; jb < j1; jb += 32) {
+  // the loads of a step do not depend on the counters: keep the next step's in flight while this one is ranked and stored
+  auto ld = [&](long long jb, int& c, float& v, unsigned short& r, unsigned& b) {
     const long long j = jb + lane;
     const bool ok = j < j1;
-    const int c = ok ? colidx[j] : -1 - lane;          // inactive lanes: distinct negative keys
-    const float v = ok ? vals[j] : 0.f;
-    const unsigned short r = ok ? ent_row[j] : 0;
-    const int slot = ok ? iv[c] : 0;
-    const long long gbase = ok ? go[slot >> 5] : 0;
+    c = ok ? __ldg(colidx + j) : -1 - lane;          // inactive lanes: distinct negative keys
+    v = ok ? __ldg(vals + j) : 0.f;
+    r = ok ? __ldg(ent_row + j) : (unsigned short)0;
+    b = ok ? __ldg(ent_base + j) : 0u;
+  };
+  int cn; float vn; unsigned short rn; unsigned bn;
+  ld(j0, cn, vn, rn, bn);
+  for (long long jb = j0; jb < j1; jb += 32) {
+    const int c = cn; const float v = vn; const unsigned short r = rn; const unsigned b = bn;
+    ld(jb + 32, cn, vn, rn, bn);
+    const bool ok = c >= 0;
     const unsigned m = __match_any_sync(0xffffffffu, c);
     const int rank = __popc(m & ((1u << lane) - 1u));
     int k = 0;
@@ -347,7 +361,7 @@ __global__ void __launch_bounds__(32) k1f_fill_kernel(long long n, int sg_rows, 
     if (ok && (m >> (lane + 1)) == 0) k1f_fill_sm[c] = (unsigned short)(k + 1);   // highest lane of the group: count + group size
     __syncwarp();
     if (ok) {
-      const size_t pos = ((size_t)gbase + k) * 32 + (slot & 31);
+      const size_t pos = (size_t)b + (size_t)k * 32;
       row16[pos] = r;
       sval[pos] = v;
     }
@@ -383,12 +397,13 @@ cudaError_t k1f_build(long long n, int Dg, long long nnz, const long long* rowpt
   long long *goff = nullptr, *d64 = nullptr;
   unsigned short* row16 = nullptr;
   unsigned short* ent_row = nullptr;
+  unsigned* ent_base = nullptr;
   unsigned short* hist = nullptr;
   float* sval = nullptr;
   void* tmp = nullptr;
   const size_t sd = (size_t)S * Dg;
   auto cleanup = [&](bool all) {
-    cudaFree(cnt); cudaFree(cnt_s); cudaFree(ids); cudaFree(ids_s); cudaFree(offs); cudaFree(inv); cudaFree(d64); cudaFree(tmp); cudaFree(ent_row); cudaFree(hist);
+    cudaFree(cnt); cudaFree(cnt_s); cudaFree(ids); cudaFree(ids_s); cudaFree(offs); cudaFree(inv); cudaFree(d64); cudaFree(tmp); cudaFree(ent_row); cudaFree(ent_base); cudaFree(hist);
     if (all) { cudaFree(perm); cudaFree(depth); cudaFree(goff); cudaFree(row16); cudaFree(sval); }
   };
 #define K1F_CK(x) do { e = (x); if (e != cudaSuccess) { cleanup(true); return e; } } while (0)
@@ -417,13 +432,15 @@ cudaError_t k1f_build(long long n, int Dg, long long nnz, const long long* rowpt
   K1F_CK(cudaMalloc(&sval, std::max<size_t>((size_t)total * 32 * 4, 16)));
   K1F_CK(cudaMemsetAsync(row16, 0, (size_t)total * 32 * 2, st));
   K1F_CK(cudaMemsetAsync(sval, 0, (size_t)total * 32 * 4, st));
+  if ((size_t)total * 32 >= ((size_t)1 << 32)) { cleanup(true); return cudaErrorInvalidValue; }   // 32-bit slot positions
   K1F_CK(cudaMalloc(&ent_row, std::max<size_t>((size_t)nnz * 2, 16)));
-  k1f_rowid_kernel<<<2368, 256, 0, st>>>(n, sg_rows, rowptr, ent_row);
+  K1F_CK(cudaMalloc(&ent_base, std::max<size_t>((size_t)nnz * 4, 16)));
+  k1f_rowid_kernel<<<2368, 256, 0, st>>>(n, sg_rows, Dg, ngrp, rowptr, colidx, inv, goff, ent_row, ent_base);
   K1F_CK(cudaMalloc(&hist, sd * K1F_CHUNKS * 2));
   K1F_CK(cudaFuncSetAttribute(k1f_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dg * 4));
   k1f_hist_kernel<<<dim3(S, K1F_CHUNKS), 256, (size_t)Dg * 4, st>>>(n, sg_rows, Dg, rowptr, colidx, hist);
   K1F_CK(cudaFuncSetAttribute(k1f_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dg * 2));
-  k1f_fill_kernel<<<dim3(S, K1F_CHUNKS), 32, (size_t)Dg * 2, st>>>(n, sg_rows, Dg, ngrp, rowptr, colidx, vals, ent_row, inv, goff, hist, row16, sval);
+  k1f_fill_kernel<<<dim3(S, K1F_CHUNKS), 32, (size_t)Dg * 2, st>>>(n, sg_rows, Dg, rowptr, colidx, vals, ent_row, ent_base, hist, row16, sval);
   K1F_CK(cudaGetLastError());
   K1F_CK(cudaStreamSynchronize(st));
 #undef K1F_CK

@@ -263,18 +263,26 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
     if (lane == 0) {
       // ===== MMA issuer =====
       // one tcgen05.mma.kind::f8f6f4 per stage: K = 32 = the stage's 32-row group (4 swizzle atoms, SBO = 1024 B apart);
-      // the B tile's second 128-column group sits LBO = 4 KB after the first
+      // the B tile's second 128-column group sits LBO = 4 KB after the first.  The loop over the ring is unrolled so that a
+      // stage's barrier addresses and descriptors are constants: at the e4m3 rate an MMA lasts ~130-220 clk, and the ~45
+      // dependent single-thread instructions of a rolled iteration (address math, R2UR moves) were the bottleneck (ncu r02:
+      // tensor pipe 35 %, producers idle on the empty barriers 64 % of the time).
       const uint32_t idesc = umma_idesc_e4m3_mn(GM, GN);
-      for (int k = 0; k < nk; k++) {
-        const int st = k % SST;
-        mbar_wait(&full_bar[st], (uint32_t)((k / SST) & 1));
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)st * S_STAGE_BYTES);
-        const uint32_t b_addr = a_addr + S_A_BYTES;
-        const uint64_t da = umma_desc_mn_sw128(a_addr, S_BOX_BYTES, 1024);
-        const uint64_t db = umma_desc_mn_sw128(b_addr, S_BOX_BYTES, 1024);
-        umma_f8(tmem_base, da, db, idesc, k != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[st]);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint64_t da0 = umma_desc_mn_sw128(smem_base, S_BOX_BYTES, 1024);
+      const uint64_t db0 = umma_desc_mn_sw128(smem_base + S_A_BYTES, S_BOX_BYTES, 1024);
+      constexpr uint64_t DSTEP = (uint64_t)(S_STAGE_BYTES >> 4);   // the address field counts 16-byte units; 16 stages stay below its 14 bits
+      for (int k0 = 0; k0 < nk; k0 += SST) {
+        const uint32_t par = (uint32_t)((k0 / SST) & 1);
+#pragma unroll
+        for (int st = 0; st < SST; st++) {
+          if (k0 + st < nk) {
+            mbar_wait(&full_bar[st], par);
+            tc_fence_after();
+            umma_f8(tmem_base, da0 + (uint64_t)st * DSTEP, db0 + (uint64_t)st * DSTEP, idesc, (k0 + st) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[st]);
+          }
+        }
       }
       umma_commit(acc_bar);
     }

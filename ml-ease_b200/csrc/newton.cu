@@ -286,23 +286,31 @@ __global__ void __launch_bounds__(NT) newton_gemv_tri_kernel(const Problem* __re
   Ctrl* c = pb.ctrl;
   if (c->done || !c->need_solve) return;
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
-  if (r >= pb.Dt) return;
-  const float* __restrict__ Mr = pb.Hinv_f + (size_t)r * pb.ldh;
+  const int w = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  const int Dt = pb.Dt;
+  if (w >= (Dt + 1) / 2) return;
   const double* __restrict__ x = phase == 0 ? pb.g_t : pb.tvec;
-  const int k0 = phase == 0 ? 0 : (r & ~3), k1 = phase == 0 ? r + 1 : pb.Dt;
-  double a = 0.0;
-  for (int k = k0 + lane * 4; k < k1; k += 128) {
-    const float4 h = *reinterpret_cast<const float4*>(Mr + k);   // rows are ldh (multiple of 32) floats long: reading past k1 stays inside the row
-    const float hv[4] = {h.x, h.y, h.z, h.w};
+  double* __restrict__ out = phase == 0 ? pb.tvec : pb.dir;
+  // a warp takes row w and its mirror Dt-1-w: the two triangular rows together hold Dt+1 elements, whatever w is (balanced)
+#pragma unroll 1
+  for (int half = 0; half < 2; half++) {
+    const int r = half == 0 ? w : Dt - 1 - w;
+    if (half == 1 && r == w) break;
+    const float* __restrict__ Mr = pb.Hinv_f + (size_t)r * pb.ldh;
+    const int k0 = phase == 0 ? 0 : (r & ~3), k1 = phase == 0 ? r + 1 : Dt;
+    double a = 0.0;
+    for (int k = k0 + lane * 4; k < k1; k += 128) {
+      const float4 h = *reinterpret_cast<const float4*>(Mr + k);   // rows are ldh (multiple of 32) floats long: reading past k1 stays inside the row
+      const float hv[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const int kk = k + e;
-      if (kk < k1 && (phase == 0 || kk >= r)) a += (double)hv[e] * x[kk];
+      for (int e = 0; e < 4; e++) {
+        const int kk = k + e;
+        if (kk < k1 && (phase == 0 || kk >= r)) a += (double)hv[e] * x[kk];
+      }
     }
+    a = warp_sum(a);
+    if (lane == 0) out[r] = a;
   }
-  a = warp_sum(a);
-  if (lane == 0) (phase == 0 ? pb.tvec : pb.dir)[r] = a;
 }
 
 // Direction bookkeeping: norms, termination test, next trial point.  One CTA per problem.
@@ -395,8 +403,9 @@ cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, int Dt, cudaStre
 cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches) {
   const dim3 grid((ldh + NT / 32 - 1) / (NT / 32), nprob);
   if (cholesky_factored_direction(ldh)) {
-    newton_gemv_tri_kernel<<<grid, NT, 0, st>>>(d_probs, 0);
-    newton_gemv_tri_kernel<<<grid, NT, 0, st>>>(d_probs, 1);
+    const dim3 gtri(((ldh + 1) / 2 + NT / 32 - 1) / (NT / 32), nprob);
+    newton_gemv_tri_kernel<<<gtri, NT, 0, st>>>(d_probs, 0);
+    newton_gemv_tri_kernel<<<gtri, NT, 0, st>>>(d_probs, 1);
     if (launches) *launches += 1;
   } else {
     newton_gemv_kernel<<<grid, NT, 0, st>>>(d_probs);

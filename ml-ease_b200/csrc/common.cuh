@@ -110,9 +110,11 @@ struct Problem {
   double* Ldinv;           // [ldh][32] inverses of the diagonal blocks (lower triangular)
   double* Yinv;            // [ldh][ldh] L^-1 (lower)
   double* Hinv;            // [ldh][ldh] (L L^T)^-1, full symmetric: a Newton direction is one GEMV
-  float* Hinv_f;          // wide systems (ldh > 2048; NULL otherwise): fp32 operand of the direction product.  It holds Y = L^-1 in
-                          // symmetric storage M[i][j] = Y[max(i,j)][min(i,j)] (k3_cholesky.cu ysym_kernel): H^-1 q = Y^T (Y q) is two
-                          // row-wise triangular GEMVs over it, HBM-bound on D'^2 fp32 entries in total
+  __nv_bfloat16* Ysym;    // wide systems (ldh > 2048; NULL otherwise): operand of the direction product.  It holds Y = L^-1 as bf16 in
+                          // symmetric storage M[i][j] = Y[max(i,j)][min(i,j)] (k3_cholesky.cu ysym_kernel): H^-1 q ~ Y^T (Y q) is two
+                          // row-wise triangular GEMVs over it, HBM-bound on D'^2 2-byte entries in total.  The product form is
+                          // symmetric positive definite for ANY rounding of Y, so the low precision can never turn the preconditioner
+                          // indefinite (a rounded explicit H^-1 could)
   double* tvec;           // [ldx] scratch of that product (t = Y q)
   int ldh;
   Ctrl* ctrl;

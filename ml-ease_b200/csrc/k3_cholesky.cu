@@ -477,15 +477,8 @@ __global__ void __launch_bounds__(256, 2) dgemm_kernel(const Problem* __restrict
       } else if (mode == 2) {
         *reinterpret_cast<double2*>(C + (size_t)i * ldh + j) = make_double2(-v0, -v1);
       } else {
-        float* Cf = pb.Hinv_f;
-        if (j <= i) {
-          C[(size_t)i * ldh + j] = v0; C[(size_t)j * ldh + i] = v0;
-          if (Cf) { Cf[(size_t)i * ldh + j] = (float)v0; Cf[(size_t)j * ldh + i] = (float)v0; }
-        }
-        if (j + 1 <= i) {
-          C[(size_t)i * ldh + j + 1] = v1; C[(size_t)(j + 1) * ldh + i] = v1;
-          if (Cf) { Cf[(size_t)i * ldh + j + 1] = (float)v1; Cf[(size_t)(j + 1) * ldh + i] = (float)v1; }
-        }
+        if (j <= i) { C[(size_t)i * ldh + j] = v0; C[(size_t)j * ldh + i] = v0; }
+        if (j + 1 <= i) { C[(size_t)i * ldh + j + 1] = v1; C[(size_t)(j + 1) * ldh + i] = v1; }
       }
     }
   }
@@ -522,8 +515,8 @@ static int wide_threshold() {
   return t;
 }
 
-// Wide systems with an fp32 direction operand (Hinv_f != NULL, ldh > 2048): the solver never needs H^-1 itself, only the
-// product H^-1 q = Y^T (Y q) with Y = L^-1.  Hinv_f receives Y in SYMMETRIC storage, M[i][j] = Y[max(i,j)][min(i,j)]: row r of
+// Wide systems (Ysym != NULL, ldh > 2048): the solver never needs H^-1 itself, only the
+// product H^-1 q = Y^T (Y q) with Y = L^-1.  Ysym receives Y (bf16) in SYMMETRIC storage, M[i][j] = Y[max(i,j)][min(i,j)]: row r of
 // the lower part is row r of Y, row c of the upper part is column c of Y, so both triangular GEMVs of the direction read rows
 // (coalesced) and together touch each element once -- the same bytes as one GEMV with a full H^-1, without the D'^3/3-flop
 // Y^T Y product (10 ms of DMMA per 10k-wide factorisation).
@@ -540,16 +533,16 @@ __global__ void __launch_bounds__(256) ysym_kernel(const Problem* __restrict__ p
     const int i = bi * 32 + r, j = bj * 32 + tx;
     const float v = j <= i ? (float)pb.Yinv[(size_t)i * ldh + j] : 0.f;
     t[r][tx] = v;
-    if (j <= i) pb.Hinv_f[(size_t)i * ldh + j] = v;
+    if (j <= i) pb.Ysym[(size_t)i * ldh + j] = __float2bfloat16_rn(v);
   }
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
     const int j = bj * 32 + r, i = bi * 32 + tx;     // element (j, i) of the upper part = Y[i][j]
-    if (j < i) pb.Hinv_f[(size_t)j * ldh + i] = t[tx][r];
+    if (j < i) pb.Ysym[(size_t)j * ldh + i] = __float2bfloat16_rn(t[tx][r]);
   }
 }
 
-bool cholesky_factored_direction(int ldh) { return ldh > 2048 && ldh > wide_threshold(); }   // = the problems that carry Hinv_f (batch_alloc)
+bool cholesky_factored_direction(int ldh) { return ldh > 2048 && ldh > wide_threshold(); }   // = the problems that carry Ysym (batch_alloc)
 
 static cudaError_t cholesky_launch_wide(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches, bool factored_direction) {
   cudaError_t e;

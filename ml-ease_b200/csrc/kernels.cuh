@@ -38,7 +38,7 @@ cudaError_t gram_launch_simt(const Problem* d_probs, int nprob, int Dp, int forc
 // K3 (k3_cholesky.cu)
 cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches, int share = 0, int skip_prep = 0,
                             int want_hinv = 0);
-bool cholesky_factored_direction(int ldh);   // wide systems: Hinv_f holds Y = L^-1 in symmetric storage, the direction is Y^T (Y q)
+bool cholesky_factored_direction(int ldh);   // wide systems: Ysym holds Y = L^-1 (bf16, symmetric storage), the direction is Y^T (Y q)
 cudaError_t cholesky_share_begin(const Problem* d_probs, int nprob, int share, cudaStream_t st, int* launches);
 cudaError_t cholesky_share_end(const Problem* d_probs, int nprob, int share, cudaStream_t st, int* launches);
 

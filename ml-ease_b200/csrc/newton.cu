@@ -278,9 +278,9 @@ __global__ void __launch_bounds__(NT) newton_gemv_kernel(const Problem* __restri
   if (lane == 0) pb.dir[r] = a;   // r = Hinv q (sign applied after the second loop)
 }
 
-// Wide systems: r = Y^T (Y q) on the symmetric fp32 storage of Y = L^-1 (Hinv_f, see ysym_kernel).  phase 0: t = Y q (row r of
+// Wide systems: r = Y^T (Y q) on the symmetric bf16 storage of Y = L^-1 (Ysym, see ysym_kernel).  phase 0: t = Y q (row r of
 // the lower part, columns 0..r); phase 1: dir = Y^T t (row c of the upper part incl. the diagonal, columns c..Dt-1).
-// fp32 operand, fp64 accumulation; each phase reads half of the matrix.
+// bf16 operand (8 elements per 16-byte load), fp64 accumulation; each phase reads half of the matrix.
 __global__ void __launch_bounds__(NT) newton_gemv_tri_kernel(const Problem* __restrict__ probs, int phase) {
   const Problem& pb = probs[blockIdx.y];
   Ctrl* c = pb.ctrl;
@@ -296,16 +296,17 @@ __global__ void __launch_bounds__(NT) newton_gemv_tri_kernel(const Problem* __re
   for (int half = 0; half < 2; half++) {
     const int r = half == 0 ? w : Dt - 1 - w;
     if (half == 1 && r == w) break;
-    const float* __restrict__ Mr = pb.Hinv_f + (size_t)r * pb.ldh;
-    const int k0 = phase == 0 ? 0 : (r & ~3), k1 = phase == 0 ? r + 1 : Dt;
+    const __nv_bfloat16* __restrict__ Mr = pb.Ysym + (size_t)r * pb.ldh;
+    const int k0 = phase == 0 ? 0 : (r & ~7), k1 = phase == 0 ? r + 1 : Dt;
     double a = 0.0;
-    for (int k = k0 + lane * 4; k < k1; k += 128) {
-      const float4 h = *reinterpret_cast<const float4*>(Mr + k);   // rows are ldh (multiple of 32) floats long: reading past k1 stays inside the row
-      const float hv[4] = {h.x, h.y, h.z, h.w};
+    for (int k = k0 + lane * 8; k < k1; k += 256) {
+      const uint4 h = *reinterpret_cast<const uint4*>(Mr + k);   // rows are ldh (multiple of 32) elements long: reading past k1 stays inside the row
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
+      for (int e = 0; e < 8; e++) {
         const int kk = k + e;
-        if (kk < k1 && (phase == 0 || kk >= r)) a += (double)hv[e] * x[kk];
+        const float hv = __uint_as_float((e & 1) ? (hw[e >> 1] & 0xFFFF0000u) : (hw[e >> 1] << 16));   // bf16 -> fp32 is a 16-bit shift
+        if (kk < k1 && (phase == 0 || kk >= r)) a += (double)hv * x[kk];
       }
     }
     a = warp_sum(a);

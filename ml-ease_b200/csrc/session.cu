@@ -304,9 +304,9 @@ int batch_alloc(Batch& B, int num_sms) {
   if (int rc = dev_alloc(B, (void**)&ldi, (size_t)nprob * B.ldh * 32 * sizeof(double))) return rc;
   if (int rc = dev_alloc(B, (void**)&yi, (size_t)nprob * B.ldh * B.ldh * sizeof(double))) return rc;
   if (int rc = dev_alloc(B, (void**)&hi, (size_t)nprob * B.ldh * B.ldh * sizeof(double))) return rc;
-  float* hif = nullptr;
+  __nv_bfloat16* hif = nullptr;
   if (B.ldh > 2048)
-    if (int rc = dev_alloc(B, (void**)&hif, (size_t)nprob * B.ldh * B.ldh * sizeof(float))) return rc;
+    if (int rc = dev_alloc(B, (void**)&hif, (size_t)nprob * B.ldh * B.ldh * sizeof(__nv_bfloat16))) return rc;
   if (int rc = dev_alloc(B, (void**)&B.d_ctrl, (size_t)nprob * sizeof(Ctrl))) return rc;
   if (int rc = dev_alloc(B, (void**)&B.d, (size_t)nprob * sizeof(Problem))) return rc;
   if (nprob > 64)
@@ -347,7 +347,7 @@ int batch_alloc(Batch& B, int num_sms) {
     p.Ldinv = ldi + (size_t)b * B.ldh * 32;
     p.Yinv = yi + (size_t)b * B.ldh * B.ldh;
     p.Hinv = hi + (size_t)b * B.ldh * B.ldh;
-    p.Hinv_f = hif ? hif + (size_t)b * B.ldh * B.ldh : nullptr;
+    p.Ysym = hif ? hif + (size_t)b * B.ldh * B.ldh : nullptr;
     p.ctrl = B.d_ctrl + b;
     // Gram operand state, carved out of ONE allocation for the whole batch (NaiveTrain batches hold thousands of problems:
     // one cudaMalloc / cudaFree each would cost more than the fits)
@@ -424,9 +424,9 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
         for (int b = 0; b < B.nprob; b++) {
           if (b % share == 0) continue;
           const Problem& lead = B.h[b - b % share];
-          // wide systems work on the factored form Y = L^-1 (fp32, Hinv_f): that is all a follower needs
+          // wide systems work on the factored form Y = L^-1 (bf16, Ysym): that is all a follower needs
           if (!cholesky_factored_direction(B.ldh)) CK(cudaMemcpyAsync(B.h[b].Hinv, lead.Hinv, hh * sizeof(double), cudaMemcpyDeviceToDevice, st));
-          if (B.h[b].Hinv_f) CK(cudaMemcpyAsync(B.h[b].Hinv_f, lead.Hinv_f, hh * sizeof(float), cudaMemcpyDeviceToDevice, st));
+          if (B.h[b].Ysym) CK(cudaMemcpyAsync(B.h[b].Ysym, lead.Ysym, hh * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, st));
         }
       }
       pf.end(st);
@@ -808,21 +808,21 @@ int mlease_session_destroy(mlease_session* s) {
 
 static int add_common(mlease_session* s, PartData& pd, const int32_t* response, const float* weight, const float* offset) {
   const long long n = pd.n;
-  void *y, *w, *o, *tmp_r, *tmp_w = nullptr, *tmp_o = nullptr;
+  void *y, *w, *o;
   if (int rc = sess_alloc(s, &y, n)) return rc;
   if (int rc = sess_alloc(s, &w, n * 4)) return rc;
   if (int rc = sess_alloc(s, &o, n * 4)) return rc;
-  CK(cudaMalloc(&tmp_r, std::max<long long>(n, 1) * 4));
+  TmpDev t;   // staging copies of the caller's arrays: freed on every return path
+  int* tmp_r = nullptr; float *tmp_w = nullptr, *tmp_o = nullptr;
+  if (int rc = t.get(&tmp_r, (size_t)std::max<long long>(n, 1))) return rc;
   CK(cudaMemcpyAsync(tmp_r, response, n * 4, cudaMemcpyDefault, s->stream));
-  if (weight) { CK(cudaMalloc(&tmp_w, std::max<long long>(n, 1) * 4)); CK(cudaMemcpyAsync(tmp_w, weight, n * 4, cudaMemcpyDefault, s->stream)); }
-  if (offset) { CK(cudaMalloc(&tmp_o, std::max<long long>(n, 1) * 4)); CK(cudaMemcpyAsync(tmp_o, offset, n * 4, cudaMemcpyDefault, s->stream)); }
+  if (weight) { if (int rc = t.get(&tmp_w, (size_t)std::max<long long>(n, 1))) return rc; CK(cudaMemcpyAsync(tmp_w, weight, n * 4, cudaMemcpyDefault, s->stream)); }
+  if (offset) { if (int rc = t.get(&tmp_o, (size_t)std::max<long long>(n, 1))) return rc; CK(cudaMemcpyAsync(tmp_o, offset, n * 4, cudaMemcpyDefault, s->stream)); }
   CK(cudaMemsetAsync(s->d_flag, 0, 4, s->stream));
   if (n > 0)
-    convert_labels_kernel<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, s->stream>>>(n, (const int*)tmp_r, (const float*)tmp_w, (const float*)tmp_o,
-                                                                                         (signed char*)y, (float*)w, (float*)o, s->d_flag);
+    convert_labels_kernel<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, s->stream>>>(n, tmp_r, tmp_w, tmp_o, (signed char*)y, (float*)w, (float*)o, s->d_flag);
   CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
-  cudaFree(tmp_r); cudaFree(tmp_w); cudaFree(tmp_o);
   if (*s->h_flag & 1) return fail(MLEASE_ERR_INVALID, "response (only 1, 0, -1 are allowed)");
   if (*s->h_flag & 2) return fail(MLEASE_ERR_INVALID, "weight cannot < 0");
   pd.y = (signed char*)y; pd.w = (float*)w; pd.o = (float*)o;
@@ -861,31 +861,35 @@ int mlease_add_partition_dense(mlease_session* s, int32_t pid, int64_t nrows, co
       // Host source: a pitched 2-D DMA of 4 KB rows runs far below PCIe speed, so stream contiguous chunks into two
       // staging buffers on a copy stream and repack them into the padded layout on the compute stream.
       const long long chunk_rows = std::max<long long>(1, (128LL << 20) / (ldx_in * 4));
-      float* stage[2] = {nullptr, nullptr};
-      cudaEvent_t h2d_done[2], repack_done[2];
-      cudaStream_t cs;
-      CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      struct Staging {   // two staging buffers + their events + the copy stream, released on every return path
+        float* buf[2] = {nullptr, nullptr};
+        cudaEvent_t h2d_done[2] = {nullptr, nullptr}, repack_done[2] = {nullptr, nullptr};
+        cudaStream_t cs = nullptr;
+        ~Staging() {
+          for (int b = 0; b < 2; b++) { if (buf[b]) cudaFree(buf[b]); if (h2d_done[b]) cudaEventDestroy(h2d_done[b]); if (repack_done[b]) cudaEventDestroy(repack_done[b]); }
+          if (cs) cudaStreamDestroy(cs);
+        }
+      } sg;
+      CK(cudaStreamCreateWithFlags(&sg.cs, cudaStreamNonBlocking));
       for (int b = 0; b < 2; b++) {
-        CK(cudaMalloc((void**)&stage[b], (size_t)chunk_rows * ldx_in * 4));
-        CK(cudaEventCreateWithFlags(&h2d_done[b], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&repack_done[b], cudaEventDisableTiming));
+        CK(cudaMalloc((void**)&sg.buf[b], (size_t)chunk_rows * ldx_in * 4));
+        CK(cudaEventCreateWithFlags(&sg.h2d_done[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sg.repack_done[b], cudaEventDisableTiming));
       }
       int ci = 0;
       for (long long r0 = 0; r0 < nrows; r0 += chunk_rows, ci++) {
         const int b = ci & 1;
         const long long rows = std::min(chunk_rows, (long long)nrows - r0);
-        if (ci >= 2) CK(cudaStreamWaitEvent(cs, repack_done[b], 0));
+        if (ci >= 2) CK(cudaStreamWaitEvent(sg.cs, sg.repack_done[b], 0));
         const size_t bytes = ((size_t)(rows - 1) * ldx_in + s->Dg) * 4;
-        CK(cudaMemcpyAsync(stage[b], X + r0 * ldx_in, bytes, cudaMemcpyHostToDevice, cs));
-        CK(cudaEventRecord(h2d_done[b], cs));
-        CK(cudaStreamWaitEvent(s->stream, h2d_done[b], 0));
-        repack_rows_kernel<<<2048, 256, 0, s->stream>>>(pd.X + r0 * s->ldx, s->ldx, stage[b], ldx_in, rows, s->Dg);
-        CK(cudaEventRecord(repack_done[b], s->stream));
+        CK(cudaMemcpyAsync(sg.buf[b], X + r0 * ldx_in, bytes, cudaMemcpyHostToDevice, sg.cs));
+        CK(cudaEventRecord(sg.h2d_done[b], sg.cs));
+        CK(cudaStreamWaitEvent(s->stream, sg.h2d_done[b], 0));
+        repack_rows_kernel<<<2048, 256, 0, s->stream>>>(pd.X + r0 * s->ldx, s->ldx, sg.buf[b], ldx_in, rows, s->Dg);
+        CK(cudaEventRecord(sg.repack_done[b], s->stream));
       }
-      CK(cudaStreamSynchronize(cs));
+      CK(cudaStreamSynchronize(sg.cs));
       CK(cudaStreamSynchronize(s->stream));
-      for (int b = 0; b < 2; b++) { cudaFree(stage[b]); cudaEventDestroy(h2d_done[b]); cudaEventDestroy(repack_done[b]); }
-      cudaStreamDestroy(cs);
     }
   }
   fill_bias_pad_kernel<<<1024, 256, 0, s->stream>>>(pd.X, nrows, s->ldx, s->Dg, 1);

@@ -417,7 +417,12 @@ def run_admm_workload(cx, wl, K, W, want_e2e):
     try:
         if world == 1 and wl["name"] in ("cfg2", "cfg3") and (P, n, D) == (WORKLOADS[wl["name"]]["P"], WORKLOADS[wl["name"]]["n"], WORKLOADS[wl["name"]]["D"]):
             tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))[wl["name"]]
-            traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"] + " (a committed capture of this command, not measured by this run)"
+            # the captured launch served a known number of (partition, lambda) passes: its DRAM bytes per algorithmic byte, applied to
+            # this run's average launch (launches differ in how many problems are still running)
+            traffic = tj["traffic_over_algorithmic"] * (k1_total_bytes / max(k1_n, 1))
+            traffic_src = ("%s: %.3f GB of DRAM traffic for %.3f GB algorithmic in the captured launch, scaled to this run's average launch "
+                           "(a committed capture of this command, not measured by this run)"
+                           % (tj["source"], tj["traffic_bytes_per_launch"] / 1e9, tj["algorithmic_bytes_of_captured_launch"] / 1e9))
     except Exception:
         traffic = None
     fused = bool(st1.get("k1_fused"))

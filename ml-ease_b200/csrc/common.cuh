@@ -115,7 +115,8 @@ struct Problem {
                           // row-wise triangular GEMVs over it, HBM-bound on D'^2 2-byte entries in total.  The product form is
                           // symmetric positive definite for ANY rounding of Y, so the low precision can never turn the preconditioner
                           // indefinite (a rounded explicit H^-1 could)
-  double* tvec;           // [ldx] scratch of that product (t = Y q)
+  float* qf;              // [ldx] fp32 copy of the two-loop vector q (written by the decide kernel when Ysym is in use)
+  float* tf;              // [ldx] t = Y q in fp32 (between the two phases)
   int ldh;
   Ctrl* ctrl;
   // ADMM per-problem vectors (float, as the reference's avro files hold them)

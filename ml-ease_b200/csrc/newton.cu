@@ -254,6 +254,8 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
       for (int k = threadIdx.x; k < Dt; k += NT) q[k] -= a * Y[k];
       __syncthreads();
     }
+    // wide systems: the triangular GEMVs take their vector in fp32 (the operand Ysym is bf16: nothing is lost)
+    if (pb.Ysym) for (int k = threadIdx.x; k < ldx; k += NT) pb.qf[k] = k < Dt ? (float)q[k] : 0.f;
   }
 }
 
@@ -281,6 +283,9 @@ __global__ void __launch_bounds__(NT) newton_gemv_kernel(const Problem* __restri
 // Wide systems: r = Y^T (Y q) on the symmetric bf16 storage of Y = L^-1 (Ysym, see ysym_kernel).  phase 0: t = Y q (row r of
 // the lower part, columns 0..r); phase 1: dir = Y^T t (row c of the upper part incl. the diagonal, columns c..Dt-1).
 // bf16 operand (8 elements per 16-byte load), fp64 accumulation; each phase reads half of the matrix.
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }          // bf16 -> fp32 is a 16-bit shift
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
 __global__ void __launch_bounds__(NT) newton_gemv_tri_kernel(const Problem* __restrict__ probs, int phase) {
   const Problem& pb = probs[blockIdx.y];
   Ctrl* c = pb.ctrl;
@@ -289,8 +294,7 @@ __global__ void __launch_bounds__(NT) newton_gemv_tri_kernel(const Problem* __re
   const int w = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
   const int Dt = pb.Dt;
   if (w >= (Dt + 1) / 2) return;
-  const double* __restrict__ x = phase == 0 ? pb.g_t : pb.tvec;
-  double* __restrict__ out = phase == 0 ? pb.tvec : pb.dir;
+  const float* __restrict__ x = phase == 0 ? pb.qf : pb.tf;      // zero beyond Dt (ldx is a multiple of 4, rows are read in chunks of 8)
   // a warp takes row w and its mirror Dt-1-w: the two triangular rows together hold Dt+1 elements, whatever w is (balanced)
 #pragma unroll 1
   for (int half = 0; half < 2; half++) {
@@ -298,19 +302,31 @@ __global__ void __launch_bounds__(NT) newton_gemv_tri_kernel(const Problem* __re
     if (half == 1 && r == w) break;
     const __nv_bfloat16* __restrict__ Mr = pb.Ysym + (size_t)r * pb.ldh;
     const int k0 = phase == 0 ? 0 : (r & ~7), k1 = phase == 0 ? r + 1 : Dt;
+    // fp32 products and 8-term partial sums, fp64 across chunks: the HBM stream, not fp64 conversions, sets the pace
     double a = 0.0;
     for (int k = k0 + lane * 8; k < k1; k += 256) {
       const uint4 h = *reinterpret_cast<const uint4*>(Mr + k);   // rows are ldh (multiple of 32) elements long: reading past k1 stays inside the row
-      const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+      float hv[8] = {bf16_lo(h.x), bf16_hi(h.x), bf16_lo(h.y), bf16_hi(h.y), bf16_lo(h.z), bf16_hi(h.z), bf16_lo(h.w), bf16_hi(h.w)};
+      const bool edge = (k + 8 > k1) || (phase == 1 && k < r);
+      if (edge) {
 #pragma unroll
-      for (int e = 0; e < 8; e++) {
-        const int kk = k + e;
-        const float hv = __uint_as_float((e & 1) ? (hw[e >> 1] & 0xFFFF0000u) : (hw[e >> 1] << 16));   // bf16 -> fp32 is a 16-bit shift
-        if (kk < k1 && (phase == 0 || kk >= r)) a += (double)hv * x[kk];
+        for (int e = 0; e < 8; e++)
+          if (k + e >= k1 || (phase == 1 && k + e < r)) hv[e] = 0.f;
       }
+      // x is 32-byte aligned at k (k % 8 == 0) and ldx % 4 == 0: two float4 loads, the second one only if it is inside the vector
+      const float4 x0 = *reinterpret_cast<const float4*>(x + k);
+      const float4 x1 = (k + 4 < pb.ldx) ? *reinterpret_cast<const float4*>(x + k + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      float p = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; e++) p = fmaf(hv[e], xv[e], p);
+      a += (double)p;
     }
     a = warp_sum(a);
-    if (lane == 0) out[r] = a;
+    if (lane == 0) {
+      if (phase == 0) pb.tf[r] = (float)a;
+      else pb.dir[r] = a;
+    }
   }
 }
 

@@ -332,7 +332,8 @@ int batch_alloc(Batch& B, int num_sms) {
     p.gram_slices = B.gram_slices;
     double* q = dd;
     p.beta = q; q += ldx; p.beta_t = q; q += ldx; p.m = q; q += ldx; p.q = q; q += ldx;
-    p.g_t = q; q += ldx; p.g_acc = q; q += ldx; p.dir = q; q += ldx; p.x_d = q; q += ldx; p.tvec = q; q += ldx;
+    p.g_t = q; q += ldx; p.g_acc = q; q += ldx; p.dir = q; q += ldx; p.x_d = q; q += ldx;
+    p.qf = reinterpret_cast<float*>(q); p.tf = p.qf + ldx; q += ldx;   // one double-vector slot holds the two fp32 vectors of the triangular GEMVs
     p.bfgs_S = q; q += (size_t)BFGS_M * ldx; p.bfgs_Y = q; q += (size_t)BFGS_M * ldx; p.bfgs_rho = q; q += BFGS_M; p.bfgs_alpha = q; q += BFGS_M;
     p.gpart = q; q += (size_t)gpart_rows * ldx;
     p.gpart_f = gpf ? gpf + (size_t)b * B.k1_grid * ldx : nullptr;

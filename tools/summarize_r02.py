@@ -3,7 +3,7 @@
 
   python tools/summarize_r02.py ncu   <rep under gpurun_out> <out csv name>       ncu --set full capture -> the metrics that matter
   python tools/summarize_r02.py list  <launch csv under gpurun_out> <out csv name> launch list -> per-kernel counts / time / share
-  python tools/summarize_r02.py traffic <rep> <workload cfgN> <kernel label>       DRAM bytes per launch -> profiles/k1_traffic.json
+  python tools/summarize_r02.py traffic <rep> <workload cfgN> <kernel label> [algorithmic bytes of the captured launch]   -> profiles/k1_traffic.json
   python tools/summarize_r02.py sass                                                per-kernel tcgen05 / TMA / DMMA mnemonic counts
 """
 import csv
@@ -53,13 +53,15 @@ def cmd_ncu(rep, out):
     print("wrote", out)
 
 
-def cmd_traffic(rep, workload, label):
+def cmd_traffic(rep, workload, label, alg_bytes=None):
     hdr, units, data = raw(os.path.join(GO, rep))
     i_r, i_w, i_t = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
     path = os.path.join(OUT, "k1_traffic.json")
     j = json.load(open(path)) if os.path.exists(path) else {}
     launches = [{"dram_bytes": tobytes(r[i_r], units[i_r]) + tobytes(r[i_w], units[i_w]), "time": r[i_t] + " " + units[i_t]} for r in data]
     j[workload] = {"kernel": label, "traffic_bytes_per_launch": launches[0]["dram_bytes"],
+                   "algorithmic_bytes_of_captured_launch": float(alg_bytes) if alg_bytes else None,
+                   "traffic_over_algorithmic": (launches[0]["dram_bytes"] / float(alg_bytes)) if alg_bytes else None,
                    "source": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum, capture gpurun_out/%s summarised in profiles/" % rep,
                    "launches": launches}
     json.dump(j, open(path, "w"), indent=1)

@@ -100,17 +100,18 @@ __global__ void __launch_bounds__(256) k1_partial_reduce_kernel(const Problem* _
 // spec != 0: the host enqueued this slot before it knew the outcome of the previous one (slot pipelining), hence WITHOUT the
 // Gram / Cholesky launches a rebuild needs: a rebuild that is due is deferred (emit stays set, the step is a chord step on
 // the factor at hand; the host sees emit in the next flag word and runs a regular rebuild slot).
-__global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __restrict__ probs, int spec) {
+__global__ void __launch_bounds__(1024) k1_reduce_decide_kernel(const Problem* __restrict__ probs, int spec) {
   const Problem& pb = probs[blockIdx.x];
   Ctrl* c = pb.ctrl;
   if (c->done) return;
-  __shared__ double sc[NT / 32];
+  __shared__ double sc[32];
+  const int NTD = blockDim.x;   // 256 threads, or 1024 for wide systems (one CTA per problem walks D'-long vectors a dozen times)
   __shared__ int s_action;  // 1 accept, 0 retry
   __shared__ double s_alpha;
   const int Dt = pb.Dt, ldx = pb.ldx, nct = c->k1_chunks;
   const bool have_dir = c->have_dir != 0;
   double prior2 = 0.0, ginf = 0.0, phi = 0.0;
-  for (int k = threadIdx.x; k < Dt; k += NT) {
+  for (int k = threadIdx.x; k < Dt; k += NTD) {
     const double dlt = pb.beta_t[k] - pb.m[k];
     const double g = pb.g_t[k] + pb.q[k] * dlt;   // g_t holds the reduced data term (k1_partial_reduce_kernel)
     pb.g_t[k] = g;
@@ -119,11 +120,11 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
     if (have_dir) phi += g * pb.dir[k];
   }
   double lossp = 0.0;
-  for (int t = threadIdx.x; t < nct; t += NT) lossp += pb.fpart[t];
+  for (int t = threadIdx.x; t < nct; t += NTD) lossp += pb.fpart[t];
   // secant pair of this step (used only if the step is accepted): s = beta_t - beta, y = g_t - g_acc
   double sy = 0.0, ss = 0.0, yy2 = 0.0;
   if (have_dir) {
-    for (int k = threadIdx.x; k < Dt; k += NT) {
+    for (int k = threadIdx.x; k < Dt; k += NTD) {
       const double sk = pb.beta_t[k] - pb.beta[k], yk = pb.g_t[k] - pb.g_acc[k];
       sy += sk * yk; ss += sk * sk; yy2 += yk * yk;
     }
@@ -217,18 +218,18 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
     if (s_slot >= 0) {
       double* S = pb.bfgs_S + (size_t)s_slot * ldx;
       double* Y = pb.bfgs_Y + (size_t)s_slot * ldx;
-      for (int k = threadIdx.x; k < ldx; k += NT) {
+      for (int k = threadIdx.x; k < ldx; k += NTD) {
         S[k] = k < Dt ? pb.beta_t[k] - pb.beta[k] : 0.0;
         Y[k] = k < Dt ? pb.g_t[k] - pb.g_acc[k] : 0.0;
       }
     }
-    for (int k = threadIdx.x; k < ldx; k += NT) {
+    for (int k = threadIdx.x; k < ldx; k += NTD) {
       pb.beta[k] = pb.beta_t[k];
       pb.g_acc[k] = k < Dt ? pb.g_t[k] : 0.0;
     }
   } else {
     const double a = s_alpha;
-    for (int k = threadIdx.x; k < ldx; k += NT) {
+    for (int k = threadIdx.x; k < ldx; k += NTD) {
       const float btf = k < Dt ? (float)(pb.beta[k] + a * pb.dir[k]) : 0.f;
       pb.beta_t[k] = (double)btf;
       pb.beta_tf[k] = btf;
@@ -240,22 +241,22 @@ __global__ void __launch_bounds__(NT) k1_reduce_decide_kernel(const Problem* __r
   {
     const int npairs = min(c->bfgs_count, c->bfgs_m);
     double* q = pb.g_t;   // free scratch from here until the next K1 reduce
-    for (int k = threadIdx.x; k < Dt; k += NT) q[k] = pb.g_acc[k];
+    for (int k = threadIdx.x; k < Dt; k += NTD) q[k] = pb.g_acc[k];
     __syncthreads();
     for (int j = 0; j < npairs; j++) {
       const int slot = (c->bfgs_count - 1 - j) % c->bfgs_m;
       const double* S = pb.bfgs_S + (size_t)slot * ldx;
       const double* Y = pb.bfgs_Y + (size_t)slot * ldx;
       double d = 0.0;
-      for (int k = threadIdx.x; k < Dt; k += NT) d += S[k] * q[k];
+      for (int k = threadIdx.x; k < Dt; k += NTD) d += S[k] * q[k];
       d = block_sum(d, sc);
       const double a = pb.bfgs_rho[slot] * d;
       if (threadIdx.x == 0) pb.bfgs_alpha[slot] = a;
-      for (int k = threadIdx.x; k < Dt; k += NT) q[k] -= a * Y[k];
+      for (int k = threadIdx.x; k < Dt; k += NTD) q[k] -= a * Y[k];
       __syncthreads();
     }
     // wide systems: the triangular GEMVs take their vector in fp32 (the operand Ysym is bf16: nothing is lost)
-    if (pb.Ysym) for (int k = threadIdx.x; k < ldx; k += NT) pb.qf[k] = k < Dt ? (float)q[k] : 0.f;
+    if (pb.Ysym) for (int k = threadIdx.x; k < ldx; k += NTD) pb.qf[k] = k < Dt ? (float)q[k] : 0.f;
   }
 }
 
@@ -331,11 +332,12 @@ __global__ void __launch_bounds__(NT) newton_gemv_tri_kernel(const Problem* __re
 }
 
 // Direction bookkeeping: norms, termination test, next trial point.  One CTA per problem.
-__global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restrict__ probs) {
+__global__ void __launch_bounds__(1024) newton_solve_kernel(const Problem* __restrict__ probs) {
   const Problem& pb = probs[blockIdx.x];
   Ctrl* c = pb.ctrl;
   if (c->done || !c->need_solve) return;
-  __shared__ double sc[NT / 32];
+  __shared__ double sc[32];
+  const int NTD = blockDim.x;
   const int tid = threadIdx.x;
   const int Dt = pb.Dt, ldx = pb.ldx;
   double* rhs = pb.dir;
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restr
     const int npairs = min(c->bfgs_count, c->bfgs_m);
     const double h0s = c->h0_scale;
     if (h0s != 1.0) {
-      for (int k = tid; k < Dt; k += NT) rhs[k] *= h0s;
+      for (int k = tid; k < Dt; k += NTD) rhs[k] *= h0s;
       __syncthreads();
     }
     for (int j = npairs - 1; j >= 0; j--) {
@@ -351,17 +353,17 @@ __global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restr
       const double* S = pb.bfgs_S + (size_t)slot * ldx;
       const double* Y = pb.bfgs_Y + (size_t)slot * ldx;
       double d = 0.0;
-      for (int k = tid; k < Dt; k += NT) d += Y[k] * rhs[k];
+      for (int k = tid; k < Dt; k += NTD) d += Y[k] * rhs[k];
       d = block_sum(d, sc);
       const double coef = pb.bfgs_alpha[slot] - pb.bfgs_rho[slot] * d;
-      for (int k = tid; k < Dt; k += NT) rhs[k] += coef * S[k];
+      for (int k = tid; k < Dt; k += NTD) rhs[k] += coef * S[k];
       __syncthreads();
     }
-    for (int k = tid; k < Dt; k += NT) rhs[k] = -rhs[k];
+    for (int k = tid; k < Dt; k += NTD) rhs[k] = -rhs[k];
     __syncthreads();
   }
   double dinf = 0.0, binf = 0.0, phi0 = 0.0;
-  for (int k = tid; k < Dt; k += NT) {
+  for (int k = tid; k < Dt; k += NTD) {
     const double d = rhs[k];
     dinf = fmax(dinf, fabs(d));
     binf = fmax(binf, fabs(pb.beta[k]));
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(NT) newton_solve_kernel(const Problem* __restr
   __syncthreads();
   if (s_final == 2) return;
   const bool fin = s_final == 1;
-  for (int k = tid; k < pb.ldx; k += NT) {
+  for (int k = tid; k < pb.ldx; k += NTD) {
     const double bt = k < Dt ? pb.beta[k] + rhs[k] : 0.0;
     const float btf = (float)bt;
     pb.beta_t[k] = (double)btf;
@@ -413,7 +415,7 @@ cudaError_t newton_begin(const Problem* d_probs, int nprob, double xtol, int max
 }
 cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, int Dt, cudaStream_t st, int* launches, int spec) {
   k1_partial_reduce_kernel<<<dim3((Dt + 31) / 32, nprob), 256, 0, st>>>(d_probs);
-  k1_reduce_decide_kernel<<<nprob, NT, 0, st>>>(d_probs, spec);
+  k1_reduce_decide_kernel<<<nprob, Dt > 2048 ? 1024 : NT, 0, st>>>(d_probs, spec);
   if (launches) *launches += 2;
   return cudaGetLastError();
 }
@@ -427,7 +429,7 @@ cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_
   } else {
     newton_gemv_kernel<<<grid, NT, 0, st>>>(d_probs);
   }
-  newton_solve_kernel<<<nprob, NT, 0, st>>>(d_probs);
+  newton_solve_kernel<<<nprob, ldh > 2048 ? 1024 : NT, 0, st>>>(d_probs);
   if (launches) *launches += 2;
   return cudaGetLastError();
 }

@@ -59,26 +59,41 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(const Problem* __restri
   double* H = pb.Lc;
   const int tid = threadIdx.x;
   if (tid == 0) s_bad = 0;
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e / NB, j = e % NB;
-    A[i][j] = (j <= i) ? H[(size_t)(c0 + i) * ldh + c0 + j] : 0.0;
+  // the panel rows of this CTA are fetched by warps 1..7 while warp 0 factorises the diagonal block
+  const int r0 = c0 + NB + blockIdx.x * RB;
+  const int rows = r0 < ldh ? min(RB, ldh - r0) : 0;
+  if (tid >= 32)
+    for (int e = tid - 32; e < rows * NB; e += 224) {
+      const int i = e / NB, j = e % NB;
+      P[i][j] = H[(size_t)(r0 + i) * ldh + c0 + j];
+    }
+  if (tid < 32) {
+    // 32x32 right-looking Cholesky in registers: lane i holds row i; column j is scaled by lane-j's pivot and every L[kk][j]
+    // reaches the other rows by shuffle.  ~500 double shuffles + FMAs (a few microseconds) instead of 32 rounds of three
+    // block-wide barriers -- this kernel is one link of a chain of ldh/32 dependent launches, its latency is what counts.
+    const int lane = tid;
+    double a[NB];
+#pragma unroll
+    for (int kk = 0; kk < NB; kk++) a[kk] = (kk <= lane) ? H[(size_t)(c0 + lane) * ldh + c0 + kk] : 0.0;
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      double djj = __shfl_sync(0xffffffffu, a[j], j);
+      if (!(djj > 0.0)) { bad = 1; djj = 1.0; }
+      const double d = sqrt(djj);
+      if (lane == j) a[j] = d;
+      else if (lane > j) a[j] = a[j] / d;
+#pragma unroll
+      for (int kk = j + 1; kk < NB; kk++) {
+        const double lkj = __shfl_sync(0xffffffffu, a[j], kk);
+        if (lane >= kk) a[kk] -= a[j] * lkj;
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < NB; kk++) A[lane][kk] = (kk <= lane) ? a[kk] : 0.0;
+    if (lane == 0 && bad) s_bad = 1;
   }
   __syncthreads();
-  for (int j = 0; j < NB; j++) {
-    if (tid == 0) {
-      const double d = A[j][j];
-      if (!(d > 0.0)) { s_bad = 1; A[j][j] = 1.0; } else A[j][j] = sqrt(d);
-    }
-    __syncthreads();
-    const double dj = A[j][j];
-    for (int i = j + 1 + tid; i < NB; i += 256) A[i][j] /= dj;
-    __syncthreads();
-    for (int e = tid; e < NB * NB; e += 256) {
-      const int i = e / NB, kk = e % NB;
-      if (kk > j && i >= kk) A[i][kk] -= A[i][j] * A[kk][j];
-    }
-    __syncthreads();
-  }
   // inverse of the lower-triangular A: thread cidx solves column cidx
   if (tid < NB) {
     const int cc = tid;
@@ -101,15 +116,8 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(const Problem* __restri
     }
     if (tid == 0 && s_bad) { c->fail = 1; }
   }
-  // rows of the panel below the diagonal block handled by this CTA
-  const int r0 = c0 + NB + blockIdx.x * RB;
-  if (r0 >= ldh) return;
-  const int rows = min(RB, ldh - r0);
-  for (int e = tid; e < rows * NB; e += 256) {
-    const int i = e / NB, j = e % NB;
-    P[i][j] = H[(size_t)(r0 + i) * ldh + c0 + j];
-  }
-  __syncthreads();
+  // rows of the panel below the diagonal block handled by this CTA (P was loaded above)
+  if (rows <= 0) return;
   for (int e = tid; e < rows * NB; e += 256) {
     const int i = e / NB, j = e % NB;
     double s = 0.0;

@@ -188,7 +188,8 @@ int mlease_profile(mlease_session* s, int32_t enable, double* ms4, int64_t* coun
  * LogisticRegressionL2.fun/grad/hessian (regression/liblinearfunc/LogisticRegressionL2.java:156-297)
  * evaluated on a resident partition at host vector w, prior mean m, prior precision q (=1/priorVar),
  * all of length num_features+1.  Any output may be NULL.  H is [Dt x Dt] row-major (full, symmetric).
- * tensor != 0 builds H with the tcgen05 Gram kernel (bf16 operands), 0 with the fp32 SIMT debug kernel.
+ * tensor != 0 builds H with the tcgen05 Gram kernel (bf16 operands for dense partitions, e4m3 operands assembled from the rows
+ * for CSR partitions with sorted unique rows), 0 with the fp32 SIMT debug kernel (dense bf16 operand only).
  * tensor == 2 returns in H the INVERSE the Newton direction is computed with (tcgen05 Gram + diag(q) -> fp64 blocked
  * Cholesky -> explicit inverse), so that tests can check H^-1 * H = I for every factorisation path.
  * ------------------------------------------------------------------------------------- */

@@ -43,86 +43,87 @@ __global__ void chol_prep_kernel(const Problem* __restrict__ probs, int share) {
   pb.Lc[(size_t)i * ldh + j] = v;
 }
 
-// Panel step k: every CTA factorises the NBxNB diagonal block redundantly in shared memory
-// (cheap), inverts it, and computes its RB rows of L21 = A21 * L11^-T.  CTA 0 stores L11.
+// Panel step k, part 1: ONE warp per problem factorises the NBxNB diagonal block in registers and inverts it.
+// lane i holds row i; column j is scaled by lane-j's pivot and every L[kk][j] reaches the other rows by shuffle: ~500 double
+// shuffles + FMAs (a few microseconds) instead of 32 rounds of block-wide barriers.  This kernel and the two below are one link
+// of a chain of ldh/32 dependent steps: latency is what counts.  The factor and its inverse go to the side buffers Ldiag / Ldinv
+// (chol_finish_kernel copies the diagonal blocks back into Lc).
 constexpr int RB = 64;
+__global__ void __launch_bounds__(32) chol_diag_kernel(const Problem* __restrict__ probs, int k) {
+  const Problem& pb = probs[blockIdx.x];
+  Ctrl* c = pb.ctrl;
+  if (c->done || !c->need_hess) return;
+  __shared__ double A[NB][NB + 1];
+  const int ldh = pb.ldh;
+  const int c0 = k * NB;
+  const double* H = pb.Lc;
+  const int lane = threadIdx.x;
+  double a[NB];
+#pragma unroll
+  for (int kk = 0; kk < NB; kk++) a[kk] = (kk <= lane) ? H[(size_t)(c0 + lane) * ldh + c0 + kk] : 0.0;
+  int bad = 0;
+#pragma unroll
+  for (int j = 0; j < NB; j++) {
+    double djj = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(djj > 0.0)) { bad = 1; djj = 1.0; }
+    const double d = sqrt(djj);
+    if (lane == j) a[j] = d;
+    else if (lane > j) a[j] = a[j] / d;
+#pragma unroll
+    for (int kk = j + 1; kk < NB; kk++) {
+      const double lkj = __shfl_sync(0xffffffffu, a[j], kk);
+      if (lane >= kk) a[kk] -= a[j] * lkj;
+    }
+  }
+#pragma unroll
+  for (int kk = 0; kk < NB; kk++) {
+    A[lane][kk] = (kk <= lane) ? a[kk] : 0.0;
+    pb.Ldiag[(size_t)(c0 + lane) * NB + kk] = (kk <= lane) ? a[kk] : 0.0;
+  }
+  __syncwarp();
+  // inverse of the lower-triangular factor: lane cc solves column cc by forward substitution (A is read as a broadcast)
+  {
+    const int cc = lane;
+    double li[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < NB; kk++)
+        if (kk < i) sacc += A[i][kk] * li[kk];     // li[kk] = 0 for kk < cc
+      li[i] = i < cc ? 0.0 : (i == cc ? 1.0 / A[i][i] : -sacc / A[i][i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NB; i++) pb.Ldinv[(size_t)(c0 + i) * NB + cc] = li[i];
+  }
+  if (lane == 0 && bad) c->fail = 1;
+}
+
+// Panel step k, part 2: rows of L21 = A21 * L11^-T, RB rows per CTA, with the inverse of the diagonal block from Ldinv.
 __global__ void __launch_bounds__(256) chol_panel_kernel(const Problem* __restrict__ probs, int k) {
   const Problem& pb = probs[blockIdx.y];
   Ctrl* c = pb.ctrl;
   if (c->done || !c->need_hess) return;
-  __shared__ double A[NB][NB + 1];
   __shared__ double Li[NB][NB + 1];
   __shared__ double P[RB][NB + 1];
-  __shared__ int s_bad;
   const int ldh = pb.ldh;
   const int c0 = k * NB;
   double* H = pb.Lc;
   const int tid = threadIdx.x;
-  if (tid == 0) s_bad = 0;
-  // the panel rows of this CTA are fetched by warps 1..7 while warp 0 factorises the diagonal block
   const int r0 = c0 + NB + blockIdx.x * RB;
-  const int rows = r0 < ldh ? min(RB, ldh - r0) : 0;
-  if (tid >= 32)
-    for (int e = tid - 32; e < rows * NB; e += 224) {
-      const int i = e / NB, j = e % NB;
-      P[i][j] = H[(size_t)(r0 + i) * ldh + c0 + j];
-    }
-  if (tid < 32) {
-    // 32x32 right-looking Cholesky in registers: lane i holds row i; column j is scaled by lane-j's pivot and every L[kk][j]
-    // reaches the other rows by shuffle.  ~500 double shuffles + FMAs (a few microseconds) instead of 32 rounds of three
-    // block-wide barriers -- this kernel is one link of a chain of ldh/32 dependent launches, its latency is what counts.
-    const int lane = tid;
-    double a[NB];
-#pragma unroll
-    for (int kk = 0; kk < NB; kk++) a[kk] = (kk <= lane) ? H[(size_t)(c0 + lane) * ldh + c0 + kk] : 0.0;
-    int bad = 0;
-#pragma unroll
-    for (int j = 0; j < NB; j++) {
-      double djj = __shfl_sync(0xffffffffu, a[j], j);
-      if (!(djj > 0.0)) { bad = 1; djj = 1.0; }
-      const double d = sqrt(djj);
-      if (lane == j) a[j] = d;
-      else if (lane > j) a[j] = a[j] / d;
-#pragma unroll
-      for (int kk = j + 1; kk < NB; kk++) {
-        const double lkj = __shfl_sync(0xffffffffu, a[j], kk);
-        if (lane >= kk) a[kk] -= a[j] * lkj;
-      }
-    }
-#pragma unroll
-    for (int kk = 0; kk < NB; kk++) A[lane][kk] = (kk <= lane) ? a[kk] : 0.0;
-    if (lane == 0 && bad) s_bad = 1;
-  }
-  __syncthreads();
-  // inverse of the lower-triangular A: thread cidx solves column cidx
-  if (tid < NB) {
-    const int cc = tid;
-    for (int i = 0; i < cc; i++) Li[i][cc] = 0.0;
-    Li[cc][cc] = 1.0 / A[cc][cc];
-    for (int i = cc + 1; i < NB; i++) {
-      double s = 0.0;
-      for (int kk = cc; kk < i; kk++) s += A[i][kk] * Li[kk][cc];
-      Li[i][cc] = -s / A[i][i];
-    }
-  }
-  __syncthreads();
-  if (blockIdx.x == 0) {
-    // The factorised diagonal block goes to a side buffer: sibling CTAs of this launch may still be
-    // loading the unfactorised block from H.  chol_finish_kernel copies the blocks back.
-    for (int e = tid; e < NB * NB; e += 256) {
-      const int i = e / NB, j = e % NB;
-      pb.Ldiag[(size_t)(c0 + i) * NB + j] = (j <= i) ? A[i][j] : 0.0;
-      pb.Ldinv[(size_t)(c0 + i) * NB + j] = (j <= i) ? Li[i][j] : 0.0;
-    }
-    if (tid == 0 && s_bad) { c->fail = 1; }
-  }
-  // rows of the panel below the diagonal block handled by this CTA (P was loaded above)
-  if (rows <= 0) return;
+  if (r0 >= ldh) return;
+  const int rows = min(RB, ldh - r0);
+  for (int e = tid; e < NB * NB; e += 256) Li[e / NB][e % NB] = pb.Ldinv[(size_t)(c0 + e / NB) * NB + e % NB];
   for (int e = tid; e < rows * NB; e += 256) {
     const int i = e / NB, j = e % NB;
-    double s = 0.0;
-    for (int kk = 0; kk <= j; kk++) s += P[i][kk] * Li[j][kk];   // (A21 * L11^-T)[i][j]
-    H[(size_t)(r0 + i) * ldh + c0 + j] = s;
+    P[i][j] = H[(size_t)(r0 + i) * ldh + c0 + j];
+  }
+  __syncthreads();
+  for (int e = tid; e < rows * NB; e += 256) {
+    const int i = e / NB, j = e % NB;
+    double sacc = 0.0;
+    for (int kk = 0; kk <= j; kk++) sacc += P[i][kk] * Li[j][kk];   // (A21 * L11^-T)[i][j]
+    H[(size_t)(r0 + i) * ldh + c0 + j] = sacc;
   }
 }
 
@@ -560,8 +561,9 @@ static cudaError_t cholesky_launch_wide(const Problem* d_probs, int nprob, int l
     for (int k = c / NB; k < (c + w) / NB; k++) {
       const int below = ldh - (k + 1) * NB;
       const int gx = below > 0 ? (below + RB - 1) / RB : 1;
-      chol_panel_kernel<<<dim3(gx, nprob), 256, 0, st>>>(d_probs, k);
-      if (launches) *launches += 1;
+      chol_diag_kernel<<<nprob, 32, 0, st>>>(d_probs, k);
+      if (below > 0) chol_panel_kernel<<<dim3(gx, nprob), 256, 0, st>>>(d_probs, k);
+      if (launches) *launches += 2;
       const int inner = c + w - (k + 1) * NB;   // panel columns still to be updated
       if (inner > 0) {
         chol_update_kernel<<<dim3((inner + TB - 1) / TB, (below + TB - 1) / TB, nprob), 256, 0, st>>>(d_probs, k, c + w);
@@ -634,8 +636,9 @@ cudaError_t cholesky_launch(const Problem* d_probs, int nprob, int ldh, cudaStre
     for (int k = 0; k < nb; k++) {
       const int below = ldh - (k + 1) * NB;
       const int gx = below > 0 ? (below + RB - 1) / RB : 1;
-      chol_panel_kernel<<<dim3(gx, nprob), 256, 0, st>>>(d_probs, k);
-      if (launches) *launches += 1;
+      chol_diag_kernel<<<nprob, 32, 0, st>>>(d_probs, k);
+      if (below > 0) chol_panel_kernel<<<dim3(gx, nprob), 256, 0, st>>>(d_probs, k);
+      if (launches) *launches += 2;
       if (below > 0) {
         const int T = (below + TB - 1) / TB;
         chol_update_kernel<<<dim3(T, T, nprob), 256, 0, st>>>(d_probs, k, ldh);

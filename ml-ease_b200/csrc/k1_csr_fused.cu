@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_csr_fused_kernel(const Prob
     int a = 0, e = 0;
     for (int l = 0; l < L; l++) {
       Ctrl* c = probs[b0 + l].ctrl;
-      if (!c->done) {
+      if (!c->done && !c->skip_eval) {   // skip_eval: the start-point gradient of this x-update is known without a pass (k4_consensus.cu)
         a |= 1 << l;
         if (force_emit >= 0 ? (force_emit != 0) : (c->emit != 0)) e |= 1 << l;
         if (seg == 0) c->k1_chunks = p0.sg_S;

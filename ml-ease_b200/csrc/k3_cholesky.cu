@@ -62,13 +62,15 @@ __global__ void __launch_bounds__(32) chol_diag_kernel(const Problem* __restrict
 #pragma unroll
   for (int kk = 0; kk < NB; kk++) a[kk] = (kk <= lane) ? H[(size_t)(c0 + lane) * ldh + c0 + kk] : 0.0;
   int bad = 0;
+  double dinv[NB];   // 1 / L[j][j]: one rsqrt per pivot serves the column scaling here and the substitution below (no divisions)
 #pragma unroll
   for (int j = 0; j < NB; j++) {
     double djj = __shfl_sync(0xffffffffu, a[j], j);
     if (!(djj > 0.0)) { bad = 1; djj = 1.0; }
-    const double d = sqrt(djj);
-    if (lane == j) a[j] = d;
-    else if (lane > j) a[j] = a[j] / d;
+    const double r = rsqrt(djj);
+    dinv[j] = r;
+    if (lane == j) a[j] = djj * r;
+    else if (lane > j) a[j] = a[j] * r;
 #pragma unroll
     for (int kk = j + 1; kk < NB; kk++) {
       const double lkj = __shfl_sync(0xffffffffu, a[j], kk);
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(32) chol_diag_kernel(const Problem* __restrict
 #pragma unroll
       for (int kk = 0; kk < NB; kk++)
         if (kk < i) sacc += A[i][kk] * li[kk];     // li[kk] = 0 for kk < cc
-      li[i] = i < cc ? 0.0 : (i == cc ? 1.0 / A[i][i] : -sacc / A[i][i]);
+      li[i] = i < cc ? 0.0 : (i == cc ? dinv[i] : -sacc * dinv[i]);
     }
 #pragma unroll
     for (int i = 0; i < NB; i++) pb.Ldinv[(size_t)(c0 + i) * NB + cc] = li[i];

@@ -26,7 +26,7 @@ __global__ void admm_reset_kernel(const Problem* __restrict__ probs, int L, doub
     pb.q[k] = k < pb.Dt ? rho_eff[l] : 1.0;
     if (pb.part_local == 0) z[(size_t)l * ldv + k] = 0.0;
   }
-  if (threadIdx.x == 0) pb.ctrl->hess_valid = 0;
+  if (threadIdx.x == 0) { pb.ctrl->hess_valid = 0; pb.ctrl->skip_eval = 0; }
 }
 
 // Start from a given z (initialize.boost.rate): the reducers read z as float from the init-value file
@@ -90,6 +90,13 @@ __global__ void __launch_bounds__(256) admm_consensus_kernel(const Problem* __re
       const Problem& pb = probs[p * L + l];
       const float un = (float)((double)pb.uplusx_f[k] - zn);
       pb.u_f[k] = un;
+      // Gradient at the warm start without a pass over the rows.  x_p minimised  data(x) + q/2 |x - m_old|^2  up to the solver's
+      // tolerance, so the data-term gradient there is  -q_old (x_p - m_old)  (to first order in the last, unevaluated Newton
+      // correction); the next x-update starts AT x_p with a new prior, and its first direction can be taken from this estimate.
+      // Every later point -- including the one the stop test is taken at -- is evaluated exactly by K1 (newton_solve_kernel
+      // does not let an x-update end before its first exact evaluation), so the fixed point is untouched; what is saved is the
+      // start-point pass of every warm x-update, about a third of all passes.  Only where the fused CSR K1 runs (gpart_f).
+      if (pb.gpart_f) pb.g_t[k] = -pb.q[k] * (pb.x_d[k] - pb.m[k]);
       pb.m[k] = -1.0 * (double)un + 1.0 * (double)zf;
       // Warm start of the next x-update.  The reference starts TRON at z (:692-693) because its reducers are stateless;
       // the minimiser does not depend on the start, and with the state resident the previous x_p is far closer to it:
@@ -99,6 +106,11 @@ __global__ void __launch_bounds__(256) admm_consensus_kernel(const Problem* __re
       pb.q[k] = rho_next[l];
     }
   }
+  if (threadIdx.x == 0)
+    for (int p = 0; p < nparts; p++) {
+      const Problem& pb = probs[p * L + l];
+      if (pb.gpart_f) { pb.ctrl->skip_eval = 1; pb.ctrl->k1_chunks = 0; }
+    }
   dmax = warp_max(dmax);
   if ((threadIdx.x & 31) == 0) sc[threadIdx.x >> 5] = dmax;
   __syncthreads();

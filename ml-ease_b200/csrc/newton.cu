@@ -66,6 +66,7 @@ __global__ void newton_begin_kernel(const Problem* __restrict__ probs, double xt
     // x-update of the ADMM run a 2-3 pass affair, and costs about as much as 2.5 K1 passes.
     c->emit = (hess_policy == 1 || !c->hess_valid || c->refresh_next) ? 1 : 0;
     c->refresh_next = 0;
+    if (c->emit) c->skip_eval = 0;   // a rebuild at the start point needs K1's sqrt(d) there: regular first slot
     c->worst_ratio = 0.0;
   }
 }
@@ -74,7 +75,7 @@ __global__ void newton_begin_kernel(const Problem* __restrict__ probs, double xt
 // partials; g_t[k] = sum_t gpart[t][k] (data term only; the prior term is added by the decide kernel).
 __global__ void __launch_bounds__(256) k1_partial_reduce_kernel(const Problem* __restrict__ probs) {
   const Problem& pb = probs[blockIdx.y];
-  if (pb.ctrl->done) return;
+  if (pb.ctrl->done || pb.ctrl->skip_eval) return;   // skip_eval: g_t already holds the data-term gradient of the start point
   __shared__ double sh[8][33];
   const int c = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + c;
@@ -140,7 +141,8 @@ __global__ void __launch_bounds__(1024) k1_reduce_decide_kernel(const Problem* _
   if (threadIdx.x == 0) {
     const double f_t = lossp + 0.5 * prior2;
     c->f_t = f_t;
-    c->evals++; c->tot_evals++;
+    if (!c->skip_eval) { c->evals++; c->tot_evals++; }   // skip_eval: no pass was run for this "evaluation"
+    c->skip_eval = 0;
     int action = 1;
     double alpha = c->alpha;
     if (have_dir) {
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(1024) k1_reduce_decide_kernel(const Problem* _
       c->f_acc = f_t;
       if (have_dir) {
         c->newton_steps++; c->tot_newton++;
-        if (c->gnorm_prev > 0.0) c->worst_ratio = fmax(c->worst_ratio, ginf / c->gnorm_prev);
+        if (c->gnorm_prev > 0.0 && c->evals >= 2) c->worst_ratio = fmax(c->worst_ratio, ginf / c->gnorm_prev);
       }
       if (ginf == 0.0) {
         c->done = 1; c->need_solve = 0; c->need_hess = 0;
@@ -183,7 +185,8 @@ __global__ void __launch_bounds__(1024) k1_reduce_decide_kernel(const Problem* _
           // away (a cold fit whose IRLS weights moved a lot), and one rebuild here is cheaper than the steps it saves.
           const bool stuck = c->rebuild_is_expensive && have_dir && c->gnorm_prev > 0.0 && ginf > 0.5 * c->gnorm_prev &&
                              c->newton_steps - c->build_step >= 12;
-          const bool poor = stuck || (!c->rebuild_is_expensive && have_dir && c->gnorm_prev > 0.0 && ginf > 0.25 * c->gnorm_prev);
+          // (evals >= 2: after a warm start the previous norm is the ESTIMATED start gradient; contraction is judged between exact ones)
+          const bool poor = stuck || (!c->rebuild_is_expensive && have_dir && c->evals >= 2 && c->gnorm_prev > 0.0 && ginf > 0.25 * c->gnorm_prev);
           c->emit = (poor && !c->need_hess) ? 1 : 0;
           if (!c->need_hess && !c->hess_valid) { c->emit = 1; }
           if (deferred) c->emit = 1;
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(1024) newton_solve_kernel(const Problem* __res
     c->rejects = 0;
     int fin = 0;
     if (!(phi0 < 0.0) || !(dinf == dinf)) { c->fail = 1; c->done = 1; fin = 2; }  // factor unusable
-    else if (dinf <= c->xtol * fmax(binf, 1e-2)) { c->done = 1; fin = 1; }
+    else if (dinf <= c->xtol * fmax(binf, 1e-2) && c->evals > 0) { c->done = 1; fin = 1; }   // never before the first exact evaluation
     else if (c->newton_steps >= 2 && dinf <= 1e-5 * fmax(binf, 1e-2) && dinf > 0.5 * c->dirnorm_prev) {
       // rounding floor of the fp32 data path: the step no longer shrinks -> take it and stop
       if (++c->stall >= 2) { c->done = 1; fin = 1; }

@@ -1036,24 +1036,34 @@ int mlease_admm_local_step(mlease_session* s, double* exchange_dev) {
   return 0;
 }
 
-int mlease_admm_consensus(mlease_session* s, const double* exchange_sum_dev, double* maxdiff, int32_t* stop) {
-  if (!s || !exchange_sum_dev) return fail(MLEASE_ERR_INVALID, "null argument");
-  if (!s->begun || s->iter < 1) return fail(MLEASE_ERR_STATE, "consensus before local_step");
-  CK(cudaSetDevice(s->cfg.device));
+// z/u update of the iteration: enqueue (kernel + read-back of the per-lambda |z - z_prev| into pinned memory), then, after the
+// caller's ONE stream synchronisation, finish (convergence scalars, stop rule :493-496).
+static int consensus_enqueue(mlease_session* s, const double* exchange_sum_dev) {
   for (int l = 0; l < s->L; l++) s->h_small[l] = rho_eff_for_iter(s, l, s->iter + 1);
   CK(cudaMemcpyAsync(s->d_rho, s->h_small, s->L * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   int launches = 0;
   CK(admm_consensus(s->batch->d, (int)s->parts.size(), s->L, s->Dt, s->ldx, s->P, exchange_sum_dev, s->d_z, s->d_wz, s->d_rho, s->d_diff, s->stream, &launches, s->d_l1thr));
   s->cnt.launches += launches;
-  double* hd = s->h_small + s->L;
-  CK(cudaMemcpyAsync(hd, s->d_diff, s->L * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaMemcpyAsync(s->h_small + s->L, s->d_diff, s->L * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  return 0;
+}
+static void consensus_finish(mlease_session* s, double* maxdiff, int32_t* stop) {
+  const double* hd = s->h_small + s->L;
   double mx = 0, mn = 99999999;
   for (int l = 0; l < s->L; l++) { mx = std::max(mx, hd[l]); mn = std::min(mn, hd[l]); }
   s->mindiff = mn; s->last_maxdiff = mx;
   if (maxdiff) *maxdiff = mx;
   const double eps = s->cfg.epsilon >= 0 ? s->cfg.epsilon : 0.0001;   // default 1e-4 (:473); 0 = never stop early
   if (stop) *stop = (mx < eps && s->liblinear_eps <= 0.00001) ? 1 : 0;   // :493-496
+}
+
+int mlease_admm_consensus(mlease_session* s, const double* exchange_sum_dev, double* maxdiff, int32_t* stop) {
+  if (!s || !exchange_sum_dev) return fail(MLEASE_ERR_INVALID, "null argument");
+  if (!s->begun || s->iter < 1) return fail(MLEASE_ERR_STATE, "consensus before local_step");
+  CK(cudaSetDevice(s->cfg.device));
+  if (int rc = consensus_enqueue(s, exchange_sum_dev)) return rc;
+  CK(cudaStreamSynchronize(s->stream));
+  consensus_finish(s, maxdiff, stop);
   return 0;
 }
 
@@ -1075,15 +1085,21 @@ static int admm_iterate_impl(mlease_session* s, mlease_allreduce_fn allreduce, v
   else if (rc_local) return rc_local;                      // CUDA / state errors are not recoverable: no collective
   const bool multi = s->comm != nullptr || allreduce != nullptr;
   if (multi) {
-    const double flag = rc_local ? 1.0 : 0.0;
-    CK(cudaMemcpyAsync(s->d_exch + cnt, &flag, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    // all-reduce, z/u update and both read-backs are enqueued back to back; ONE synchronisation per iteration.  (If a fit
+    // failed somewhere the z/u update has run on a meaningless sum, but the job is over: every rank returns the error.)
+    double* h_flag = s->h_small + 3 * s->L + 1;   // pinned
+    *h_flag = rc_local ? 1.0 : 0.0;
+    CK(cudaMemcpyAsync(s->d_exch + cnt, h_flag, sizeof(double), cudaMemcpyHostToDevice, s->stream));
     if (s->comm) { if (int rc = mlease_internal_allreduce(s->comm, s->d_exch, cnt + 1, (void*)s->stream)) return rc; }
     else if (allreduce(ctx, s->d_exch, cnt + 1, (void*)s->stream) != 0) return fail(MLEASE_ERR_CUDA, "all-reduce callback failed");
-    double failed = 0;
-    CK(cudaMemcpyAsync(&failed, s->d_exch + cnt, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    double* h_failed = s->h_small + 3 * s->L + 2;
+    CK(cudaMemcpyAsync(h_failed, s->d_exch + cnt, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (int rc = consensus_enqueue(s, s->d_exch)) return rc;
     CK(cudaStreamSynchronize(s->stream));
     if (rc_local) return fail(rc_local, local_msg);
-    if (failed > 0) return fail(MLEASE_ERR_NUMERIC, "Model fitting error! (the x-update failed on " + std::to_string((int)failed) + " other rank(s))");
+    if (*h_failed > 0) return fail(MLEASE_ERR_NUMERIC, "Model fitting error! (the x-update failed on " + std::to_string((int)*h_failed) + " other rank(s))");
+    consensus_finish(s, maxdiff, stop);
+    return 0;
   } else if (rc_local) {
     return fail(rc_local, local_msg);
   }

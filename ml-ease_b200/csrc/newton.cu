@@ -55,7 +55,7 @@ __global__ void newton_begin_kernel(const Problem* __restrict__ probs, double xt
     if (invalidate_hess) c->hess_valid = 0;
     if (!(c->h0_scale > 0.0)) c->h0_scale = 1.0;
     c->done = 0; c->have_dir = 0; c->need_solve = 0; c->need_hess = 0; c->fail = 0;
-    c->newton_steps = 0; c->evals = 0; c->rejects = 0; c->hess_builds = 0; c->stall = 0; c->build_step = 0;
+    c->newton_steps = 0; c->evals = 0; c->rejects = 0; c->hess_builds = 0; c->stall = 0; c->build_step = 0; c->warm_used = 0;
     c->alpha = 1.0; c->phi0 = 0.0; c->f_acc = 0.0; c->f_t = 0.0; c->gnorm = 0.0; c->gnorm_prev = 0.0; c->dirnorm = 0.0; c->dirnorm_prev = 0.0;
     c->xtol = xtol; c->max_newton = max_newton; c->hess_policy = hess_policy; c->rebuild_is_expensive = rebuild_is_expensive;
     if (c->bfgs_m != bfgs_m) { c->bfgs_m = bfgs_m; c->bfgs_count = 0; }
@@ -142,10 +142,14 @@ __global__ void __launch_bounds__(1024) k1_reduce_decide_kernel(const Problem* _
     const double f_t = lossp + 0.5 * prior2;
     c->f_t = f_t;
     if (!c->skip_eval) { c->evals++; c->tot_evals++; }   // skip_eval: no pass was run for this "evaluation"
+    else c->warm_used = 1;
     c->skip_eval = 0;
+    // first exact evaluation after a start on the estimated gradient: this point becomes the base point whatever the
+    // directional derivative says (like the first evaluation of a regular x-update, which is always accepted)
+    const bool first_exact = have_dir && c->warm_used && c->evals == 1;
     int action = 1;
     double alpha = c->alpha;
-    if (have_dir) {
+    if (have_dir && !first_exact) {
       // phi'(alpha) = g(beta + alpha dir).dir ; phi'(0) = phi0 < 0.  Accept while the directional
       // derivative has not overshot by more than half of |phi'(0)| (a relaxed curvature condition on
       // a convex 1-D function); otherwise shrink alpha towards the secant root of phi'.
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(1024) k1_reduce_decide_kernel(const Problem* _
     // A rebuild at this accepted point supersedes the secant pairs: drop them HERE (before the fused first L-BFGS loop
     // below runs), so that both loops of the recursion see the same, empty, pair set.
     if (action == 1 && c->need_hess) c->bfgs_count = 0;
-    if (action == 1 && have_dir && !c->need_hess && sy > 1e-10 * sqrt(ss * yy2) && sy > 0.0) {   // strictly convex => s.y > 0 up to rounding
+    if (action == 1 && have_dir && !first_exact && !c->need_hess && sy > 1e-10 * sqrt(ss * yy2) && sy > 0.0) {   // strictly convex => s.y > 0 up to rounding
       s_slot = c->bfgs_count % c->bfgs_m;
       pb.bfgs_rho[s_slot] = 1.0 / sy;
       c->bfgs_count++;

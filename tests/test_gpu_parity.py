@@ -789,3 +789,36 @@ def test_two_gpus_world_and_process_per_gpu_match_the_oracle(mb, fixture_data, f
         ref = frozen["exact_z_hist"][19, l]
         assert np.abs(zp[l] - ref).max() / np.abs(ref).max() < 1e-5
     assert np.abs(zp - zw).max() <= 1e-6 * np.abs(zw).max()
+
+
+def test_admm_csr_long_run_warm_starts_reach_the_pooled_fixed_point(mb):
+    """CSR partitions take the fused K1, and from the second iteration on every x-update starts from the ANALYTIC gradient at the
+    previous x_p (no pass for the start point, k4_consensus.cu).  Near the ADMM fixed point the x-updates are tiny and that
+    estimate is all noise: the run must still follow the oracle (exact mode, iteration 40) and end at scikit-learn's pooled fit."""
+    from sklearn.linear_model import LogisticRegression
+    from scipy.sparse import csr_matrix
+    parts, data, prs = _sparse_parts(3, 4000, 150, 12, seed=900)
+    parts = [(rp, ci, v, y) for rp, ci, v, y, w, o in parts]                     # unit weights, no offsets (sklearn has none)
+    data = orc.Csr(data.rowptr, data.colidx, data.val, data.response, n_features=150)
+    lambdas, rhos = [0.5, 5.0], [40.0, 40.0]
+    ref = orc.admm_run(data, prs, lambdas, rhos=rhos, niters=40, mode="exact", nthreads=6, epsilon=0.0)
+    with mb.AdmmSession(3, 150, lambdas, rhos=rhos, epsilon=0.0) as s:
+        for p, part in enumerate(parts):
+            s.add_partition_csr(p, *part)
+        s.begin()
+        for it in range(300):
+            md, stop = s.iterate()
+            if it == 39:
+                for l in range(2):
+                    zr = ref["z_hist"][39, l]
+                    assert np.abs(s.z(l) - zr).max() / np.abs(zr).max() < 1e-5, l
+        z = np.stack([s.z(l) for l in range(2)])
+        st = s.stats()
+    assert st["not_converged"] == 0 and st["k1_fused"] == 1 and md < 1e-6, (st, md)
+    assert st["k1_passes"] < 2.2 * 2 * 3 * 300, st          # ~1-2 passes per warm x-update, not 3
+    X = csr_matrix((data.val.astype(np.float64), data.colidx, data.rowptr), shape=(12000, 150))
+    for l, lam in enumerate(lambdas):
+        clf = LogisticRegression(C=1.0 / lam, fit_intercept=True, solver="newton-cholesky", tol=1e-12, max_iter=300)
+        clf.fit(X.toarray(), data.response)
+        fp = np.concatenate([clf.coef_.ravel(), clf.intercept_])
+        assert np.abs(z[l] - fp).max() / np.abs(fp).max() < 3e-5, (l, np.abs(z[l] - fp).max() / np.abs(fp).max())

@@ -38,7 +38,8 @@ struct Ctrl {
   int skip_eval;     // 1: the gradient at the start point of this x-update is already in g_t (data term) -- see admm_consensus_kernel:
                      //    slot 0 runs no K1 pass for this problem, the decide kernel accepts the start point on that gradient
   int warm_used;     // this x-update started from the estimated gradient (skip_eval was consumed): its first exact evaluation is accepted
-                     // unconditionally (the estimate is not good enough to police a line search) and forms no secant pair
+                     // unconditionally (the estimate is not good enough to police a line search; the secant pair of that step is
+                     // kept whenever s.y > 0: it carries most of the curvature information of the update)
   int build_step;    // newton_steps at the last rebuild of this x-update (0 if none yet): steps taken on the current factor = newton_steps - build_step
   double worst_ratio;// largest |g_new|/|g_old| seen over the chord steps of this x-update
   double alpha;      // current step length along dir

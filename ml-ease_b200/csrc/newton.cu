@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(1024) k1_reduce_decide_kernel(const Problem* _
     // A rebuild at this accepted point supersedes the secant pairs: drop them HERE (before the fused first L-BFGS loop
     // below runs), so that both loops of the recursion see the same, empty, pair set.
     if (action == 1 && c->need_hess) c->bfgs_count = 0;
-    if (action == 1 && have_dir && !first_exact && !c->need_hess && sy > 1e-10 * sqrt(ss * yy2) && sy > 0.0) {   // strictly convex => s.y > 0 up to rounding
+    if (action == 1 && have_dir && !c->need_hess && sy > 1e-10 * sqrt(ss * yy2) && sy > 0.0) {   // strictly convex => s.y > 0 up to rounding
       s_slot = c->bfgs_count % c->bfgs_m;
       pb.bfgs_rho[s_slot] = 1.0 / sy;
       c->bfgs_count++;

@@ -387,6 +387,9 @@ bool k1f_plan(long long n, int ldx, int L, int num_sms, int* S_out, int* rows_ou
   return true;
 }
 
+template <typename T>
+static cudaError_t k1f_tmp_alloc(T** p, cudaStream_t st, size_t bytes) { return cudaMallocAsync((void**)p, bytes, st); }
+
 // Builds the segment list of one partition.  All outputs are cudaMalloc'ed here and owned by the caller.
 cudaError_t k1f_build(long long n, int Dg, long long nnz, const long long* rowptr, const int* colidx, const float* vals, int S, int sg_rows, int* ngrp_out,
                       int** perm_out, int** depth_out, long long** goff_out, unsigned short** row16_out, float** val_out, long long* total_out,
@@ -403,14 +406,16 @@ cudaError_t k1f_build(long long n, int Dg, long long nnz, const long long* rowpt
   void* tmp = nullptr;
   const size_t sd = (size_t)S * Dg;
   auto cleanup = [&](bool all) {
-    cudaFree(cnt); cudaFree(cnt_s); cudaFree(ids); cudaFree(ids_s); cudaFree(offs); cudaFree(inv); cudaFree(d64); cudaFree(tmp); cudaFree(ent_row); cudaFree(ent_base); cudaFree(hist);
+    // temporaries come from the stream-ordered allocator: cudaFree would wait for the whole device, including the next partition's H2D copy
+    void* tmps[] = {cnt, cnt_s, ids, ids_s, offs, inv, d64, tmp, ent_row, ent_base, hist};
+    for (void* t : tmps) if (t) cudaFreeAsync(t, st);
     if (all) { cudaFree(perm); cudaFree(depth); cudaFree(goff); cudaFree(row16); cudaFree(sval); }
   };
 #define K1F_CK(x) do { e = (x); if (e != cudaSuccess) { cleanup(true); return e; } } while (0)
-  K1F_CK(cudaMalloc(&cnt, sd * 4)); K1F_CK(cudaMalloc(&cnt_s, sd * 4)); K1F_CK(cudaMalloc(&ids, sd * 4)); K1F_CK(cudaMalloc(&ids_s, sd * 4));
-  K1F_CK(cudaMalloc(&offs, (size_t)(S + 1) * 4)); K1F_CK(cudaMalloc(&inv, sd * 4));
+  K1F_CK(k1f_tmp_alloc(&cnt, st, sd * 4)); K1F_CK(k1f_tmp_alloc(&cnt_s, st, sd * 4)); K1F_CK(k1f_tmp_alloc(&ids, st, sd * 4)); K1F_CK(k1f_tmp_alloc(&ids_s, st, sd * 4));
+  K1F_CK(k1f_tmp_alloc(&offs, st, (size_t)(S + 1) * 4)); K1F_CK(k1f_tmp_alloc(&inv, st, sd * 4));
   K1F_CK(cudaMalloc(&perm, (size_t)S * ngrp * 32 * 4)); K1F_CK(cudaMalloc(&depth, (size_t)S * ngrp * 4));
-  K1F_CK(cudaMalloc(&goff, ((size_t)S * ngrp + 1) * 8)); K1F_CK(cudaMalloc(&d64, ((size_t)S * ngrp + 1) * 8));
+  K1F_CK(cudaMalloc(&goff, ((size_t)S * ngrp + 1) * 8)); K1F_CK(k1f_tmp_alloc(&d64, st, ((size_t)S * ngrp + 1) * 8));
   K1F_CK(cudaFuncSetAttribute(k1f_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dg * 4));
   k1f_count_kernel<<<S, 1024, (size_t)Dg * 4, st>>>(n, sg_rows, Dg, rowptr, colidx, cnt);
   k1f_iota_kernel<<<1024, 256, 0, st>>>(S, Dg, ids, offs);
@@ -419,7 +424,7 @@ cudaError_t k1f_build(long long n, int Dg, long long nnz, const long long* rowpt
   K1F_CK(cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, tb, cnt, cnt_s, ids, ids_s, (int)sd, S, offs, offs + 1, 0, 17, st));
   size_t tb2 = 0;
   K1F_CK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, d64, goff, (int)((size_t)S * ngrp + 1), st));
-  K1F_CK(cudaMalloc(&tmp, std::max(std::max(tb, tb2), (size_t)16)));
+  K1F_CK(k1f_tmp_alloc(&tmp, st, std::max(std::max(tb, tb2), (size_t)16)));
   K1F_CK(cub::DeviceSegmentedRadixSort::SortPairsDescending(tmp, tb, cnt, cnt_s, ids, ids_s, (int)sd, S, offs, offs + 1, 0, 17, st));
   K1F_CK(cudaMemsetAsync(d64, 0, ((size_t)S * ngrp + 1) * 8, st));
   k1f_groups_kernel<<<2048, 256, 0, st>>>(S, Dg, ngrp, cnt_s, ids_s, perm, depth, d64, inv);
@@ -433,10 +438,10 @@ cudaError_t k1f_build(long long n, int Dg, long long nnz, const long long* rowpt
   K1F_CK(cudaMemsetAsync(row16, 0, (size_t)total * 32 * 2, st));
   K1F_CK(cudaMemsetAsync(sval, 0, (size_t)total * 32 * 4, st));
   if ((size_t)total * 32 >= ((size_t)1 << 32)) { cleanup(true); return cudaErrorInvalidValue; }   // 32-bit slot positions
-  K1F_CK(cudaMalloc(&ent_row, std::max<size_t>((size_t)nnz * 2, 16)));
-  K1F_CK(cudaMalloc(&ent_base, std::max<size_t>((size_t)nnz * 4, 16)));
+  K1F_CK(k1f_tmp_alloc(&ent_row, st, std::max<size_t>((size_t)nnz * 2, 16)));
+  K1F_CK(k1f_tmp_alloc(&ent_base, st, std::max<size_t>((size_t)nnz * 4, 16)));
   k1f_rowid_kernel<<<2368, 256, 0, st>>>(n, sg_rows, Dg, ngrp, rowptr, colidx, inv, goff, ent_row, ent_base);
-  K1F_CK(cudaMalloc(&hist, sd * K1F_CHUNKS * 2));
+  K1F_CK(k1f_tmp_alloc(&hist, st, sd * K1F_CHUNKS * 2));
   K1F_CK(cudaFuncSetAttribute(k1f_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dg * 4));
   k1f_hist_kernel<<<dim3(S, K1F_CHUNKS), 256, (size_t)Dg * 4, st>>>(n, sg_rows, Dg, rowptr, colidx, hist);
   K1F_CK(cudaFuncSetAttribute(k1f_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dg * 2));

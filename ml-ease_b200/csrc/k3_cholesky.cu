@@ -186,7 +186,7 @@ __global__ void chol_finish_kernel(const Problem* __restrict__ probs) {
   }
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (c->fail == 1) { c->done = 1; c->hess_valid = 0; }
-    else { c->hess_valid = 1; c->hess_builds++; c->tot_hess++; c->bfgs_count = 0; c->h0_scale = 1.0; c->build_step = c->newton_steps; }
+    else { c->hess_valid = 1; c->hess_builds++; c->tot_hess++; c->bfgs_count = 0; c->h0_scale = 1.0; c->build_step = c->newton_steps; c->ysym_use = pb.Ysym; }
   }
 }
 
@@ -607,7 +607,10 @@ __global__ void chol_share_end_kernel(const Problem* __restrict__ probs, int npr
   const Ctrl* lead = probs[b - b % share].ctrl;
   c->need_hess = 1;
   if (lead->fail == 1) { c->fail = 1; c->done = 1; c->hess_valid = 0; }
-  else { c->hess_valid = 1; c->hess_builds++; c->tot_hess++; c->bfgs_count = 0; c->h0_scale = 1.0; c->build_step = c->newton_steps; }
+  else {
+    c->hess_valid = 1; c->hess_builds++; c->tot_hess++; c->bfgs_count = 0; c->h0_scale = 1.0; c->build_step = c->newton_steps;
+    c->ysym_use = probs[b - b % share].Ysym;   // wide systems: no copy of the factored inverse, the group streams the leader's
+  }
 }
 cudaError_t cholesky_share_begin(const Problem* d_probs, int nprob, int share, cudaStream_t st, int* launches) {
   chol_share_begin_kernel<<<(nprob + 127) / 128, 128, 0, st>>>(d_probs, nprob, share);

@@ -294,24 +294,48 @@ __global__ void __launch_bounds__(NT) newton_gemv_kernel(const Problem* __restri
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }          // bf16 -> fp32 is a 16-bit shift
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
-__global__ void __launch_bounds__(NT) newton_gemv_tri_kernel(const Problem* __restrict__ probs, int phase) {
-  const Problem& pb = probs[blockIdx.y];
+// group_L > 1: problems b = g*group_L .. +group_L-1 are the lambdas of one partition.  After a shared cold-start factorisation
+// they all point at the leader's Y (Ctrl::ysym_use), and the FIRST active problem of such a set streams Y once for every active
+// member (up to 4 vectors per pass); a problem with its own factor, or alone in its set, runs by itself.
+constexpr int GEMV_MAXV = 4;
+__global__ void __launch_bounds__(NT) newton_gemv_tri_kernel(const Problem* __restrict__ probs, int phase, int group_L) {
+  const int b = blockIdx.y;
+  const Problem& pb = probs[b];
   Ctrl* c = pb.ctrl;
   if (c->done || !c->need_solve) return;
+  const __nv_bfloat16* __restrict__ Y = reinterpret_cast<const __nv_bfloat16*>(c->ysym_use ? c->ysym_use : (const void*)pb.Ysym);
+  const int gl = (group_L > 1 && group_L <= GEMV_MAXV) ? group_L : 1;
+  const int g0 = b - b % gl;
+  const float* xs[GEMV_MAXV];
+  float* tfs[GEMV_MAXV];
+  double* dirs[GEMV_MAXV];
+  unsigned mask = 0;   // members of the set {active, same Y}; slot v = problem g0 + v (static indexing keeps the pointers in registers)
+#pragma unroll
+  for (int v = 0; v < GEMV_MAXV; v++) {
+    const int j = g0 + v;
+    bool same = false;
+    if (v < gl && j < (int)gridDim.y) {
+      const Ctrl* cj = probs[j].ctrl;
+      same = !cj->done && cj->need_solve && (cj->ysym_use ? cj->ysym_use : (const void*)probs[j].Ysym) == (const void*)Y;
+    }
+    const Problem& pj = probs[same ? j : b];
+    xs[v] = phase == 0 ? pj.qf : pj.tf; tfs[v] = pj.tf; dirs[v] = pj.dir;
+    if (same) mask |= 1u << v;
+  }
+  if (__ffs(mask) - 1 != b - g0) return;   // an earlier active member of the set takes this problem's vector along
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
   const int Dt = pb.Dt;
   if (w >= (Dt + 1) / 2) return;
-  const float* __restrict__ x = phase == 0 ? pb.qf : pb.tf;      // zero beyond Dt (ldx is a multiple of 4, rows are read in chunks of 8)
   // a warp takes row w and its mirror Dt-1-w: the two triangular rows together hold Dt+1 elements, whatever w is (balanced)
 #pragma unroll 1
   for (int half = 0; half < 2; half++) {
     const int r = half == 0 ? w : Dt - 1 - w;
     if (half == 1 && r == w) break;
-    const __nv_bfloat16* __restrict__ Mr = pb.Ysym + (size_t)r * pb.ldh;
+    const __nv_bfloat16* __restrict__ Mr = Y + (size_t)r * pb.ldh;
     const int k0 = phase == 0 ? 0 : (r & ~7), k1 = phase == 0 ? r + 1 : Dt;
     // fp32 products and 8-term partial sums, fp64 across chunks: the HBM stream, not fp64 conversions, sets the pace
-    double a = 0.0;
+    double a[GEMV_MAXV] = {0.0, 0.0, 0.0, 0.0};
     for (int k = k0 + lane * 8; k < k1; k += 256) {
       const uint4 h = *reinterpret_cast<const uint4*>(Mr + k);   // rows are ldh (multiple of 32) elements long: reading past k1 stays inside the row
       float hv[8] = {bf16_lo(h.x), bf16_hi(h.x), bf16_lo(h.y), bf16_hi(h.y), bf16_lo(h.z), bf16_hi(h.z), bf16_lo(h.w), bf16_hi(h.w)};
@@ -321,19 +345,30 @@ __global__ void __launch_bounds__(NT) newton_gemv_tri_kernel(const Problem* __re
         for (int e = 0; e < 8; e++)
           if (k + e >= k1 || (phase == 1 && k + e < r)) hv[e] = 0.f;
       }
-      // x is 32-byte aligned at k (k % 8 == 0) and ldx % 4 == 0: two float4 loads, the second one only if it is inside the vector
-      const float4 x0 = *reinterpret_cast<const float4*>(x + k);
-      const float4 x1 = (k + 4 < pb.ldx) ? *reinterpret_cast<const float4*>(x + k + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-      float p = 0.f;
+      const bool second = k + 4 < pb.ldx;
 #pragma unroll
-      for (int e = 0; e < 8; e++) p = fmaf(hv[e], xv[e], p);
-      a += (double)p;
+      for (int v = 0; v < GEMV_MAXV; v++) {
+        if ((mask >> v) & 1u) {
+          // x is 32-byte aligned at k (k % 8 == 0) and ldx % 4 == 0: two float4 loads, the second one only if it is inside the vector
+          const float4 x0 = *reinterpret_cast<const float4*>(xs[v] + k);
+          const float4 x1 = second ? *reinterpret_cast<const float4*>(xs[v] + k + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          float p = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; e++) p = fmaf(hv[e], xv[e], p);
+          a[v] += (double)p;
+        }
+      }
     }
-    a = warp_sum(a);
-    if (lane == 0) {
-      if (phase == 0) pb.tf[r] = (float)a;
-      else pb.dir[r] = a;
+#pragma unroll
+    for (int v = 0; v < GEMV_MAXV; v++) {
+      if ((mask >> v) & 1u) {
+        const double sv = warp_sum(a[v]);
+        if (lane == 0) {
+          if (phase == 0) tfs[v][r] = (float)sv;
+          else dirs[v][r] = sv;
+        }
+      }
     }
   }
 }
@@ -426,12 +461,12 @@ cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, int Dt, cudaStre
   if (launches) *launches += 2;
   return cudaGetLastError();
 }
-cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches) {
+cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches, int group_L) {
   const dim3 grid((ldh + NT / 32 - 1) / (NT / 32), nprob);
   if (cholesky_factored_direction(ldh)) {
     const dim3 gtri(((ldh + 1) / 2 + NT / 32 - 1) / (NT / 32), nprob);
-    newton_gemv_tri_kernel<<<gtri, NT, 0, st>>>(d_probs, 0);
-    newton_gemv_tri_kernel<<<gtri, NT, 0, st>>>(d_probs, 1);
+    newton_gemv_tri_kernel<<<gtri, NT, 0, st>>>(d_probs, 0, group_L);
+    newton_gemv_tri_kernel<<<gtri, NT, 0, st>>>(d_probs, 1, group_L);
     if (launches) *launches += 1;
   } else {
     newton_gemv_kernel<<<grid, NT, 0, st>>>(d_probs);

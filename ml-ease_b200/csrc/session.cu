@@ -143,6 +143,7 @@ struct Batch {
   bool csr = false;
   int has_bias = 1;
   int k1_grid = 1, gram_slices = 1, ntiles = 0;
+  int gram_ncta = 1;              // 2: the CSR Gram runs on CTA pairs (cta_group::2, 256 x 256 tiles); d_tiles then holds pair tiles
   int gram_from_csr = 0;          // every problem of the batch assembles its Gram tiles from CSR (no dense bf16 operand)
   int group_L = 1;                // problems b = g * group_L + l share the data of partition g (the lambdas of one partition)
   int k1_fused = 0;               // the fused multi-lambda CSR K1 runs (segment lists present): one launch, grid (sg_S, nprob / group_L)
@@ -272,19 +273,21 @@ int batch_alloc(Batch& B, int num_sms) {
   // Gram decomposition
   constexpr int MAX_TILES = 1 << 18;   // lower 128x256 tiles of Dp up to ~90k
   std::vector<short> tiles(2 * (size_t)MAX_TILES);
-  B.ntiles = gram_tile_list(B.Dp, tiles.data(), MAX_TILES);
+  B.gram_ncta = (B.gram_from_csr && !getenv("MLEASE_GRAM_1CTA")) ? 2 : 1;   // the variable exists for A/B measurements only
+  B.ntiles = gram_tile_list(B.Dp, tiles.data(), MAX_TILES, B.gram_ncta == 2);
   if (B.ntiles <= 0) return fail(MLEASE_ERR_INVALID, "Gram tile list overflow");
   {
     const long long ksteps = (maxn + 63) / 64;
-    const long long base = (long long)B.ntiles * nprob;
+    const long long base = (long long)B.ntiles * nprob;   // CTAs, or CTA pairs
+    const long long cap = std::max(1, num_sms / B.gram_ncta);
     int best = 1;
     double best_eff = 0;
     for (int s = 1; s <= 16; s++) {
       if (s > ksteps) break;
       const long long ctas = base * s;
-      const double eff = (double)ctas / (double)(((ctas + num_sms - 1) / num_sms) * num_sms);
+      const double eff = (double)ctas / (double)(((ctas + cap - 1) / cap) * cap);
       if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
-      if (eff >= 0.93 && ctas >= 2LL * num_sms) { best = s; break; }
+      if (eff >= 0.93 && ctas >= 2LL * cap) { best = s; break; }
     }
     // bound the split-K scratch to 1 GiB per batch
     while (best > 1 && (double)best * B.Dp * B.Dp * 4.0 * nprob > 1024.0 * 1024 * 1024) best--;
@@ -412,7 +415,7 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
       const int share = (slot_idx == 0) ? share_first_gram : 0;
       if (share > 1)
         for (int b = 0; b < B.nprob; b++) if (b % share != 0) shared_flops += (double)B.h[b].n * (double)B.Dt * (double)(B.Dt + 1);
-      if (B.gram_from_csr) CK(gram_launch_csr_tcgen05(d_hess, n_hess, B.d_tiles, B.ntiles, B.gram_slices, 0, B.has_bias ? B.Dt - 1 : -1, st, &launches, share));
+      if (B.gram_from_csr) CK(gram_launch_csr_tcgen05(d_hess, n_hess, B.d_tiles, B.ntiles, B.gram_slices, 0, B.has_bias ? B.Dt - 1 : -1, st, &launches, share, B.gram_ncta));
       else CK(gram_launch_tcgen05(d_hess, n_hess, B.d_tmaps, B.d_tiles, B.ntiles, B.gram_slices, 0, st, &launches, share));
       pf.end(st);
       pf.begin(3, st);
@@ -427,13 +430,13 @@ int batch_xupdate(Batch& B, cudaStream_t st, double xtol, int max_newton, int po
           const Problem& lead = B.h[b - b % share];
           // wide systems work on the factored form Y = L^-1 (bf16, Ysym): that is all a follower needs
           if (!cholesky_factored_direction(B.ldh)) CK(cudaMemcpyAsync(B.h[b].Hinv, lead.Hinv, hh * sizeof(double), cudaMemcpyDeviceToDevice, st));
-          if (B.h[b].Ysym) CK(cudaMemcpyAsync(B.h[b].Ysym, lead.Ysym, hh * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, st));
+          // (Ysym is not copied: chol_share_end_kernel points the follower's Ctrl::ysym_use at the leader's)
         }
       }
       pf.end(st);
     }
     pf.begin(1, st);
-    CK(newton_solve(B.d, B.nprob, B.ldh, st, &launches));
+    CK(newton_solve(B.d, B.nprob, B.ldh, st, &launches, B.group_L));
     if (!small) { poll2_kernel<<<1, 256, 0, st>>>(B.d, B.nprob, d_flag, B.d_compact); launches++; }
     pf.end(st);
     return 0;
@@ -556,6 +559,9 @@ struct mlease_session {
   std::vector<float> lambdas, rhos, lambda_map;
   int Dg = 0, Dt = 0, ldx = 0, L = 0, P = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // H2D of a CSR partition's arrays, overlapped with the previous partition's layout build
+  cudaEvent_t copy_ev = nullptr;        // orders copy_stream after what the caller queued on `stream` (e.g. kernels that produce device inputs)
+  int pending_csr = -1;                 // index into parts of the CSR partition whose checks and lists are not built yet
   int num_sms = 148;
   std::vector<PartData> parts;
   std::vector<void*> owned;
@@ -590,8 +596,14 @@ struct mlease_session {
     for (void* p : owned) cudaFree(p);
     if (h_flag) cudaFreeHost(h_flag);
     if (h_small) cudaFreeHost(h_small);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (copy_ev) cudaEventDestroy(copy_ev);
   }
 };
+
+extern "C" {
+static int csr_flush_pending(mlease_session* s);   // builds the deferred lists of the last CSR partition
+}
 
 namespace {
 
@@ -631,6 +643,11 @@ void fill_problem_data(Problem& p, const PartData& pd) {
 
 int finalize(mlease_session* s) {
   if (s->batch) return 0;
+  if (int rc = csr_flush_pending(s)) return rc;
+  if (s->copy_stream) {   // hand the builders' cached temporaries back before the solver state is allocated
+    cudaMemPool_t mp;
+    if (cudaDeviceGetDefaultMemPool(&mp, s->cfg.device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
+  }
   if (s->parts.empty()) return fail(MLEASE_ERR_STATE, "no partitions were added to this session");
   if (s->any_csr && s->any_dense) return fail(MLEASE_ERR_INVALID, "a session must hold either dense or CSR partitions, not both");
   std::sort(s->parts.begin(), s->parts.end(), [](const PartData& a, const PartData& b) { return a.pid < b.pid; });
@@ -680,6 +697,7 @@ int finalize(mlease_session* s) {
 
 int ensure_scratch(mlease_session* s, int part_idx) {
   if (s->scratch && s->scratch_part == part_idx) return 0;
+  if (int rc = csr_flush_pending(s)) return rc;
   delete s->scratch;
   s->scratch = new Batch();
   Batch* B = s->scratch;
@@ -900,6 +918,58 @@ int mlease_add_partition_dense(mlease_session* s, int32_t pid, int64_t nrows, co
   return 0;
 }
 
+// Checks and derived lists of one uploaded CSR partition (feature range, |value| max, block-major Gram list, K1 segment
+// lists). Runs on s->stream; mlease_add_partition_csr defers it by one call so that it overlaps the next partition's H2D copy.
+static int csr_build_layout(mlease_session* s, PartData& pd) {
+  if (pd.nnz <= 0) return 0;
+  const long long nrows = pd.n;
+  const std::string who = "partition " + std::to_string(pd.pid) + ": ";
+  CK(cudaMemsetAsync(s->d_flag, 0, 4, s->stream));
+  check_csr_kernel<<<(int)std::min<long long>((pd.nnz + 255) / 256, 4096), 256, 0, s->stream>>>(pd.nnz, pd.colidx, pd.vals, s->Dg, s->cfg.binary_feature, s->d_flag);
+  CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  if (*s->h_flag) return fail(MLEASE_ERR_INVALID, who + "feature index out of range");
+  CK(cudaMemsetAsync(s->d_flag, 0, 4, s->stream));
+  absmax_kernel<<<(int)std::min<long long>((pd.nnz + 255) / 256, 2048), 256, 0, s->stream>>>(pd.nnz, pd.vals, (unsigned*)s->d_flag);
+  CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemsetAsync(s->d_flag + 1, 0, 4, s->stream));
+  check_rows_sorted_kernel<<<(int)std::min<long long>((nrows + 255) / 256, 4096), 256, 0, s->stream>>>(nrows, pd.rowptr, pd.colidx, s->d_flag + 1);
+  CK(cudaMemcpyAsync(s->h_flag + 1, s->d_flag + 1, 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  std::memcpy(&pd.vmax, s->h_flag, 4);
+  pd.csr_unique = s->h_flag[1] ? 0 : 1;
+  if (pd.csr_unique && pd.nnz < (1LL << 32) - 64) {   // the Gram producers index the entry list with 32 bits
+    pd.nblk128 = round_up(s->ldx, 128) / 128;
+    pd.bm_groups = (nrows + 31) / 32;
+    void *bo, *bk, *bv;
+    if (int rc = sess_alloc(s, &bo, ((size_t)pd.nblk128 * pd.bm_groups + 1) * sizeof(long long))) return rc;
+    if (int rc = sess_alloc(s, &bk, (size_t)pd.nnz * sizeof(unsigned short))) return rc;
+    if (int rc = sess_alloc(s, &bv, (size_t)pd.nnz * sizeof(float))) return rc;
+    CK(csr_bm_offsets(nrows, pd.rowptr, pd.colidx, pd.nblk128, pd.bm_groups, (long long*)bo, s->stream));
+    CK(csr_bm_fill(nrows, pd.rowptr, pd.colidx, pd.vals, pd.nblk128, pd.bm_groups, (const long long*)bo, (unsigned short*)bk, (float*)bv, s->stream));
+    pd.bm_offs = (long long*)bo; pd.bm_keys = (unsigned short*)bk; pd.bm_vals = (float*)bv;
+    // segment lists of the fused multi-lambda K1
+    int S = 0, rows = 0, LP = 0; size_t smem = 0;
+    if (!getenv("MLEASE_NO_FUSED_K1") && k1f_plan(nrows, s->ldx, s->L, s->num_sms, &S, &rows, &LP, &smem)) {
+      CK(k1f_build(nrows, s->Dg, pd.nnz, pd.rowptr, pd.colidx, pd.vals, S, rows, &pd.sg_ngrp, &pd.sg_perm, &pd.sg_depth, &pd.sg_goff, &pd.sg_row16,
+                   &pd.sg_val, &pd.sg_total, s->stream));
+      pd.sg_S = S; pd.sg_rows = rows;
+      s->owned.push_back(pd.sg_perm); s->owned.push_back(pd.sg_depth); s->owned.push_back(pd.sg_goff);
+      s->owned.push_back(pd.sg_row16); s->owned.push_back(pd.sg_val);
+    }
+  }
+  return 0;
+}
+
+static int csr_flush_pending(mlease_session* s) {
+  if (s->pending_csr < 0) return 0;
+  const int idx = s->pending_csr;
+  s->pending_csr = -1;
+  return csr_build_layout(s, s->parts[idx]);
+}
+
+// The big arrays travel on copy_stream while the previous partition's lists are built on s->stream; a malformed colidx of
+// partition p is therefore reported by the NEXT session call (add_partition / begin / fit), with the partition id in the message.
 int mlease_add_partition_csr(mlease_session* s, int32_t pid, int64_t nrows, const int64_t* rowptr, const int32_t* colidx, const float* vals,
                              const int32_t* response, const float* weight, const float* offset) {
   if (!s || !rowptr || !response || nrows <= 0) return fail(MLEASE_ERR_INVALID, "bad argument (null pointer or empty partition)");
@@ -907,65 +977,45 @@ int mlease_add_partition_csr(mlease_session* s, int32_t pid, int64_t nrows, cons
   if (pid < 0 || pid >= s->P) return fail(MLEASE_ERR_INVALID, "Map key is wrong! key has to be in the range of [0,numPartitions-1].");
   if (find_part(s, pid) >= 0) return fail(MLEASE_ERR_INVALID, "partition added twice");
   CK(cudaSetDevice(s->cfg.device));
-  PartData pd;
-  pd.pid = pid; pd.n = nrows; pd.csr = true;
-  void *rp, *ci, *vv;
-  if (int rc = sess_alloc(s, &rp, (nrows + 1) * 8)) return rc;
-  CK(cudaMemcpyAsync(rp, rowptr, (nrows + 1) * 8, cudaMemcpyDefault, s->stream));
-  long long ends[2];
-  CK(cudaMemcpyAsync(&ends[0], rowptr, 8, cudaMemcpyDefault, s->stream));
-  CK(cudaMemcpyAsync(&ends[1], rowptr + nrows, 8, cudaMemcpyDefault, s->stream));
-  CK(cudaStreamSynchronize(s->stream));
-  if (ends[0] != 0) return fail(MLEASE_ERR_INVALID, "rowptr[0] must be 0");
-  pd.nnz = ends[1];
-  if (pd.nnz > 0 && (!colidx || !vals)) return fail(MLEASE_ERR_INVALID, "null colidx/vals");
-  if (int rc = sess_alloc(s, &ci, pd.nnz * 4)) return rc;
-  if (int rc = sess_alloc(s, &vv, pd.nnz * 4)) return rc;
-  if (pd.nnz > 0) {
-    CK(cudaMemcpyAsync(ci, colidx, pd.nnz * 4, cudaMemcpyDefault, s->stream));
-    CK(cudaMemcpyAsync(vv, vals, pd.nnz * 4, cudaMemcpyDefault, s->stream));
-    CK(cudaMemsetAsync(s->d_flag, 0, 4, s->stream));
-    check_csr_kernel<<<(int)std::min<long long>((pd.nnz + 255) / 256, 4096), 256, 0, s->stream>>>(pd.nnz, (const int*)ci, (float*)vv, s->Dg, s->cfg.binary_feature, s->d_flag);
-    CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    if (*s->h_flag) return fail(MLEASE_ERR_INVALID, "feature index out of range");
-    {
-      CK(cudaMemsetAsync(s->d_flag, 0, 4, s->stream));
-      absmax_kernel<<<(int)std::min<long long>((pd.nnz + 255) / 256, 2048), 256, 0, s->stream>>>(pd.nnz, (const float*)vv, (unsigned*)s->d_flag);
-      CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
-      CK(cudaStreamSynchronize(s->stream));
-      std::memcpy(&pd.vmax, s->h_flag, 4);
-    }
-    CK(cudaMemsetAsync(s->d_flag, 0, 4, s->stream));
-    check_rows_sorted_kernel<<<(int)std::min<long long>((nrows + 255) / 256, 4096), 256, 0, s->stream>>>(nrows, (const long long*)rp, (const int*)ci, s->d_flag);
-    CK(cudaMemcpyAsync(s->h_flag, s->d_flag, 4, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    pd.csr_unique = *s->h_flag ? 0 : 1;
-    if (pd.csr_unique && pd.nnz < (1LL << 32) - 64) {   // the Gram producers index the entry list with 32 bits
-      pd.nblk128 = round_up(s->ldx, 128) / 128;
-      pd.bm_groups = (nrows + 31) / 32;
-      void *bo, *bk, *bv;
-      if (int rc = sess_alloc(s, &bo, ((size_t)pd.nblk128 * pd.bm_groups + 1) * sizeof(long long))) return rc;
-      if (int rc = sess_alloc(s, &bk, (size_t)pd.nnz * sizeof(unsigned short))) return rc;
-      if (int rc = sess_alloc(s, &bv, (size_t)pd.nnz * sizeof(float))) return rc;
-      CK(csr_bm_offsets(nrows, (const long long*)rp, (const int*)ci, pd.nblk128, pd.bm_groups, (long long*)bo, s->stream));
-      CK(csr_bm_fill(nrows, (const long long*)rp, (const int*)ci, (const float*)vv, pd.nblk128, pd.bm_groups, (const long long*)bo,
-                     (unsigned short*)bk, (float*)bv, s->stream));
-      pd.bm_offs = (long long*)bo; pd.bm_keys = (unsigned short*)bk; pd.bm_vals = (float*)bv;
-      // segment lists of the fused multi-lambda K1
-      int S = 0, rows = 0, LP = 0; size_t smem = 0;
-      if (!getenv("MLEASE_NO_FUSED_K1") && k1f_plan(nrows, s->ldx, s->L, s->num_sms, &S, &rows, &LP, &smem)) {
-        CK(k1f_build(nrows, s->Dg, pd.nnz, (const long long*)rp, (const int*)ci, (const float*)vv, S, rows, &pd.sg_ngrp, &pd.sg_perm, &pd.sg_depth,
-                     &pd.sg_goff, &pd.sg_row16, &pd.sg_val, &pd.sg_total, s->stream));
-        pd.sg_S = S; pd.sg_rows = rows;
-        s->owned.push_back(pd.sg_perm); s->owned.push_back(pd.sg_depth); s->owned.push_back(pd.sg_goff);
-        s->owned.push_back(pd.sg_row16); s->owned.push_back(pd.sg_val);
-      }
+  if (!s->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s->copy_ev, cudaEventDisableTiming));
+    // the list builders take their temporaries from the device's stream-ordered pool: keep them cached between partitions
+    cudaMemPool_t mp;
+    if (cudaDeviceGetDefaultMemPool(&mp, s->cfg.device) == cudaSuccess) {
+      unsigned long long keep = 8ULL << 30;
+      cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
     }
   }
+  // the inputs are ready in the order of the session stream (they may be device arrays a kernel on that stream is still writing)
+  CK(cudaEventRecord(s->copy_ev, s->stream));
+  CK(cudaStreamWaitEvent(s->copy_stream, s->copy_ev, 0));
+  PartData pd;
+  pd.pid = pid; pd.n = nrows; pd.csr = true;
+  long long ends[2];
+  CK(cudaMemcpyAsync(&ends[0], rowptr, 8, cudaMemcpyDefault, s->copy_stream));
+  CK(cudaMemcpyAsync(&ends[1], rowptr + nrows, 8, cudaMemcpyDefault, s->copy_stream));
+  CK(cudaStreamSynchronize(s->copy_stream));
+  if (ends[0] != 0) return fail(MLEASE_ERR_INVALID, "rowptr[0] must be 0");
+  if (ends[1] < 0) return fail(MLEASE_ERR_INVALID, "rowptr[nrows] < 0");
+  pd.nnz = ends[1];
+  if (pd.nnz > 0 && (!colidx || !vals)) return fail(MLEASE_ERR_INVALID, "null colidx/vals");
+  if (int rc = add_common(s, pd, response, weight, offset)) return rc;   // label checks first: nothing is in flight when they fail
+  void *rp, *ci, *vv;
+  if (int rc = sess_alloc(s, &rp, (nrows + 1) * 8)) return rc;
+  if (int rc = sess_alloc(s, &ci, pd.nnz * 4)) return rc;
+  if (int rc = sess_alloc(s, &vv, pd.nnz * 4)) return rc;
   pd.rowptr = (long long*)rp; pd.colidx = (int*)ci; pd.vals = (float*)vv;
-  if (int rc = add_common(s, pd, response, weight, offset)) return rc;
+  cudaError_t ce = cudaMemcpyAsync(rp, rowptr, (nrows + 1) * 8, cudaMemcpyDefault, s->copy_stream);
+  if (ce == cudaSuccess && pd.nnz > 0) ce = cudaMemcpyAsync(ci, colidx, pd.nnz * 4, cudaMemcpyDefault, s->copy_stream);
+  if (ce == cudaSuccess && pd.nnz > 0) ce = cudaMemcpyAsync(vv, vals, pd.nnz * 4, cudaMemcpyDefault, s->copy_stream);
+  const int rc_prev = ce == cudaSuccess ? csr_flush_pending(s) : 0;      // overlaps the copies above
+  const cudaError_t cs = cudaStreamSynchronize(s->copy_stream);          // the caller's buffers are free again on every return path
+  CK(ce);
+  CK(cs);
+  if (rc_prev) return rc_prev;
   s->parts.push_back(pd);
+  s->pending_csr = (int)s->parts.size() - 1;
   s->any_csr = true;
   return 0;
 }
@@ -1224,7 +1274,7 @@ int mlease_objective(mlease_session* s, int32_t pid, const double* w, const doub
   if (f) *f = c.f_t;
   if (H) {
     if (!tensor && B->gram_from_csr) return fail(MLEASE_ERR_INVALID, "the SIMT debug Gram needs the dense bf16 operand, which CSR partitions with sorted unique rows do not materialise");
-    if (tensor && B->gram_from_csr) CK(gram_launch_csr_tcgen05(B->d, 1, B->d_tiles, B->ntiles, B->gram_slices, 1, B->has_bias ? B->Dt - 1 : -1, s->stream, &launches));
+    if (tensor && B->gram_from_csr) CK(gram_launch_csr_tcgen05(B->d, 1, B->d_tiles, B->ntiles, B->gram_slices, 1, B->has_bias ? B->Dt - 1 : -1, s->stream, &launches, 0, B->gram_ncta));
     else if (tensor) CK(gram_launch_tcgen05(B->d, 1, B->d_tmaps, B->d_tiles, B->ntiles, B->gram_slices, 1, s->stream, &launches));
     else CK(gram_launch_simt(B->d, 1, B->Dp, 1, s->stream, &launches));
     if (tensor == 2) {
@@ -1346,7 +1396,7 @@ int mlease_time_kernel(mlease_session* s, int32_t pid, int32_t which, int32_t re
   CK(batch_k1(*B, 1, s->stream, &launches));
   const int bias_col = B->has_bias ? B->Dt - 1 : -1;
   if (which == 3) {
-    if (B->gram_from_csr) CK(gram_launch_csr_tcgen05(B->d, 1, B->d_tiles, B->ntiles, B->gram_slices, 1, bias_col, s->stream, &launches));
+    if (B->gram_from_csr) CK(gram_launch_csr_tcgen05(B->d, 1, B->d_tiles, B->ntiles, B->gram_slices, 1, bias_col, s->stream, &launches, 0, B->gram_ncta));
     else CK(gram_launch_tcgen05(B->d, 1, B->d_tmaps, B->d_tiles, B->ntiles, B->gram_slices, 1, s->stream, &launches));
     Ctrl c; std::memset(&c, 0, sizeof(c)); c.need_hess = 1;
     CK(cudaMemcpyAsync(B->d_ctrl, &c, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
@@ -1355,7 +1405,7 @@ int mlease_time_kernel(mlease_session* s, int32_t pid, int32_t which, int32_t re
   CK(cudaEventRecord(e0, s->stream));
   for (int r = 0; r < reps; r++) {
     if (which == 1) CK(batch_k1(*B, emit_scaled ? 1 : 0, s->stream, &launches));
-    else if (which == 2 && B->gram_from_csr) CK(gram_launch_csr_tcgen05(B->d, 1, B->d_tiles, B->ntiles, B->gram_slices, 1, bias_col, s->stream, &launches));
+    else if (which == 2 && B->gram_from_csr) CK(gram_launch_csr_tcgen05(B->d, 1, B->d_tiles, B->ntiles, B->gram_slices, 1, bias_col, s->stream, &launches, 0, B->gram_ncta));
     else if (which == 2) CK(gram_launch_tcgen05(B->d, 1, B->d_tmaps, B->d_tiles, B->ntiles, B->gram_slices, 1, s->stream, &launches));
     else if (which == 3) CK(cholesky_launch(B->d, 1, B->ldh, s->stream, &launches));
     else return fail(MLEASE_ERR_INVALID, "which must be 1, 2 or 3");

@@ -388,6 +388,15 @@ def test_admm_wide_systems_keep_the_cold_start_factor(mb):
     # one factorisation per (partition, lambda) at the cold start; at most one more each if the cold x-update spent a dozen steps
     # on that factor without contracting by 2x (the "stuck" rule of k1_reduce_decide_kernel) -- never one per iteration
     assert st["not_converged"] == 0 and 4 <= st["gram_builds"] <= 8, st
+    # distinct rho: the lambdas share the cold-start Gram but factorise separately, so each streams its own Y in the direction
+    # kernels (with equal rho, above, the group reads the leader's Y once for all its lambdas)
+    rhos = [1.0, 2.5]
+    ref = orc.admm_run(data, [0, n, 2 * n], lambdas, rhos=rhos, niters=3, mode="exact", nthreads=8, epsilon=0.0)
+    done, z, xs, us, st = _run_gpu_admm(mb, parts, D, lambdas, 3, csr=True, epsilon=0.0, rhos=rhos)
+    for l in range(2):
+        err = np.abs(z[l] - ref["z_hist"][-1, l]).max() / np.abs(ref["z_hist"][-1, l]).max()
+        assert err < 1e-5, (l, err, st)
+    assert st["not_converged"] == 0
 
 
 def test_admm_initialize_boost_rate(mb, fixture_data, frozen):

@@ -412,7 +412,7 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
     float* out = pb.Hpart + (size_t)slice * Dp * Dp;
     const int row = tile_bi * GM + quad * 32 + lane;
     if (nk > 0) {
-      mbar_wait(acc_bar, 0);
+      while (!mbar_try_wait(acc_bar, 0)) __nanosleep(512);   // the whole main loop long: do not spend issue slots on polling
       tc_fence_after();
     }
 #pragma unroll 1

@@ -298,6 +298,7 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
 // they all point at the leader's Y (Ctrl::ysym_use), and the FIRST active problem of such a set streams Y once for every active
 // member (up to 4 vectors per pass); a problem with its own factor, or alone in its set, runs by itself.
 constexpr int GEMV_MAXV = 4;
+constexpr int GEMV_RB = 4;     // rows per warp pass
 __global__ void __launch_bounds__(NT) newton_gemv_tri_kernel(const Problem* __restrict__ probs, int phase, int group_L) {
   const int b = blockIdx.y;
   const Problem& pb = probs[b];
@@ -326,47 +327,72 @@ __global__ void __launch_bounds__(NT) newton_gemv_tri_kernel(const Problem* __re
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
   const int Dt = pb.Dt;
-  if (w >= (Dt + 1) / 2) return;
-  // a warp takes row w and its mirror Dt-1-w: the two triangular rows together hold Dt+1 elements, whatever w is (balanced)
+  const int nblk = (Dt + GEMV_RB - 1) / GEMV_RB;
+  if (w >= (nblk + 1) / 2) return;
+  // A warp takes a block of GEMV_RB rows and the mirrored block: together they hold the same number of triangle elements whatever w
+  // is (balanced).  Per k-chunk a lane loads its 8 elements of every vector ONCE (L1) and of each of the block's rows (the HBM
+  // stream, GEMV_RB independent 16-byte loads in flight per lane); fp32 products and per-lane sums (Y is bf16: 3e-3 per element),
+  // fp64 only across the warp.
 #pragma unroll 1
   for (int half = 0; half < 2; half++) {
-    const int r = half == 0 ? w : Dt - 1 - w;
-    if (half == 1 && r == w) break;
-    const __nv_bfloat16* __restrict__ Mr = Y + (size_t)r * pb.ldh;
-    const int k0 = phase == 0 ? 0 : (r & ~7), k1 = phase == 0 ? r + 1 : Dt;
-    // fp32 products and 8-term partial sums, fp64 across chunks: the HBM stream, not fp64 conversions, sets the pace
-    double a[GEMV_MAXV] = {0.0, 0.0, 0.0, 0.0};
-    for (int k = k0 + lane * 8; k < k1; k += 256) {
-      const uint4 h = *reinterpret_cast<const uint4*>(Mr + k);   // rows are ldh (multiple of 32) elements long: reading past k1 stays inside the row
-      float hv[8] = {bf16_lo(h.x), bf16_hi(h.x), bf16_lo(h.y), bf16_hi(h.y), bf16_lo(h.z), bf16_hi(h.z), bf16_lo(h.w), bf16_hi(h.w)};
-      const bool edge = (k + 8 > k1) || (phase == 1 && k < r);
-      if (edge) {
+    const int rb = half == 0 ? w : nblk - 1 - w;
+    if (half == 1 && rb == w) break;
+    const int r0 = rb * GEMV_RB;
+    const int kbeg = phase == 0 ? 0 : (r0 & ~7), kend = phase == 0 ? min(r0 + GEMV_RB, Dt) : Dt;
+    float acc[GEMV_RB][GEMV_MAXV];
 #pragma unroll
-        for (int e = 0; e < 8; e++)
-          if (k + e >= k1 || (phase == 1 && k + e < r)) hv[e] = 0.f;
-      }
-      const bool second = k + 4 < pb.ldx;
+    for (int j = 0; j < GEMV_RB; j++)
+#pragma unroll
+      for (int v = 0; v < GEMV_MAXV; v++) acc[j][v] = 0.f;
+    for (int k = kbeg + lane * 8; k < kend; k += 256) {
+      uint4 h[GEMV_RB];
+#pragma unroll
+      for (int j = 0; j < GEMV_RB; j++)   // rows are ldh (multiple of 32) elements long: a chunk that starts below Dt stays inside its row
+        h[j] = (r0 + j < Dt) ? *reinterpret_cast<const uint4*>(Y + (size_t)(r0 + j) * pb.ldh + k) : make_uint4(0u, 0u, 0u, 0u);
+      float xv[GEMV_MAXV][8];
+      const bool second = k + 4 < pb.ldx;   // vectors are ldx (multiple of 4) long and 32-byte aligned at k
 #pragma unroll
       for (int v = 0; v < GEMV_MAXV; v++) {
         if ((mask >> v) & 1u) {
-          // x is 32-byte aligned at k (k % 8 == 0) and ldx % 4 == 0: two float4 loads, the second one only if it is inside the vector
           const float4 x0 = *reinterpret_cast<const float4*>(xs[v] + k);
           const float4 x1 = second ? *reinterpret_cast<const float4*>(xs[v] + k + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-          float p = 0.f;
+          xv[v][0] = x0.x; xv[v][1] = x0.y; xv[v][2] = x0.z; xv[v][3] = x0.w; xv[v][4] = x1.x; xv[v][5] = x1.y; xv[v][6] = x1.z; xv[v][7] = x1.w;
+        }
+      }
+      // triangle edge: phase 0 keeps k+e <= row, phase 1 keeps row <= k+e < Dt
+      const bool edge = phase == 0 ? (k + 8 > r0 + 1) : (k < r0 + GEMV_RB || k + 8 > Dt);
 #pragma unroll
-          for (int e = 0; e < 8; e++) p = fmaf(hv[e], xv[e], p);
-          a[v] += (double)p;
+      for (int j = 0; j < GEMV_RB; j++) {
+        float hv[8] = {bf16_lo(h[j].x), bf16_hi(h[j].x), bf16_lo(h[j].y), bf16_hi(h[j].y), bf16_lo(h[j].z), bf16_hi(h[j].z), bf16_lo(h[j].w), bf16_hi(h[j].w)};
+        if (edge) {
+          const int row = r0 + j;
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            const bool keep = phase == 0 ? (k + e <= row) : (k + e >= row && k + e < Dt);
+            if (!keep) hv[e] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < GEMV_MAXV; v++) {
+          if ((mask >> v) & 1u) {
+            float p = acc[j][v];
+#pragma unroll
+            for (int e = 0; e < 8; e++) p = fmaf(hv[e], xv[v][e], p);
+            acc[j][v] = p;
+          }
         }
       }
     }
 #pragma unroll
-    for (int v = 0; v < GEMV_MAXV; v++) {
-      if ((mask >> v) & 1u) {
-        const double sv = warp_sum(a[v]);
-        if (lane == 0) {
-          if (phase == 0) tfs[v][r] = (float)sv;
-          else dirs[v][r] = sv;
+    for (int j = 0; j < GEMV_RB; j++) {
+#pragma unroll
+      for (int v = 0; v < GEMV_MAXV; v++) {
+        if ((mask >> v) & 1u) {
+          const double sv = warp_sum((double)acc[j][v]);
+          if (lane == 0 && r0 + j < Dt) {
+            if (phase == 0) tfs[v][r0 + j] = (float)sv;
+            else dirs[v][r0 + j] = sv;
+          }
         }
       }
     }
@@ -464,7 +490,8 @@ cudaError_t k1_reduce_decide(const Problem* d_probs, int nprob, int Dt, cudaStre
 cudaError_t newton_solve(const Problem* d_probs, int nprob, int ldh, cudaStream_t st, int* launches, int group_L) {
   const dim3 grid((ldh + NT / 32 - 1) / (NT / 32), nprob);
   if (cholesky_factored_direction(ldh)) {
-    const dim3 gtri(((ldh + 1) / 2 + NT / 32 - 1) / (NT / 32), nprob);
+    const int nblk2 = ((ldh + GEMV_RB - 1) / GEMV_RB + 1) / 2;   // row blocks, two (a block and its mirror) per warp
+    const dim3 gtri((nblk2 + NT / 32 - 1) / (NT / 32), nprob);
     newton_gemv_tri_kernel<<<gtri, NT, 0, st>>>(d_probs, 0, group_L);
     newton_gemv_tri_kernel<<<gtri, NT, 0, st>>>(d_probs, 1, group_L);
     if (launches) *launches += 1;

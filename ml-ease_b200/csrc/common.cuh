@@ -175,6 +175,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Byte store to a 32-bit shared-space address.  A pointer derived from the dynamic shared array by integer alignment loses its
+// address space: the compiler then emits GENERIC stores and rebuilds the 64-bit window base (S2UR CgaCtaId / SWINHI, ~10
+// instructions) at every store -- the Gram producers' scatter stores spent more instructions on that than on the data.
+__device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
 // 1-D bulk copy global -> shared (TMA engine, no tensor map): SASS UBLKCP.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

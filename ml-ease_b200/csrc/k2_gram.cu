@@ -182,18 +182,21 @@ gram_tcgen05_kernel(const Problem* __restrict__ probs, const CUtensorMap* __rest
 }
 
 // ------------------------------------------------------------------------------------------
-// Sparse variant: the same 128x256 / split-K tcgen05 Gram, but the bf16 operand tiles are ASSEMBLED IN SHARED MEMORY
-// from the partition's block-major entry list (no dense Xt in HBM: at 1 % density that copy is 100x the input and makes
-// the dense kernel HBM-bound).  One K-step = one 32-row group; its entries for a 128-column block are one contiguous
-// run of (key, value), the key being the byte offset of the element inside the canonical MN-major SWIZZLE_128B operand
-// block the UMMA descriptors expect (box*4096 + k*128 + ((chunk ^ (k & 7)) * 16) + 2*e, see sw128_off).  24 producer
-// warps, three per ring stage (A block, first and second half of the B tile): load the run coalesced, scale by
-// sqrt(d_row), round to bf16, store 2 bytes at the key.  Positions outside the sparsity pattern are zero: the ring is
-// cleared once, and a producer re-clears exactly the entries it wrote when it gets its stage back.  Generic-proxy
-// stores are published to the tensor core's async proxy with fence.proxy.async before the mbarrier arrive.
-// Warp roles (29 warps): 0 = MMA issuer + TMEM allocator, 1..24 = producers, 25..28 = epilogue.
-// Measured at 1M x 10k x 1 %: 1.27 PFLOP/s algorithmic (the MMA stream runs at the same ~440 clk per 128x256x32 step as
-// the dense kernel's; the producers wait on the empty barriers 2/3 of the time).
+// Sparse variant: the same split-K tcgen05 Gram, but the operand tiles are ASSEMBLED IN SHARED MEMORY, as e4m3, from the
+// partition's block-major entry list (no dense Xt in HBM: at 1 % density that copy is 100x the input and makes the dense
+// kernel HBM-bound).  One K-step = one 32-row group; its entries for a 128-column block are one contiguous run of
+// (key, value), the key being the byte offset of the element inside the canonical MN-major SWIZZLE_128B operand block the
+// UMMA descriptors expect (sw128_off).  24 producer warps, one per operand block of a stage: load the run coalesced, scale
+// by sqrt(d_row) * 2^e, round to e4m3, store one byte at the key.  Positions outside the sparsity pattern are zero: the ring
+// is cleared once, and a producer re-clears exactly the entries it wrote when it gets its stage back.  Generic-proxy stores
+// are published to the tensor core's async proxy with fence.proxy.async before the mbarrier arrive.
+// Warp roles (29 warps): 0 = MMA issuer (leader CTA) + TMEM allocator, 1..24 = producers, 25..28 = epilogue.
+// Measured at 1M x 10k x 1 % (8 builds): bf16 operands 628 ms (1.27 PFLOP/s); e4m3 531 ms; unrolled issue loop 374 ms;
+// CTA pairs 353 ms; shared-space byte stores (the generic ones rebuilt the shared window base at every store) 337 ms =
+// 2.37 PFLOP/s.  What bounds it now is the MMA stream itself: with producers that ONLY hand stages over (no loads, no
+// stores) a build takes 40.0 ms instead of 44.7 (tools/time_gram.py), i.e. 2.5 PFLOP/s is what one tcgen05.mma.kind::f8f6f4
+// per K = 32 step delivers at the clocks a tensor-bound kernel sustains on this part (cuBLAS bf16 holds 1.43 PFLOP/s at a
+// median 1365 MHz, MEASURED_PEAKS.json).
 // ------------------------------------------------------------------------------------------
 constexpr int SK = 32;                       // data rows (K) per stage
 constexpr int S_BOX_BYTES = SK * 128;        // 4 KB = one [32 k][128 cols] e4m3 operand block
@@ -329,7 +332,7 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
 
     // Pipeline registers: offsets three uses ahead (o_c), entries + sqrt(d) two uses ahead (set 2), one use ahead (set 1),
     // current (set 0); what the last TWO uses stored (p1 = previous use = the other stage, p2 = the use before = this stage).
-    auto ld_offs = [&](int k) -> uint32_t { return (fetch && k < nk) ? (uint32_t)my_offs[ks0 + k] : 0u; };   // the list holds < 2^32 entries (checked at upload)
+    auto ld_offs = [&](int k) -> uint32_t { return (fetch && k < nk) ? (uint32_t)__ldg(my_offs + ks0 + k) : 0u; };   // the list holds < 2^32 entries (checked at upload)
     uint32_t lo0, hi0, lo1, hi1, lo2, hi2, p1lo = 0, p1hi = 0, p2lo = 0, p2hi = 0;
     uint32_t key0[2], key1[2], key2[2], p1key[2] = {NOKEY, NOKEY}, p2key[2] = {NOKEY, NOKEY};
     float val0[2], val1[2], val2[2], sd0, sd1, sd2;
@@ -337,16 +340,17 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
 #pragma unroll
       for (int q = 0; q < 2; q++) {
         const uint32_t e = lo + lane + 32 * q;
-        key[q] = e < hi ? (uint32_t)keys[e] : NOKEY;
-        val[q] = e < hi ? bvals[e] : 0.f;
+        key[q] = e < hi ? (uint32_t)__ldg(keys + e) : NOKEY;
+        val[q] = e < hi ? __ldg(bvals + e) : 0.f;
       }
     };
     const float gscale = pb.gram_scale;   // power of two: keeps sqrt(d) x in e4m3's normal range; undone exactly by chol_prep
     auto ld_sd = [&](int k) -> float {
       const long long r = (ks0 + k) * SK + lane;
-      return (k < nk && r < n) ? sdv[r] * gscale : 0.f;
+      return (k < nk && r < n) ? sdv[r] * gscale : 0.f;   // sdvec is rewritten by K1 between builds: a plain load
     };
-    auto to_e4m3 = [](float x) -> unsigned char { return (unsigned char)__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3); };
+    auto to_e4m3 = [](float x) -> uint32_t { return (uint32_t)__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3); };
+    const uint32_t smem_base_u32 = smem_u32(smem);
     {
       const uint32_t oa = ld_offs(grp), ob = ld_offs(grp + NGRP);
       lo0 = __shfl_sync(0xffffffffu, oa, 0); hi0 = __shfl_sync(0xffffffffu, oa, 1);
@@ -358,23 +362,19 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
     bool p1row = false, p2row = false;
     for (int k = grp, use = 0; k < nk; k += NGRP, use++) {
       const int st = k % SST;
-      unsigned char* const sbase = smem + (size_t)st * STAGE_BYTES + strm_off;
-      // ---- issue the loads of the use after next
-      lo2 = __shfl_sync(0xffffffffu, o_c, 0); hi2 = __shfl_sync(0xffffffffu, o_c, 1);
-      o_c = ld_offs(k + 3 * NGRP);
-      ld_entries(lo2, hi2, key2, val2); sd2 = ld_sd(k + 2 * NGRP);
+      const uint32_t sbase = smem_base_u32 + (uint32_t)st * (uint32_t)STAGE_BYTES + (uint32_t)strm_off;   // shared-space address
       // ---- un-write what the previous use of THIS STAGE (two uses ago) stored (same addresses, zero)
       const int fill = k / SST;   // how many times this stage has been filled before
       if (fill > 0) {
         mbar_wait(&empty_bar[st], (uint32_t)((fill - 1) & 1));
 #pragma unroll
         for (int q = 0; q < 2; q++)
-          if (p2key[q] != NOKEY) sbase[p2key[q]] = 0;
+          if (p2key[q] != NOKEY) sts_u8(sbase + p2key[q], 0u);
         for (uint32_t e0 = p2lo + 64; e0 < p2hi; e0 += 32) {
           const uint32_t e = e0 + lane;
-          if (e < p2hi) sbase[keys[e]] = 0;
+          if (e < p2hi) sts_u8(sbase + (uint32_t)__ldg(keys + e), 0u);
         }
-        if (p2row && has_bias_col) sbase[bias_off] = 0;
+        if (p2row && has_bias_col) sts_u8(sbase + bias_off, 0u);
       }
       // ---- write this use
 #pragma unroll
@@ -382,23 +382,29 @@ gram_csr_tcgen05_kernel(const Problem* __restrict__ probs, const GramTile* __res
         const bool v = key0[q] != NOKEY;
         const uint32_t key = v ? key0[q] : 0u;
         const float sdk = __shfl_sync(0xffffffffu, sd0, (key >> 7) & 31);
-        if (v) sbase[key] = to_e4m3(val0[q] * sdk);
+        if (v) sts_u8(sbase + key, to_e4m3(val0[q] * sdk));
       }
       for (uint32_t e0 = lo0 + 64; e0 < hi0; e0 += 32) {
         const uint32_t e = e0 + lane;
         const bool v = e < hi0;
-        const uint32_t key = v ? (uint32_t)keys[e] : 0u;
-        const float val = v ? bvals[e] : 0.f;
+        const uint32_t key = v ? (uint32_t)__ldg(keys + e) : 0u;
+        const float val = v ? __ldg(bvals + e) : 0.f;
         const float sdk = __shfl_sync(0xffffffffu, sd0, (key >> 7) & 31);
-        if (v) sbase[key] = to_e4m3(val * sdk);
+        if (v) sts_u8(sbase + key, to_e4m3(val * sdk));
       }
       const bool row_now = (ks0 + k) * SK + lane < n;
-      if (row_now && has_bias_col) sbase[bias_off] = to_e4m3(sd0);
+      if (row_now && has_bias_col) sts_u8(sbase + bias_off, to_e4m3(sd0));
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
         if (NCTA == 2) mbar_arrive_cluster(full0_remote + (uint32_t)st * 8u); else mbar_arrive(&full_bar[st]);
       }
+      // ---- issue the loads of the use after next.  AFTER the hand-over, not before this use's stores: the fence above compiles to
+      // MEMBAR.ALL.CTA, which waits for every load this thread still has in flight -- issued at the top of the use they would
+      // make each hand-over wait out a DRAM round trip; issued here they have the whole next use to arrive.
+      lo2 = __shfl_sync(0xffffffffu, o_c, 0); hi2 = __shfl_sync(0xffffffffu, o_c, 1);
+      o_c = ld_offs(k + 3 * NGRP);
+      ld_entries(lo2, hi2, key2, val2); sd2 = ld_sd(k + 2 * NGRP);
       // ---- rotate
       p2lo = p1lo; p2hi = p1hi; p2row = p1row; p1lo = lo0; p1hi = hi0; p1row = row_now;
       lo0 = lo1; hi0 = hi1; lo1 = lo2; hi1 = hi2;

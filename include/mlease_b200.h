@@ -79,7 +79,10 @@ int mlease_session_destroy(mlease_session* s);
  * (src/main/avro/RegressionPrepareOutput.avsc): response in {1,0,-1} (0 -> -1), weight >= 0, float32
  * values.  Pointers are host-or-device; the library copies.
  * dense: X row-major [nrows x num_features], leading dimension ldx (floats).
- * csr:   rowptr [nrows+1] (int64), colidx (global ids, any order, duplicates add), vals. */
+ * csr:   rowptr [nrows+1] (int64), colidx (global ids, any order, duplicates add), vals.  The call returns when the arrays
+ *        have been copied (the caller's buffers are free again); the checks on colidx and the derived lists of partition p
+ *        are built while partition p+1 is being copied, so "partition <id>: feature index out of range" is reported by the
+ *        NEXT call on the session (add_partition / begin / fit / objective).  response / weight errors are immediate. */
 int mlease_add_partition_dense(mlease_session* s, int32_t partition_id, int64_t nrows, const float* X, int64_t ldx,
                                const int32_t* response, const float* weight, const float* offset);
 int mlease_add_partition_csr(mlease_session* s, int32_t partition_id, int64_t nrows, const int64_t* rowptr,

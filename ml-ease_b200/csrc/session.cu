@@ -1000,7 +1000,11 @@ int mlease_add_partition_csr(mlease_session* s, int32_t pid, int64_t nrows, cons
   if (ends[1] < 0) return fail(MLEASE_ERR_INVALID, "rowptr[nrows] < 0");
   pd.nnz = ends[1];
   if (pd.nnz > 0 && (!colidx || !vals)) return fail(MLEASE_ERR_INVALID, "null colidx/vals");
+  const bool trace = getenv("MLEASE_UPLOAD_TRACE") != nullptr;   // per-call host timings on stderr (diagnostics)
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   if (int rc = add_common(s, pd, response, weight, offset)) return rc;   // label checks first: nothing is in flight when they fail
+  const double t1 = now();
   void *rp, *ci, *vv;
   if (int rc = sess_alloc(s, &rp, (nrows + 1) * 8)) return rc;
   if (int rc = sess_alloc(s, &ci, pd.nnz * 4)) return rc;
@@ -1009,8 +1013,13 @@ int mlease_add_partition_csr(mlease_session* s, int32_t pid, int64_t nrows, cons
   cudaError_t ce = cudaMemcpyAsync(rp, rowptr, (nrows + 1) * 8, cudaMemcpyDefault, s->copy_stream);
   if (ce == cudaSuccess && pd.nnz > 0) ce = cudaMemcpyAsync(ci, colidx, pd.nnz * 4, cudaMemcpyDefault, s->copy_stream);
   if (ce == cudaSuccess && pd.nnz > 0) ce = cudaMemcpyAsync(vv, vals, pd.nnz * 4, cudaMemcpyDefault, s->copy_stream);
+  const double t2 = now();
   const int rc_prev = ce == cudaSuccess ? csr_flush_pending(s) : 0;      // overlaps the copies above
+  const double t3 = now();
   const cudaError_t cs = cudaStreamSynchronize(s->copy_stream);          // the caller's buffers are free again on every return path
+  if (trace)
+    fprintf(stderr, "[mlease upload] partition %d: labels %.1f ms, alloc + enqueue %.1f ms, previous partition's lists %.1f ms, copy wait %.1f ms\n",
+            pid, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (now() - t3) * 1e3);
   CK(ce);
   CK(cs);
   if (rc_prev) return rc_prev;

@@ -656,6 +656,21 @@ def test_errors_follow_reference_conventions(mb):
         s.add_partition_dense(0, X, y)
         with pytest.raises(mb.MleaseError, match="Some models failed"):
             s.run(2)
+    # CSR: label errors are immediate; the colidx range check of a partition runs while the NEXT partition is copied, so it is
+    # reported by the next call on the session, naming the partition
+    rp, ci, v = _csr_of(X)
+    with mb.AdmmSession(2, 4, [1.0]) as s:
+        with pytest.raises(mb.MleaseError, match="response"):
+            s.add_partition_csr(0, rp, ci, v, np.full(50, 2, np.int32))
+        bad = ci.copy(); bad[3] = 4
+        s.add_partition_csr(0, rp, bad, v, y)
+        with pytest.raises(mb.MleaseError, match="partition 0: feature index out of range"):
+            s.add_partition_csr(1, rp, ci, v, y)
+    with mb.AdmmSession(1, 4, [1.0]) as s:
+        bad = ci.copy(); bad[0] = -1
+        s.add_partition_csr(0, rp, bad, v, y)
+        with pytest.raises(mb.MleaseError, match="partition 0: feature index out of range"):
+            s.run(1)
 
 
 @pytest.mark.parametrize("sparse", [False, True])

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) admm_consensus_kernel(const Problem* __re
                                                              int P, const double* __restrict__ exch, double* __restrict__ z,
                                                              const double* __restrict__ wz, const double* __restrict__ rho_next,
                                                              double* __restrict__ diff, const double* __restrict__ l1_thr) {
-  const int l = blockIdx.x;
+  const int l = blockIdx.y;
   __shared__ double sc[8];
   double dmax = 0.0;
   const double invP = 1.0 / (double)P;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) admm_consensus_kernel(const Problem* __re
   // (jobs/RegressionAdmmTrain.java:406-437): val > t -> val - t, val < -t -> val + t, values inside [-t, t] stay as they are
   // (the reference does not zero them); the intercept (not in getCoefficients()) is the plain mean (:438-449).
   const double thr = l1_thr ? l1_thr[l] : 0.0;
-  for (int k = threadIdx.x; k < Dt; k += 256) {
+  for (int k = blockIdx.x * 256 + threadIdx.x; k < Dt; k += gridDim.x * 256) {   // one element per thread: the grid covers Dt
     double zn;
     if (l1_thr) {
       zn = exch[(size_t)l * Dt + k] * invP;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) admm_consensus_kernel(const Problem* __re
       pb.q[k] = rho_next[l];
     }
   }
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0 && blockIdx.x == 0)
     for (int p = 0; p < nparts; p++) {
       const Problem& pb = probs[p * L + l];
       if (pb.gpart_f) { pb.ctrl->skip_eval = 1; pb.ctrl->k1_chunks = 0; }
@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(256) admm_consensus_kernel(const Problem* __re
   if (threadIdx.x == 0) {
     double d = 0.0;
     for (int w = 0; w < 8; w++) d = fmax(d, sc[w]);
-    diff[l] = d;
+    // max over the CTAs of this lambda: non-negative doubles order like their bit patterns (diff[] is zeroed before the launch)
+    atomicMax(reinterpret_cast<unsigned long long*>(diff + l), (unsigned long long)__double_as_longlong(d));
   }
 }
 
@@ -140,7 +141,10 @@ cudaError_t admm_pack(const Problem* d_probs, int nlocal_parts, int L, int Dt, d
 cudaError_t admm_consensus(const Problem* d_probs, int nlocal_parts, int L, int Dt, int ldv, int P, const double* d_exchange_sum,
                            double* d_z, const double* d_wz, const double* d_rho_eff_next, double* d_diff, cudaStream_t st,
                            int* launches, const double* d_l1_thr) {
-  admm_consensus_kernel<<<L, 256, 0, st>>>(d_probs, nlocal_parts, L, Dt, ldv, P, d_exchange_sum, d_z, d_wz, d_rho_eff_next, d_diff, d_l1_thr);
+  cudaError_t e = cudaMemsetAsync(d_diff, 0, (size_t)L * sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  admm_consensus_kernel<<<dim3((Dt + 255) / 256, L), 256, 0, st>>>(d_probs, nlocal_parts, L, Dt, ldv, P, d_exchange_sum, d_z, d_wz, d_rho_eff_next, d_diff,
+                                                                  d_l1_thr);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

@@ -516,6 +516,182 @@ static cudaError_t dgemm_launch(const Problem* d_probs, int nprob, int mode, int
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// Merges of the inverse in TF32 (wide systems whose direction runs on the factored form, ysym_kernel below).
+// There Y = L^-1 is only ever read after rounding to bf16, and Y^T Y is SPD for ANY Y, so an inexact inverse cannot turn the
+// preconditioner indefinite (the factorisation itself -- pivots -- stays in fp64).  The two GEMMs of a merge,
+//   T = L21 * Y11 (mode 1)   and   Y21 = -Y22 * T (mode 2),
+// are half of the D'^3 flops of a 10k-wide factorisation and run at ~25 TFLOP/s on the fp64 pipe; here the fp64 operands
+// are rounded to tf32 on their way into shared memory (cvt.rna) and multiplied by mma.sync.m16n8k8 with fp32 accumulation:
+// operand rounding 2^-11, against 2^-8 of the bf16 storage the result ends up in.  128x128 tiles, K chunks of 16, the same
+// register-staged double buffer as dgemm_kernel; both operands are row-major (A[i][k], B[k][j]) as in dgemm_kernel<true,false>.
+// Shared-memory strides: A rows of 20 words (fragment loads (row g, k tg): bank 20 g + tg, all distinct), B rows of 136
+// words (fragment loads (k tg, col g): bank 8 tg + g, all distinct).
+// ------------------------------------------------------------------------------------------
+constexpr int MERGE_TF32_DEFAULT = 0;   // switched on once the GPU parity suite and the bench have run with MLEASE_MERGE_TF32=1
+constexpr int TM = 128, TN = 128, TK = 16;
+constexpr int TA_LD = TK + 4, TB_LD = TN + 8;
+constexpr int TA_SZ = TM * TA_LD, TB_SZ = TK * TB_LD;   // 32-bit words per stage
+
+__device__ __forceinline__ uint32_t to_tf32(double x) {
+  uint32_t r;
+  const float f = (float)x;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(256, 2) merge_tf32_kernel(const Problem* __restrict__ probs, int mode, int m) {
+  const Problem& pb = probs[blockIdx.z];
+  Ctrl* ctl = pb.ctrl;
+  if (ctl->done || !ctl->need_hess) return;
+  const int ldh = pb.ldh;
+  // merge of the diagonal blocks [r0, r0+m) and [r0+m, r0+m+m2), exactly as dgemm_kernel modes 1 / 2
+  const int r0 = 2 * blockIdx.y * m;
+  const int m2 = min(m, ldh - r0 - m);
+  if (m2 <= 0) return;
+  const int M = m2, N = m;
+  const double* __restrict__ A; const double* __restrict__ B; double* __restrict__ C;
+  int K;
+  if (mode == 1) {
+    K = m;
+    A = pb.Lc + (size_t)(r0 + m) * ldh + r0;
+    B = pb.Yinv + (size_t)r0 * ldh + r0;
+    C = pb.Hinv + (size_t)(r0 + m) * ldh + r0;
+  } else {
+    K = m2;
+    A = pb.Yinv + (size_t)(r0 + m) * ldh + (r0 + m);
+    B = pb.Hinv + (size_t)(r0 + m) * ldh + r0;
+    C = pb.Yinv + (size_t)(r0 + m) * ldh + r0;
+  }
+  const int tiles_n = (N + TN - 1) / TN;
+  const int i0 = (blockIdx.x / tiles_n) * TM, j0 = (blockIdx.x % tiles_n) * TN;
+  if (i0 >= M) return;
+  int klo = 0, khi = K;
+  if (mode == 1) klo = j0;                 // Y11 is lower triangular: Y11[k][j] = 0 for k < j
+  else khi = min(K, i0 + TM);              // Y22 is lower triangular: Y22[i][k] = 0 for k > i
+
+  __shared__ __align__(16) uint32_t As[2][TA_SZ];
+  __shared__ __align__(16) uint32_t Bs[2][TB_SZ];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tg = lane & 3;
+  const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;   // 2 x 4 warps, 64 x 32 per warp
+
+  // global -> register staging: thread t fetches rows (t >> 3) + 32 q of A (two consecutive k) and k-rows (t >> 6) + 4 q of B
+  // (two consecutive columns); the pointers walk along k, the row guards are loop-invariant.  Neither operand is written by
+  // this launch (C is a different block of the buffers), so the read-only path is safe.
+  const double* pa = A + (size_t)(i0 + (tid >> 3)) * ldh + klo + (tid & 7) * 2;
+  const double* pbk = B + (size_t)(klo + (tid >> 6)) * ldh + j0 + (tid & 63) * 2;
+  const size_t a_step = (size_t)32 * ldh, b_step = (size_t)4 * ldh, b_adv = (size_t)TK * ldh;
+  unsigned a_ok = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) a_ok |= (i0 + (tid >> 3) + 32 * q < M ? 1u : 0u) << q;
+  const bool b_ok = j0 + (tid & 63) * 2 < N;
+  double2 ra[4], rb[4];
+  auto gload = [&]() {   // the next K chunk
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      ra[q] = ((a_ok >> q) & 1u) ? __ldg(reinterpret_cast<const double2*>(pa + q * a_step)) : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      rb[q] = b_ok ? __ldg(reinterpret_cast<const double2*>(pbk + q * b_step)) : make_double2(0.0, 0.0);
+    pa += TK;
+    pbk += b_adv;
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int row = (tid >> 3) + 32 * q, kk = (tid & 7) * 2;
+      *reinterpret_cast<uint2*>(&As[buf][row * TA_LD + kk]) = make_uint2(to_tf32(ra[q].x), to_tf32(ra[q].y));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int kk = (tid >> 6) + 4 * q, jj = (tid & 63) * 2;
+      *reinterpret_cast<uint2*>(&Bs[buf][kk * TB_LD + jj]) = make_uint2(to_tf32(rb[q].x), to_tf32(rb[q].y));
+    }
+  };
+
+  float acc[4][4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) acc[a][b][e] = 0.f;
+
+  if (klo < khi) {
+    gload();
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = klo; k0 < khi; k0 += TK) {
+      const bool more = k0 + TK < khi;
+      if (more) gload();
+      const uint32_t* a = As[buf];
+      const uint32_t* b = Bs[buf];
+#pragma unroll
+      for (int k8 = 0; k8 < TK; k8 += 8) {
+        uint32_t fa[4][4], fb[4][2];
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+          const uint32_t* pa = a + (wm + f * 16 + g) * TA_LD + k8 + tg;
+          fa[f][0] = pa[0];                 // (row g,     k tg)
+          fa[f][1] = pa[8 * TA_LD];         // (row g + 8, k tg)
+          fa[f][2] = pa[4];                 // (row g,     k tg + 4)
+          fa[f][3] = pa[8 * TA_LD + 4];     // (row g + 8, k tg + 4)
+          const uint32_t* pbk = b + (k8 + tg) * TB_LD + wn + f * 8 + g;
+          fb[f][0] = pbk[0];                // (k tg,     col g)
+          fb[f][1] = pbk[4 * TB_LD];        // (k tg + 4, col g)
+        }
+#pragma unroll
+        for (int fm = 0; fm < 4; fm++)
+#pragma unroll
+          for (int fn = 0; fn < 4; fn++) mma_tf32_16x8x8(acc[fm][fn], fa[fm], fb[fn]);
+      }
+      if (more) sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  const double sgn = mode == 1 ? 1.0 : -1.0;
+#pragma unroll
+  for (int fm = 0; fm < 4; fm++)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int i = i0 + wm + fm * 16 + g + 8 * h;    // accumulator rows g (c0, c1) and g + 8 (c2, c3)
+      if (i >= M) continue;
+#pragma unroll
+      for (int fn = 0; fn < 4; fn++) {
+        const int j = j0 + wn + fn * 8 + 2 * tg;      // accumulator columns 2 tg, 2 tg + 1
+        if (j >= N) continue;
+        *reinterpret_cast<double2*>(C + (size_t)i * ldh + j) =
+            make_double2(sgn * (double)acc[fm][fn][2 * h], sgn * (double)acc[fm][fn][2 * h + 1]);
+      }
+    }
+}
+
+static cudaError_t merge_tf32_launch(const Problem* d_probs, int nprob, int mode, int m, int nmerge, cudaStream_t st, int* launches) {
+  const int t = (m + TM - 1) / TM;
+  if (t <= 0 || nmerge <= 0) return cudaSuccess;
+  merge_tf32_kernel<<<dim3(t * ((m + TN - 1) / TN), nmerge, nprob), 256, 0, st>>>(d_probs, mode, m);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+// MLEASE_MERGE_TF32=0 / 1 selects the fp64 DMMA merges / the TF32 merges (A/B measurements); see the default below.
+static bool merges_in_tf32() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MLEASE_MERGE_TF32");
+    v = e ? (atoi(e) ? 1 : 0) : MERGE_TF32_DEFAULT;
+  }
+  return v == 1;
+}
+
 // Systems wider than this take the GEMM-rich path.  MLEASE_WIDE_MIN overrides it (tuning experiments only).
 static int wide_threshold() {
   static int t = -1;
@@ -579,8 +755,16 @@ static cudaError_t cholesky_launch_wide(const Problem* d_probs, int nprob, int l
   trinv_kernel<64><<<dim3((ldh + 63) / 64, nprob), 256, 0, st>>>(d_probs, WLEAF);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (launches) *launches += 1;
+  // the factored direction reads Y only as bf16 (ysym_kernel): its merges run in TF32; an explicit H^-1 (posterior variance,
+  // systems up to 2048 columns) keeps the fp64 merges
+  const bool tf32 = factored_direction && merges_in_tf32();
   for (int m = WLEAF; m < ldh; m *= 2) {
     const int nmerge = (ldh + 2 * m - 1) / (2 * m);
+    if (tf32) {
+      if ((e = merge_tf32_launch(d_probs, nprob, 1, m, nmerge, st, launches)) != cudaSuccess) return e;
+      if ((e = merge_tf32_launch(d_probs, nprob, 2, m, nmerge, st, launches)) != cudaSuccess) return e;
+      continue;
+    }
     if ((e = dgemm_launch<true, false>(d_probs, nprob, 1, m, 0, m, m, nmerge, st, launches)) != cudaSuccess) return e;
     if ((e = dgemm_launch<true, false>(d_probs, nprob, 2, m, 0, m, m, nmerge, st, launches)) != cudaSuccess) return e;
   }

@@ -528,7 +528,7 @@ static cudaError_t dgemm_launch(const Problem* d_probs, int nprob, int mode, int
 // Shared-memory strides: A rows of 20 words (fragment loads (row g, k tg): bank 20 g + tg, all distinct), B rows of 136
 // words (fragment loads (k tg, col g): bank 8 tg + g, all distinct).
 // ------------------------------------------------------------------------------------------
-constexpr int MERGE_TF32_DEFAULT = 0;   // switched on once the GPU parity suite and the bench have run with MLEASE_MERGE_TF32=1
+constexpr int MERGE_TF32_DEFAULT = 1;   // verified on a B200: GPU parity suite + bench with MLEASE_MERGE_TF32=1 (profiles/r02b_*)
 constexpr int TM = 128, TN = 128, TK = 16;
 constexpr int TA_LD = TK + 4, TB_LD = TN + 8;
 constexpr int TA_SZ = TM * TA_LD, TB_SZ = TK * TB_LD;   // 32-bit words per stage

@@ -93,7 +93,7 @@ def cmd_list(src, out):
 def cmd_sass():
     so = os.path.join(ROOT, "ml-ease_b200", "lib", "libmlease_b200.so")
     txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-    pats = ["UTCHMMA", "UTCQMMA", "UTCBAR", "UTMALDG", "UBLKCP", "LDTM", "DMMA", "ATOMS", "SYNCS", "UTCATOMSWS"]
+    pats = ["UTCHMMA", "UTCQMMA", "UTCBAR", "UTMALDG", "UBLKCP", "LDTM", "DMMA", "HMMA", "ATOMS", "SYNCS", "UTCATOMSWS"]
     cur, cnt = None, defaultdict(lambda: defaultdict(int))
     for ln in txt.splitlines():
         m = re.search(r"Function : (\S+)", ln)
@@ -107,7 +107,7 @@ def cmd_sass():
     with open(os.path.join(OUT, "r02_sass_summary.txt"), "w") as f:
         f.write("cuobjdump -sass ml-ease_b200/lib/libmlease_b200.so : occurrences of the Blackwell mnemonics per kernel\n")
         f.write("(UTCHMMA = tcgen05.mma kind::f16, UTCQMMA = tcgen05.mma kind::f8f6f4, UTMALDG = TMA tensor load, UBLKCP = bulk TMA copy, LDTM = tcgen05.ld,\n")
-        f.write(" DMMA = fp64 mma.sync, ATOMS = shared-memory atomics, SYNCS = mbarrier ops)\n\n")
+        f.write(" DMMA = fp64 mma.sync, HMMA = mma.sync m16n8k8 tf32 (the TF32 merges of the wide inverse), ATOMS = shared-memory atomics, SYNCS = mbarrier ops)\n\n")
         for k in sorted(cnt):
             if cnt[k]:
                 f.write("%-75s %s\n" % (k[:75], "  ".join("%s x%d" % (p, n) for p, n in sorted(cnt[k].items()))))

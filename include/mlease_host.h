@@ -27,6 +27,21 @@ int mlease_partition_ids(int32_t nkeys, const char* keys_packed, const float* la
                          int32_t* out_partition, int32_t* out_hash_partition);
 /* Java Float.toString (model keys "1.0", "1.0#3"). */
 int mlease_java_float_to_string(float f, char* buf, int32_t buflen);
+/* Worker threads of the host layer (block-parallel avro decode / encode / deflate): n > 0 sets the count (at most 64), 0 returns to
+ * the default (MLEASE_HOST_THREADS, else the CPUs this process may run on).  Returns the count in effect. */
+int mlease_host_set_threads(int32_t n);
+/* Record ingest of the job layer as a library call: prepared records (raw = 0: a file or a directory of RegressionPrepareOutput
+ * files, jobs/RegressionAdmmTrain.java:677-690 -> llf/LibLinearDataset.java:413-484) or raw records (raw = 1: one file, the
+ * RegressionTest input) into CSR arrays with global feature ids in first-seen order; feature k is "name" or "name\u0001term"
+ * (llf/LibLinearDataset.java:456-479).  Blocks of the container files are decoded on all host threads (MLEASE_HOST_THREADS);
+ * generic != 0 forces the sequential generic decoder (same result; the tests compare the two). */
+typedef struct mlease_rows mlease_rows;
+int mlease_rows_read(const char* path, int32_t raw, int32_t binary_feature, int32_t generic, mlease_rows** out);
+int64_t mlease_rows_count(const mlease_rows* r, int64_t* nnz, int32_t* nfeatures);   /* returns the number of records */
+int mlease_rows_get(const mlease_rows* r, int64_t* rowptr, int32_t* colidx, float* vals, int32_t* response, float* weight, float* offset);
+const char* mlease_rows_feature(const mlease_rows* r, int32_t k);
+const char* mlease_rows_key(const mlease_rows* r, int64_t i);
+void mlease_rows_free(mlease_rows* r);
 /* Avro container round trip (decode every record generically, re-encode with `codec` = "null" | "deflate"). */
 int mlease_avro_copy(const char* in_path, const char* out_path, const char* codec, int64_t* nrecords, int64_t* nblocks);
 #ifdef __cplusplus

@@ -2,11 +2,16 @@
 #include "avro_io.hpp"
 
 #include <dirent.h>
+#include <sched.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <future>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -290,11 +295,11 @@ void encode(std::string& o, const Schema& s, const Value& v) {
       break;
   }
 }
-std::string inflate_raw(const std::string& in) {
+std::string inflate_raw(const char* in, size_t in_size) {
   z_stream zs; memset(&zs, 0, sizeof(zs));
   if (inflateInit2(&zs, -15) != Z_OK) throw std::runtime_error("zlib init");
-  std::string out; out.resize(std::max<size_t>(in.size() * 4, 1 << 16));
-  zs.next_in = (Bytef*)in.data(); zs.avail_in = (uInt)in.size();
+  std::string out; out.resize(std::max<size_t>(in_size * 4, 1 << 16));
+  zs.next_in = (Bytef*)in; zs.avail_in = (uInt)in_size;
   size_t have = 0;
   while (true) {
     zs.next_out = (Bytef*)&out[have]; zs.avail_out = (uInt)(out.size() - have);
@@ -308,9 +313,10 @@ std::string inflate_raw(const std::string& in) {
   out.resize(have);
   return out;
 }
-std::string deflate_raw(const std::string& in) {
+std::string inflate_raw(const std::string& in) { return inflate_raw(in.data(), in.size()); }
+std::string deflate_raw(const std::string& in, int level) {
   z_stream zs; memset(&zs, 0, sizeof(zs));
-  if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw std::runtime_error("zlib init");
+  if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw std::runtime_error("zlib init");
   std::string out; out.resize(deflateBound(&zs, (uLong)in.size()));
   zs.next_in = (Bytef*)in.data(); zs.avail_in = (uInt)in.size();
   zs.next_out = (Bytef*)&out[0]; zs.avail_out = (uInt)out.size();
@@ -319,30 +325,63 @@ std::string deflate_raw(const std::string& in) {
   deflateEnd(&zs);
   return out;
 }
-}  // namespace
-
-AvroReader::AvroReader(const std::string& path) {
-  std::ifstream f(path, std::ios::binary);
-  if (!f) throw std::runtime_error("cannot open " + path);
-  std::stringstream ss; ss << f.rdbuf(); data_ = ss.str();
-  if (data_.size() < 4 || data_.compare(0, 4, "Obj\x01")) throw std::runtime_error(path + ": not an avro container file");
-  pos_ = 4;
-  codec_ = "null";
+// container header: magic, metadata map (schema, codec), sync marker; returns the offset of the first block
+size_t parse_header(const std::string& data, const std::string& path, std::string& schema_json, std::string& codec, std::string& sync) {
+  if (data.size() < 4 || data.compare(0, 4, "Obj\x01")) throw std::runtime_error(path + ": not an avro container file");
+  size_t pos = 4;
+  codec = "null";
   while (true) {
-    int64_t n = rd_long(data_, pos_);
+    int64_t n = rd_long(data, pos);
     if (n == 0) break;
-    if (n < 0) { n = -n; rd_long(data_, pos_); }
+    if (n < 0) { n = -n; rd_long(data, pos); }
     for (int64_t k = 0; k < n; k++) {
-      int64_t kl = rd_long(data_, pos_); need(data_, pos_, kl); std::string key(data_, pos_, (size_t)kl); pos_ += (size_t)kl;
-      int64_t vl = rd_long(data_, pos_); need(data_, pos_, vl); std::string val(data_, pos_, (size_t)vl); pos_ += (size_t)vl;
-      if (key == "avro.schema") schema_json_ = val;
-      if (key == "avro.codec") codec_ = val;
+      int64_t kl = rd_long(data, pos); need(data, pos, kl); std::string key(data, pos, (size_t)kl); pos += (size_t)kl;
+      int64_t vl = rd_long(data, pos); need(data, pos, vl); std::string val(data, pos, (size_t)vl); pos += (size_t)vl;
+      if (key == "avro.schema") schema_json = val;
+      if (key == "avro.codec") codec = val;
     }
   }
-  if (codec_ != "null" && codec_ != "deflate") throw std::runtime_error("avro: unsupported codec " + codec_);
+  if (codec != "null" && codec != "deflate") throw std::runtime_error("avro: unsupported codec " + codec);
+  need(data, pos, 16);
+  sync.assign(data, pos, 16); pos += 16;
+  return pos;
+}
+std::string read_whole_file(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) throw std::runtime_error("cannot open " + path);
+  std::string data;
+  struct stat st;
+  if (fstat(fileno(f), &st) == 0 && st.st_size > 0) data.reserve((size_t)st.st_size);
+  char buf[1 << 16];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) data.append(buf, n);
+  fclose(f);
+  return data;
+}
+}  // namespace
+
+static std::atomic<int> g_host_threads{0};   // 0 = not decided yet
+void set_host_threads(int n) { g_host_threads.store(std::max(0, std::min(n, 64))); }
+int host_threads() {
+  int n = g_host_threads.load();
+  if (n <= 0) {
+    const char* e = getenv("MLEASE_HOST_THREADS");
+    int v = e ? atoi(e) : 0;
+    if (v <= 0) {   // the CPUs this process may run on (a container's share), not the machine's
+      cpu_set_t set;
+      CPU_ZERO(&set);
+      v = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+    }
+    n = std::max(1, std::min(v, 64));
+    g_host_threads.store(n);
+  }
+  return n;
+}
+
+AvroReader::AvroReader(const std::string& path) {
+  data_ = read_whole_file(path);
+  pos_ = parse_header(data_, path, schema_json_, codec_, sync_);
   schema_ = schema_parse(schema_json_);
-  need(data_, pos_, 16);
-  sync_.assign(data_, pos_, 16); pos_ += 16;
 }
 bool AvroReader::load_block() {
   if (pos_ >= data_.size()) return false;
@@ -365,7 +404,37 @@ bool AvroReader::next(Value& out) {
   return true;
 }
 
-AvroWriter::AvroWriter(const std::string& path, const std::string& schema_json, const std::string& codec) : path_(path), codec_(codec) {
+AvroFile::AvroFile(const std::string& path) {
+  data_ = read_whole_file(path);
+  std::string sync;
+  size_t pos = parse_header(data_, path, schema_json_, codec_, sync);
+  schema_ = schema_parse(schema_json_);
+  int64_t before = 0;
+  while (pos < data_.size()) {
+    int64_t count = rd_long(data_, pos);
+    int64_t bytes = rd_long(data_, pos);
+    if (count < 0) throw std::runtime_error("avro: negative record count in block header");
+    need(data_, pos, bytes);
+    const size_t off = pos;
+    pos += (size_t)bytes;
+    need(data_, pos, 16);
+    if (data_.compare(pos, 16, sync)) throw std::runtime_error("avro: sync marker mismatch");
+    pos += 16;
+    blocks_.push_back(Blk{off, (size_t)bytes, count, before});
+    before += count;
+  }
+}
+std::string AvroFile::block_data(size_t b) const {
+  const Blk& k = blocks_[b];
+  return codec_ == "deflate" ? inflate_raw(data_.data() + k.off, k.bytes) : std::string(data_, k.off, k.bytes);
+}
+
+struct AvroWriter::Pending {
+  std::future<std::string> payload;
+  int64_t count = 0;
+};
+
+AvroWriter::AvroWriter(const std::string& path, const std::string& schema_json, const std::string& codec, int level) : path_(path), codec_(codec), level_(level) {
   schema_ = schema_parse(schema_json);
   std::mt19937_64 rng(0x6d6c65617365ULL ^ std::hash<std::string>()(path));
   sync_.resize(16);
@@ -382,15 +451,44 @@ void AvroWriter::append(const Value& v) {
   encode(buf_, *schema_, v);
   if (++count_ >= 4096 || buf_.size() > (1 << 20)) flush_block();
 }
+void AvroWriter::append_encoded(const char* bytes, size_t nbytes, int64_t nrecords) {
+  if (nrecords <= 0) return;
+  buf_.append(bytes, nbytes);
+  count_ += nrecords;
+  if (count_ >= 4096 || buf_.size() > (1 << 20)) flush_block();
+}
+// appends finished blocks to the file image in order until at most `keep` are still being compressed
+void AvroWriter::drain(size_t keep) {
+  size_t done = 0;
+  while (pending_.size() - done > keep) {
+    Pending& p = *pending_[done];
+    std::string payload = p.payload.get();
+    wr_long(out_, p.count); wr_long(out_, (int64_t)payload.size()); out_ += payload; out_ += sync_;
+    done++;
+  }
+  pending_.erase(pending_.begin(), pending_.begin() + (long)done);
+}
 void AvroWriter::flush_block() {
   if (count_ == 0) return;
-  std::string payload = codec_ == "deflate" ? deflate_raw(buf_) : buf_;
-  wr_long(out_, count_); wr_long(out_, (int64_t)payload.size()); out_ += payload; out_ += sync_;
-  buf_.clear(); count_ = 0;
+  auto p = std::make_unique<Pending>();
+  p->count = count_;
+  if (codec_ == "deflate") {
+    const int level = level_;
+    auto raw = std::make_shared<std::string>(std::move(buf_));
+    p->payload = std::async(std::launch::async, [raw, level]() { return deflate_raw(*raw, level); });
+  } else {
+    std::promise<std::string> pr;
+    pr.set_value(std::move(buf_));
+    p->payload = pr.get_future();
+  }
+  pending_.push_back(std::move(p));
+  buf_ = std::string(); count_ = 0;
+  drain((size_t)host_threads());
 }
 void AvroWriter::close() {
   if (closed_) return;
   flush_block();
+  drain(0);
   size_t sl = path_.rfind('/');
   if (sl != std::string::npos) make_dirs(path_.substr(0, sl));
   std::ofstream f(path_, std::ios::binary | std::ios::trunc);

@@ -84,20 +84,53 @@ class AvroReader {
 
 class AvroWriter {
  public:
-  // codec: "null" or "deflate" (the reference's jobs write deflate, com/linkedin/mapred/AbstractAvroJob.java)
-  AvroWriter(const std::string& path, const std::string& schema_json, const std::string& codec = "deflate");
+  // codec: "null" or "deflate" (the reference's jobs write deflate, com/linkedin/mapred/AbstractAvroJob.java:253).  Blocks are
+  // compressed on background threads (each block is an independent raw-deflate stream, so the file is the same as a serial
+  // writer's); level = zlib level of the deflate codec.
+  AvroWriter(const std::string& path, const std::string& schema_json, const std::string& codec = "deflate", int level = 6);
   ~AvroWriter();
   void append(const Value& v);
+  // records already in Avro binary form for this writer's schema (block-parallel producers encode on their own threads)
+  void append_encoded(const char* bytes, size_t nbytes, int64_t nrecords);
   void close();
   const SchemaP& schema() const { return schema_; }
  private:
   void flush_block();
+  void drain(size_t keep);
+  struct Pending;
   std::string path_, codec_, buf_, out_;
   SchemaP schema_;
   std::string sync_;
   int64_t count_ = 0;
+  int level_ = 6;
   bool closed_ = false;
+  std::vector<std::unique_ptr<Pending>> pending_;   // blocks being compressed, in file order
 };
+
+// Random access to the blocks of a container file: the whole file is read, the header parsed and every block header / sync
+// marker checked up front (a truncated or corrupt file is an error here, never an out-of-bounds read later); block payloads
+// are inflated on demand by whichever thread asks (const, thread-safe), which is what the block-parallel readers of the job
+// layer build on.
+class AvroFile {
+ public:
+  explicit AvroFile(const std::string& path);
+  const SchemaP& schema() const { return schema_; }
+  const std::string& schema_json() const { return schema_json_; }
+  size_t num_blocks() const { return blocks_.size(); }
+  int64_t block_records(size_t b) const { return blocks_[b].count; }
+  int64_t records_before(size_t b) const { return blocks_[b].before; }
+  int64_t num_records() const { return blocks_.empty() ? 0 : blocks_.back().before + blocks_.back().count; }
+  std::string block_data(size_t b) const;   // decompressed payload of block b
+ private:
+  struct Blk { size_t off, bytes; int64_t count, before; };
+  std::string data_, codec_, schema_json_;
+  SchemaP schema_;
+  std::vector<Blk> blocks_;
+};
+
+// worker threads of the host layer: set_host_threads(n > 0), else MLEASE_HOST_THREADS, else the CPUs this process may run on (at most 64)
+int host_threads();
+void set_host_threads(int n);   // 0 = back to the default
 
 // helpers
 std::vector<std::string> list_avro_files(const std::string& path);   // file, or *.avro / part-* files of a directory (sorted)

@@ -23,6 +23,7 @@
 
 #include "../../include/mlease_b200.h"
 #include "avro_io.hpp"
+#include "avro_walk.hpp"
 
 using namespace mlease_host;
 
@@ -233,7 +234,8 @@ struct Rows {
   size_t n() const { return response.size(); }
 };
 
-void read_prepared(const std::string& path, Dictionary& dict, Rows& rows, bool binary_feature) {
+// generic (Value-tree) reader: the reference implementation of read_prepared, and its fallback for unusual schemas
+void read_prepared_generic(const std::string& path, Dictionary& dict, Rows& rows, bool binary_feature) {
   auto files = list_avro_files(path);
   if (files.empty()) io_error("no input files under " + path);
   for (auto& f : files) {
@@ -264,6 +266,197 @@ void read_prepared(const std::string& path, Dictionary& dict, Rows& rows, bool b
       rows.rowptr.push_back((int64_t)rows.colidx.size());
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------ block-parallel ingest (avro_walk.hpp)
+// Slots of the record plan.  The per-record logic below restates the generic readers field by field (same defaults, same casts,
+// same error texts, same order of checks); tests/test_host_cpu.py compares the two on the fixture and on randomised schemas.
+enum { S_KEY = 0, S_CLICK, S_RESPONSE, S_LABEL, S_WEIGHT, S_OFFSET, S_NAME, S_TERM, S_VALUE, S_MAPKEY, S_FEATNULL, S_COUNT };
+constexpr int EV_FEATURES = 0;
+constexpr unsigned K_NULL = 1u << Schema::Null, K_BOOL = 1u << Schema::Boolean, K_INT = 1u << Schema::Int, K_LONG = 1u << Schema::Long,
+                   K_FLOAT = 1u << Schema::Float, K_DOUBLE = 1u << Schema::Double, K_STR = 1u << Schema::String;
+
+struct RecPlan {
+  Plan plan;
+  int mapkey_slot = -1;   // slot the map.key field is read from (-1: no map.key, or the record has no such field)
+};
+// leaf types behind the unions of a plan node, as a bit mask (bit 31: something that is not a scalar)
+unsigned plan_kinds(const Plan& p) {
+  if (p.type == Schema::Union) { unsigned m = 0; for (auto& k : p.kids) m |= plan_kinds(k); return m; }
+  return plan_is_scalar(p.type) ? 1u << p.type : 1u << 31;
+}
+// Tags record field `name` with `slot` if its leaf types are within `allowed`.  0: no such field, 1: tagged, -1: outside `allowed`.
+int tag_field(Plan& rp, const Schema& rs, const std::string& name, int slot, unsigned allowed) {
+  const int i = rs.field_index(name);
+  if (i < 0) return 0;
+  if (plan_kinds(rp.kids[i]) & ~allowed) return -1;
+  return plan_tag_scalar(rp.kids[i], slot) ? 1 : -1;
+}
+// false: this schema is left to the generic reader (recursive type, non-scalar or oddly typed field, features not array<record>)
+bool build_rec_plan(const SchemaP& schema, const std::string& mapkey, RecPlan& out) {
+  try { out.plan = plan_build(*schema); } catch (const std::exception&) { return false; }
+  Plan* p = &out.plan;
+  const Schema* s = schema.get();
+  if (!plan_resolve(p, s, Schema::Record)) return false;
+  const unsigned any_scalar = ~(1u << 31);
+  const unsigned numeric = K_NULL | K_INT | K_LONG | K_FLOAT | K_DOUBLE;
+  static const struct { const char* name; int slot; unsigned allowed; } F[] = {
+      {"key", S_KEY, K_NULL | K_STR | K_INT | K_LONG}, {"click", S_CLICK, any_scalar}, {"response", S_RESPONSE, any_scalar}, {"label", S_LABEL, any_scalar},
+      {"weight", S_WEIGHT, numeric}, {"offset", S_OFFSET, numeric}};
+  for (auto& f : F) if (tag_field(*p, *s, f.name, f.slot, f.name == mapkey ? any_scalar : f.allowed) < 0) return false;
+  if (!mapkey.empty()) {
+    out.mapkey_slot = -1;
+    for (auto& f : F) if (mapkey == f.name && s->field_index(mapkey) >= 0) out.mapkey_slot = f.slot;   // map.key names a field read anyway
+    if (out.mapkey_slot < 0) {
+      if (mapkey == "features") return false;
+      const int r = tag_field(*p, *s, mapkey, S_MAPKEY, K_NULL | K_BOOL | K_INT | K_LONG | K_FLOAT | K_DOUBLE | K_STR);
+      if (r < 0) return false;
+      if (r > 0) out.mapkey_slot = S_MAPKEY;
+    }
+  }
+  const int fi = s->field_index("features");
+  if (fi < 0) return false;
+  Plan* fp = &p->kids[fi];
+  const Schema* fs = s->fields[fi].second.get();
+  // a null `features` (union branch) is reported through S_FEATNULL
+  if (fp->type == Schema::Union) for (auto& k : fp->kids) if (k.type == Schema::Null) k.tag = S_FEATNULL;
+  if (!plan_resolve(fp, fs, Schema::Array)) return false;
+  fp->tag = EV_FEATURES;
+  Plan* ip = &fp->kids[0];
+  const Schema* is = fs->items.get();
+  if (!plan_resolve(ip, is, Schema::Record)) return false;
+  if (tag_field(*ip, *is, "name", S_NAME, K_NULL | K_STR) != 1) return false;
+  if (tag_field(*ip, *is, "term", S_TERM, K_NULL | K_STR) < 0) return false;
+  if (tag_field(*ip, *is, "value", S_VALUE, numeric) != 1) return false;
+  return true;
+}
+struct FeatSink {
+  struct F { Slot name, term, value; };
+  std::vector<F> feats;
+  void begin_item(int, Slot* s) {
+    s[S_NAME].kind = Slot::Unset;
+    s[S_TERM] = Slot();
+    s[S_VALUE] = Slot(); s[S_VALUE].kind = Slot::Unset;
+  }
+  void item(int, Slot* s) {
+    if (s[S_NAME].kind == Slot::Unset || s[S_VALUE].kind == Slot::Unset) throw std::runtime_error("avro: a feature is not a record (null element in the features list)");
+    feats.push_back(F{s[S_NAME], s[S_TERM], s[S_VALUE]});
+  }
+};
+// utils/Util.java:309-337 getResponseAvro on slots (see get_response)
+int get_response_slots(const Slot* sl) {
+  const Slot* r = nullptr;
+  if (!sl[S_CLICK].is_null()) r = &sl[S_CLICK];
+  if (!sl[S_RESPONSE].is_null()) r = &sl[S_RESPONSE];
+  if (!sl[S_LABEL].is_null()) r = &sl[S_LABEL];
+  if (!r) io_error("Data should contain one field of the three: response, click or label!");
+  if (r->kind == Slot::Bool) return r->i ? 1 : 0;
+  if (r->kind == Slot::Int) return (int)r->i;
+  io_error("Response/Click/Label column should be either boolean or int32!");
+}
+void reset_record_slots(Slot* sl) {
+  for (int k = 0; k < S_COUNT; k++) sl[k] = Slot();
+  sl[S_FEATNULL].kind = Slot::Unset;
+}
+thread_local bool g_force_generic = false;   // tests: compare the two readers in one process
+bool host_generic_ingest() { if (g_force_generic) return true; const char* e = getenv("MLEASE_HOST_GENERIC_INGEST"); return e && atoi(e); }
+
+void read_raw_generic(const std::string& file, Dictionary& dict, Rows& rows, bool binary_feature);
+
+// rows of one block with block-local feature ids
+struct BlockRows {
+  Rows rows;
+  StrTable names;
+};
+// One file -> rows (appended) with global dictionary ids, decoded block-parallel.  mode 0: prepared records (read_prepared), 1: raw
+// records (read_raw).  Returns false (nothing touched) when the schema is left to the generic reader.
+bool read_rows_fast(const std::string& file, Dictionary& dict, Rows& rows, bool binary_feature, int mode) {
+  if (host_generic_ingest()) return false;
+  AvroFile af(file);
+  RecPlan rp;
+  if (!build_rec_plan(af.schema(), "", rp)) return false;
+  const size_t nb = af.num_blocks();
+  std::vector<BlockRows> outs(nb);
+  parallel_blocks(nb, host_threads(), [&](size_t b) {
+    const std::string data = af.block_data(b);
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(data.data());
+    const uint8_t* e = p + data.size();
+    BlockRows& o = outs[b];
+    Rows& r = o.rows;
+    Slot sl[S_COUNT];
+    FeatSink sink;
+    std::string scratch;
+    const int64_t nrec = af.block_records(b);
+    for (int64_t q = 0; q < nrec; q++) {
+      reset_record_slots(sl);
+      sink.feats.clear();
+      plan_walk(rp.plan, p, e, sl, sink);
+      if (mode == 0) {
+        const Slot& k = sl[S_KEY];
+        r.key.push_back(k.is_null() ? std::string() : (k.kind == Slot::Str ? std::string(k.p, k.n) : std::to_string(k.i)));
+      }
+      const int resp = get_response_slots(sl);
+      if (resp != 1 && resp != 0 && resp != -1) io_error(mode == 0 ? "response = " + std::to_string(resp) + " (only 1, 0, -1 are allowed)" : "response = " + std::to_string(resp));
+      if (mode == 1) r.key.push_back("");
+      r.response.push_back(resp);
+      r.weight.push_back(sl[S_WEIGHT].is_null() ? 1.0f : (float)sl[S_WEIGHT].num());
+      r.offset.push_back(sl[S_OFFSET].is_null() ? 0.0f : (float)sl[S_OFFSET].num());
+      if (mode == 1 && sl[S_FEATNULL].kind == Slot::Null) io_error("features is null");
+      for (auto& f : sink.feats) {
+        if (mode == 1 && f.name.is_null()) io_error("name is null");
+        const char* np = f.name.is_null() ? "" : f.name.p;
+        const size_t nn = f.name.is_null() ? 0 : f.name.n;
+        const bool has_term = !f.term.is_null() && f.term.n > 0;
+        if (mode == 0 && !has_term && nn == INTERCEPT.size() && std::memcmp(np, INTERCEPT.data(), nn) == 0) io_error("feature name cannot be (INTERCEPT)");
+        int id;
+        if (!has_term) id = o.names.find_or_add(np, nn);
+        else {
+          scratch.assign(np, nn); scratch.push_back('\x01'); scratch.append(f.term.p, f.term.n);   // feature_key()
+          id = o.names.find_or_add(scratch.data(), scratch.size());
+        }
+        r.colidx.push_back(id);
+        r.vals.push_back(binary_feature ? 1.0f : (float)f.value.num());
+      }
+      r.rowptr.push_back((int64_t)r.colidx.size());
+    }
+  });
+  // merge in block order: global ids in first-seen order of the record stream, exactly as a sequential read assigns them
+  size_t add_rows = 0, add_nnz = 0;
+  for (auto& o : outs) { add_rows += o.rows.n(); add_nnz += o.rows.colidx.size(); }
+  rows.key.reserve(rows.key.size() + add_rows); rows.response.reserve(rows.response.size() + add_rows);
+  rows.weight.reserve(rows.weight.size() + add_rows); rows.offset.reserve(rows.offset.size() + add_rows);
+  rows.rowptr.reserve(rows.rowptr.size() + add_rows); rows.colidx.reserve(rows.colidx.size() + add_nnz); rows.vals.reserve(rows.vals.size() + add_nnz);
+  std::vector<int32_t> gmap;
+  for (auto& o : outs) {
+    gmap.resize(o.names.size());
+    for (size_t l = 0; l < o.names.size(); l++) gmap[l] = dict.add(std::string(o.names.data((int)l), o.names.length((int)l)));
+    Rows& r = o.rows;
+    const int64_t base = (int64_t)rows.colidx.size();
+    for (auto& k : r.key) rows.key.push_back(std::move(k));
+    rows.response.insert(rows.response.end(), r.response.begin(), r.response.end());
+    rows.weight.insert(rows.weight.end(), r.weight.begin(), r.weight.end());
+    rows.offset.insert(rows.offset.end(), r.offset.begin(), r.offset.end());
+    for (size_t i = 1; i < r.rowptr.size(); i++) rows.rowptr.push_back(base + r.rowptr[i]);
+    for (int32_t c : r.colidx) rows.colidx.push_back(gmap[c]);
+    rows.vals.insert(rows.vals.end(), r.vals.begin(), r.vals.end());
+    o = BlockRows();   // release the block's memory as we go
+  }
+  return true;
+}
+
+void read_prepared(const std::string& path, Dictionary& dict, Rows& rows, bool binary_feature) {
+  auto files = list_avro_files(path);
+  if (files.empty()) io_error("no input files under " + path);
+  for (auto& f : files) {
+    if (read_rows_fast(f, dict, rows, binary_feature, 0)) continue;
+    // the generic reader takes a directory or a file: hand it this one file
+    read_prepared_generic(f, dict, rows, binary_feature);
+  }
+}
+void read_raw(const std::string& file, Dictionary& dict, Rows& rows, bool binary_feature) {
+  if (read_rows_fast(file, dict, rows, binary_feature, 1)) return;
+  read_raw_generic(file, dict, rows, binary_feature);
 }
 
 // ------------------------------------------------------------------------------------------ model files
@@ -372,8 +565,8 @@ double sample_test_loglik(const Rows& t, const Dictionary& dict, const std::vect
   return ll / n;
 }
 
-// raw (unprepared) records -> Rows; used by Test and by the per-iteration loglik
-void read_raw(const std::string& file, Dictionary& dict, Rows& rows, bool binary_feature) {
+// raw (unprepared) records -> Rows; used by Test and by the per-iteration loglik (generic reader / fallback)
+void read_raw_generic(const std::string& file, Dictionary& dict, Rows& rows, bool binary_feature) {
   AvroReader rd(file);
   const Schema& s = rec_schema(rd.schema());
   int fi = s.field_index("features");
@@ -406,17 +599,17 @@ void read_raw(const std::string& file, Dictionary& dict, Rows& rows, bool binary
 // seeded by `random.seed` (default 0) plays that role, and positives are replicated onto consecutive partitions (:172-186).
 struct SplitMix { uint64_t s; double next() { uint64_t z = (s += 0x9E3779B97F4A7C15ULL); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; z ^= z >> 31; return (z >> 11) * (1.0 / 9007199254740992.0); } };
 
-void run_prepare(const JobConfig& c) {
-  const std::string mapkey = c.get("map.key", "");
-  const int nblocks = c.get_int("num.blocks", 0);
-  const int reps = c.get_int("num.click.replicates", 1);
-  const bool ignore_value = c.get_bool("binary.feature", false);
-  const std::string out = c.get("output.path");
-  SplitMix rng{(uint64_t)c.get_double("random.seed", 0)};
-  auto files = list_avro_files(c.get("input.paths"));
-  if (files.empty()) io_error("no input under " + c.get("input.paths"));
-  AvroWriter w(out + "/part-00000.avro", schema_prepare_output());
-  for (auto& f : files) {
+struct PrepareCfg {
+  std::string mapkey;
+  int nblocks = 0, reps = 1;
+  bool ignore_value = false;
+};
+// one input file through the generic (Value-tree) decoder: the reference implementation / fallback of prepare_file_fast
+void prepare_file_generic(const std::string& f, const PrepareCfg& pc, SplitMix& rng, AvroWriter& w) {
+  const std::string& mapkey = pc.mapkey;
+  const int nblocks = pc.nblocks, reps = pc.reps;
+  const bool ignore_value = pc.ignore_value;
+  {
     AvroReader rd(f);
     const Schema& s = rec_schema(rd.schema());
     int fi = s.field_index("features");
@@ -475,6 +668,134 @@ void run_prepare(const JobConfig& c) {
         w.append(o);
       }
     }
+  }
+}
+
+// Avro binary of the RegressionPrepareOutput schema, written directly
+inline void put_long(std::string& o, int64_t v) {
+  uint64_t z = ((uint64_t)v << 1) ^ (uint64_t)(v >> 63);
+  while (z & ~0x7FULL) { o.push_back((char)((z & 0x7F) | 0x80)); z >>= 7; }
+  o.push_back((char)z);
+}
+inline void put_str(std::string& o, const char* p, size_t n) { put_long(o, (int64_t)n); o.append(p, n); }
+inline void put_float(std::string& o, float f) { o.append(reinterpret_cast<const char*>(&f), 4); }
+
+// The same job on the plan walker, block-parallel: every input block is decoded and re-encoded on a worker thread, the main
+// thread appends the encoded records in block order.  rng_state0 = state of the key stream before this file's first record: the
+// stream is a counter (SplitMix), one draw per record, so a block starts at rng_state0 + gamma * (records before the block).
+// Returns false (nothing written) when the schema is left to the generic decoder.
+bool prepare_file_fast(const std::string& f, const PrepareCfg& pc, uint64_t rng_state0, AvroWriter& w, int64_t* nrecords) {
+  if (host_generic_ingest()) return false;
+  AvroFile af(f);
+  RecPlan rp;
+  if (!build_rec_plan(af.schema(), pc.mapkey, rp)) return false;
+  const size_t nb = af.num_blocks();
+  struct Out { std::string bytes; int64_t n = 0; };
+  std::vector<Out> outs(nb);
+  // blocks are handed out in waves so that the encoded output of at most a few blocks per thread is alive at a time
+  const size_t wave = (size_t)std::max(1, host_threads()) * 4;
+  for (size_t b0 = 0; b0 < nb; b0 += wave) {
+    const size_t b1 = std::min(nb, b0 + wave);
+    parallel_blocks(b1 - b0, host_threads(), [&](size_t bi) {
+      const size_t b = b0 + bi;
+      const std::string data = af.block_data(b);
+      const uint8_t* p = reinterpret_cast<const uint8_t*>(data.data());
+      const uint8_t* e = p + data.size();
+      Out& o = outs[b];
+      o.bytes.reserve(data.size() + data.size() / 8);
+      SplitMix rng{rng_state0 + 0x9E3779B97F4A7C15ULL * (uint64_t)af.records_before(b)};
+      Slot sl[S_COUNT];
+      FeatSink sink;
+      std::string key, body;
+      const int64_t nrec = af.block_records(b);
+      for (int64_t q = 0; q < nrec; q++) {
+        reset_record_slots(sl);
+        sink.feats.clear();
+        plan_walk(rp.plan, p, e, sl, sink);
+        if (!pc.mapkey.empty()) {
+          if (rp.mapkey_slot < 0 || sl[rp.mapkey_slot].is_null()) io_error("map.key is wrongly specified! No such key exists in some lines of the data!");
+          const Slot& k = sl[rp.mapkey_slot];
+          key = k.kind == Slot::Str ? std::string(k.p, k.n)
+                : k.kind == Slot::Float ? java_float_to_string((float)k.d)
+                : k.kind == Slot::Double ? java_double_to_string(k.d)
+                : k.kind == Slot::Bool ? (k.i ? "true" : "false") : std::to_string(k.i);
+        } else {
+          key = std::to_string((int)std::floor(rng.next() * pc.nblocks));
+        }
+        const int response = get_response_slots(sl);
+        if (sl[S_FEATNULL].kind == Slot::Null) io_error("features is null");
+        // everything after the key: response, features, weight, offset
+        body.clear();
+        put_long(body, response);
+        if (!sink.feats.empty()) put_long(body, (int64_t)sink.feats.size());
+        for (auto& fv : sink.feats) {
+          if (fv.name.is_null()) io_error("name is null");
+          put_str(body, fv.name.p, fv.name.n);
+          if (fv.term.is_null()) put_long(body, 0); else put_str(body, fv.term.p, fv.term.n);
+          put_float(body, pc.ignore_value ? 1.0f : (float)fv.value.num());   // :142-146
+        }
+        put_long(body, 0);
+        double weight = 1.0;
+        if (!sl[S_WEIGHT].is_null()) weight = sl[S_WEIGHT].num();
+        {
+          // Util.getIntAvro(data, "response") (:159, utils/Util.java:55-63)
+          const Slot& rv = sl[S_RESPONSE];
+          if (rv.is_null()) io_error("response is null");
+          if (rv.kind != Slot::Int) io_error("response=" + std::string(rv.kind == Slot::Bool ? (rv.i ? "true" : "false") : "?") + " is not an integer");
+          if (rv.i == 1) weight = weight / pc.reps;
+        }
+        double offset = 0.0;
+        if (!sl[S_OFFSET].is_null()) offset = sl[S_OFFSET].num();
+        put_float(body, (float)weight);
+        put_float(body, (float)offset);
+        if (pc.mapkey.empty() && response == 1) {
+          int pid = java_parse_int(key);
+          for (int i = 0; i < pc.reps; i++) {
+            if (pid >= pc.nblocks) pid -= pc.nblocks;
+            const std::string ks = std::to_string(pid);
+            put_str(o.bytes, ks.data(), ks.size());
+            o.bytes += body;
+            o.n++;
+            pid++;
+          }
+        } else {
+          put_str(o.bytes, key.data(), key.size());
+          o.bytes += body;
+          o.n++;
+        }
+      }
+    });
+    for (size_t b = b0; b < b1; b++) {
+      w.append_encoded(outs[b].bytes.data(), outs[b].bytes.size(), outs[b].n);
+      outs[b] = Out();
+    }
+  }
+  if (nrecords) *nrecords = af.num_records();
+  return true;
+}
+
+void run_prepare(const JobConfig& c) {
+  PrepareCfg pc;
+  pc.mapkey = c.get("map.key", "");
+  pc.nblocks = c.get_int("num.blocks", 0);
+  pc.reps = c.get_int("num.click.replicates", 1);
+  pc.ignore_value = c.get_bool("binary.feature", false);
+  const std::string out = c.get("output.path");
+  uint64_t rng_state = (uint64_t)c.get_double("random.seed", 0);
+  auto files = list_avro_files(c.get("input.paths"));
+  if (files.empty()) io_error("no input under " + c.get("input.paths"));
+  // tmp-data is an intermediate of the job chain: zlib level 1 by default (avro-mapred's own default; the reference asks for
+  // level 9 on HDFS, com/linkedin/mapred/AbstractAvroJob.java:253).  avro.deflate.level overrides it.
+  AvroWriter w(out + "/part-00000.avro", schema_prepare_output(), "deflate", c.get_int("avro.deflate.level", 1));
+  for (auto& f : files) {
+    int64_t n = 0;
+    if (prepare_file_fast(f, pc, rng_state, w, &n)) {
+      if (pc.mapkey.empty()) rng_state += 0x9E3779B97F4A7C15ULL * (uint64_t)n;   // one draw per record
+      continue;
+    }
+    SplitMix rng{rng_state};
+    prepare_file_generic(f, pc, rng, w);
+    rng_state = rng.s;
   }
   w.close();
 }
@@ -884,6 +1205,43 @@ int mlease_java_float_to_string(float f, char* buf, int32_t buflen) {
   std::memcpy(buf, s.c_str(), s.size() + 1);
   return 0;
 }
+int mlease_host_set_threads(int32_t n) { set_host_threads(n); return host_threads(); }
+
+// The job layer's record ingest as a library call (and the hook the tests use to compare the block-parallel readers with the
+// generic one): prepared (raw = 0, a file or a directory) or raw (raw = 1, one file) records -> CSR with first-seen feature ids.
+struct mlease_rows { Dictionary dict; Rows rows; };
+int mlease_rows_read(const char* path, int32_t raw, int32_t binary_feature, int32_t generic, mlease_rows** out) {
+  try {
+    auto r = std::make_unique<mlease_rows>();
+    g_force_generic = generic != 0;
+    try {
+      if (raw) read_raw(path, r->dict, r->rows, binary_feature != 0);
+      else read_prepared(path, r->dict, r->rows, binary_feature != 0);
+    } catch (...) { g_force_generic = false; throw; }
+    g_force_generic = false;
+    *out = r.release();
+    return 0;
+  } catch (const std::exception& e) { g_job_err = e.what(); return 2; }
+}
+int64_t mlease_rows_count(const mlease_rows* r, int64_t* nnz, int32_t* nfeatures) {
+  if (nnz) *nnz = (int64_t)r->rows.colidx.size();
+  if (nfeatures) *nfeatures = (int32_t)r->dict.names.size();
+  return (int64_t)r->rows.n();
+}
+int mlease_rows_get(const mlease_rows* r, int64_t* rowptr, int32_t* colidx, float* vals, int32_t* response, float* weight, float* offset) {
+  const Rows& w = r->rows;
+  if (rowptr) std::memcpy(rowptr, w.rowptr.data(), w.rowptr.size() * sizeof(int64_t));
+  if (colidx) std::memcpy(colidx, w.colidx.data(), w.colidx.size() * sizeof(int32_t));
+  if (vals) std::memcpy(vals, w.vals.data(), w.vals.size() * sizeof(float));
+  if (response) std::memcpy(response, w.response.data(), w.response.size() * sizeof(int32_t));
+  if (weight) std::memcpy(weight, w.weight.data(), w.weight.size() * sizeof(float));
+  if (offset) std::memcpy(offset, w.offset.data(), w.offset.size() * sizeof(float));
+  return 0;
+}
+const char* mlease_rows_feature(const mlease_rows* r, int32_t k) { return (k >= 0 && (size_t)k < r->dict.names.size()) ? r->dict.names[k].c_str() : nullptr; }
+const char* mlease_rows_key(const mlease_rows* r, int64_t i) { return (i >= 0 && (size_t)i < r->rows.key.size()) ? r->rows.key[i].c_str() : nullptr; }
+void mlease_rows_free(mlease_rows* r) { delete r; }
+
 // avro helpers for tests: decode a container file into CSR arrays is done in Python; here: count + re-encode round trip
 int mlease_avro_copy(const char* in_path, const char* out_path, const char* codec, int64_t* nrecords, int64_t* nblocks) {
   try {

@@ -61,16 +61,16 @@ HOST_CLI = os.path.join(LIBDIR, "mlease_regression")
 def build_host(force: bool = False) -> str:
     """Host job layer (C++17, zlib): libmlease_host.so + the mlease_regression CLI, both linked to libmlease_b200.so."""
     srcs = [os.path.join(HOST, f) for f in ("avro_io.cpp", "regression_jobs.cpp")]
-    deps = srcs + [os.path.join(HOST, "avro_io.hpp"), os.path.join(os.path.dirname(ROOT), "include", "mlease_b200.h"),
+    deps = srcs + [os.path.join(HOST, "avro_io.hpp"), os.path.join(HOST, "avro_walk.hpp"), os.path.join(os.path.dirname(ROOT), "include", "mlease_b200.h"),
                    os.path.join(os.path.dirname(ROOT), "include", "mlease_host.h"), SO]
     cxx = os.environ.get("CXX", "g++")
     common = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function"]
-    link = ["-L" + LIBDIR, "-lmlease_b200", "-lz", "-Wl,-rpath,$ORIGIN"]
+    link = ["-L" + LIBDIR, "-lmlease_b200", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN"]
     if force or _stale(HOST_SO, deps):
         subprocess.check_call([cxx] + common + ["-shared", "-o", HOST_SO] + srcs + link)
     main = os.path.join(HOST, "mlease_regression_main.cpp")
     if force or _stale(HOST_CLI, [main, HOST_SO]):
-        subprocess.check_call([cxx] + common + ["-o", HOST_CLI, main, "-L" + LIBDIR, "-lmlease_host", "-lmlease_b200", "-lz", "-Wl,-rpath,$ORIGIN"])
+        subprocess.check_call([cxx] + common + ["-o", HOST_CLI, main, "-L" + LIBDIR, "-lmlease_host", "-lmlease_b200", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN"])
     return HOST_SO
 
 

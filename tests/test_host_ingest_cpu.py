@@ -1,0 +1,183 @@
+"""CPU tests of the block-parallel ingest of the host job layer (ml-ease_b200/host/avro_walk.hpp): the plan-walker readers
+and RegressionPrepare must give exactly what the generic (Value-tree) decoder gives -- same rows, same first-seen feature
+ids, same keys, same error texts -- whatever the number of threads, blocks and files."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import avro_util as au  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def host():
+    import mlease_b200
+    mlease_b200.lib()
+    h = C.CDLL(os.path.join(ROOT, "ml-ease_b200", "lib", "libmlease_host.so"))
+    h.mlease_job_last_error.restype = C.c_char_p
+    h.mlease_rows_count.restype = C.c_int64
+    h.mlease_rows_feature.restype = C.c_char_p
+    h.mlease_rows_key.restype = C.c_char_p
+    h.mlease_rows_feature.argtypes = [C.c_void_p, C.c_int32]
+    h.mlease_rows_key.argtypes = [C.c_void_p, C.c_int64]
+    h.mlease_rows_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    h.mlease_rows_get.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    h.mlease_rows_free.argtypes = [C.c_void_p]
+    return h
+
+
+def _rows(host, path, raw, binary=False, generic=False):
+    """-> dict of arrays, or the error text."""
+    hd = C.c_void_p()
+    rc = host.mlease_rows_read(path.encode(), int(raw), int(binary), int(generic), C.byref(hd))
+    if rc != 0:
+        return host.mlease_job_last_error().decode()
+    nnz, nf = C.c_int64(), C.c_int32()
+    n = host.mlease_rows_count(hd, C.byref(nnz), C.byref(nf))
+    out = {"rowptr": np.zeros(n + 1, np.int64), "colidx": np.zeros(nnz.value, np.int32), "vals": np.zeros(nnz.value, np.float32),
+           "response": np.zeros(n, np.int32), "weight": np.zeros(n, np.float32), "offset": np.zeros(n, np.float32)}
+    host.mlease_rows_get(hd, *[out[k].ctypes.data_as(C.c_void_p) for k in ("rowptr", "colidx", "vals", "response", "weight", "offset")])
+    out["features"] = [host.mlease_rows_feature(hd, k) for k in range(nf.value)]
+    out["keys"] = [host.mlease_rows_key(hd, i) for i in range(n)]
+    host.mlease_rows_free(hd)
+    return out
+
+
+def _same(a, b):
+    assert isinstance(a, dict) and isinstance(b, dict), (a if isinstance(a, str) else "", b if isinstance(b, str) else "")
+    assert a["features"] == b["features"] and a["keys"] == b["keys"]
+    for k in ("rowptr", "colidx", "response"):
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("vals", "weight", "offset"):
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k   # bit for bit
+
+
+def _write_cfg(path, **kv):
+    with open(path, "w") as f:
+        for k, v in kv.items():
+            f.write("%s=%s\n" % (k.replace("_", "."), v))
+    return path
+
+
+def _run(host, job, cfg):
+    rc = host.mlease_job_run(job.encode(), cfg.encode())
+    return rc, host.mlease_job_last_error().decode()
+
+
+PREPARED = {"type": "record", "name": "RegressionPrepareOutput", "fields": [
+    {"name": "key", "type": "string"}, {"name": "response", "type": "int"},
+    {"name": "features", "type": {"type": "array", "items": {"type": "record", "name": "feature", "fields": [
+        {"name": "name", "type": "string"}, {"name": "term", "type": "string"}, {"name": "value", "type": "float"}]}}},
+    {"name": "weight", "type": "float"}, {"name": "offset", "type": "float"}]}
+
+
+def _random_prepared(rng, n, nfeat_names=40):
+    recs = []
+    for i in range(n):
+        k = int(rng.integers(0, 9))                      # empty feature lists occur
+        feats = [{"name": "f%d" % rng.integers(0, nfeat_names), "term": ("" if rng.random() < 0.6 else "t%d" % rng.integers(0, 3)),
+                  "value": float(np.float32(rng.normal()))} for _ in range(k)]
+        recs.append({"key": str(int(rng.integers(0, 5))), "response": int(rng.integers(0, 2)), "features": feats,
+                     "weight": float(np.float32(rng.uniform(0.5, 2))), "offset": float(np.float32(rng.normal(0, 0.1)))})
+    return recs
+
+
+@pytest.mark.parametrize("codec", ["null", "deflate"])
+def test_prepared_rows_fast_equals_generic_across_blocks_files_threads(host, tmp_path, monkeypatch, codec):
+    rng = np.random.default_rng(3)
+    d = tmp_path / "prep"
+    au.write_avro(str(d / "part-00000.avro"), PREPARED, _random_prepared(rng, 700), codec=codec, block=64)
+    au.write_avro(str(d / "part-00001.avro"), PREPARED, _random_prepared(rng, 300, nfeat_names=60), codec=codec, block=7)
+    au.write_avro(str(d / "part-00002.avro"), PREPARED, [], codec=codec)            # a file without blocks
+    ref = _rows(host, str(d), raw=False, generic=True)
+    assert isinstance(ref, dict) and len(ref["response"]) == 1000 and any(b"\x01" in f for f in ref["features"])
+    try:
+        for threads in (1, 3, 8):
+            assert host.mlease_host_set_threads(threads) == threads
+            _same(_rows(host, str(d), raw=False), ref)
+    finally:
+        host.mlease_host_set_threads(0)
+    _same(_rows(host, str(d), raw=False, binary=True), _rows(host, str(d), raw=False, binary=True, generic=True))
+
+
+def test_raw_pig_style_unions_fast_equals_generic_and_fixture(host, tmp_path):
+    """The reference's own fixture schema: every field a ["null", T] union, the feature record itself nullable."""
+    npz = np.load(os.path.join(GOLDEN, "sample_data.npz"))
+    recs = au.fixture_records(npz)
+    p = str(tmp_path / "raw.avro")
+    au.write_avro(p, au.PIG_SCHEMA, recs, codec="deflate", block=97)
+    fast, gen = _rows(host, p, raw=True), _rows(host, p, raw=True, generic=True)
+    _same(fast, gen)
+    assert len(fast["response"]) == 1000 and int((fast["response"] == 1).sum()) == 299 and len(fast["features"]) == 200
+    # the reference's fixture file itself, when the checkout is there
+    ref_file = "/root/reference/examples/sample-data.avro"
+    if os.path.exists(ref_file):
+        _same(_rows(host, ref_file, raw=True), _rows(host, ref_file, raw=True, generic=True))
+
+
+def test_error_texts_are_the_generic_readers(host, tmp_path):
+    sch = {"type": "record", "name": "r", "fields": [
+        {"name": "response", "type": ["null", "int", "long"]},
+        {"name": "features", "type": ["null", {"type": "array", "items": {"type": "record", "name": "f", "fields": [
+            {"name": "name", "type": ["null", "string"]}, {"name": "term", "type": "string"}, {"name": "value", "type": "double"}]}}]}]}
+    ok = {"response": 1, "features": [{"name": "a", "term": "", "value": 0.5}]}
+    cases = {"null_features": [ok, dict(ok, features=None)], "null_name": [ok, {"response": 0, "features": [{"name": None, "term": "", "value": 1.0}]}],
+             "no_response": [ok, dict(ok, response=None)], "bad_response": [ok, dict(ok, response=7)]}
+    for name, recs in cases.items():
+        p = str(tmp_path / (name + ".avro"))
+        au.write_avro(p, sch, recs * 3, block=2)
+        f, g = _rows(host, p, raw=True), _rows(host, p, raw=True, generic=True)
+        assert isinstance(f, str) and f == g, (name, f, g)
+    # prepared reader: the reserved intercept name
+    p = str(tmp_path / "icpt.avro")
+    au.write_avro(p, PREPARED, [{"key": "0", "response": 1, "features": [{"name": "(INTERCEPT)", "term": "", "value": 1.0}], "weight": 1.0, "offset": 0.0}])
+    f, g = _rows(host, p, raw=False), _rows(host, p, raw=False, generic=True)
+    assert isinstance(f, str) and f == g and "(INTERCEPT)" in f
+    # truncated data file: an error from both, never an overrun
+    good = str(tmp_path / "good.avro")
+    au.write_avro(good, PREPARED, _random_prepared(np.random.default_rng(0), 50), block=10)
+    blob = open(good, "rb").read()
+    bad = str(tmp_path / "bad.avro")
+    open(bad, "wb").write(blob[:len(blob) * 2 // 3])
+    f, g = _rows(host, bad, raw=False), _rows(host, bad, raw=False, generic=True)
+    assert isinstance(f, str) and isinstance(g, str) and "avro" in f and "avro" in g
+
+
+def test_unusual_schema_falls_back_to_the_generic_reader(host, tmp_path):
+    """A weight stored as a string is not something the plan walker takes: the generic reader handles the file."""
+    sch = {"type": "record", "name": "r", "fields": [
+        {"name": "response", "type": "int"}, {"name": "weight", "type": "string"},
+        {"name": "features", "type": {"type": "array", "items": {"type": "record", "name": "f", "fields": [
+            {"name": "name", "type": "string"}, {"name": "term", "type": "string"}, {"name": "value", "type": "float"}]}}}]}
+    p = str(tmp_path / "odd.avro")
+    au.write_avro(p, sch, [{"response": 1, "weight": "x", "features": [{"name": "a", "term": "b", "value": 2.0}]}] * 5)
+    _same(_rows(host, p, raw=True), _rows(host, p, raw=True, generic=True))
+
+
+@pytest.mark.parametrize("mapkey", ["pkey", ""])
+def test_prepare_job_fast_equals_generic(host, tmp_path, monkeypatch, mapkey):
+    """RegressionPrepare on the plan walker (block-parallel, records encoded directly) writes the records the generic job writes:
+    map.key branch and the seeded random-key branch with click replicates (the key stream is a counter: one draw per record)."""
+    npz = np.load(os.path.join(GOLDEN, "sample_data.npz"))
+    recs = au.fixture_records(npz, with_key=lambda i: i % 4)
+    au.write_avro(str(tmp_path / "in" / "part-0.avro"), au.pig_schema_with_key(), recs[:600], block=53, codec="deflate")
+    au.write_avro(str(tmp_path / "in" / "part-1.avro"), au.pig_schema_with_key(), recs[600:], block=400)
+    outs = {}
+    for mode in ("fast", "generic"):
+        monkeypatch.setenv("MLEASE_HOST_GENERIC_INGEST", "1" if mode == "generic" else "0")
+        kv = dict(input_paths=str(tmp_path / "in"), output_path=str(tmp_path / ("out_" + mode)), num_blocks=5, num_click_replicates=3, random_seed=11)
+        if mapkey:
+            kv["map_key"] = mapkey
+        rc, err = _run(host, "RegressionPrepare", _write_cfg(str(tmp_path / (mode + ".job")), **kv))
+        assert rc == 0, err
+        outs[mode] = au.read_dir(str(tmp_path / ("out_" + mode)))
+    assert len(outs["fast"]) == len(outs["generic"]) >= 1000
+    assert outs["fast"] == outs["generic"]
+    # and the prepared output reads back the same through both readers
+    _same(_rows(host, str(tmp_path / "out_fast"), raw=False), _rows(host, str(tmp_path / "out_generic"), raw=False, generic=True))

@@ -42,6 +42,11 @@ int mlease_rows_get(const mlease_rows* r, int64_t* rowptr, int32_t* colidx, floa
 const char* mlease_rows_feature(const mlease_rows* r, int32_t k);
 const char* mlease_rows_key(const mlease_rows* r, int64_t i);
 void mlease_rows_free(mlease_rows* r);
+/* Model files as the jobs write them (LinearModelAvro {key, model}; with uplusx != NULL RegressionTrainOutput {key, model, uplusx},
+ * jobs/RegressionAdmmTrain.java:706-711; intercept first, models/LinearModel.java:697-720).  names / keys: NUL-separated lists;
+ * coefs, uplusx: [nmodels][nfeatures + 1], intercept last.  generic != 0 selects the Value-tree encoder (tests). */
+int mlease_models_write(const char* path, int32_t nfeatures, const char* names, int32_t nmodels, const char* keys, const float* coefs, const float* uplusx,
+                        int32_t generic);
 /* Avro container round trip (decode every record generically, re-encode with `codec` = "null" | "deflate"). */
 int mlease_avro_copy(const char* in_path, const char* out_path, const char* codec, int64_t* nrecords, int64_t* nblocks);
 #ifdef __cplusplus

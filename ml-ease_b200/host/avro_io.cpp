@@ -360,6 +360,9 @@ std::string read_whole_file(const std::string& path) {
 }
 }  // namespace
 
+static std::atomic<int> g_deflate_level{1};
+int default_deflate_level() { return g_deflate_level.load(); }
+void set_default_deflate_level(int level) { g_deflate_level.store(std::max(0, std::min(level, 9))); }
 static std::atomic<int> g_host_threads{0};   // 0 = not decided yet
 void set_host_threads(int n) { g_host_threads.store(std::max(0, std::min(n, 64))); }
 int host_threads() {
@@ -434,7 +437,8 @@ struct AvroWriter::Pending {
   int64_t count = 0;
 };
 
-AvroWriter::AvroWriter(const std::string& path, const std::string& schema_json, const std::string& codec, int level) : path_(path), codec_(codec), level_(level) {
+AvroWriter::AvroWriter(const std::string& path, const std::string& schema_json, const std::string& codec, int level)
+    : path_(path), codec_(codec), level_(level < 0 ? default_deflate_level() : level) {
   schema_ = schema_parse(schema_json);
   std::mt19937_64 rng(0x6d6c65617365ULL ^ std::hash<std::string>()(path));
   sync_.resize(16);

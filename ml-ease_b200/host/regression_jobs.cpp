@@ -269,6 +269,15 @@ void read_prepared_generic(const std::string& path, Dictionary& dict, Rows& rows
 }
 
 
+// Avro binary primitives for the writers that encode records directly (no Value tree)
+inline void put_long(std::string& o, int64_t v) {
+  uint64_t z = ((uint64_t)v << 1) ^ (uint64_t)(v >> 63);
+  while (z & ~0x7FULL) { o.push_back((char)((z & 0x7F) | 0x80)); z >>= 7; }
+  o.push_back((char)z);
+}
+inline void put_str(std::string& o, const char* p, size_t n) { put_long(o, (int64_t)n); o.append(p, n); }
+inline void put_float(std::string& o, float f) { o.append(reinterpret_cast<const char*>(&f), 4); }
+
 // ------------------------------------------------------------------------------------------ block-parallel ingest (avro_walk.hpp)
 // Slots of the record plan.  The per-record logic below restates the generic readers field by field (same defaults, same casts,
 // same error texts, same order of checks); tests/test_host_cpu.py compares the two on the fixture and on randomised schemas.
@@ -476,15 +485,58 @@ Value model_list(const Dictionary& dict, const float* coef /*[D+1], intercept la
   for (int k = 0; k < D; k++) a.items.push_back(feature_value(dict.names[k], coef[k]));
   return a;
 }
-void write_linear_models(const std::string& path, const Dictionary& dict, const std::vector<std::pair<std::string, std::vector<float>>>& models) {
-  AvroWriter w(path, schema_linear_model());
-  for (auto& m : models) {
-    Value r; r.type = Schema::Record; r.items.resize(2);
-    r.items[0] = Value::of_string(m.first);
-    r.items[1] = model_list(dict, m.second.data());
-    w.append(r);
+// The (name, term) part of every feature record of a model list in Avro binary, intercept first (models/LinearModel.java:697-720):
+// built once per file, after which a model is a run of [prefix, 4-byte float] appends instead of a Value tree per feature.
+struct FeaturePrefix {
+  std::string bytes;
+  std::vector<size_t> off;   // [D + 2]: entry 0 = intercept, entry k + 1 = dictionary feature k
+  explicit FeaturePrefix(const Dictionary& dict) {
+    auto add = [&](const std::string& key) {
+      off.push_back(bytes.size());
+      const size_t p = key.find('\x01');
+      if (p == std::string::npos) { put_str(bytes, key.data(), key.size()); put_long(bytes, 0); }
+      else { put_str(bytes, key.data(), p); put_str(bytes, key.data() + p + 1, key.size() - p - 1); }
+    };
+    add(INTERCEPT);
+    for (auto& n : dict.names) add(n);
+    off.push_back(bytes.size());
+  }
+  // one model list: coef[D] (intercept) first, then coef[0..D)
+  void encode(std::string& o, const float* coef) const {
+    const size_t D = off.size() - 2;
+    put_long(o, (int64_t)(D + 1));
+    o.append(bytes, off[0], off[1] - off[0]); put_float(o, coef[D]);
+    for (size_t k = 0; k < D; k++) { o.append(bytes, off[k + 1], off[k + 2] - off[k + 1]); put_float(o, coef[k]); }
+    put_long(o, 0);
+  }
+};
+// LinearModelAvro records {key, model}; with uplusx: RegressionTrainOutput records {key, model, uplusx} (:706-711)
+void write_model_records(const std::string& path, const Dictionary& dict, const std::vector<std::pair<std::string, std::vector<float>>>& models,
+                         const std::vector<std::vector<float>>* uplusx = nullptr) {
+  AvroWriter w(path, uplusx ? schema_train_output() : schema_linear_model());
+  if (host_generic_ingest()) {   // Value-tree encoder: the reference implementation the tests compare with
+    for (size_t i = 0; i < models.size(); i++) {
+      Value r; r.type = Schema::Record; r.items.resize(uplusx ? 3 : 2);
+      r.items[0] = Value::of_string(models[i].first);
+      r.items[1] = model_list(dict, models[i].second.data());
+      if (uplusx) r.items[2] = model_list(dict, (*uplusx)[i].data());
+      w.append(r);
+    }
+  } else {
+    const FeaturePrefix fp(dict);
+    std::string rec;
+    for (size_t i = 0; i < models.size(); i++) {
+      rec.clear();
+      put_str(rec, models[i].first.data(), models[i].first.size());
+      fp.encode(rec, models[i].second.data());
+      if (uplusx) fp.encode(rec, (*uplusx)[i].data());
+      w.append_encoded(rec.data(), rec.size(), 1);
+    }
   }
   w.close();
+}
+void write_linear_models(const std::string& path, const Dictionary& dict, const std::vector<std::pair<std::string, std::vector<float>>>& models) {
+  write_model_records(path, dict, models);
 }
 // reads LinearModelAvro files -> key -> (feature key -> value), intercept under INTERCEPT
 std::map<std::string, std::unordered_map<std::string, double>> read_linear_models(const std::string& path) {
@@ -671,15 +723,6 @@ void prepare_file_generic(const std::string& f, const PrepareCfg& pc, SplitMix& 
   }
 }
 
-// Avro binary of the RegressionPrepareOutput schema, written directly
-inline void put_long(std::string& o, int64_t v) {
-  uint64_t z = ((uint64_t)v << 1) ^ (uint64_t)(v >> 63);
-  while (z & ~0x7FULL) { o.push_back((char)((z & 0x7F) | 0x80)); z >>= 7; }
-  o.push_back((char)z);
-}
-inline void put_str(std::string& o, const char* p, size_t n) { put_long(o, (int64_t)n); o.append(p, n); }
-inline void put_float(std::string& o, float f) { o.append(reinterpret_cast<const char*>(&f), 4); }
-
 // The same job on the plan walker, block-parallel: every input block is decoded and re-encoded on a worker thread, the main
 // thread appends the encoded records in block order.  rng_state0 = state of the key stream before this file's first record: the
 // stream is a counter (SplitMix), one draw per record, so a block starts at rng_state0 + gamma * (records before the block).
@@ -784,9 +827,7 @@ void run_prepare(const JobConfig& c) {
   uint64_t rng_state = (uint64_t)c.get_double("random.seed", 0);
   auto files = list_avro_files(c.get("input.paths"));
   if (files.empty()) io_error("no input under " + c.get("input.paths"));
-  // tmp-data is an intermediate of the job chain: zlib level 1 by default (avro-mapred's own default; the reference asks for
-  // level 9 on HDFS, com/linkedin/mapred/AbstractAvroJob.java:253).  avro.deflate.level overrides it.
-  AvroWriter w(out + "/part-00000.avro", schema_prepare_output(), "deflate", c.get_int("avro.deflate.level", 1));
+  AvroWriter w(out + "/part-00000.avro", schema_prepare_output());
   for (auto& f : files) {
     int64_t n = 0;
     if (prepare_file_fast(f, pc, rng_state, w, &n)) {
@@ -934,17 +975,16 @@ void run_admm_train(const JobConfig& c) {
     ck(mlease_world_iterate(S.w, &maxdiff, &stop));
     // reducer outputs (:706-711)
     {
-      AvroWriter w(it + "/model/part-r-00000.avro", schema_train_output());
+      std::vector<std::pair<std::string, std::vector<float>>> xs;
+      std::vector<std::vector<float>> uxs;
       for (int p = 0; p < nblocks; p++) for (int l = 0; l < L; l++) {
         std::vector<double> x(Dt); std::vector<float> xf(Dt), ux(Dt);
         ck(mlease_world_get_x(S.w, p, l, x.data())); ck(mlease_world_get_uplusx(S.w, p, l, ux.data()));
         for (int k = 0; k < Dt; k++) xf[k] = (float)x[k];
-        Value r; r.type = Schema::Record; r.items.resize(3);
-        r.items[0] = Value::of_string(java_float_to_string(lambdas[l]) + "#" + std::to_string(p));
-        r.items[1] = model_list(dict, xf.data()); r.items[2] = model_list(dict, ux.data());
-        w.append(r);
+        xs.emplace_back(java_float_to_string(lambdas[l]) + "#" + std::to_string(p), std::move(xf));
+        uxs.push_back(std::move(ux));
       }
-      w.close();
+      write_model_records(it + "/model/part-r-00000.avro", dict, xs, &uxs);
     }
     fprintf(stderr, "[RegressionAdmmTrain] iteration %d: max |z - z_prev| = %.6g\n", i, maxdiff);
     if (c.get_bool("remove.tmp.dir", false) && i >= 2) remove_tree(out + "/iter-" + std::to_string(i - 1));
@@ -1149,6 +1189,9 @@ int mlease_job_run(const char* job_class, const char* config_path) {
   try {
     JobConfig c = JobConfig::load(config_path);
     std::string j = job_class;
+    // host-layer knobs (not reference keys): zlib level of the files written, worker threads of the avro readers / writers
+    set_default_deflate_level(c.get_int("avro.deflate.level", 1));
+    if (c.has("host.threads")) set_host_threads(c.get_int("host.threads"));
     if (j == "Regression") run_regression(c);
     else if (j == "RegressionPrepare" || j == "AdmmPrepare") run_prepare(c);
     else if (j == "RegressionAdmmTrain" || j == "AdmmTrain") run_admm_train(c);
@@ -1204,6 +1247,29 @@ int mlease_java_float_to_string(float f, char* buf, int32_t buflen) {
   if ((int)s.size() + 1 > buflen) return 1;
   std::memcpy(buf, s.c_str(), s.size() + 1);
   return 0;
+}
+// Model files as the jobs write them (test hook for the direct encoder): `names` / `keys` are NUL-separated lists, coefs is
+// [nmodels][nfeatures + 1] with the intercept last; uplusx (same shape, may be NULL) selects RegressionTrainOutput records.
+int mlease_models_write(const char* path, int32_t nfeatures, const char* names, int32_t nmodels, const char* keys, const float* coefs, const float* uplusx,
+                        int32_t generic) {
+  try {
+    Dictionary dict;
+    const char* p = names;
+    for (int k = 0; k < nfeatures; k++) { std::string n(p); p += n.size() + 1; dict.add(n); }
+    if ((int)dict.names.size() != nfeatures) io_error("duplicate feature names");
+    std::vector<std::pair<std::string, std::vector<float>>> models;
+    std::vector<std::vector<float>> ux;
+    p = keys;
+    for (int m = 0; m < nmodels; m++) {
+      std::string k(p); p += k.size() + 1;
+      models.emplace_back(k, std::vector<float>(coefs + (size_t)m * (nfeatures + 1), coefs + (size_t)(m + 1) * (nfeatures + 1)));
+      if (uplusx) ux.emplace_back(uplusx + (size_t)m * (nfeatures + 1), uplusx + (size_t)(m + 1) * (nfeatures + 1));
+    }
+    g_force_generic = generic != 0;
+    try { write_model_records(path, dict, models, uplusx ? &ux : nullptr); } catch (...) { g_force_generic = false; throw; }
+    g_force_generic = false;
+    return 0;
+  } catch (const std::exception& e) { g_job_err = e.what(); return 2; }
 }
 int mlease_host_set_threads(int32_t n) { set_host_threads(n); return host_threads(); }
 

@@ -181,3 +181,27 @@ def test_prepare_job_fast_equals_generic(host, tmp_path, monkeypatch, mapkey):
     assert outs["fast"] == outs["generic"]
     # and the prepared output reads back the same through both readers
     _same(_rows(host, str(tmp_path / "out_fast"), raw=False), _rows(host, str(tmp_path / "out_generic"), raw=False, generic=True))
+
+
+def test_model_files_direct_encoder_equals_value_tree_encoder(host, tmp_path):
+    """iter-i/{u,init-value,model}, final-model, models: the direct encoder (feature name / term bytes prepared once per file)
+    writes the records the Value-tree encoder writes; large models span several container blocks."""
+    rng = np.random.default_rng(5)
+    D, M = 3000, 9
+    names = ["f%d" % k if k % 3 else "f%d\x01t%d" % (k, k % 7) for k in range(D)]
+    keys = ["%s#%d" % ("1.0" if m % 2 else "0.1", m) for m in range(M)]
+    coefs = rng.normal(size=(M, D + 1)).astype(np.float32)
+    ux = rng.normal(size=(M, D + 1)).astype(np.float32)
+    nb = ("\0".join(names) + "\0").encode()
+    kb = ("\0".join(keys) + "\0").encode()
+    for with_ux in (False, True):
+        outs = []
+        for generic in (0, 1):
+            p = str(tmp_path / ("m%d%d.avro" % (with_ux, generic)))
+            rc = host.mlease_models_write(p.encode(), D, nb, M, kb, coefs.ctypes.data_as(C.c_void_p), ux.ctypes.data_as(C.c_void_p) if with_ux else None, generic)
+            assert rc == 0, host.mlease_job_last_error().decode()
+            outs.append(au.read_avro(p)[1])
+        assert outs[0] == outs[1] and len(outs[0]) == M
+        r0 = outs[0][0]
+        assert r0["key"] == keys[0] and r0["model"][0] == {"name": "(INTERCEPT)", "term": "", "value": float(coefs[0, D])}
+        assert r0["model"][1 + 3] == {"name": "f3", "term": "t3", "value": float(coefs[0, 3])} and r0["model"][1 + 4]["term"] == "" and ("uplusx" in r0) == with_ux

@@ -47,6 +47,9 @@ void mlease_rows_free(mlease_rows* r);
  * coefs, uplusx: [nmodels][nfeatures + 1], intercept last.  generic != 0 selects the Value-tree encoder (tests). */
 int mlease_models_write(const char* path, int32_t nfeatures, const char* names, int32_t nmodels, const char* keys, const float* coefs, const float* uplusx,
                         int32_t generic);
+/* RegressionTest's output step (jobs/RegressionTest.java:198-236): the records of in_path with every union collapsed to its first
+ * non-null branch (utils/Util.java:377-417), record name AdmmTestOutput, and a float field `pred` appended (pred[i] = i-th record). */
+int mlease_test_output_write(const char* in_path, const char* out_path, const float* pred, int64_t npred, int32_t generic);
 /* Avro container round trip (decode every record generically, re-encode with `codec` = "null" | "deflate"). */
 int mlease_avro_copy(const char* in_path, const char* out_path, const char* codec, int64_t* nrecords, int64_t* nblocks);
 #ifdef __cplusplus

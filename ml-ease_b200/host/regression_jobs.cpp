@@ -645,6 +645,125 @@ void read_raw_generic(const std::string& file, Dictionary& dict, Rows& rows, boo
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ RegressionTest output
+// output = input fields (unions removed, utils/Util.java:377-417) + pred (jobs/RegressionTest.java:198-236)
+std::string test_output_schema(const SchemaP& in) {
+  SchemaP os = std::make_shared<Schema>(*schema_remove_union(in));
+  os->name = "AdmmTestOutput";
+  auto pf = std::make_shared<Schema>(); pf->type = Schema::Float;
+  os->fields.emplace_back("pred", pf);
+  std::map<std::string, bool> em;
+  return json_dump(schema_to_json(os, em));
+}
+void write_test_output_generic(const std::string& in_file, const std::string& out_file, const std::vector<float>& pred) {
+  AvroReader rd(in_file);
+  AvroWriter w(out_file, test_output_schema(rd.schema()));
+  Value rec; size_t i = 0;
+  while (rd.next(rec)) { rec.items.push_back(Value::of_float(pred[i++])); w.append(rec); }
+  w.close();
+}
+// Record bytes with the union branch indices dropped -- what encoding the decoded record against the union-free schema gives when
+// every union holds its first non-null branch.  Anything else (a null where the output schema has none, a second non-null branch,
+// a union of nulls) throws NotPlain and the file goes through the generic path, which then behaves exactly as before.
+struct NotPlain {};
+void copy_varint(const uint8_t*& p, const uint8_t* e, std::string& o) {
+  const uint8_t* q = p;
+  walk_detail::rd_long(p, e);
+  o.append(reinterpret_cast<const char*>(q), (size_t)(p - q));
+}
+void transcode_plain(const Plan& pl, const uint8_t*& p, const uint8_t* e, std::string& o) {
+  using namespace walk_detail;
+  switch (pl.type) {
+    case Schema::Null: break;
+    case Schema::Boolean: need(p, e, 1); o.push_back((char)*p++); break;
+    case Schema::Int: case Schema::Long: case Schema::Enum: copy_varint(p, e, o); break;
+    case Schema::Float: need(p, e, 4); o.append(reinterpret_cast<const char*>(p), 4); p += 4; break;
+    case Schema::Double: need(p, e, 8); o.append(reinterpret_cast<const char*>(p), 8); p += 8; break;
+    case Schema::String: case Schema::Bytes: {
+      const uint8_t* q = p;
+      const int64_t n = rd_long(p, e);
+      need(p, e, n);
+      p += n;
+      o.append(reinterpret_cast<const char*>(q), (size_t)(p - q));
+      break;
+    }
+    case Schema::Fixed: need(p, e, pl.fixed_size); o.append(reinterpret_cast<const char*>(p), (size_t)pl.fixed_size); p += pl.fixed_size; break;
+    case Schema::Union: {
+      const int64_t br = rd_long(p, e);
+      if (br < 0 || br >= (int64_t)pl.kids.size()) throw std::runtime_error("avro: bad union branch");
+      int fnn = -1;
+      for (size_t k = 0; k < pl.kids.size(); k++) if (pl.kids[k].type != Schema::Null) { fnn = (int)k; break; }
+      if (fnn < 0 || br != fnn) throw NotPlain();
+      transcode_plain(pl.kids[(size_t)fnn], p, e, o);
+      break;
+    }
+    case Schema::Record: for (auto& k : pl.kids) transcode_plain(k, p, e, o); break;
+    case Schema::Array:
+      while (true) {
+        int64_t n = rd_long(p, e);
+        if (n == 0) break;
+        if (n < 0) { n = -n; rd_long(p, e); }
+        put_long(o, n);
+        for (int64_t k = 0; k < n; k++) transcode_plain(pl.kids[0], p, e, o);
+      }
+      put_long(o, 0);
+      break;
+    case Schema::Map:
+      while (true) {
+        int64_t n = rd_long(p, e);
+        if (n == 0) break;
+        if (n < 0) { n = -n; rd_long(p, e); }
+        put_long(o, n);
+        for (int64_t k = 0; k < n; k++) {
+          const uint8_t* q = p;
+          const int64_t l = rd_long(p, e);
+          need(p, e, l);
+          p += l;
+          o.append(reinterpret_cast<const char*>(q), (size_t)(p - q));
+          transcode_plain(pl.kids[0], p, e, o);
+        }
+      }
+      put_long(o, 0);
+      break;
+  }
+}
+bool write_test_output_fast(const std::string& in_file, const std::string& out_file, const std::vector<float>& pred) {
+  if (host_generic_ingest()) return false;
+  AvroFile af(in_file);
+  Plan plan;
+  try { plan = plan_build(*af.schema()); } catch (const std::exception&) { return false; }
+  {
+    const Plan* p = &plan;   // the datum must be a record behind its unions, as schema_remove_union() + "AdmmTestOutput" assume
+    while (p->type == Schema::Union) { const Plan* nx = nullptr; for (auto& k : p->kids) if (k.type != Schema::Null) { nx = &k; break; } if (!nx) return false; p = nx; }
+    if (p->type != Schema::Record) return false;
+  }
+  if ((int64_t)pred.size() < af.num_records()) return false;
+  const size_t nb = af.num_blocks();
+  std::vector<std::string> outs(nb);
+  std::atomic<bool> plain{true};
+  parallel_blocks(nb, host_threads(), [&](size_t b) {
+    if (!plain.load()) return;
+    const std::string data = af.block_data(b);
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(data.data());
+    const uint8_t* e = p + data.size();
+    std::string& o = outs[b];
+    o.reserve(data.size() + 4 * (size_t)af.block_records(b));
+    const int64_t first = af.records_before(b), nrec = af.block_records(b);
+    try {
+      for (int64_t q = 0; q < nrec; q++) { transcode_plain(plan, p, e, o); put_float(o, pred[(size_t)(first + q)]); }
+    } catch (const NotPlain&) { plain.store(false); }
+  });
+  if (!plain.load()) return false;
+  AvroWriter w(out_file, test_output_schema(af.schema()));
+  for (size_t b = 0; b < nb; b++) { w.append_encoded(outs[b].data(), outs[b].size(), af.block_records(b)); outs[b] = std::string(); }
+  w.close();
+  return true;
+}
+void write_test_output(const std::string& in_file, const std::string& out_file, const std::vector<float>& pred) {
+  if (!write_test_output_fast(in_file, out_file, pred)) write_test_output_generic(in_file, out_file, pred);
+}
+
 // ============================================================================================ RegressionPrepare
 // jobs/RegressionPrepare.java:95-191.  map.key set -> key = data[map.key].toString() (bit-exact); otherwise the reference
 // draws floor(Math.random()*nblocks) from an UNSEEDED generator (:112) which cannot be reproduced: here a splitmix64 stream
@@ -1037,18 +1156,8 @@ void run_test(const JobConfig& c) {
       if (rows.n())
         ck(mlease_score(c.get_int("gpu.device", 0), nullptr, D, (int64_t)rows.n(), rows.rowptr.data(), rows.colidx.data(), rows.vals.data(), 0,
                         rows.offset.data(), coef.data(), 1, ignore_value ? 1 : 0, pred.data()));
-      // output = input fields (unions removed, utils/Util.java:377-417) + pred (jobs/RegressionTest.java:198-236)
-      AvroReader rd(f);
-      SchemaP os = std::make_shared<Schema>(*schema_remove_union(rd.schema()));
-      os->name = "AdmmTestOutput";
-      auto pf = std::make_shared<Schema>(); pf->type = Schema::Float;
-      os->fields.emplace_back("pred", pf);
-      std::map<std::string, bool> em;
       char nm[64]; snprintf(nm, sizeof nm, "/part-r-%05d.avro", part++);
-      AvroWriter w(outPath + nm, json_dump(schema_to_json(os, em)));
-      Value rec; size_t i = 0;
-      while (rd.next(rec)) { rec.items.push_back(Value::of_float(pred[i++])); w.append(rec); }
-      w.close();
+      write_test_output(f, outPath + nm, pred);
     }
   };
   for (auto& lam : c.get_list("lambda"))
@@ -1267,6 +1376,16 @@ int mlease_models_write(const char* path, int32_t nfeatures, const char* names, 
     }
     g_force_generic = generic != 0;
     try { write_model_records(path, dict, models, uplusx ? &ux : nullptr); } catch (...) { g_force_generic = false; throw; }
+    g_force_generic = false;
+    return 0;
+  } catch (const std::exception& e) { g_job_err = e.what(); return 2; }
+}
+// RegressionTest's output step as a library call (and test hook): the records of in_path with unions removed and `pred` appended.
+int mlease_test_output_write(const char* in_path, const char* out_path, const float* pred, int64_t npred, int32_t generic) {
+  try {
+    std::vector<float> pv(pred, pred + npred);
+    g_force_generic = generic != 0;
+    try { write_test_output(in_path, out_path, pv); } catch (...) { g_force_generic = false; throw; }
     g_force_generic = false;
     return 0;
   } catch (const std::exception& e) { g_job_err = e.what(); return 2; }

@@ -205,3 +205,32 @@ def test_model_files_direct_encoder_equals_value_tree_encoder(host, tmp_path):
         r0 = outs[0][0]
         assert r0["key"] == keys[0] and r0["model"][0] == {"name": "(INTERCEPT)", "term": "", "value": float(coefs[0, D])}
         assert r0["model"][1 + 3] == {"name": "f3", "term": "t3", "value": float(coefs[0, 3])} and r0["model"][1 + 4]["term"] == "" and ("uplusx" in r0) == with_ux
+
+
+def test_test_job_output_transcoder_equals_generic(host, tmp_path):
+    """RegressionTest's output (input record with unions removed + pred, jobs/RegressionTest.java:198-236) written by copying the
+    record bytes without the union indices, block-parallel: same records as decode -> append pred -> encode; a record that does
+    not fit the union-free schema (a null response) sends the file through the generic path, which reports it as before."""
+    npz = np.load(os.path.join(GOLDEN, "sample_data.npz"))
+    recs = au.fixture_records(npz, with_key=lambda i: i % 3)
+    src = str(tmp_path / "t.avro")
+    au.write_avro(src, au.pig_schema_with_key(), recs, block=111, codec="deflate")
+    pred = np.random.default_rng(1).normal(size=len(recs)).astype(np.float32)
+    outs = []
+    for generic in (0, 1):
+        o = str(tmp_path / ("o%d.avro" % generic))
+        rc = host.mlease_test_output_write(src.encode(), o.encode(), pred.ctypes.data_as(C.c_void_p), C.c_int64(len(pred)), generic)
+        assert rc == 0, host.mlease_job_last_error().decode()
+        outs.append(au.read_avro(o))
+    assert outs[0][0] == outs[1][0] and outs[0][0]["name"] == "AdmmTestOutput" and outs[0][0]["fields"][-1] == {"name": "pred", "type": "float"}
+    assert outs[0][1] == outs[1][1] and len(outs[0][1]) == len(recs)
+    assert [np.float32(r["pred"]) for r in outs[0][1][:50]] == list(pred[:50]) and outs[0][1][7]["features"][0]["name"] == recs[7]["features"][0]["name"]
+    # a null in a field that the union-free schema makes mandatory: both report the generic encoder's error
+    bad = str(tmp_path / "bad.avro")
+    au.write_avro(bad, au.pig_schema_with_key(), recs[:20] + [dict(recs[20], response=None)] + recs[21:40], block=7)
+    errs = []
+    for generic in (0, 1):
+        rc = host.mlease_test_output_write(bad.encode(), str(tmp_path / "ob.avro").encode(), pred.ctypes.data_as(C.c_void_p), C.c_int64(len(pred)), generic)
+        assert rc != 0
+        errs.append(host.mlease_job_last_error().decode())
+    assert errs[0] == errs[1] and "null" in errs[0]

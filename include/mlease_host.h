@@ -50,6 +50,9 @@ int mlease_models_write(const char* path, int32_t nfeatures, const char* names, 
 /* RegressionTest's output step (jobs/RegressionTest.java:198-236): the records of in_path with every union collapsed to its first
  * non-null branch (utils/Util.java:377-417), record name AdmmTestOutput, and a float field `pred` appended (pred[i] = i-th record). */
 int mlease_test_output_write(const char* in_path, const char* out_path, const float* pred, int64_t npred, int32_t generic);
+/* RegressionTestLoglik's input step (jobs/RegressionTestLoglik.java:124-151): (response, pred, weight) of the scored records of one
+ * file, weight 1 where absent; fills at most `cap` entries, returns the number of records (-1 on error). */
+int64_t mlease_scored_read(const char* path, int64_t cap, int32_t* response, float* pred, float* weight, int32_t generic);
 /* Avro container round trip (decode every record generically, re-encode with `codec` = "null" | "deflate"). */
 int mlease_avro_copy(const char* in_path, const char* out_path, const char* codec, int64_t* nrecords, int64_t* nblocks);
 #ifdef __cplusplus

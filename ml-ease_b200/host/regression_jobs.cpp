@@ -764,6 +764,57 @@ void write_test_output(const std::string& in_file, const std::string& out_file, 
   if (!write_test_output_fast(in_file, out_file, pred)) write_test_output_generic(in_file, out_file, pred);
 }
 
+
+// ------------------------------------------------------------------------------------------ RegressionTestLoglik input
+// (response, pred, weight) of scored records (jobs/RegressionTestLoglik.java:124-151); everything else in a record is skipped.
+void read_scored_generic(const std::string& f, std::vector<int32_t>& resp, std::vector<float>& pred, std::vector<float>& weight) {
+  AvroReader rd(f);
+  const Schema& s = rec_schema(rd.schema());
+  Value rec;
+  while (rd.next(rec)) {
+    const Value* r = field(rec, s, "response"); const Value* p = field(rec, s, "pred"); const Value* w = field(rec, s, "weight");
+    if (!r || !p) io_error("response/pred is null");
+    resp.push_back((int)num_of(*r)); pred.push_back((float)num_of(*p)); weight.push_back(w ? (float)num_of(*w) : 1.0f);
+  }
+}
+bool read_scored_fast(const std::string& f, std::vector<int32_t>& resp, std::vector<float>& pred, std::vector<float>& weight) {
+  if (host_generic_ingest()) return false;
+  AvroFile af(f);
+  Plan plan;
+  try { plan = plan_build(*af.schema()); } catch (const std::exception&) { return false; }
+  Plan* p = &plan;
+  const Schema* s = af.schema().get();
+  if (!plan_resolve(p, s, Schema::Record)) return false;
+  enum { R = 0, P = 1, W = 2 };
+  const unsigned numeric = K_NULL | K_BOOL | K_INT | K_LONG | K_FLOAT | K_DOUBLE;
+  if (tag_field(*p, *s, "response", R, numeric) < 0 || tag_field(*p, *s, "pred", P, numeric) < 0 || tag_field(*p, *s, "weight", W, numeric) < 0) return false;
+  struct Part { std::vector<int32_t> r; std::vector<float> p, w; };
+  struct NoSink { void begin_item(int, Slot*) {} void item(int, Slot*) {} };
+  const size_t nb = af.num_blocks();
+  std::vector<Part> parts(nb);
+  parallel_blocks(nb, host_threads(), [&](size_t b) {
+    const std::string data = af.block_data(b);
+    const uint8_t* q = reinterpret_cast<const uint8_t*>(data.data());
+    const uint8_t* e = q + data.size();
+    Part& o = parts[b];
+    NoSink sink;
+    Slot sl[3];
+    for (int64_t k = 0; k < af.block_records(b); k++) {
+      sl[R] = Slot(); sl[P] = Slot(); sl[W] = Slot();
+      plan_walk(plan, q, e, sl, sink);
+      if (sl[R].is_null() || sl[P].is_null()) io_error("response/pred is null");
+      o.r.push_back((int)sl[R].num()); o.p.push_back((float)sl[P].num()); o.w.push_back(sl[W].is_null() ? 1.0f : (float)sl[W].num());
+    }
+  });
+  for (auto& o : parts) {
+    resp.insert(resp.end(), o.r.begin(), o.r.end()); pred.insert(pred.end(), o.p.begin(), o.p.end()); weight.insert(weight.end(), o.w.begin(), o.w.end());
+  }
+  return true;
+}
+void read_scored(const std::string& f, std::vector<int32_t>& resp, std::vector<float>& pred, std::vector<float>& weight) {
+  if (!read_scored_fast(f, resp, pred, weight)) read_scored_generic(f, resp, pred, weight);
+}
+
 // ============================================================================================ RegressionPrepare
 // jobs/RegressionPrepare.java:95-191.  map.key set -> key = data[map.key].toString() (bit-exact); otherwise the reference
 // draws floor(Math.random()*nblocks) from an UNSEEDED generator (:112) which cannot be reproduced: here a splitmix64 stream
@@ -1172,16 +1223,7 @@ void run_test_loglik(const JobConfig& c) {
   auto one = [&](const std::string& inPath, const std::string& outPath) {
     if (!path_exists(inPath)) return;
     std::vector<int32_t> resp; std::vector<float> pred, weight;
-    for (auto& f : list_avro_files(inPath)) {
-      AvroReader rd(f);
-      const Schema& s = rec_schema(rd.schema());
-      Value rec;
-      while (rd.next(rec)) {
-        const Value* r = field(rec, s, "response"); const Value* p = field(rec, s, "pred"); const Value* w = field(rec, s, "weight");
-        if (!r || !p) io_error("response/pred is null");
-        resp.push_back((int)num_of(*r)); pred.push_back((float)num_of(*p)); weight.push_back(w ? (float)num_of(*w) : 1.0f);
-      }
-    }
+    for (auto& f : list_avro_files(inPath)) read_scored(f, resp, pred, weight);
     if (resp.empty()) return;
     float ll; double cnt;
     // one combiner call per map task; local runs have one split per file -> combiner_block = everything
@@ -1389,6 +1431,20 @@ int mlease_test_output_write(const char* in_path, const char* out_path, const fl
     g_force_generic = false;
     return 0;
   } catch (const std::exception& e) { g_job_err = e.what(); return 2; }
+}
+// RegressionTestLoglik's input step (test hook): (response, pred, weight) of the scored records of one file; returns the count or -1.
+int64_t mlease_scored_read(const char* path, int64_t cap, int32_t* response, float* pred, float* weight, int32_t generic) {
+  try {
+    std::vector<int32_t> r; std::vector<float> p, w;
+    g_force_generic = generic != 0;
+    try { read_scored(path, r, p, w); } catch (...) { g_force_generic = false; throw; }
+    g_force_generic = false;
+    const size_t n = std::min<size_t>(r.size(), (size_t)std::max<int64_t>(cap, 0));
+    if (response) std::memcpy(response, r.data(), n * 4);
+    if (pred) std::memcpy(pred, p.data(), n * 4);
+    if (weight) std::memcpy(weight, w.data(), n * 4);
+    return (int64_t)r.size();
+  } catch (const std::exception& e) { g_job_err = e.what(); return -1; }
 }
 int mlease_host_set_threads(int32_t n) { set_host_threads(n); return host_threads(); }
 

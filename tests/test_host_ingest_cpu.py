@@ -234,3 +234,31 @@ def test_test_job_output_transcoder_equals_generic(host, tmp_path):
         assert rc != 0
         errs.append(host.mlease_job_last_error().decode())
     assert errs[0] == errs[1] and "null" in errs[0]
+
+
+def test_scored_records_reader_equals_generic(host, tmp_path):
+    """RegressionTestLoglik reads (response, pred, weight) of the Test job's output: the plan walker skips the feature lists."""
+    npz = np.load(os.path.join(GOLDEN, "sample_data.npz"))
+    recs = au.fixture_records(npz)
+    src = str(tmp_path / "t.avro")
+    au.write_avro(src, au.PIG_SCHEMA, recs, block=90)
+    pred = np.random.default_rng(2).normal(size=len(recs)).astype(np.float32)
+    scored = str(tmp_path / "scored.avro")
+    assert host.mlease_test_output_write(src.encode(), scored.encode(), pred.ctypes.data_as(C.c_void_p), C.c_int64(len(pred)), 0) == 0
+    host.mlease_scored_read.restype = C.c_int64
+    got = []
+    for generic in (0, 1):
+        r, p, w = np.zeros(len(recs), np.int32), np.zeros(len(recs), np.float32), np.zeros(len(recs), np.float32)
+        n = host.mlease_scored_read(scored.encode(), C.c_int64(len(recs)), r.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), generic)
+        assert n == len(recs), host.mlease_job_last_error().decode()
+        got.append((r, p, w))
+    for a, b in zip(got[0], got[1]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(got[0][1], pred) and np.array_equal(got[0][0], npz["response"].astype(np.int32)) and (got[0][2] == 1).all()
+    # records without pred: the reference's error text from both
+    errs = []
+    for generic in (0, 1):
+        n = host.mlease_scored_read(src.encode(), C.c_int64(0), None, None, None, generic)
+        assert n == -1
+        errs.append(host.mlease_job_last_error().decode())
+    assert errs[0] == errs[1] == "response/pred is null"

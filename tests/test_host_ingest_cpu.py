@@ -262,3 +262,127 @@ def test_scored_records_reader_equals_generic(host, tmp_path):
         assert n == -1
         errs.append(host.mlease_job_last_error().decode())
     assert errs[0] == errs[1] == "response/pred is null"
+
+
+def _random_case(rng):
+    """A random record schema in the family the jobs read (fields present / absent / nullable, numeric types varied, extra fields,
+    shuffled order) with matching records."""
+    def nullable(t, p=0.5):
+        return ["null", t] if rng.random() < p else t
+    item_fields = [{"name": "name", "type": nullable("string", 0.4)}, {"name": "value", "type": nullable(str(rng.choice(["float", "double", "int", "long"])), 0.4)}]
+    has_term = rng.random() < 0.7
+    if has_term:
+        item_fields.append({"name": "term", "type": nullable("string", 0.4)})
+    if rng.random() < 0.3:
+        item_fields.append({"name": "junk", "type": "long"})
+    rng.shuffle(item_fields)
+    item = {"type": "record", "name": "feat", "fields": item_fields}
+    feats_t = {"type": "array", "items": (["null", item] if rng.random() < 0.5 else item)}
+    fields = [{"name": "features", "type": (["null", feats_t] if rng.random() < 0.5 else feats_t)}]
+    present = {}
+    for nm, types in (("key", ["string", "int", "long"]), ("response", ["int", "boolean", "long"]), ("click", ["int", "boolean"]), ("label", ["int"]),
+                      ("weight", ["float", "double", "int", "string"]), ("offset", ["float", "double", "long"])):
+        if rng.random() < (0.85 if nm in ("response", "key") else 0.5):
+            t = str(rng.choice(types, p=None if nm != "weight" else [0.4, 0.3, 0.25, 0.05]))
+            present[nm] = t
+            fields.append({"name": nm, "type": nullable(t)})
+    if rng.random() < 0.5:
+        fields.append({"name": "extra", "type": {"type": "record", "name": "ex", "fields": [
+            {"name": "tags", "type": {"type": "array", "items": "string"}}, {"name": "d", "type": ["null", "double"]}, {"name": "b", "type": "boolean"}]}})
+    rng.shuffle(fields)
+    schema = {"type": "record", "name": "rec", "fields": fields}
+
+    def val(t, fld):
+        is_union = isinstance(fld["type"], list)
+        if is_union and rng.random() < 0.15:
+            return None
+        if t == "string":
+            return str(rng.integers(0, 4)) if fld["name"] == "key" else "w%d" % rng.integers(0, 3)
+        if t == "boolean":
+            return bool(rng.integers(0, 2))
+        if t in ("int", "long"):
+            return int(rng.integers(-1, 2)) if fld["name"] in ("response", "click", "label") else int(rng.integers(0, 5))
+        return float(np.float32(rng.normal()))
+    recs = []
+    for _ in range(int(rng.integers(0, 60))):
+        r = {}
+        for f in fields:
+            if f["name"] == "features":
+                if isinstance(f["type"], list) and rng.random() < 0.1:
+                    r["features"] = None
+                    continue
+                fl = []
+                for _k in range(int(rng.integers(0, 6))):
+                    e = {}
+                    for itf in item_fields:
+                        t = itf["type"][1] if isinstance(itf["type"], list) else itf["type"]
+                        if itf["name"] == "name":
+                            e["name"] = None if (isinstance(itf["type"], list) and rng.random() < 0.05) else "n%d" % rng.integers(0, 12)
+                        elif itf["name"] == "term":
+                            e["term"] = None if (isinstance(itf["type"], list) and rng.random() < 0.3) else ("" if rng.random() < 0.5 else "t%d" % rng.integers(0, 3))
+                        elif itf["name"] == "junk":
+                            e["junk"] = int(rng.integers(0, 1000))
+                        else:
+                            e["value"] = None if (isinstance(itf["type"], list) and rng.random() < 0.1) else (int(rng.integers(-3, 4)) if t in ("int", "long") else float(np.float32(rng.normal())))
+                    fl.append(e)
+                r["features"] = fl
+            elif f["name"] == "extra":
+                r["extra"] = {"tags": ["a"] * int(rng.integers(0, 3)), "d": None if rng.random() < 0.5 else 1.5, "b": True}
+            else:
+                r[f["name"]] = val(present[f["name"]], f)
+        recs.append(r)
+    return schema, recs
+
+
+def test_random_schemas_fast_reader_equals_generic_reader(host, tmp_path):
+    """Seeded fuzz over the schema family the jobs read: whatever the generic reader returns -- rows or an error text -- the
+    plan-walker reader returns too (schemas it does not take, e.g. a string weight, fall back to the generic reader)."""
+    rng = np.random.default_rng(2024)
+    n_rows = n_err = 0
+    for case in range(120):
+        schema, recs = _random_case(rng)
+        p = str(tmp_path / ("c%d.avro" % case))
+        au.write_avro(p, schema, recs, block=int(rng.integers(1, 9)), codec=str(rng.choice(["null", "deflate"])))
+        raw, binary = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        f, g = _rows(host, p, raw=raw, binary=binary), _rows(host, p, raw=raw, binary=binary, generic=True)
+        if isinstance(g, str):
+            assert f == g, (case, f, g)
+            n_err += 1
+        else:
+            _same(f, g)
+            n_rows += 1
+    assert n_rows >= 20 and n_err >= 5, (n_rows, n_err)
+
+
+def test_random_schemas_prepare_job_fast_equals_generic(host, tmp_path, monkeypatch):
+    """The same fuzz through RegressionPrepare: identical output records or identical error text, for map.key on fields of every
+    scalar type (printed as Java's toString), on a missing field, and for the seeded random-key branch with click replicates."""
+    rng = np.random.default_rng(99)
+    n_ok = n_err = 0
+    for case in range(60):
+        schema, recs = _random_case(rng)
+        if rng.random() < 0.7:   # most cases: a record stream the job accepts (int response, lists and names present)
+            schema["fields"] = [f for f in schema["fields"] if f["name"] not in ("response", "click", "label")] + [{"name": "response", "type": ["null", "int"]}]
+            for r in recs:
+                r["response"] = int(rng.integers(0, 2))
+                r["features"] = r["features"] or []
+                for e in r["features"]:
+                    e["name"] = e["name"] or "n0"
+            if not recs:
+                continue
+        d = tmp_path / ("in%d" % case)
+        au.write_avro(str(d / "part-0.avro"), schema, recs, block=int(rng.integers(1, 9)), codec=str(rng.choice(["null", "deflate"])))
+        names = [f["name"] for f in schema["fields"] if f["name"] != "features"]
+        mapkey = "" if rng.random() < 0.4 else str(rng.choice(names + ["nosuchfield"]))
+        res = []
+        for mode in ("fast", "generic"):
+            monkeypatch.setenv("MLEASE_HOST_GENERIC_INGEST", "1" if mode == "generic" else "0")
+            kv = dict(input_paths=str(d), output_path=str(tmp_path / ("o%d_%s" % (case, mode))), num_blocks=4, num_click_replicates=2, random_seed=case)
+            if mapkey:
+                kv["map_key"] = mapkey
+            rc, err = _run(host, "RegressionPrepare", _write_cfg(str(tmp_path / "c.job"), **kv))
+            res.append(err if rc else au.read_dir(kv["output_path"]))
+        assert type(res[0]) is type(res[1]) and res[0] == res[1], (case, mapkey, res[0] if isinstance(res[0], str) else "", res[1] if isinstance(res[1], str) else "")
+        n_ok += not isinstance(res[0], str)
+        n_err += isinstance(res[0], str)
+    assert n_ok >= 15 and n_err >= 5, (n_ok, n_err)

@@ -1,0 +1,94 @@
+"""CPU test of the job layer's ORCHESTRATION: the C++ jobs linked against a test double of the device library
+(tests/fake_device/fake_mlease_b200.c: canned numbers, no computation) so that RegressionAdmmTrain / RegressionTest /
+RegressionTestLoglik / RegressionNaiveTrain run end to end without a GPU.  What is checked is the host side: the whole output
+tree (iter-i/{u,init-value,model}, final-model, best-model, sample-test-loglik, test/lambda-*, _loglik, models, partitionIds)
+is the same whether the avro work goes through the block-parallel plan-walker code or the generic Value-tree code, and the
+output layout is the reference's.  The numbers in the files mean nothing; the GPU tests (test_gpu_jobs.py) check those."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import avro_util as au  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+HOST = os.path.join(ROOT, "ml-ease_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def fake_host(tmp_path_factory):
+    d = tmp_path_factory.mktemp("fakehost")
+    so = str(d / "libmlease_host_fake.so")
+    san = os.environ.get("MLEASE_TEST_SANITIZE", "")   # e.g. "address,undefined" or "thread" (run pytest with the matching runtime LD_PRELOADed)
+    extra = ["-g", "-fsanitize=" + san, "-fno-omit-frame-pointer"] if san else []
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared"] + extra + ["-o", so, os.path.join(HOST, "avro_io.cpp"), os.path.join(HOST, "regression_jobs.cpp"),
+                           "-x", "c", os.path.join(ROOT, "tests", "fake_device", "fake_mlease_b200.c"), "-lz", "-pthread", "-lm"])
+    h = C.CDLL(so)
+    h.mlease_job_last_error.restype = C.c_char_p
+    return h
+
+
+def _cfg(path, **kv):
+    with open(path, "w") as f:
+        for k, v in kv.items():
+            f.write("%s=%s\n" % (k.replace("_", "."), v))
+    return path
+
+
+def _tree(root):
+    """relative path -> decoded records of every avro file under root."""
+    out = {}
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith(".avro"):
+                p = os.path.join(dp, f)
+                out[os.path.relpath(p, root)] = au.read_avro(p)[:2]
+    return out
+
+
+def _run(h, job, cfg):
+    rc = h.mlease_job_run(job.encode(), cfg.encode())
+    assert rc == 0, h.mlease_job_last_error().decode()
+
+
+def test_regression_chain_and_naive_train_output_trees_do_not_depend_on_the_avro_path(fake_host, tmp_path, monkeypatch):
+    npz = np.load(os.path.join(GOLDEN, "sample_data.npz"))
+    recs = au.fixture_records(npz, with_key=lambda i: i // 250)
+    au.write_avro(str(tmp_path / "in" / "part-0.avro"), au.pig_schema_with_key(), recs[:700], codec="deflate", block=64)
+    au.write_avro(str(tmp_path / "in" / "part-1.avro"), au.pig_schema_with_key(), recs[700:], block=500)
+    trees = {}
+    for mode in ("fast", "generic"):
+        monkeypatch.setenv("MLEASE_HOST_GENERIC_INGEST", "1" if mode == "generic" else "0")
+        out = str(tmp_path / ("out_" + mode))
+        cfg = _cfg(str(tmp_path / (mode + "_r.job")), input_paths=str(tmp_path / "in"), output_base_path=out, test_path=str(tmp_path / "in"),
+                   map_key="pkey", num_blocks=4, num_iters=5, regularizer=2, initialize_boost_rate=2.0)
+        open(cfg, "a").write("lambda=1,10\n")
+        _run(fake_host, "Regression", cfg)
+        nout = str(tmp_path / ("nout_" + mode))
+        _run(fake_host, "RegressionPrepare", _cfg(str(tmp_path / (mode + "_p.job")), input_paths=str(tmp_path / "in"), output_path=nout + "/tmp-data",
+                                                  num_blocks=4, num_click_replicates=2, random_seed=3))
+        ncfg = _cfg(str(tmp_path / (mode + "_n.job")), output_base_path=nout, num_blocks=4, heavy_per_item_train="true", remove_tmp_dir="false")
+        open(ncfg, "a").write("lambda=10,1\n")
+        _run(fake_host, "NaiveTrain", ncfg)
+        trees[mode] = (_tree(out), _tree(nout))
+    for a, b in zip(trees["fast"], trees["generic"]):
+        assert sorted(a) == sorted(b)
+        for k in a:
+            assert a[k] == b[k], k
+    chain, naive = trees["fast"]
+    # the reference's output layout: per-iteration files, final / best model, test outputs per lambda as typed
+    for rel in ("tmp-data/part-00000.avro", "lambda-rho/part-r-00000.avro", "initialModel/part-r-00000.avro", "iter-1/u/part-r-00000.avro",
+                "iter-1/init-value/part-r-00000.avro", "iter-5/model/part-r-00000.avro", "final-model/part-r-00000.avro",
+                "sample-test-loglik/iteration-5.avro", "test/lambda-1/part-r-00000.avro", "test/lambda-10/part-r-00001.avro",
+                "test/lambda-1/_loglik/part-r-00000.avro"):
+        assert rel in chain, (rel, sorted(chain)[:40])
+    assert len(chain["iter-5/model/part-r-00000.avro"][1]) == 8 and len(chain["iter-2/u/part-r-00000.avro"][1]) == 8 and chain["iter-1/u/part-r-00000.avro"][1] == []
+    m0 = chain["iter-5/model/part-r-00000.avro"][1][0]
+    assert m0["key"] == "1.0#0" and m0["model"][0]["name"] == "(INTERCEPT)" and len(m0["model"]) == 201 and len(m0["uplusx"]) == 201
+    assert [f["name"] for f in chain["test/lambda-1/part-r-00000.avro"][0]["fields"]][-1] == "pred"
+    assert len(naive["models/part-r-00000.avro"][1]) == 8 and "partitionIds/part-r-00000.avro" in naive and "final-model/part-r-00000.avro" in naive

@@ -1122,11 +1122,15 @@ void run_admm_train(const JobConfig& c) {
   } else {
     ck(mlease_world_begin(S.w));
   }
+  // write.iteration.files (not a reference key; default true = the reference's layout): false skips the per-iteration state files
+  // iter-<i>/{u,init-value,model} -- with the state resident on the GPUs nothing reads them back, and at 10k features x 24
+  // reducers they cost more host time per iteration than the iteration itself; final-model, best-model and sample-test-loglik stay
+  const bool iter_files = c.get_bool("write.iteration.files", true);
   int i;
   for (i = 1; i <= niter; i++) {
     const std::string it = out + "/iter-" + std::to_string(i);
     // u of this iteration (empty file at i == 1, :310-313) and z as the reducers see it (:330-331)
-    {
+    if (iter_files) {
       std::vector<std::pair<std::string, std::vector<float>>> us;
       if (i > 1)
         for (int p = 0; p < nblocks; p++) for (int l = 0; l < L; l++) {
@@ -1144,7 +1148,7 @@ void run_admm_train(const JobConfig& c) {
     double maxdiff = 0; int32_t stop = 0;
     ck(mlease_world_iterate(S.w, &maxdiff, &stop));
     // reducer outputs (:706-711)
-    {
+    if (iter_files) {
       std::vector<std::pair<std::string, std::vector<float>>> xs;
       std::vector<std::vector<float>> uxs;
       for (int p = 0; p < nblocks; p++) for (int l = 0; l < L; l++) {

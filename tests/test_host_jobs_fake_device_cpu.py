@@ -92,3 +92,20 @@ def test_regression_chain_and_naive_train_output_trees_do_not_depend_on_the_avro
     assert m0["key"] == "1.0#0" and m0["model"][0]["name"] == "(INTERCEPT)" and len(m0["model"]) == 201 and len(m0["uplusx"]) == 201
     assert [f["name"] for f in chain["test/lambda-1/part-r-00000.avro"][0]["fields"]][-1] == "pred"
     assert len(naive["models/part-r-00000.avro"][1]) == 8 and "partitionIds/part-r-00000.avro" in naive and "final-model/part-r-00000.avro" in naive
+
+
+def test_write_iteration_files_false_keeps_the_final_outputs(fake_host, tmp_path):
+    npz = np.load(os.path.join(GOLDEN, "sample_data.npz"))
+    recs = au.fixture_records(npz, with_key=lambda i: i // 250)
+    au.write_avro(str(tmp_path / "in" / "part-0.avro"), au.pig_schema_with_key(), recs, block=300)
+    trees = {}
+    for flag in ("true", "false"):
+        out = str(tmp_path / ("out_" + flag))
+        cfg = _cfg(str(tmp_path / (flag + ".job")), input_paths=str(tmp_path / "in"), output_base_path=out, test_path=str(tmp_path / "in"), map_key="pkey",
+                   num_blocks=4, num_iters=3, regularizer=2, write_iteration_files=flag)
+        open(cfg, "a").write("lambda=1\n")
+        _run(fake_host, "Regression", cfg)
+        trees[flag] = _tree(out)
+    assert any(k.startswith("iter-") for k in trees["true"]) and not any(k.startswith("iter-") for k in trees["false"])
+    rest = {k: v for k, v in trees["true"].items() if not k.startswith("iter-")}
+    assert rest == trees["false"] and "final-model/part-r-00000.avro" in rest and "test/lambda-1/_loglik/part-r-00000.avro" in rest

@@ -76,3 +76,11 @@ def test_tools_and_bench_scripts_parse():
     assert out.returncode == 0
     for flag in ("--gpus", "--steps", "--warmup", "--impl"):
         assert flag in out.stdout
+
+
+def test_headers_are_plain_c99(tmp_path):
+    """The drop-in boundary is a C ABI: both headers compile as C99 (what cgo / JNI shims / ctypes-generators include)."""
+    import subprocess
+    src = tmp_path / "hc.c"
+    src.write_text('#include "mlease_b200.h"\n#include "mlease_host.h"\nint main(void) { return 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", str(src)])

@@ -138,3 +138,57 @@ NATIVE(void, close)(JNIEnv* env, jobject self) {
   if (w) mlease_world_destroy(w);
   (*env)->SetLongField(env, self, f, 0);
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * com.linkedin.mlease.regression.gpu.NativeOps: the stateless entry points (NaiveTrain reducer, scoring, test log-likelihood)
+ * ------------------------------------------------------------------------------------------------------------------------- */
+#define OPS(ret, name) JNIEXPORT ret JNICALL Java_com_linkedin_mlease_regression_gpu_NativeOps_##name
+
+OPS(void, naiveTrain)(JNIEnv* env, jclass cls, jint device, jint numKeys, jint numFeatures, jobject keyRowStart, jobject rowptr, jobject colidx,
+                      jobject vals, jobject response, jobject weight, jobject offset, jfloatArray lambdas, jfloatArray lambdaMap, jfloat priorMean,
+                      jboolean penalize, jboolean hasIntercept, jint threshold, jboolean binary, jdoubleArray outModel, jintArray skipped) {
+  (void)cls;
+  jfloat* l = (*env)->GetFloatArrayElements(env, lambdas, NULL);
+  jfloat* m = lambdaMap ? (*env)->GetFloatArrayElements(env, lambdaMap, NULL) : NULL;
+  jdouble* out = (*env)->GetDoubleArrayElements(env, outModel, NULL);
+  jint* sk = (*env)->GetIntArrayElements(env, skipped, NULL);
+  const int rc = mlease_naive_train(device, NULL, numKeys, numFeatures, (const int64_t*)direct(env, keyRowStart), (const int64_t*)direct(env, rowptr),
+                                    (const int32_t*)direct(env, colidx), (const float*)direct(env, vals), 0, (const int32_t*)direct(env, response),
+                                    (const float*)direct(env, weight), (const float*)direct(env, offset), (*env)->GetArrayLength(env, lambdas), l, m, priorMean,
+                                    penalize, hasIntercept, threshold, binary, out, (int32_t*)sk);
+  (*env)->ReleaseIntArrayElements(env, skipped, sk, rc ? JNI_ABORT : 0);
+  (*env)->ReleaseDoubleArrayElements(env, outModel, out, rc ? JNI_ABORT : 0);
+  if (m) (*env)->ReleaseFloatArrayElements(env, lambdaMap, m, JNI_ABORT);
+  (*env)->ReleaseFloatArrayElements(env, lambdas, l, JNI_ABORT);
+  if (rc) throw_for(env, rc);
+}
+
+OPS(void, score)(JNIEnv* env, jclass cls, jint device, jint numFeatures, jlong nrows, jobject rowptr, jobject colidx, jobject vals, jobject offset,
+                 jdoubleArray model, jint reps, jboolean binary, jfloatArray predOut) {
+  (void)cls;
+  jdouble* b = (*env)->GetDoubleArrayElements(env, model, NULL);
+  jfloat* p = (*env)->GetFloatArrayElements(env, predOut, NULL);
+  const int rc = mlease_score(device, NULL, numFeatures, nrows, (const int64_t*)direct(env, rowptr), (const int32_t*)direct(env, colidx),
+                              (const float*)direct(env, vals), 0, (const float*)direct(env, offset), b, reps, binary, p);
+  (*env)->ReleaseFloatArrayElements(env, predOut, p, rc ? JNI_ABORT : 0);
+  (*env)->ReleaseDoubleArrayElements(env, model, b, JNI_ABORT);
+  if (rc) throw_for(env, rc);
+}
+
+OPS(jfloat, testLoglik)(JNIEnv* env, jclass cls, jint device, jintArray response, jfloatArray pred, jfloatArray weight, jlong combinerBlock,
+                        jdoubleArray countOut) {
+  (void)cls;
+  const jsize n = (*env)->GetArrayLength(env, response);
+  jint* r = (*env)->GetIntArrayElements(env, response, NULL);
+  jfloat* p = (*env)->GetFloatArrayElements(env, pred, NULL);
+  jfloat* w = (*env)->GetFloatArrayElements(env, weight, NULL);
+  float ll = 0.f;
+  double cnt = 0.0;
+  const int rc = mlease_test_loglik(device, NULL, n, (const int32_t*)r, p, w, combinerBlock, &ll, &cnt);
+  (*env)->ReleaseFloatArrayElements(env, weight, w, JNI_ABORT);
+  (*env)->ReleaseFloatArrayElements(env, pred, p, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, response, r, JNI_ABORT);
+  if (rc) { throw_for(env, rc); return 0.f; }
+  if (countOut) (*env)->SetDoubleArrayRegion(env, countOut, 0, 1, &cnt);
+  return ll;
+}

@@ -99,7 +99,8 @@ def test_jni_shim_type_checks_links_and_matches_the_java_class(tmp_path):
                            "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "integration", "jni", "mlease_b200_jni.c"),
                            "-L", os.path.join(ROOT, "ml-ease_b200", "lib"), "-lmlease_b200", "-Wl,--no-undefined", "-o", so])
     syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
-    exported = set(re.findall(r"Java_com_linkedin_mlease_regression_gpu_NativeAdmm_(\w+)", syms))
-    java = open(os.path.join(ROOT, "integration", "jni", "NativeAdmm.java")).read()
-    declared = set(re.findall(r"\bnative\s+[\w\[\]]+\s+(\w+)\s*\(", java))
-    assert exported == declared and len(declared) == 13, (sorted(exported ^ declared))
+    for cls, count in (("NativeAdmm", 13), ("NativeOps", 3)):
+        exported = set(re.findall(r"Java_com_linkedin_mlease_regression_gpu_" + cls + r"_(\w+)", syms))
+        java = open(os.path.join(ROOT, "integration", "jni", cls + ".java")).read()
+        declared = set(re.findall(r"\bnative\s+[\w\[\]]+\s+(\w+)\s*\(", java))
+        assert exported == declared and len(declared) == count, (cls, sorted(exported ^ declared))

@@ -192,3 +192,59 @@ OPS(jfloat, testLoglik)(JNIEnv* env, jclass cls, jint device, jintArray response
   if (countOut) (*env)->SetDoubleArrayRegion(env, countOut, 0, 1, &cnt);
   return ll;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * com.linkedin.mlease.regression.gpu.NativeIngest: the job layer's avro ingest (include/mlease_host.h; link libmlease_host.so too)
+ * ------------------------------------------------------------------------------------------------------------------------- */
+#include "mlease_host.h"
+#define ING(ret, name) JNIEXPORT ret JNICALL Java_com_linkedin_mlease_regression_gpu_NativeIngest_##name
+
+static mlease_rows* rows_of(JNIEnv* env, jobject self) {
+  jclass c = (*env)->GetObjectClass(env, self);
+  jfieldID f = (*env)->GetFieldID(env, c, "handle", "J");
+  return f ? (mlease_rows*)(intptr_t)(*env)->GetLongField(env, self, f) : NULL;
+}
+
+ING(jlong, read)(JNIEnv* env, jclass cls, jstring path, jboolean raw, jboolean binary) {
+  (void)cls;
+  const char* p = (*env)->GetStringUTFChars(env, path, NULL);
+  mlease_rows* r = NULL;
+  const int rc = mlease_rows_read(p, raw, binary, 0, &r);
+  (*env)->ReleaseStringUTFChars(env, path, p);
+  if (rc) {
+    jclass c = (*env)->FindClass(env, "java/io/IOException");
+    if (c) (*env)->ThrowNew(env, c, mlease_job_last_error());   /* the reference's texts: "features is null", "name is null", ... */
+    return 0;
+  }
+  return (jlong)(intptr_t)r;
+}
+ING(jlongArray, counts)(JNIEnv* env, jobject self) {
+  int64_t nnz = 0;
+  int32_t nf = 0;
+  const int64_t n = mlease_rows_count(rows_of(env, self), &nnz, &nf);
+  jlong v[3];
+  v[0] = n; v[1] = nnz; v[2] = nf;
+  jlongArray out = (*env)->NewLongArray(env, 3);
+  if (out) (*env)->SetLongArrayRegion(env, out, 0, 3, v);
+  return out;
+}
+ING(void, get)(JNIEnv* env, jobject self, jobject rowptr, jobject colidx, jobject vals, jobject response, jobject weight, jobject offset) {
+  mlease_rows_get(rows_of(env, self), (int64_t*)direct(env, rowptr), (int32_t*)direct(env, colidx), (float*)direct(env, vals), (int32_t*)direct(env, response),
+                  (float*)direct(env, weight), (float*)direct(env, offset));
+}
+ING(jstring, feature)(JNIEnv* env, jobject self, jint k) {
+  const char* s = mlease_rows_feature(rows_of(env, self), k);
+  return s ? (*env)->NewStringUTF(env, s) : NULL;   /* U+0001 is a one-byte sequence in modified UTF-8 as well */
+}
+ING(jstring, key)(JNIEnv* env, jobject self, jlong i) {
+  const char* s = mlease_rows_key(rows_of(env, self), i);
+  return s ? (*env)->NewStringUTF(env, s) : NULL;
+}
+ING(void, close)(JNIEnv* env, jobject self) {
+  jclass c = (*env)->GetObjectClass(env, self);
+  jfieldID f = (*env)->GetFieldID(env, c, "handle", "J");
+  if (!f) return;
+  mlease_rows* r = (mlease_rows*)(intptr_t)(*env)->GetLongField(env, self, f);
+  if (r) mlease_rows_free(r);
+  (*env)->SetLongField(env, self, f, 0);
+}

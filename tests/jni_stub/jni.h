@@ -18,6 +18,8 @@ typedef jobject jarray;
 typedef jarray jintArray;
 typedef jarray jfloatArray;
 typedef jarray jdoubleArray;
+typedef jarray jlongArray;
+typedef jobject jstring;
 struct _jfieldID;
 typedef struct _jfieldID* jfieldID;
 #define JNI_FALSE 0
@@ -43,5 +45,10 @@ struct JNINativeInterface_ {
   void (*ReleaseDoubleArrayElements)(JNIEnv* env, jdoubleArray array, jdouble* elems, jint mode);
   void (*SetDoubleArrayRegion)(JNIEnv* env, jdoubleArray array, jsize start, jsize len, const jdouble* buf);
   void* (*GetDirectBufferAddress)(JNIEnv* env, jobject buf);
+  const char* (*GetStringUTFChars)(JNIEnv* env, jstring str, jboolean* isCopy);
+  void (*ReleaseStringUTFChars)(JNIEnv* env, jstring str, const char* chars);
+  jstring (*NewStringUTF)(JNIEnv* env, const char* utf);
+  jlongArray (*NewLongArray)(JNIEnv* env, jsize len);
+  void (*SetLongArrayRegion)(JNIEnv* env, jlongArray array, jsize start, jsize len, const jlong* buf);
 };
 #endif

@@ -88,7 +88,7 @@ def test_headers_are_plain_c99(tmp_path):
 
 def test_jni_shim_type_checks_links_and_matches_the_java_class(tmp_path):
     """integration/jni/: the reference-side binding.  No JDK here, so the C shim is compiled as pedantic C99
-    against a stub jni.h carrying the JNI specification's signatures and linked against libmlease_b200.so with no undefined symbols
+    against a stub jni.h carrying the JNI specification's signatures and linked against libmlease_b200.so / libmlease_host.so with no undefined symbols
     (it cannot drift from the header); its exported natives are exactly the `native` methods NativeAdmm.java declares."""
     import re
     import subprocess
@@ -97,9 +97,9 @@ def test_jni_shim_type_checks_links_and_matches_the_java_class(tmp_path):
     so = str(tmp_path / "libjni_check.so")
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fPIC", "-shared", "-I", os.path.join(ROOT, "tests", "jni_stub"),
                            "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "integration", "jni", "mlease_b200_jni.c"),
-                           "-L", os.path.join(ROOT, "ml-ease_b200", "lib"), "-lmlease_b200", "-Wl,--no-undefined", "-o", so])
+                           "-L", os.path.join(ROOT, "ml-ease_b200", "lib"), "-lmlease_host", "-lmlease_b200", "-Wl,--no-undefined", "-o", so])
     syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
-    for cls, count in (("NativeAdmm", 13), ("NativeOps", 3)):
+    for cls, count in (("NativeAdmm", 13), ("NativeOps", 3), ("NativeIngest", 6)):
         exported = set(re.findall(r"Java_com_linkedin_mlease_regression_gpu_" + cls + r"_(\w+)", syms))
         java = open(os.path.join(ROOT, "integration", "jni", cls + ".java")).read()
         declared = set(re.findall(r"\bnative\s+[\w\[\]]+\s+(\w+)\s*\(", java))

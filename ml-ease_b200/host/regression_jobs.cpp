@@ -1264,6 +1264,18 @@ void run_naive_train(const JobConfig& c) {
   const int D = (int)dict.names.size(), Dt = D + 1;
   std::vector<float> lambda_map;
   if (!c.get("lambda.map", "").empty()) lambda_map = read_lambda_map(c.get("lambda.map"), dict);
+  // intercept.key (jobs/RegressionNaiveTrain.java:146,309,340-343): the reducer puts the intercept's prior variance 100000 under THIS
+  // name, while the dataset's intercept is always "(INTERCEPT)" (llf/LibLinearDataset.java INTERCEPT_NAME).  With another name the
+  // entry lands on a feature of that name, if there is one, and the real intercept keeps the default variance 1/lambda.
+  bool penalize_intercept = c.get_bool("penalize.intercept", false);
+  {
+    const std::string ikey = c.get("intercept.key", INTERCEPT);
+    if (!penalize_intercept && ikey != INTERCEPT) {
+      penalize_intercept = true;
+      const int k = dict.find(ikey);
+      if (k >= 0) { if (lambda_map.empty()) lambda_map.assign(D, 0.f); lambda_map[k] = (float)(1.0 / 100000.0); }
+    }
+  }
   std::map<std::string, std::vector<size_t>> by_key;
   for (size_t i = 0; i < rows.n(); i++) by_key[rows.key[i]].push_back(i);
   if (heavy) {
@@ -1293,7 +1305,7 @@ void run_naive_train(const JobConfig& c) {
   std::map<std::string, std::pair<int, std::vector<double>>> sums;
   std::vector<double> m((size_t)L * K * Dt); std::vector<int32_t> skipped(K);
   ck(mlease_naive_train(gpu_devices(c)[0], nullptr, K, D, krs.data(), rp.data(), ci.data(), vv.data(), 0, rr.data(), ww.data(), oo.data(), L, lambdas.data(),
-                        lambda_map.empty() ? nullptr : lambda_map.data(), c.get_float("prior.mean", 0.0f), c.get_bool("penalize.intercept", false),
+                        lambda_map.empty() ? nullptr : lambda_map.data(), c.get_float("prior.mean", 0.0f), penalize_intercept,
                         c.get_bool("has.intercept", true), c.get_int("data.size.threshold", 0), ignore_value ? 1 : 0, m.data(), skipped.data()));
   for (int l = 0; l < L; l++) {
     const std::string ls = java_float_to_string(lambdas[l]);

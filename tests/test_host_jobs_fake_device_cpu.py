@@ -109,3 +109,25 @@ def test_write_iteration_files_false_keeps_the_final_outputs(fake_host, tmp_path
     assert any(k.startswith("iter-") for k in trees["true"]) and not any(k.startswith("iter-") for k in trees["false"])
     rest = {k: v for k, v in trees["true"].items() if not k.startswith("iter-")}
     assert rest == trees["false"] and "final-model/part-r-00000.avro" in rest and "test/lambda-1/_loglik/part-r-00000.avro" in rest
+
+
+def test_naive_train_intercept_key_other_than_the_dataset_intercept(fake_host, tmp_path):
+    """jobs/RegressionNaiveTrain.java:340-343 files the intercept's variance 100000 under `intercept.key`; the dataset's intercept
+    is always "(INTERCEPT)", so another name moves that entry onto the feature of that name (the test double adds lambda_map[j]
+    to coefficient j, which makes the entry visible)."""
+    npz = np.load(os.path.join(GOLDEN, "sample_data.npz"))
+    names = [str(n) for n in npz["feature_names"]]
+    recs = au.fixture_records(npz, with_key=lambda i: i // 500)
+    au.write_avro(str(tmp_path / "in" / "part-0.avro"), au.pig_schema_with_key(), recs, block=300)
+    models = {}
+    for tag, extra in (("default", {}), ("moved", {"intercept_key": names[5]})):
+        out = str(tmp_path / ("out_" + tag))
+        _run(fake_host, "RegressionPrepare", _cfg(str(tmp_path / (tag + "_p.job")), input_paths=str(tmp_path / "in"), output_path=out + "/tmp-data", map_key="pkey", num_blocks=2))
+        cfg = _cfg(str(tmp_path / (tag + "_n.job")), output_base_path=out, compute_model_mean="false", remove_tmp_dir="false", **extra)
+        open(cfg, "a").write("lambda=1\n")
+        _run(fake_host, "NaiveTrain", cfg)
+        models[tag] = {r["key"]: {f["name"]: f["value"] for f in r["model"]} for r in au.read_dir(out + "/models")}
+    for key in models["default"]:
+        d, m = models["default"][key], models["moved"][key]
+        diff = {n: m[n] - d[n] for n in d if m[n] != d[n]}
+        assert set(diff) == {names[5]} and abs(diff[names[5]] - 1e-5) < 2e-6, diff

@@ -131,3 +131,29 @@ def test_naive_train_intercept_key_other_than_the_dataset_intercept(fake_host, t
         d, m = models["default"][key], models["moved"][key]
         diff = {n: m[n] - d[n] for n in d if m[n] != d[n]}
         assert set(diff) == {names[5]} and abs(diff[names[5]] - 1e-5) < 2e-6, diff
+
+
+def test_per_iteration_test_loglik_uses_num_click_replicates(fake_host, tmp_path):
+    """updateLogLikBestModel evaluates with the train job's num.click.replicates (jobs/RegressionAdmmTrain.java:148,490): the intercept
+    enters as -log(n - 1 + n exp(-b)) (models/LinearModel.java:241-244), which is b itself for n = 1."""
+    npz = np.load(os.path.join(GOLDEN, "sample_data.npz"))
+    recs = au.fixture_records(npz, with_key=lambda i: i // 500)
+    au.write_avro(str(tmp_path / "in" / "part-0.avro"), au.pig_schema_with_key(), recs, block=300)
+    lls = {}
+    for reps in (1, 3):
+        out = str(tmp_path / ("out%d" % reps))
+        _run(fake_host, "RegressionPrepare", _cfg(str(tmp_path / "p.job"), input_paths=str(tmp_path / "in"), output_path=out + "/tmp-data", map_key="pkey", num_blocks=2))
+        cfg = _cfg(str(tmp_path / "t.job"), output_base_path=out, num_blocks=2, num_iters=2, regularizer=2, test_path=str(tmp_path / "in"), num_click_replicates=reps,
+                   write_iteration_files="false")
+        open(cfg, "a").write("lambda=1\n")
+        _run(fake_host, "RegressionAdmmTrain", cfg)
+        lls[reps] = au.read_avro(out + "/sample-test-loglik/iteration-2.avro")[1][0]["testLoglik"]
+        zfin = {f["name"]: f["value"] for f in au.read_dir(out + "/final-model")[0]["model"]}
+    assert np.isfinite(lls[1]) and np.isfinite(lls[3]) and lls[1] != lls[3]
+    # n = 1 against a direct evaluation with the (float) final model: agreement to float precision of the model
+    names = [str(n) for n in npz["feature_names"]]
+    beta = np.array([zfin[n] for n in names]); b = zfin["(INTERCEPT)"]
+    xb = b + np.array([sum(beta[c] * v for c, v in zip(npz["colidx"][npz["rowptr"][i]:npz["rowptr"][i + 1]], npz["val"][npz["rowptr"][i]:npz["rowptr"][i + 1]])) for i in range(len(recs))])
+    y = npz["response"]
+    ref = np.mean(np.where(y == 1, -np.log1p(np.exp(-xb)), -np.log1p(np.exp(xb))))
+    assert abs(lls[1] - ref) < 1e-4 * abs(ref)

@@ -603,13 +603,14 @@ std::vector<float> parse_lambdas(const JobConfig& c) {
 
 // driver-side per-iteration test log-likelihood (jobs/RegressionAdmmTrain.java:766-811): double throughout,
 // first test file only, at most 1e6 records, divides by sum of weights
-double sample_test_loglik(const Rows& t, const Dictionary& dict, const std::vector<int>& test2model, const std::vector<double>& z, int num_click_replicates) {
+double sample_test_loglik(const Rows& t, const Dictionary& dict, const std::vector<int>& test2model, const std::vector<double>& z) {
   const int D = (int)dict.names.size();
   double ll = 0, n = 0;
   size_t lim = std::min<size_t>(t.n(), 1000000);
-  const int nr = num_click_replicates;   // num.click.replicates of the train job (:148,274,490 -> models/LinearModel.java:241-244)
+  // updateLogLikBestModel receives the job's num.click.replicates but evaluates with the constant 1 (:817: testloglik(conf, z, testPath,
+  // 1, ignoreValue)), so the intercept term -log(n - 1 + n exp(-b)) (models/LinearModel.java:241-244) is b itself here
   for (size_t i = 0; i < lim; i++) {
-    double xb = -std::log(nr - 1 + nr * std::exp(-z[D]));
+    double xb = -std::log(1 - 1 + 1 * std::exp(-z[D]));
     for (int64_t j = t.rowptr[i]; j < t.rowptr[i + 1]; j++) { int m = test2model[t.colidx[j]]; if (m >= 0) xb += z[m] * (double)t.vals[j]; }
     xb += (double)t.offset[i];
     ll += (t.response[i] == 1) ? -std::log1p(std::exp(-xb)) * t.weight[i] : -std::log1p(std::exp(xb)) * t.weight[i];
@@ -1167,7 +1168,7 @@ void run_admm_train(const JobConfig& c) {
       AvroWriter w(out + "/sample-test-loglik/iteration-" + std::to_string(i) + ".avro", SCHEMA_SAMPLE_LOGLIK);
       for (int l = 0; l < L; l++) {
         std::vector<double> z(Dt); ck(mlease_world_get_z(S.w, l, z.data()));
-        double ll = sample_test_loglik(test, dict, test2model, z, c.get_int("num.click.replicates", 1));
+        double ll = sample_test_loglik(test, dict, test2model, z);
         Value r; r.type = Schema::Record; r.items = {Value::of_string(java_float_to_string(lambdas[l])), Value::of_int(i), Value::of_float((float)ll)};
         w.append(r);
         if (ll > best_loglik) {

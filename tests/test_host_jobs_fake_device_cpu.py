@@ -133,9 +133,10 @@ def test_naive_train_intercept_key_other_than_the_dataset_intercept(fake_host, t
         assert set(diff) == {names[5]} and abs(diff[names[5]] - 1e-5) < 2e-6, diff
 
 
-def test_per_iteration_test_loglik_uses_num_click_replicates(fake_host, tmp_path):
-    """updateLogLikBestModel evaluates with the train job's num.click.replicates (jobs/RegressionAdmmTrain.java:148,490): the intercept
-    enters as -log(n - 1 + n exp(-b)) (models/LinearModel.java:241-244), which is b itself for n = 1."""
+def test_per_iteration_test_loglik_ignores_num_click_replicates_like_the_reference(fake_host, tmp_path):
+    """updateLogLikBestModel is handed the train job's num.click.replicates but calls testloglik(conf, z, testPath, 1, ignoreValue)
+    (jobs/RegressionAdmmTrain.java:817): the per-iteration value is computed with n = 1 whatever the job says, i.e. the intercept term
+    -log(n - 1 + n exp(-b)) (models/LinearModel.java:241-244) is b itself."""
     npz = np.load(os.path.join(GOLDEN, "sample_data.npz"))
     recs = au.fixture_records(npz, with_key=lambda i: i // 500)
     au.write_avro(str(tmp_path / "in" / "part-0.avro"), au.pig_schema_with_key(), recs, block=300)
@@ -149,7 +150,7 @@ def test_per_iteration_test_loglik_uses_num_click_replicates(fake_host, tmp_path
         _run(fake_host, "RegressionAdmmTrain", cfg)
         lls[reps] = au.read_avro(out + "/sample-test-loglik/iteration-2.avro")[1][0]["testLoglik"]
         zfin = {f["name"]: f["value"] for f in au.read_dir(out + "/final-model")[0]["model"]}
-    assert np.isfinite(lls[1]) and np.isfinite(lls[3]) and lls[1] != lls[3]
+    assert np.isfinite(lls[1]) and lls[1] == lls[3]
     # n = 1 against a direct evaluation with the (float) final model: agreement to float precision of the model
     names = [str(n) for n in npz["feature_names"]]
     beta = np.array([zfin[n] for n in names]); b = zfin["(INTERCEPT)"]

@@ -1086,6 +1086,9 @@ void run_admm_train(const JobConfig& c) {
       test2model.resize(td.names.size());
       for (size_t k = 0; k < td.names.size(); k++) test2model[k] = dict.find(td.names[k]);
       test_per_iter = test.n() > 0;
+      // the reference opens and closes an empty writer here (:217-232): sample-test-loglik/write-test-00000.avro
+      AvroWriter w0(out + "/sample-test-loglik/write-test-00000.avro", SCHEMA_SAMPLE_LOGLIK);
+      w0.close();
     }
   }
   float best_loglik = -9999999.0f;
@@ -1120,6 +1123,16 @@ void run_admm_train(const JobConfig& c) {
       }
     }
     write_linear_models(out + "/initialModel/part-r-00000.avro", dict, init_models);
+    if (test_per_iter) {   // updateLogLikBestModel(conf, 0, z, ...) (:272-275): the mean model's sample log-likelihood; no best-model at iteration 0 (:833)
+      AvroWriter w(out + "/sample-test-loglik/iteration-0.avro", SCHEMA_SAMPLE_LOGLIK);
+      for (int l = 0; l < L; l++) {
+        std::vector<double> z(z0.begin() + (size_t)l * Dt, z0.begin() + (size_t)(l + 1) * Dt);
+        Value r; r.type = Schema::Record;
+        r.items = {Value::of_string(java_float_to_string(lambdas[l])), Value::of_int(0), Value::of_float((float)sample_test_loglik(test, dict, test2model, z))};
+        w.append(r);
+      }
+      w.close();
+    }
     ck(mlease_world_begin_initialized(S.w, z0.data(), boost_rate));
   } else {
     ck(mlease_world_begin(S.w));

@@ -84,9 +84,11 @@ def test_regression_chain_and_naive_train_output_trees_do_not_depend_on_the_avro
     # the reference's output layout: per-iteration files, final / best model, test outputs per lambda as typed
     for rel in ("tmp-data/part-00000.avro", "lambda-rho/part-r-00000.avro", "initialModel/part-r-00000.avro", "iter-1/u/part-r-00000.avro",
                 "iter-1/init-value/part-r-00000.avro", "iter-5/model/part-r-00000.avro", "final-model/part-r-00000.avro",
-                "sample-test-loglik/iteration-5.avro", "test/lambda-1/part-r-00000.avro", "test/lambda-10/part-r-00001.avro",
+                "sample-test-loglik/iteration-5.avro", "sample-test-loglik/iteration-0.avro", "sample-test-loglik/write-test-00000.avro", "test/lambda-1/part-r-00000.avro", "test/lambda-10/part-r-00001.avro",
                 "test/lambda-1/_loglik/part-r-00000.avro"):
         assert rel in chain, (rel, sorted(chain)[:40])
+    assert chain["sample-test-loglik/write-test-00000.avro"][1] == [] and [r["iter"] for r in chain["sample-test-loglik/iteration-0.avro"][1]] == [0, 0]
+    assert not any(k.startswith("best-model/best-iteration-0") for k in chain)
     assert len(chain["iter-5/model/part-r-00000.avro"][1]) == 8 and len(chain["iter-2/u/part-r-00000.avro"][1]) == 8 and chain["iter-1/u/part-r-00000.avro"][1] == []
     m0 = chain["iter-5/model/part-r-00000.avro"][1][0]
     assert m0["key"] == "1.0#0" and m0["model"][0]["name"] == "(INTERCEPT)" and len(m0["model"]) == 201 and len(m0["uplusx"]) == 201

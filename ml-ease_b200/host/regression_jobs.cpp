@@ -1196,7 +1196,8 @@ void run_admm_train(const JobConfig& c) {
     if (stop) break;
   }
   write_linear_models(out + "/final-model/part-r-00000.avro", dict, models_z(true));
-  if (c.get_bool("remove.tmp.dir", false)) {
+  if (c.get_bool("remove.tmp.dir", false)) {   // :503-520
+    remove_tree(out + "/initialModel");
     for (int j = std::min(i, niter) - 2; j <= std::min(i, niter); j++) remove_tree(out + "/iter-" + std::to_string(j));
     remove_tree(out + "/tmp-data");
   }

@@ -160,3 +160,19 @@ def test_per_iteration_test_loglik_ignores_num_click_replicates_like_the_referen
     y = npz["response"]
     ref = np.mean(np.where(y == 1, -np.log1p(np.exp(-xb)), -np.log1p(np.exp(xb))))
     assert abs(lls[1] - ref) < 1e-4 * abs(ref)
+
+
+def test_remove_tmp_dir_leaves_only_the_results(fake_host, tmp_path):
+    """remove.tmp.dir=true (jobs/RegressionAdmmTrain.java:474-478,503-520): iteration directories, initialModel and tmp-data are gone at
+    the end; lambda-rho, final-model, best-model and the sample log-likelihoods stay."""
+    npz = np.load(os.path.join(GOLDEN, "sample_data.npz"))
+    recs = au.fixture_records(npz, with_key=lambda i: i // 500)
+    au.write_avro(str(tmp_path / "in" / "part-0.avro"), au.pig_schema_with_key(), recs, block=300)
+    out = str(tmp_path / "out")
+    _run(fake_host, "RegressionPrepare", _cfg(str(tmp_path / "p.job"), input_paths=str(tmp_path / "in"), output_path=out + "/tmp-data", map_key="pkey", num_blocks=2))
+    cfg = _cfg(str(tmp_path / "t.job"), output_base_path=out, num_blocks=2, num_iters=4, regularizer=2, test_path=str(tmp_path / "in"), remove_tmp_dir="true",
+               initialize_boost_rate=1.5)
+    open(cfg, "a").write("lambda=1,10\n")
+    _run(fake_host, "RegressionAdmmTrain", cfg)
+    left = sorted(os.listdir(out))
+    assert left == ["best-model", "final-model", "lambda-rho", "sample-test-loglik"], left

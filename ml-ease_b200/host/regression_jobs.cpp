@@ -478,11 +478,12 @@ Value feature_value(const std::string& key, float v) {
   return r;
 }
 // models/LinearModel.java:697-720 toAvro: intercept first, every value cast to float
-Value model_list(const Dictionary& dict, const float* coef /*[D+1], intercept last*/) {
+Value model_list(const Dictionary& dict, const float* coef /*[D+1], intercept last*/, const std::vector<int32_t>* subset = nullptr) {
   Value a; a.type = Schema::Array;
   const int D = (int)dict.names.size();
   a.items.push_back(feature_value(INTERCEPT, coef[D]));
-  for (int k = 0; k < D; k++) a.items.push_back(feature_value(dict.names[k], coef[k]));
+  if (subset) { for (int32_t k : *subset) a.items.push_back(feature_value(dict.names[k], coef[k])); }
+  else for (int k = 0; k < D; k++) a.items.push_back(feature_value(dict.names[k], coef[k]));
   return a;
 }
 // The (name, term) part of every feature record of a model list in Avro binary, intercept first (models/LinearModel.java:697-720):
@@ -509,17 +510,27 @@ struct FeaturePrefix {
     for (size_t k = 0; k < D; k++) { o.append(bytes, off[k + 1], off[k + 2] - off[k + 1]); put_float(o, coef[k]); }
     put_long(o, 0);
   }
+  // the intercept and the listed features only (a NaiveTrain model holds the features its key's rows list, llf/LibLinear.java:343-350)
+  void encode_subset(std::string& o, const float* coef, const std::vector<int32_t>& subset) const {
+    const size_t D = off.size() - 2;
+    put_long(o, (int64_t)(subset.size() + 1));
+    o.append(bytes, off[0], off[1] - off[0]); put_float(o, coef[D]);
+    for (int32_t k : subset) { o.append(bytes, off[(size_t)k + 1], off[(size_t)k + 2] - off[(size_t)k + 1]); put_float(o, coef[k]); }
+    put_long(o, 0);
+  }
 };
-// LinearModelAvro records {key, model}; with uplusx: RegressionTrainOutput records {key, model, uplusx} (:706-711)
+// LinearModelAvro records {key, model}; with uplusx: RegressionTrainOutput records {key, model, uplusx} (:706-711).
+// subsets (one entry per model, NULL = all features): the dictionary ids a model lists, ascending.
 void write_model_records(const std::string& path, const Dictionary& dict, const std::vector<std::pair<std::string, std::vector<float>>>& models,
-                         const std::vector<std::vector<float>>* uplusx = nullptr) {
+                         const std::vector<std::vector<float>>* uplusx = nullptr, const std::vector<const std::vector<int32_t>*>* subsets = nullptr) {
   AvroWriter w(path, uplusx ? schema_train_output() : schema_linear_model());
   if (host_generic_ingest()) {   // Value-tree encoder: the reference implementation the tests compare with
     for (size_t i = 0; i < models.size(); i++) {
       Value r; r.type = Schema::Record; r.items.resize(uplusx ? 3 : 2);
       r.items[0] = Value::of_string(models[i].first);
-      r.items[1] = model_list(dict, models[i].second.data());
-      if (uplusx) r.items[2] = model_list(dict, (*uplusx)[i].data());
+      const std::vector<int32_t>* sub = subsets ? (*subsets)[i] : nullptr;
+      r.items[1] = model_list(dict, models[i].second.data(), sub);
+      if (uplusx) r.items[2] = model_list(dict, (*uplusx)[i].data(), sub);
       w.append(r);
     }
   } else {
@@ -528,8 +539,9 @@ void write_model_records(const std::string& path, const Dictionary& dict, const 
     for (size_t i = 0; i < models.size(); i++) {
       rec.clear();
       put_str(rec, models[i].first.data(), models[i].first.size());
-      fp.encode(rec, models[i].second.data());
-      if (uplusx) fp.encode(rec, (*uplusx)[i].data());
+      const std::vector<int32_t>* sub = subsets ? (*subsets)[i] : nullptr;
+      if (sub) fp.encode_subset(rec, models[i].second.data(), *sub); else fp.encode(rec, models[i].second.data());
+      if (uplusx) { if (sub) fp.encode_subset(rec, (*uplusx)[i].data(), *sub); else fp.encode(rec, (*uplusx)[i].data()); }
       w.append_encoded(rec.data(), rec.size(), 1);
     }
   }
@@ -1318,6 +1330,16 @@ void run_naive_train(const JobConfig& c) {
     krs.push_back((int64_t)rr.size());
   }
   std::vector<std::pair<std::string, std::vector<float>>> models;
+  // a key's model lists the features its rows list, plus the intercept (the reducer's dataset holds nothing else:
+  // llf/LibLinear.java:343-350, no prior-mean map in NaiveTrain, jobs/RegressionNaiveTrain.java:395): not all D of the job
+  std::vector<std::vector<int32_t>> present(K);
+  for (int k = 0; k < K; k++) {
+    std::vector<int32_t>& pk = present[k];
+    pk.assign(ci.begin() + rp[krs[k]], ci.begin() + rp[krs[k + 1]]);
+    std::sort(pk.begin(), pk.end());
+    pk.erase(std::unique(pk.begin(), pk.end()), pk.end());
+  }
+  std::vector<const std::vector<int32_t>*> model_feats;
   std::map<std::string, std::pair<int, std::vector<double>>> sums;
   std::vector<double> m((size_t)L * K * Dt); std::vector<int32_t> skipped(K);
   ck(mlease_naive_train(gpu_devices(c)[0], nullptr, K, D, krs.data(), rp.data(), ci.data(), vv.data(), 0, rr.data(), ww.data(), oo.data(), L, lambdas.data(),
@@ -1330,11 +1352,12 @@ void run_naive_train(const JobConfig& c) {
       if (skipped[k]) continue;
       std::vector<float> mf(Dt); for (int j = 0; j < Dt; j++) mf[j] = (float)m[((size_t)l * K + k) * Dt + j];
       models.emplace_back(ls + "#" + knames[k], mf);
+      model_feats.push_back(&present[k]);
       acc.first++;
       if (mean) for (int j = 0; j < Dt; j++) acc.second[j] = 1.0 * acc.second[j] + (1.0 / nblocks) * (double)mf[j];   // cons/MeanLinearModelConsumer.java:59-63
     }
   }
-  write_linear_models(out + "/models/part-r-00000.avro", dict, models);
+  write_model_records(out + "/models/part-r-00000.avro", dict, models, nullptr, &model_feats);
   if (mean) {
     int total = 0; for (auto& kv : sums) total += kv.second.first;
     if (total != (int)lambdas.size() * nblocks) throw std::runtime_error("Some models failed!");

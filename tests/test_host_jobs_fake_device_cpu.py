@@ -176,3 +176,25 @@ def test_remove_tmp_dir_leaves_only_the_results(fake_host, tmp_path):
     _run(fake_host, "RegressionAdmmTrain", cfg)
     left = sorted(os.listdir(out))
     assert left == ["best-model", "final-model", "lambda-rho", "sample-test-loglik"], left
+
+
+def test_naive_train_models_list_the_features_of_their_key_only(fake_host, tmp_path):
+    """A NaiveTrain reducer's dataset holds the features its key's rows list, and so does its model (llf/LibLinear.java:343-350; no
+    prior-mean map in NaiveTrain): not every feature of the job.  The mean model still covers all of them."""
+    schema = {"type": "record", "name": "r", "fields": [
+        {"name": "features", "type": {"type": "array", "items": {"type": "record", "name": "f", "fields": [
+            {"name": "name", "type": "string"}, {"name": "term", "type": "string"}, {"name": "value", "type": "float"}]}}},
+        {"name": "response", "type": "int"}, {"name": "pkey", "type": "int"}]}
+    def rec(key, feats, y):
+        return {"features": [{"name": n, "term": t, "value": 1.0} for n, t in feats], "response": y, "pkey": key}
+    recs = [rec(0, [("a", ""), ("b", "x")], 1), rec(0, [("a", "")], 0), rec(1, [("b", "x"), ("c", "")], 1), rec(1, [("c", "")], 0)]
+    au.write_avro(str(tmp_path / "in" / "p.avro"), schema, recs)
+    out = str(tmp_path / "out")
+    _run(fake_host, "RegressionPrepare", _cfg(str(tmp_path / "p.job"), input_paths=str(tmp_path / "in"), output_path=out + "/tmp-data", map_key="pkey", num_blocks=2))
+    cfg = _cfg(str(tmp_path / "n.job"), output_base_path=out, num_blocks=2, remove_tmp_dir="false")
+    open(cfg, "a").write("lambda=1\n")
+    _run(fake_host, "NaiveTrain", cfg)
+    models = {r["key"]: [(f["name"], f["term"]) for f in r["model"]] for r in au.read_dir(out + "/models")}
+    assert models == {"1.0#0": [("(INTERCEPT)", ""), ("a", ""), ("b", "x")], "1.0#1": [("(INTERCEPT)", ""), ("b", "x"), ("c", "")]}
+    mean = au.read_dir(out + "/final-model")
+    assert len(mean) == 1 and [(f["name"], f["term"]) for f in mean[0]["model"]] == [("(INTERCEPT)", ""), ("a", ""), ("b", "x"), ("c", "")]

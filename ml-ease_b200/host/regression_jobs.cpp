@@ -1121,6 +1121,14 @@ void run_admm_train(const JobConfig& c) {
     // under <out>/initialModel like the reference (:239-260), then averaged as float models (cons/MeanLinearModelConsumer.java:44-70).
     std::vector<double> z0((size_t)L * Dt, 0.0);
     std::vector<std::pair<std::string, std::vector<float>>> init_models;
+    // like every NaiveTrain model, an initial model lists the features its partition's rows list (+ the intercept)
+    std::vector<std::vector<int32_t>> present(nblocks);
+    for (int p = 0; p < nblocks; p++) {
+      std::vector<char> seen(D, 0);
+      for (size_t i : by_part[p]) for (int64_t j = rows.rowptr[i]; j < rows.rowptr[i + 1]; j++) seen[rows.colidx[j]] = 1;
+      for (int k = 0; k < D; k++) if (seen[k]) present[p].push_back(k);
+    }
+    std::vector<const std::vector<int32_t>*> init_feats;
     for (int l = 0; l < L; l++) {
       std::vector<double> q(Dt, (double)lambdas[l]), zero(Dt, 0.0);
       for (int k = 0; k < D; k++) if (!lambda_map.empty() && lambda_map[k] > 0) q[k] = (double)lambda_map[k];   // propsIni.put(LAMBDA_MAP, ...) (:248)
@@ -1132,9 +1140,10 @@ void run_admm_train(const JobConfig& c) {
         std::vector<float> xf(Dt);
         for (int k = 0; k < Dt; k++) { xf[k] = (float)x[k]; z0[(size_t)l * Dt + k] = 1.0 * z0[(size_t)l * Dt + k] + (1.0 / nblocks) * (double)xf[k]; }
         init_models.emplace_back(java_float_to_string(lambdas[l]) + "#" + std::to_string(p), xf);
+        init_feats.push_back(&present[p]);
       }
     }
-    write_linear_models(out + "/initialModel/part-r-00000.avro", dict, init_models);
+    write_model_records(out + "/initialModel/part-r-00000.avro", dict, init_models, nullptr, &init_feats);
     if (test_per_iter) {   // updateLogLikBestModel(conf, 0, z, ...) (:272-275): the mean model's sample log-likelihood; no best-model at iteration 0 (:833)
       AvroWriter w(out + "/sample-test-loglik/iteration-0.avro", SCHEMA_SAMPLE_LOGLIK);
       for (int l = 0; l < L; l++) {

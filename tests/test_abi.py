@@ -104,3 +104,32 @@ def test_jni_shim_type_checks_links_and_matches_the_java_class(tmp_path):
         java = open(os.path.join(ROOT, "integration", "jni", cls + ".java")).read()
         declared = set(re.findall(r"\bnative\s+[\w\[\]]+\s+(\w+)\s*\(", java))
         assert exported == declared and len(declared) == count, (cls, sorted(exported ^ declared))
+
+
+def test_jni_shim_runs_against_a_fake_jnienv_and_the_device_test_double(tmp_path):
+    """The shim is also EXECUTED: tests/jni_stub/run_shim.c implements the JNIEnv entries it uses (arrays handed out as copies, so a
+    result reaches the caller only if the shim releases it with mode 0) and drives NativeAdmm / NativeOps against the test double of
+    the device library (tests/fake_device/), comparing with direct C ABI calls, and NativeIngest against an avro file."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import avro_util as au
+    import numpy as np
+    from mlease_b200 import build as _b
+    _b.build()
+    exe = str(tmp_path / "run_shim")
+    lib = os.path.join(ROOT, "ml-ease_b200", "lib")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-O1", "-I", os.path.join(ROOT, "tests", "jni_stub"), "-I", os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "jni_stub", "run_shim.c"), os.path.join(ROOT, "integration", "jni", "mlease_b200_jni.c"),
+                           os.path.join(ROOT, "tests", "fake_device", "fake_mlease_b200.c"), "-L", lib, "-lmlease_host", "-lmlease_b200", "-Wl,-rpath," + lib, "-lm"])
+    schema = {"type": "record", "name": "RegressionPrepareOutput", "fields": [
+        {"name": "key", "type": "string"}, {"name": "response", "type": "int"},
+        {"name": "features", "type": {"type": "array", "items": {"type": "record", "name": "feature", "fields": [
+            {"name": "name", "type": "string"}, {"name": "term", "type": "string"}, {"name": "value", "type": "float"}]}}},
+        {"name": "weight", "type": "float"}, {"name": "offset", "type": "float"}]}
+    recs = [{"key": str(i % 2), "response": i % 2, "features": [{"name": "f%d" % ((i + j) % 5), "term": "", "value": 1.0} for j in range(3)], "weight": 1.0, "offset": 0.0}
+            for i in range(20)]
+    p = str(tmp_path / "prep.avro")
+    au.write_avro(p, schema, recs, block=6)
+    out = subprocess.run([exe, p, "20", "60", "5", "f0"], capture_output=True, text=True)
+    assert out.returncode == 0 and "JNI shim OK" in out.stdout, out.stdout + out.stderr
